@@ -1,0 +1,138 @@
+/*
+ * nmfb200.h -- C ABI of libnmfb200.so, the B200 (sm_100a) accelerator for the per-iteration hot
+ * path of JuliaStats/NMF.jl (reference @ 2eed3ec, v1.0.3).
+ *
+ * The boundary sits at `NMF.solve!(alg, X, W, H) -> NMF.Result{T}` (reference src/multupd.jl:45,
+ * src/greedycd.jl:33), one level above the reference's internal updater protocol
+ * (prepare_state / update_wh! / evaluate_objv, src/common.jl:43-89), because a per-`update_wh!`
+ * boundary would force W and H across PCIe every iteration.  Each entry point below names the
+ * reference interface it replaces.  A Julia `ccall` binding is in nmf.jl_b200/julia/NMFB200.jl,
+ * the Python ctypes binding used by the tests is nmf.jl_b200/_lib.py; both bind exactly this file.
+ *
+ * Conventions
+ *   - plain C, no CUDA / torch types in any signature; `void* stream` is a cudaStream_t.
+ *   - every matrix is COLUMN-MAJOR with an explicit leading dimension (Julia `Matrix{T}` layout):
+ *       X  p x n (ldx >= p), W  p x k (ldw >= p), H  k x n (ldh >= k).
+ *     A C-order NumPy array of shape (n, p) is byte-identical to a Julia p x n matrix.
+ *   - the caller owns all host buffers; W and H are updated IN PLACE (the reference mutates the
+ *     caller's W, H: README.md:160-166) and X is read-only.
+ *   - every function returns an nmfb200_status; nothing throws or exits across the ABI.
+ *   - a handle is single-owner (one call at a time); distinct handles may be used from distinct
+ *     host threads.  One handle drives one GPU; multi-GPU = one handle per process/GPU joined by
+ *     nmfb200_comm_init (rows of X and W sharded across ranks, H replicated).
+ */
+#ifndef NMFB200_H
+#define NMFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NMFB200_VERSION 100 /* 0.1.0 */
+
+typedef enum nmfb200_status {
+    NMFB200_OK = 0,
+    NMFB200_EINVAL = 1,  /* -> Julia ArgumentError       (multupd.jl:27-31, greedycd.jl:25-28, interf.jl:15-33) */
+    NMFB200_EDIM = 2,    /* -> Julia DimensionMismatch   (common.jl:12-14) */
+    NMFB200_ECUDA = 3,   /* CUDA runtime / driver error; text in nmfb200_last_error */
+    NMFB200_ENCCL = 4,   /* NCCL error */
+    NMFB200_ENOMEM = 5,  /* device allocation failed */
+    NMFB200_ESTATE = 6,  /* call order violated (e.g. solve before set_X) */
+    NMFB200_ENOTSUP = 7  /* valid request this build does not accelerate */
+} nmfb200_status;
+
+/* Mirrors NMF.Result{T} (common.jl:21-34) minus the W/H aliases (the caller's own arrays). */
+typedef struct nmfb200_result {
+    int64_t niters;             /* Result.niters    (common.jl:24) */
+    int32_t converged;          /* Result.converged (common.jl:25) */
+    int32_t engine;             /* 0 = SIMT fp32/fp64 kernels, 1 = tcgen05 bf16 tensor-core kernels */
+    double objvalue;            /* Result.objvalue  (common.jl:26), already rounded to T */
+    double last_dev;            /* `dev` of the last stop_condition call (common.jl:73); full max, not partial */
+    double solve_ms;            /* device time of the iteration loop (CUDA events), excl. transfers */
+    double upload_ms;           /* host->device time of W/H (and X if passed through solve) */
+    int64_t coordinate_updates; /* GreedyCD only: inner coordinate steps taken (greedycd.jl:144-162) */
+    int64_t kernel_launches;    /* number of library kernels launched by this call */
+} nmfb200_result;
+
+typedef struct nmfb200_handle nmfb200_handle;
+
+/* Called once per iteration when verbose != 0 -- replaces the table printed at common.jl:57-58,80-81.
+ * iter = 0 is the pre-loop line (common.jl:56-58; objv_change and dev are NaN there). */
+typedef void (*nmfb200_trace_fn)(void* user, int64_t iter, double elapsed_s, double objv,
+                                 double objv_change, double dev);
+
+/* ---- lifetime ---------------------------------------------------------------------------------- */
+int nmfb200_version(void);
+const char* nmfb200_status_string(int status);
+/* device: CUDA ordinal.  flags: reserved, pass 0. */
+int nmfb200_create(nmfb200_handle** out, int device, int flags);
+int nmfb200_destroy(nmfb200_handle* h);
+const char* nmfb200_last_error(const nmfb200_handle* h);
+/* Run all work of this handle on the caller's stream (cudaStream_t); NULL = the handle's own. */
+int nmfb200_set_stream(nmfb200_handle* h, void* stream);
+/* Options (key, value):
+ *   "engine"      = "auto" | "simt" | "tc"   -- simt: exact fp32/fp64 CUDA-core kernels;
+ *                                               tc: tcgen05 bf16-operand / fp32-accumulate kernels
+ *                                               (Float32 only); auto = tc when shape allows.
+ *   "check_every" = "<int>"                  -- host polls the device convergence flag every N
+ *                                               iterations (results are independent of N). */
+int nmfb200_set_option(nmfb200_handle* h, const char* key, const char* value);
+int nmfb200_set_trace(nmfb200_handle* h, nmfb200_trace_fn fn, void* user);
+
+/* ---- data: the X argument of solve!(alg, X, W, H) ---------------------------------------------- */
+/* Uploads (or adopts, for the _dev variants: X already resident on this handle's GPU) the data
+ * matrix.  Stays resident across solves (replicates, interf.jl:85-101, reuse it).  Does the
+ * non-negativity scan of interf.jl:15 only if check_nonneg != 0 (EINVAL on a negative entry). */
+int nmfb200_set_X_f32(nmfb200_handle* h, const float* X, int64_t p, int64_t n, int64_t ldx, int check_nonneg);
+int nmfb200_set_X_f64(nmfb200_handle* h, const double* X, int64_t p, int64_t n, int64_t ldx, int check_nonneg);
+int nmfb200_set_X_dev_f32(nmfb200_handle* h, const float* dX, int64_t p, int64_t n, int64_t ldx, int check_nonneg);
+int nmfb200_set_X_dev_f64(nmfb200_handle* h, const double* dX, int64_t p, int64_t n, int64_t ldx, int check_nonneg);
+
+/* ---- solve!: one entry point per (algorithm, eltype) -------------------------------------------
+ * Common arguments: W (p x k, ldw), H (k x n, ldh) initialised by the caller, updated in place.
+ * `on_device` != 0: W and H are device pointers on this handle's GPU (no PCIe traffic).
+ * maxiter/tol/lambda_w/lambda_h/update_H/verbose: the fields of the algorithm struct.  Validation
+ * is the constructor's (EINVAL): maxiter > 1, tol > 0, lambda >= 0.  niters/converged/objvalue
+ * follow nmf_skeleton! (common.jl:45-89) and stop_condition (common.jl:92-111). */
+
+/* NMF.solve!(::MultUpdate{T} with obj=:mse, X, W, H)  -- multupd.jl:45-48, :83-116 */
+int nmfb200_solve_multmse_f32(nmfb200_handle* h, float* W, int64_t ldw, float* H, int64_t ldh, int64_t k,
+                              int64_t maxiter, float tol, float lambda_w, float lambda_h, int update_H,
+                              int verbose, int on_device, nmfb200_result* out);
+int nmfb200_solve_multmse_f64(nmfb200_handle* h, double* W, int64_t ldw, double* H, int64_t ldh, int64_t k,
+                              int64_t maxiter, double tol, double lambda_w, double lambda_h, int update_H,
+                              int verbose, int on_device, nmfb200_result* out);
+/* NMF.solve!(::MultUpdate{T} with obj=:div, X, W, H)  -- multupd.jl:45-51, :150-193.
+ * The lambda floor max(lambda, sqrt(eps(T))) of the constructor (multupd.jl:37-40) is applied here. */
+int nmfb200_solve_multdiv_f32(nmfb200_handle* h, float* W, int64_t ldw, float* H, int64_t ldh, int64_t k,
+                              int64_t maxiter, float tol, float lambda_w, float lambda_h, int update_H,
+                              int verbose, int on_device, nmfb200_result* out);
+int nmfb200_solve_multdiv_f64(nmfb200_handle* h, double* W, int64_t ldw, double* H, int64_t ldh, int64_t k,
+                              int64_t maxiter, double tol, double lambda_w, double lambda_h, int update_H,
+                              int verbose, int on_device, nmfb200_result* out);
+/* NMF.solve!(::GreedyCD{T}, X, W, H)  -- greedycd.jl:33-34, :94-178 */
+int nmfb200_solve_greedycd_f32(nmfb200_handle* h, float* W, int64_t ldw, float* H, int64_t ldh, int64_t k,
+                               int64_t maxiter, float tol, float lambda_w, float lambda_h, int update_H,
+                               int verbose, int on_device, nmfb200_result* out);
+int nmfb200_solve_greedycd_f64(nmfb200_handle* h, double* W, int64_t ldw, double* H, int64_t ldh, int64_t k,
+                               int64_t maxiter, double tol, double lambda_w, double lambda_h, int update_H,
+                               int verbose, int on_device, nmfb200_result* out);
+
+/* ---- multi-GPU: rows of X / W sharded over ranks, H replicated -----------
+ * No counterpart in the reference (single process).  One handle per rank/GPU.  The unique id is an
+ * opaque 128-byte blob (an ncclUniqueId) created on rank 0 and distributed by the host program
+ * (torch.distributed / MPI / sockets).  After comm_init every solve on the handle treats its X, W
+ * as the rank's row shard and all-reduces the k x k Gram, the k x n accumulator and the
+ * convergence partial sums once per iteration over NCCL. */
+#define NMFB200_UNIQUE_ID_BYTES 128
+int nmfb200_comm_unique_id(void* out_id_128);
+int nmfb200_comm_init(nmfb200_handle* h, int rank, int nranks, const void* id_128);
+int nmfb200_comm_destroy(nmfb200_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NMFB200_H */

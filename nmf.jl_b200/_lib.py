@@ -1,0 +1,86 @@
+"""ctypes binding of include/nmfb200.h -- one Python function per C entry point, nothing else.
+The library is required: there is no CPU or PyTorch fallback behind this module."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libnmfb200.so")
+
+OK, EINVAL, EDIM, ECUDA, ENCCL, ENOMEM, ESTATE, ENOTSUP = range(8)
+UNIQUE_ID_BYTES = 128
+
+
+class NmfResult(ctypes.Structure):
+    _fields_ = [
+        ("niters", ctypes.c_int64),
+        ("converged", ctypes.c_int32),
+        ("engine", ctypes.c_int32),
+        ("objvalue", ctypes.c_double),
+        ("last_dev", ctypes.c_double),
+        ("solve_ms", ctypes.c_double),
+        ("upload_ms", ctypes.c_double),
+        ("coordinate_updates", ctypes.c_int64),
+        ("kernel_launches", ctypes.c_int64),
+    ]
+
+
+TRACE_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_double,
+                            ctypes.c_double, ctypes.c_double)
+
+# name -> (restype, argtypes); kept in one table so tests can check it against the header
+_vp, _i, _i64, _f, _d, _cp = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double, ctypes.c_char_p
+
+
+def _solve_sig(ct):
+    return (_i, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, ct, ct, ct, _i, _i, _i, ctypes.POINTER(NmfResult)])
+
+
+SIGNATURES = {
+    "nmfb200_version": (_i, []),
+    "nmfb200_status_string": (_cp, [_i]),
+    "nmfb200_create": (_i, [ctypes.POINTER(_vp), _i, _i]),
+    "nmfb200_destroy": (_i, [_vp]),
+    "nmfb200_last_error": (_cp, [_vp]),
+    "nmfb200_set_stream": (_i, [_vp, _vp]),
+    "nmfb200_set_option": (_i, [_vp, _cp, _cp]),
+    "nmfb200_set_trace": (_i, [_vp, TRACE_FN, _vp]),
+    "nmfb200_set_X_f32": (_i, [_vp, _vp, _i64, _i64, _i64, _i]),
+    "nmfb200_set_X_f64": (_i, [_vp, _vp, _i64, _i64, _i64, _i]),
+    "nmfb200_set_X_dev_f32": (_i, [_vp, _vp, _i64, _i64, _i64, _i]),
+    "nmfb200_set_X_dev_f64": (_i, [_vp, _vp, _i64, _i64, _i64, _i]),
+    "nmfb200_solve_multmse_f32": _solve_sig(_f),
+    "nmfb200_solve_multmse_f64": _solve_sig(_d),
+    "nmfb200_solve_multdiv_f32": _solve_sig(_f),
+    "nmfb200_solve_multdiv_f64": _solve_sig(_d),
+    "nmfb200_solve_greedycd_f32": _solve_sig(_f),
+    "nmfb200_solve_greedycd_f64": _solve_sig(_d),
+    "nmfb200_comm_unique_id": (_i, [_vp]),
+    "nmfb200_comm_init": (_i, [_vp, _i, _i, _vp]),
+    "nmfb200_comm_destroy": (_i, [_vp]),
+}
+
+_lib = None
+
+
+class LibraryMissing(ImportError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """dlopen libnmfb200.so (built by nmf.jl_b200/build.py).  Raises loudly if it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LibraryMissing(
+                f"{LIB_PATH} is missing: the CUDA library is the product and has no fallback. "
+                "Build it with `python -c 'import __graft_entry__ as g; g.build()'`."
+            )
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib

@@ -1,0 +1,432 @@
+"""
+Host-side mirror of NMF.jl's operator API for the accelerated path, above the C ABI
+(include/nmfb200.h).  Julia is not available in the build image, so this Python layer is what the
+tests drive; nmf.jl_b200/julia/NMFB200.jl is the same thing written as `ccall`s.
+
+Same names, argument meaning, defaults and error behaviour as the reference:
+  Result            common.jl:21-38        nnmf               interf.jl:3-83
+  MultUpdate        multupd.jl:9-43        solve_replicates   interf.jl:85-101
+  GreedyCD          greedycd.jl:10-31      randinit           initialization.jl:4-17
+  solve             multupd.jl:45 / greedycd.jl:33  (`NMF.solve!(alg, X, W, H)`)
+ProjectedALS / ALSPGrad / CoordinateDescent / SPA exist as option types (projals.jl:18-35,
+alspgrad.jl:352-373, coorddesc.jl:24-46, spa.jl:8-15) but are not on the accelerated path; solve()
+raises NotImplementedError for them rather than falling back to a CPU implementation.
+
+Arrays: NumPy, shapes as in Julia (X p x n, W p x k, H k x n).  Column-major (Fortran-order) arrays
+are passed to the library without a copy and updated in place; other layouts are staged through a
+column-major copy and written back, so `W` and `H` are always mutated like `solve!` does.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import warnings
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+
+
+class ArgumentError(ValueError):
+    """Julia ArgumentError."""
+
+
+class DimensionMismatch(ValueError):
+    """Julia DimensionMismatch."""
+
+
+class NmfB200Error(RuntimeError):
+    """CUDA / NCCL / state errors reported by libnmfb200."""
+
+
+def _raise(status: int, msg: str):
+    if status == _lib.EINVAL:
+        raise ArgumentError(msg)
+    if status == _lib.EDIM:
+        raise DimensionMismatch(msg)
+    if status == _lib.ENOTSUP:
+        raise NotImplementedError(msg)
+    raise NmfB200Error(f"[{_lib.load().nmfb200_status_string(status).decode()}] {msg}")
+
+
+def _eps(T) -> float:
+    return float(np.finfo(np.dtype(T)).eps)
+
+
+# --------------------------------------------------------------------------------------------------
+# Result (common.jl:21-38)
+# --------------------------------------------------------------------------------------------------
+class Result:
+    __slots__ = ("W", "H", "niters", "converged", "objvalue", "info")
+
+    def __init__(self, W: np.ndarray, H: np.ndarray, niters: int, converged: bool, objv, info=None):
+        if W.shape[1] != H.shape[0]:
+            raise DimensionMismatch("Inner dimensions of W and H mismatch.")
+        self.W, self.H = W, H
+        self.niters, self.converged = int(niters), bool(converged)
+        self.objvalue = W.dtype.type(objv)
+        self.info = info or {}
+
+    def __eq__(self, other):  # common.jl:37
+        return (isinstance(other, Result) and np.array_equal(self.W, other.W) and np.array_equal(self.H, other.H)
+                and self.niters == other.niters and self.converged == other.converged and self.objvalue == other.objvalue)
+
+    def __hash__(self):  # common.jl:38
+        return hash((self.W.tobytes(), self.H.tobytes(), self.niters, self.converged, float(self.objvalue)))
+
+    def __repr__(self):
+        return (f"Result{{{self.W.dtype.name}}}(W {self.W.shape}, H {self.H.shape}, niters={self.niters}, "
+                f"converged={self.converged}, objvalue={self.objvalue})")
+
+
+# --------------------------------------------------------------------------------------------------
+# algorithm option types
+# --------------------------------------------------------------------------------------------------
+class MultUpdate:
+    """multupd.jl:9-43"""
+
+    def __init__(self, T=np.float64, *, obj="mse", maxiter=100, verbose=False, tol=None, update_H=True,
+                 lambda_w=0.0, lambda_h=0.0, lambda_=None):
+        T = np.dtype(T)
+        tol = np.cbrt(_eps(T)) if tol is None else tol
+        if obj not in ("mse", "div"):
+            raise ArgumentError("Invalid value for obj.")
+        if not maxiter > 1:
+            raise ArgumentError("maxiter must be greater than 1.")
+        if not tol > 0:
+            raise ArgumentError("tol must be positive.")
+        if not lambda_w >= 0:
+            raise ArgumentError("lambda_w must be non-negative.")
+        if not lambda_h >= 0:
+            raise ArgumentError("lambda_h must be non-negative.")
+        if lambda_ is not None and lambda_ >= 0:
+            warnings.warn("lambda is deprecated, use lambda_w and lambda_h instead.")
+            lambda_w = lambda_ if lambda_w == 0 else lambda_w
+            lambda_h = lambda_ if lambda_h == 0 else lambda_h
+        if obj == "div":
+            lambda_w = max(lambda_w, math.sqrt(_eps(T)))
+            lambda_h = max(lambda_h, math.sqrt(_eps(T)))
+        self.T, self.obj, self.maxiter, self.verbose = T, obj, int(maxiter), bool(verbose)
+        self.tol, self.update_H = T.type(tol), bool(update_H)
+        self.lambda_w, self.lambda_h = T.type(lambda_w), T.type(lambda_h)
+
+
+class GreedyCD:
+    """greedycd.jl:10-31"""
+
+    def __init__(self, T=np.float64, *, maxiter=100, verbose=False, tol=None, update_H=True, lambda_w=0.0, lambda_h=0.0):
+        T = np.dtype(T)
+        tol = np.cbrt(_eps(T)) if tol is None else tol
+        if not maxiter > 1:
+            raise ArgumentError("maxiter must be greater than 1.")
+        if not tol > 0:
+            raise ArgumentError("tol must be positive.")
+        if not lambda_w >= 0:
+            raise ArgumentError("lambda_w must be non-negative.")
+        if not lambda_h >= 0:
+            raise ArgumentError("lambda_h must be non-negative.")
+        self.T, self.maxiter, self.verbose = T, int(maxiter), bool(verbose)
+        self.tol, self.update_H = T.type(tol), bool(update_H)
+        self.lambda_w, self.lambda_h = T.type(lambda_w), T.type(lambda_h)
+
+
+class ProjectedALS:
+    """projals.jl:18-35 (no validation in the reference constructor).  Not accelerated yet."""
+
+    def __init__(self, T=np.float64, *, maxiter=100, verbose=False, tol=None, update_H=True, lambda_w=None, lambda_h=None):
+        T = np.dtype(T)
+        c = np.cbrt(_eps(T))
+        self.T, self.maxiter, self.verbose = T, int(maxiter), bool(verbose)
+        self.tol = T.type(c if tol is None else tol)
+        self.update_H = bool(update_H)
+        self.lambda_w = T.type(c if lambda_w is None else lambda_w)
+        self.lambda_h = T.type(c if lambda_h is None else lambda_h)
+
+
+class ALSPGrad:
+    """alspgrad.jl:352-373.  Not accelerated yet."""
+
+    def __init__(self, T=np.float64, *, maxiter=100, maxsubiter=200, tol=None, tolg=None, update_H=True, verbose=False):
+        T = np.dtype(T)
+        self.T, self.maxiter, self.maxsubiter = T, int(maxiter), int(maxsubiter)
+        self.tol = T.type(np.cbrt(_eps(T)) if tol is None else tol)
+        self.tolg = T.type(_eps(T) ** 0.25 if tolg is None else tolg)
+        self.update_H, self.verbose = bool(update_H), bool(verbose)
+
+
+class CoordinateDescent:
+    """coorddesc.jl:24-46.  Not accelerated yet."""
+
+    def __init__(self, T=np.float64, *, maxiter=100, verbose=False, tol=None, update_H=True, alpha=0.0, l1ratio=0.0,
+                 regularization="both", shuffle=False):
+        T = np.dtype(T)
+        self.T, self.maxiter, self.verbose = T, int(maxiter), bool(verbose)
+        self.tol = T.type(np.cbrt(_eps(T)) if tol is None else tol)
+        self.update_H = bool(update_H)
+        self.alpha, self.l1ratio = T.type(alpha), T.type(l1ratio)
+        self.regularization, self.shuffle = regularization, bool(shuffle)
+
+
+class SPA:
+    """spa.jl:8-15.  Not accelerated (non-iterative)."""
+
+    def __init__(self, T=np.float64, *, obj="mse"):
+        if obj not in ("mse", "div"):
+            raise ArgumentError("Invalid value for obj.")
+        self.T, self.obj = np.dtype(T), obj
+
+
+# --------------------------------------------------------------------------------------------------
+# Session: one GPU handle with X resident (what `solve!` would keep alive between replicates)
+# --------------------------------------------------------------------------------------------------
+_SFX = {np.dtype(np.float32): "f32", np.dtype(np.float64): "f64"}
+
+
+def _col_major(a: np.ndarray, dtype) -> np.ndarray:
+    return np.asfortranarray(a, dtype=dtype)
+
+
+class Session:
+    def __init__(self, device: int = 0, engine: str = "auto", stream: Optional[int] = None):
+        self._lib = _lib.load()
+        h = ctypes.c_void_p()
+        st = self._lib.nmfb200_create(ctypes.byref(h), int(device), 0)
+        if st != _lib.OK:
+            _raise(st, f"nmfb200_create(device={device}) failed: {self._lib.nmfb200_status_string(st).decode()}")
+        self._h = h
+        self._trace_cb = None
+        self.dtype = None
+        self.shape = None
+        self._keep = None
+        self.set_option("engine", engine)
+        if stream is not None:
+            self._check(self._lib.nmfb200_set_stream(self._h, ctypes.c_void_p(stream)))
+
+    # -- plumbing
+    def _check(self, st):
+        if st != _lib.OK:
+            _raise(st, self._lib.nmfb200_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.nmfb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_option(self, key: str, value) -> None:
+        self._check(self._lib.nmfb200_set_option(self._h, key.encode(), str(value).encode()))
+
+    def set_trace(self, fn) -> None:
+        """fn(iter, elapsed_s, objv, objv_change, dev) -- the verbose table of common.jl:57-58,80-81."""
+        if fn is None:
+            self._trace_cb = _lib.TRACE_FN(0)
+        else:
+            self._trace_cb = _lib.TRACE_FN(lambda user, it, el, ob, ch, dv: fn(it, el, ob, ch, dv))
+        self._check(self._lib.nmfb200_set_trace(self._h, self._trace_cb, None))
+
+    # -- X
+    def set_X(self, X: np.ndarray, check_nonneg: bool = False) -> None:
+        X = np.asarray(X)
+        if X.ndim != 2:
+            raise DimensionMismatch("X must be a matrix")
+        T = X.dtype
+        if T not in _SFX:
+            raise ArgumentError(f"eltype {T} not supported (Float32 / Float64)")
+        Xf = _col_major(X, T)
+        p, n = Xf.shape
+        fn = getattr(self._lib, f"nmfb200_set_X_{_SFX[T]}")
+        self._check(fn(self._h, Xf.ctypes.data_as(ctypes.c_void_p), p, n, p, int(check_nonneg)))
+        self.dtype, self.shape = T, (p, n)
+
+    def set_X_device(self, ptr: int, p: int, n: int, ldx: int, dtype, check_nonneg: bool = False, keepalive=None) -> None:
+        """X already resident on this GPU (column-major p x n at device address `ptr`)."""
+        T = np.dtype(dtype)
+        fn = getattr(self._lib, f"nmfb200_set_X_dev_{_SFX[T]}")
+        self._check(fn(self._h, ctypes.c_void_p(ptr), p, n, ldx, int(check_nonneg)))
+        self.dtype, self.shape, self._keep = T, (p, n), keepalive
+
+    # -- multi-GPU
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = ctypes.create_string_buffer(_lib.UNIQUE_ID_BYTES)
+        st = _lib.load().nmfb200_comm_unique_id(buf)
+        if st != _lib.OK:
+            _raise(st, "ncclGetUniqueId failed")
+        return buf.raw
+
+    def comm_init(self, rank: int, nranks: int, unique_id: bytes) -> None:
+        buf = ctypes.create_string_buffer(unique_id, _lib.UNIQUE_ID_BYTES)
+        self._check(self._lib.nmfb200_comm_init(self._h, rank, nranks, buf))
+
+    # -- solve
+    def solve_raw(self, alg_name: str, T, W_ptr: int, ldw: int, H_ptr: int, ldh: int, k: int, maxiter: int, tol,
+                  lambda_w, lambda_h, update_H: bool, verbose: bool, on_device: bool) -> _lib.NmfResult:
+        T = np.dtype(T)
+        fn = getattr(self._lib, f"nmfb200_solve_{alg_name}_{_SFX[T]}")
+        res = _lib.NmfResult()
+        self._check(fn(self._h, ctypes.c_void_p(W_ptr), ldw, ctypes.c_void_p(H_ptr), ldh, k, int(maxiter), float(tol),
+                       float(lambda_w), float(lambda_h), int(update_H), int(verbose), int(on_device), ctypes.byref(res)))
+        return res
+
+    def solve(self, alg, W: np.ndarray, H: np.ndarray) -> Result:
+        """NMF.solve!(alg, X, W, H) with X = the matrix given to set_X."""
+        if isinstance(alg, MultUpdate):
+            name = "multmse" if alg.obj == "mse" else "multdiv"
+        elif isinstance(alg, GreedyCD):
+            name = "greedycd"
+        elif isinstance(alg, (ProjectedALS, ALSPGrad, CoordinateDescent, SPA)):
+            raise NotImplementedError(
+                f"{type(alg).__name__} is not on the accelerated path (SURVEY.md section 8f); "
+                "this package has no CPU fallback")
+        else:
+            raise TypeError(f"unknown algorithm type {type(alg).__name__}")
+        if self.shape is None:
+            raise NmfB200Error("set_X must precede solve")
+        T = alg.T
+        if self.dtype != T or W.dtype != T or H.dtype != T:
+            raise TypeError(f"element types differ: alg {T}, X {self.dtype}, W {W.dtype}, H {H.dtype}")
+        p, n = self.shape
+        k = W.shape[1]
+        if not (W.shape[0] == p and H.shape == (k, n)):  # nmf_checksize, common.jl:5-16
+            raise DimensionMismatch("Dimensions of X, W, and H are inconsistent.")
+        Wf = W if W.flags.f_contiguous else np.asfortranarray(W)
+        Hf = H if H.flags.f_contiguous else np.asfortranarray(H)
+        if alg.verbose and self._trace_cb is None:
+            self.set_trace(_print_trace)
+        r = self.solve_raw(name, T, Wf.ctypes.data, p, Hf.ctypes.data, k, k, alg.maxiter, alg.tol, alg.lambda_w,
+                           alg.lambda_h, alg.update_H, alg.verbose, False)
+        if Wf is not W:
+            W[...] = Wf
+        if Hf is not H:
+            H[...] = Hf
+        info = {"engine": "tc" if r.engine == 1 else "simt", "solve_ms": r.solve_ms, "upload_ms": r.upload_ms,
+                "last_dev": r.last_dev, "coordinate_updates": r.coordinate_updates, "kernel_launches": r.kernel_launches}
+        return Result(W, H, r.niters, bool(r.converged), r.objvalue, info)
+
+
+def _print_trace(it, elapsed, objv, change, dev):
+    if it == 0:  # common.jl:57-58
+        print("%-5s    %-13s    %-13s    %-13s    %-13s" % ("Iter", "Elapsed time", "objv", "objv.change", "(W & H).relchange"))
+        print("%5d    %13.6e    %13.6e" % (0, 0.0, objv))
+    else:  # common.jl:80-81
+        print("%5d    %13.6e    %13.6e    %13.6e    %13.6e" % (it, elapsed, objv, change, dev))
+
+
+# --------------------------------------------------------------------------------------------------
+# solve! / randinit / nnmf
+# --------------------------------------------------------------------------------------------------
+def solve(alg, X: np.ndarray, W: np.ndarray, H: np.ndarray, *, device: int = 0, engine: str = "auto",
+          session: Optional[Session] = None) -> Result:
+    """NMF.solve!(alg, X, W, H) -> Result.  W and H are updated in place."""
+    own = session is None
+    s = session or Session(device=device, engine=engine)
+    try:
+        if own or s.shape is None:
+            s.set_X(X)
+        return s.solve(alg, W, H)
+    finally:
+        if own:
+            s.close()
+
+
+def randinit(p: int, n: int, k: int, T, *, normalize: bool = False, zeroh: bool = False, rng=None):
+    """initialization.jl:4-12 (+ normalize1_cols!, utils.jl:26-32).  Host side, runs once per solve."""
+    T = np.dtype(T)
+    rng = rng if rng is not None else np.random.default_rng()
+    W = np.asfortranarray(rng.random((p, k)), dtype=T)
+    if normalize:
+        for j in range(k):
+            W[:, j] *= T.type(1) / W[:, j].sum(dtype=T)
+    H = np.zeros((k, n), dtype=T, order="F") if zeroh else np.asfortranarray(rng.random((k, n)), dtype=T)
+    return W, H
+
+
+def solve_replicates(alg, session: Session, W, H, *, replicates: int, initH: bool, rng=None) -> Result:
+    """interf.jl:85-101; X stays resident on the GPU across replicates."""
+    ret = session.solve(alg, W, H)
+    p, n = session.shape
+    k = W.shape[1]
+    minobjv = ret.objvalue
+    for _ in range(2, replicates + 1):
+        Wr, Hr = randinit(p, n, k, alg.T, normalize=True, zeroh=not initH, rng=rng)
+        tmp = session.solve(alg, Wr, Hr)
+        if minobjv > tmp.objvalue:
+            ret, minobjv = tmp, tmp.objvalue
+    return ret
+
+
+_NOT_ACCEL_INIT = ("nndsvd", "nndsvda", "nndsvdar", "spa")
+_NOT_ACCEL_ALG = ("projals", "alspgrad", "cd", "spa")
+
+
+def nnmf(X: np.ndarray, k: int, *, init: str = "nndsvdar", initdata=None, alg: str = "greedycd", maxiter: int = 100,
+         tol=None, replicates: int = 1, W0=None, H0=None, update_H: bool = True, verbose: bool = False, rng=None,
+         device: int = 0, engine: str = "auto") -> Result:
+    """interf.jl:3-83.  Same keyword names, defaults, validation order and messages.  `rng`, `device`
+    and `engine` are additions (Julia's global RNG has no NumPy counterpart)."""
+    X = np.asarray(X)
+    T = X.dtype
+    if T not in _SFX:
+        raise ArgumentError(f"eltype {T} not supported (Float32 / Float64)")
+    tol = np.cbrt(_eps(T) / 100) if tol is None else tol
+    if not bool((X >= 0).all()):  # interf.jl:15
+        raise ArgumentError("The elements of X must be non-negative.")
+    p, n = X.shape
+    if not k <= min(p, n):  # :18
+        raise ArgumentError("The value of k should not exceed min(size(X)).")
+    if not replicates >= 1:  # :20
+        raise ArgumentError("The value of replicates must be positive.")
+    if not update_H and init != "custom":  # :22-24
+        warnings.warn("Only W will be updated.")
+    if init == "custom":  # :26-33
+        if W0 is None or H0 is None:
+            raise ArgumentError("To use :custom initialization, set W0 and H0.")
+        if not bool((np.asarray(W0) >= 0).all()):
+            raise ArgumentError("The elements of W0 must be non-negative.")
+        if tuple(W0.shape) != (p, k):
+            raise ArgumentError("Invalid size for W0.")
+        if not bool((np.asarray(H0) >= 0).all()):
+            raise ArgumentError("The elements of H0 must be non-negative.")
+        if tuple(H0.shape) != (k, n):
+            raise ArgumentError("Invalid size for H0.")
+    elif W0 is not None or H0 is not None:  # :35
+        warnings.warn("Ignore W0 and H0 except for :custom initialization.")
+    initH = alg != "projals"  # :39
+    if init == "random":  # :42-43
+        W, H = randinit(p, n, k, T, normalize=True, zeroh=not initH, rng=rng)
+    elif init == "custom":  # :52-53
+        W, H = W0, H0
+        if W.dtype != T or H.dtype != T:
+            raise TypeError("W0 and H0 must have the element type of X")  # `W::Matrix{T}` assert, :57-58
+    elif init in _NOT_ACCEL_INIT:
+        raise NotImplementedError(f"init=:{init} is not on the accelerated path yet (SURVEY.md section 8f); "
+                                  "pass init='random' or init='custom'")
+    else:
+        raise ArgumentError("Invalid value for init.")  # :55
+    if alg == "multmse":  # :64-66
+        inst = MultUpdate(T, obj="mse", maxiter=maxiter, tol=tol, verbose=verbose, update_H=update_H)
+    elif alg == "multdiv":
+        inst = MultUpdate(T, obj="div", maxiter=maxiter, tol=tol, verbose=verbose, update_H=update_H)
+    elif alg == "greedycd":
+        inst = GreedyCD(T, maxiter=maxiter, tol=tol, verbose=verbose, update_H=update_H)
+    elif alg in _NOT_ACCEL_ALG:
+        if alg == "spa" and init != "spa":
+            raise ArgumentError("Invalid value for init, use :spa instead.")  # :74-76
+        raise NotImplementedError(f"alg=:{alg} is not on the accelerated path yet (SURVEY.md section 8f)")
+    else:
+        raise ArgumentError("Invalid algorithm.")  # :79
+    with Session(device=device, engine=engine) as s:
+        s.set_X(X)
+        return solve_replicates(inst, s, W, H, replicates=replicates, initH=initH, rng=rng)

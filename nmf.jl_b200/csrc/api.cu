@@ -1,0 +1,253 @@
+// api.cu -- the extern "C" surface declared in include/nmfb200.h.  Validation mirrors the reference
+// constructors (multupd.jl:27-31, greedycd.jl:25-28) and nmf_checksize (common.jl:5-16); every C++
+// exception is converted to a status code + message at this boundary.
+#include "common.cuh"
+
+using namespace nmfb200;
+
+namespace {
+
+template <typename T>
+__global__ void count_not_nonneg_kernel(const T* __restrict__ X, int64_t p, int64_t n, int64_t ldx, unsigned long long* out) {
+    unsigned long long c = 0;
+    int64_t len = p * n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i % p, col = i / p;
+        if (!(X[r + col * ldx] >= T(0))) ++c;  // interf.jl:15 `all(t -> t >= zero(T), X)`: NaN fails too
+    }
+    c = __reduce_add_sync(0xffffffffu, (unsigned)c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+template <typename F>
+int guarded(nmfb200_handle* h, F&& f) {
+    if (!h) return NMFB200_EINVAL;
+    try {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (cur != h->device) NMF_CUDA(cudaSetDevice(h->device));
+        h->launches = 0;
+        f();
+        h->err.clear();
+        return NMFB200_OK;
+    } catch (const Error& e) {
+        h->err = e.msg;
+        cudaGetLastError();
+        return e.status;
+    } catch (const std::exception& e) {
+        h->err = e.what();
+        return NMFB200_ECUDA;
+    } catch (...) {
+        h->err = "unknown exception";
+        return NMFB200_ECUDA;
+    }
+}
+
+template <typename T>
+void set_X_impl(nmfb200_handle* h, const T* X, int64_t p, int64_t n, int64_t ldx, int check_nonneg, bool on_device) {
+    NMF_REQUIRE(X != nullptr, NMFB200_EINVAL, "X is NULL");
+    NMF_REQUIRE(p > 0 && n > 0 && ldx >= p, NMFB200_EDIM, "invalid dimensions for X");
+    if (h->x_owned) h->drop("X");
+    h->x_owned = false;
+    h->dX = nullptr;
+    h->x_elt = 0;
+    const T* dX = X;
+    int64_t dld = ldx;
+    if (!on_device) {
+        T* buf = h->buf_t<T>("X", (size_t)p * n);
+        NMF_CUDA(cudaMemcpy2DAsync(buf, p * sizeof(T), X, ldx * sizeof(T), p * sizeof(T), n, cudaMemcpyHostToDevice, h->stream));
+        dX = buf;
+        dld = p;
+        h->x_owned = true;
+    }
+    if (check_nonneg) {
+        unsigned long long* cnt = (unsigned long long*)h->buf("X.nonneg_count", 16);
+        NMF_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), h->stream));
+        count_not_nonneg_kernel<T><<<148 * 8, 256, 0, h->stream>>>(dX, p, n, dld, cnt);
+        h->launches += 1;
+        unsigned long long c = 0;
+        NMF_CUDA(cudaMemcpyAsync(&c, cnt, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+        NMF_CUDA(cudaStreamSynchronize(h->stream));
+        NMF_REQUIRE(c == 0, NMFB200_EINVAL, "The elements of X must be non-negative.");
+    }
+    NMF_CUDA(cudaStreamSynchronize(h->stream));
+    h->dX = dX;
+    h->ldx = dld;
+    h->p = p;
+    h->n = n;
+    h->x_elt = (int)sizeof(T);
+    h->x_epoch += 1;
+}
+
+template <typename T>
+void solve_impl(nmfb200_handle* h, int alg, T* W, int64_t ldw, T* H, int64_t ldh, int64_t k, int64_t maxiter, double tol,
+                double lambda_w, double lambda_h, int update_H, int verbose, int on_device, nmfb200_result* out) {
+    NMF_REQUIRE(out != nullptr && W != nullptr && H != nullptr, NMFB200_EINVAL, "NULL argument");
+    std::memset(out, 0, sizeof(*out));
+    NMF_REQUIRE(h->x_elt != 0, NMFB200_ESTATE, "nmfb200_set_X must precede solve");
+    NMF_REQUIRE(h->x_elt == (int)sizeof(T), NMFB200_ESTATE, "X was set with a different element type");
+    NMF_REQUIRE(maxiter > 1, NMFB200_EINVAL, "maxiter must be greater than 1.");   // multupd.jl:28, greedycd.jl:25
+    NMF_REQUIRE(tol > 0, NMFB200_EINVAL, "tol must be positive.");                 // multupd.jl:29, greedycd.jl:26
+    NMF_REQUIRE(lambda_w >= 0, NMFB200_EINVAL, "lambda_w must be non-negative.");  // multupd.jl:30, greedycd.jl:27
+    NMF_REQUIRE(lambda_h >= 0, NMFB200_EINVAL, "lambda_h must be non-negative.");  // multupd.jl:31, greedycd.jl:28
+    NMF_REQUIRE(k >= 1 && ldw >= h->p && ldh >= k, NMFB200_EDIM, "Dimensions of X, W, and H are inconsistent.");  // common.jl:12-14
+    SolveArgs a{alg, k, maxiter, tol, lambda_w, lambda_h, update_H, verbose, on_device};
+    bool use_tc = false;
+    if (sizeof(T) == 4 && h->engine_opt != 1) {
+        use_tc = tc_supported(h, a);
+        NMF_REQUIRE(use_tc || h->engine_opt != 2, NMFB200_ENOTSUP, "engine=tc requested but this problem is not covered by the tensor-core engine");
+    } else {
+        NMF_REQUIRE(h->engine_opt != 2, NMFB200_ENOTSUP, "engine=tc supports Float32 only");
+    }
+    if (use_tc) tc_solve(h, a, (float*)W, ldw, (float*)H, ldh, out);
+    else simt_solve<T>(h, a, W, ldw, H, ldh, out);
+}
+
+}  // namespace
+
+extern "C" {
+
+int nmfb200_version(void) { return NMFB200_VERSION; }
+
+const char* nmfb200_status_string(int status) {
+    switch (status) {
+        case NMFB200_OK: return "ok";
+        case NMFB200_EINVAL: return "invalid argument";
+        case NMFB200_EDIM: return "dimension mismatch";
+        case NMFB200_ECUDA: return "CUDA error";
+        case NMFB200_ENCCL: return "NCCL error";
+        case NMFB200_ENOMEM: return "out of device memory";
+        case NMFB200_ESTATE: return "invalid call order";
+        case NMFB200_ENOTSUP: return "not supported";
+        default: return "unknown status";
+    }
+}
+
+int nmfb200_create(nmfb200_handle** out, int device, int flags) {
+    (void)flags;
+    if (!out) return NMFB200_EINVAL;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return NMFB200_ECUDA; }
+    if (device < 0 || device >= ndev) return NMFB200_EINVAL;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return NMFB200_ECUDA;
+    if (prop.major != 10) return NMFB200_ENOTSUP;  // sm_100a only: no other code path exists in this library
+    if (cudaSetDevice(device) != cudaSuccess) return NMFB200_ECUDA;
+    nmfb200_handle* h = new (std::nothrow) nmfb200_handle();
+    if (!h) return NMFB200_ENOMEM;
+    h->device = device;
+    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return NMFB200_ECUDA; }
+    h->stream = h->own_stream;
+    *out = h;
+    return NMFB200_OK;
+}
+
+int nmfb200_destroy(nmfb200_handle* h) {
+    if (!h) return NMFB200_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    try { tc_release(h); } catch (...) {}
+    if (h->comm) { try { NcclApi::get().CommDestroy(h->comm); } catch (...) {} }
+    h->free_all();
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return NMFB200_OK;
+}
+
+const char* nmfb200_last_error(const nmfb200_handle* h) { return h ? h->err.c_str() : "NULL handle"; }
+
+int nmfb200_set_stream(nmfb200_handle* h, void* stream) {
+    return guarded(h, [&] {
+        NMF_CUDA(cudaStreamSynchronize(h->stream));
+        h->stream = stream ? (cudaStream_t)stream : h->own_stream;
+    });
+}
+
+int nmfb200_set_option(nmfb200_handle* h, const char* key, const char* value) {
+    return guarded(h, [&] {
+        NMF_REQUIRE(key && value, NMFB200_EINVAL, "NULL option");
+        std::string k(key), v(value);
+        if (k == "engine") {
+            if (v == "auto") h->engine_opt = 0;
+            else if (v == "simt") h->engine_opt = 1;
+            else if (v == "tc") h->engine_opt = 2;
+            else throw Error{NMFB200_EINVAL, "engine must be auto|simt|tc"};
+        } else if (k == "check_every") {
+            int c = atoi(value);
+            NMF_REQUIRE(c >= 1, NMFB200_EINVAL, "check_every must be >= 1");
+            h->check_every = c;
+        } else {
+            throw Error{NMFB200_EINVAL, "unknown option " + k};
+        }
+    });
+}
+
+int nmfb200_set_trace(nmfb200_handle* h, nmfb200_trace_fn fn, void* user) {
+    return guarded(h, [&] { h->trace = fn; h->trace_user = user; });
+}
+
+int nmfb200_set_X_f32(nmfb200_handle* h, const float* X, int64_t p, int64_t n, int64_t ldx, int check_nonneg) {
+    return guarded(h, [&] { set_X_impl<float>(h, X, p, n, ldx, check_nonneg, false); });
+}
+int nmfb200_set_X_f64(nmfb200_handle* h, const double* X, int64_t p, int64_t n, int64_t ldx, int check_nonneg) {
+    return guarded(h, [&] { set_X_impl<double>(h, X, p, n, ldx, check_nonneg, false); });
+}
+int nmfb200_set_X_dev_f32(nmfb200_handle* h, const float* X, int64_t p, int64_t n, int64_t ldx, int check_nonneg) {
+    return guarded(h, [&] { set_X_impl<float>(h, X, p, n, ldx, check_nonneg, true); });
+}
+int nmfb200_set_X_dev_f64(nmfb200_handle* h, const double* X, int64_t p, int64_t n, int64_t ldx, int check_nonneg) {
+    return guarded(h, [&] { set_X_impl<double>(h, X, p, n, ldx, check_nonneg, true); });
+}
+
+#define NMFB200_DEFINE_SOLVE(NAME, ALG, T)                                                                                   \
+    int NAME(nmfb200_handle* h, T* W, int64_t ldw, T* H, int64_t ldh, int64_t k, int64_t maxiter, T tol, T lambda_w,         \
+             T lambda_h, int update_H, int verbose, int on_device, nmfb200_result* out) {                                    \
+        return guarded(h, [&] {                                                                                              \
+            solve_impl<T>(h, ALG, W, ldw, H, ldh, k, maxiter, (double)tol, (double)lambda_w, (double)lambda_h, update_H,     \
+                          verbose, on_device, out);                                                                          \
+        });                                                                                                                  \
+    }
+
+NMFB200_DEFINE_SOLVE(nmfb200_solve_multmse_f32, 0, float)
+NMFB200_DEFINE_SOLVE(nmfb200_solve_multmse_f64, 0, double)
+NMFB200_DEFINE_SOLVE(nmfb200_solve_multdiv_f32, 1, float)
+NMFB200_DEFINE_SOLVE(nmfb200_solve_multdiv_f64, 1, double)
+NMFB200_DEFINE_SOLVE(nmfb200_solve_greedycd_f32, 2, float)
+NMFB200_DEFINE_SOLVE(nmfb200_solve_greedycd_f64, 2, double)
+
+int nmfb200_comm_unique_id(void* out_id_128) {
+    if (!out_id_128) return NMFB200_EINVAL;
+    try {
+        static_assert(sizeof(ncclUniqueId) == NMFB200_UNIQUE_ID_BYTES, "ncclUniqueId size");
+        ncclUniqueId id;
+        if (NcclApi::get().GetUniqueId(&id) != ncclSuccess) return NMFB200_ENCCL;
+        std::memcpy(out_id_128, &id, sizeof(id));
+        return NMFB200_OK;
+    } catch (...) {
+        return NMFB200_ENCCL;
+    }
+}
+
+int nmfb200_comm_init(nmfb200_handle* h, int rank, int nranks, const void* id_128) {
+    return guarded(h, [&] {
+        NMF_REQUIRE(id_128 && nranks >= 1 && rank >= 0 && rank < nranks, NMFB200_EINVAL, "invalid rank/nranks/id");
+        if (h->comm) { NMF_NCCL(NcclApi::get().CommDestroy(h->comm)); h->comm = nullptr; }
+        ncclUniqueId id;
+        std::memcpy(&id, id_128, sizeof(id));
+        NMF_NCCL(NcclApi::get().CommInitRank(&h->comm, nranks, id, rank));
+        h->rank = rank;
+        h->nranks = nranks;
+    });
+}
+
+int nmfb200_comm_destroy(nmfb200_handle* h) {
+    return guarded(h, [&] {
+        if (h->comm) NMF_NCCL(NcclApi::get().CommDestroy(h->comm));
+        h->comm = nullptr;
+        h->rank = 0;
+        h->nranks = 1;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,169 @@
+// common.cuh -- handle, device-buffer cache, error plumbing and NCCL loader shared by the engines.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <nccl.h>
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/nmfb200.h"
+
+namespace nmfb200 {
+
+struct Error {
+    int status;
+    std::string msg;
+};
+
+#define NMF_CUDA(expr)                                                                             \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            throw ::nmfb200::Error{e__ == cudaErrorMemoryAllocation ? NMFB200_ENOMEM : NMFB200_ECUDA, \
+                                   std::string(#expr) + ": " + cudaGetErrorString(e__) + " (" +    \
+                                       __FILE__ + ":" + std::to_string(__LINE__) + ")"};           \
+        }                                                                                          \
+    } while (0)
+
+#define NMF_REQUIRE(cond, status, text)                        \
+    do {                                                       \
+        if (!(cond)) throw ::nmfb200::Error{(status), (text)}; \
+    } while (0)
+
+// ---- NCCL through dlopen: no link-time dependency, binds to the libnccl.so.2 already in the process
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    static NcclApi& get() {
+        static NcclApi api;
+        if (!api.lib) {
+            api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+            if (!api.lib) api.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+            NMF_REQUIRE(api.lib, NMFB200_ENCCL, std::string("cannot dlopen libnccl.so.2: ") + dlerror());
+            api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.lib, "ncclGetUniqueId");
+            api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
+            api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
+            api.AllReduce = (decltype(api.AllReduce))dlsym(api.lib, "ncclAllReduce");
+            api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
+            NMF_REQUIRE(api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString,
+                        NMFB200_ENCCL, "libnccl.so.2 lacks a required symbol");
+        }
+        return api;
+    }
+};
+
+#define NMF_NCCL(expr)                                                                                     \
+    do {                                                                                                   \
+        ncclResult_t r__ = (expr);                                                                         \
+        if (r__ != ncclSuccess)                                                                            \
+            throw ::nmfb200::Error{NMFB200_ENCCL, std::string(#expr) + ": " +                              \
+                                                      ::nmfb200::NcclApi::get().GetErrorString(r__)};      \
+    } while (0)
+
+struct DevBuf {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+
+template <typename T> struct NcclType;
+template <> struct NcclType<float> { static constexpr ncclDataType_t v = ncclFloat32; };
+template <> struct NcclType<double> { static constexpr ncclDataType_t v = ncclFloat64; };
+
+}  // namespace nmfb200
+
+// The opaque handle of the C ABI.
+struct nmfb200_handle {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // options
+    int engine_opt = 0;  // 0 auto, 1 simt, 2 tc
+    int check_every = 8;
+    nmfb200_trace_fn trace = nullptr;
+    void* trace_user = nullptr;
+
+    // X (column-major p x n as given; device pointer, owned or adopted)
+    int x_elt = 0;  // 0 none, 4 f32, 8 f64
+    int64_t p = 0, n = 0, ldx = 0;
+    const void* dX = nullptr;
+    bool x_owned = false;
+    uint64_t x_epoch = 0;     // bumped on every set_X; engines key their derived caches on it
+    uint64_t tc_x_epoch = 0;  // epoch the bf16 caches were built for
+
+    // multi-GPU
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+
+    // named device buffers, kept across solves
+    std::map<std::string, nmfb200::DevBuf> bufs;
+    int64_t launches = 0;  // kernels launched by the current call
+
+    void* buf(const std::string& name, size_t bytes) {
+        nmfb200::DevBuf& b = bufs[name];
+        if (b.bytes < bytes) {
+            if (b.ptr) NMF_CUDA(cudaFree(b.ptr));
+            b.ptr = nullptr;
+            b.bytes = 0;
+            NMF_CUDA(cudaMalloc(&b.ptr, bytes ? bytes : 16));
+            b.bytes = bytes ? bytes : 16;
+        }
+        return b.ptr;
+    }
+    template <typename T> T* buf_t(const std::string& name, size_t count) { return (T*)buf(name, count * sizeof(T)); }
+    void drop(const std::string& name) {
+        auto it = bufs.find(name);
+        if (it != bufs.end()) {
+            if (it->second.ptr) cudaFree(it->second.ptr);
+            bufs.erase(it);
+        }
+    }
+    void free_all() {
+        for (auto& kv : bufs)
+            if (kv.second.ptr) cudaFree(kv.second.ptr);
+        bufs.clear();
+    }
+
+    template <typename T> void allreduce_sum(T* ptr, size_t count) {
+        if (!comm) return;
+        NMF_NCCL(nmfb200::NcclApi::get().AllReduce(ptr, ptr, count, nmfb200::NcclType<T>::v, ncclSum, comm, stream));
+    }
+    template <typename T> void allreduce_max(T* ptr, size_t count) {
+        if (!comm) return;
+        NMF_NCCL(nmfb200::NcclApi::get().AllReduce(ptr, ptr, count, nmfb200::NcclType<T>::v, ncclMax, comm, stream));
+    }
+};
+
+namespace nmfb200 {
+
+struct SolveArgs {
+    int alg;  // 0 multmse, 1 multdiv, 2 greedycd
+    int64_t k;
+    int64_t maxiter;
+    double tol, lambda_w, lambda_h;
+    int update_H, verbose, on_device;
+};
+
+// engines (one translation unit each)
+template <typename T>
+void simt_solve(nmfb200_handle* h, const SolveArgs& a, T* W, int64_t ldw, T* H, int64_t ldh, nmfb200_result* out);
+bool tc_supported(const nmfb200_handle* h, const SolveArgs& a);
+void tc_solve(nmfb200_handle* h, const SolveArgs& a, float* W, int64_t ldw, float* H, int64_t ldh, nmfb200_result* out);
+void tc_release(nmfb200_handle* h);
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace nmfb200

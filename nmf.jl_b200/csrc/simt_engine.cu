@@ -1,0 +1,664 @@
+// simt_engine.cu -- the exact engine: CUDA-core fp32 / fp64 kernels for MultUpdate(:mse), MultUpdate(:div)
+// and GreedyCD.  It serves Float64 problems (BASELINE config 1), odd shapes, and is the on-GPU
+// cross-check for the tensor-core engine.  Arithmetic is the reference's, in the reference's
+// element type T, with these deliberate departures (all documented in DESIGN.md):
+//   * MU-MSE uses (W'W)H and W(HH') instead of W'(WH) and (WH)H' (multupd.jl:99,110) -- the same
+//     mathematics without the p x n intermediate.
+//   * reductions run in parallel (pairwise order) instead of Julia's sequential order.
+// Layouts on device are the caller's: column-major X (p x n), W (p x k), H (k x n).
+#include "common.cuh"
+
+namespace nmfb200 {
+namespace {
+
+// ---- un-fused arithmetic helpers (the reference's scalar loops are not FMA-contracted) ----------
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+template <typename T> __device__ __forceinline__ T eps_of();
+template <> __device__ __forceinline__ float eps_of<float>() { return 1.1920928955078125e-07f; }
+template <> __device__ __forceinline__ double eps_of<double>() { return 2.220446049250313e-16; }
+
+// ---- generic strided GEMM: C(m,n) = sum_k A(m,k) B(k,n); 64x64x16 tiles, 256 threads, 4x4 per thread
+constexpr int GBM = 64, GBN = 64, GBK = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const T* __restrict__ A, int64_t sAm, int64_t sAk,
+                                                   const T* __restrict__ B, int64_t sBk, int64_t sBn, T* __restrict__ C,
+                                                   int64_t sCm, int64_t sCn, int64_t sCz, int kchunk) {
+    __shared__ T As[GBK][GBM + 4];
+    __shared__ T Bs[GBK][GBN + 4];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
+    const int kbeg = blockIdx.z * kchunk;
+    const int kend = min(K, kbeg + kchunk);
+    const bool a_kfast = (sAk == 1), b_kfast = (sBk == 1);
+    const int tx = tid % 16, ty = tid / 16;
+    T acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+
+    for (int k0 = kbeg; k0 < kend; k0 += GBK) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            int mm, kk;
+            if (a_kfast) { kk = tid % GBK; mm = tid / GBK + 16 * r; } else { mm = tid % GBM; kk = tid / GBM + 4 * r; }
+            int gm = m0 + mm, gk = k0 + kk;
+            As[kk][mm] = (gm < M && gk < kend) ? A[(int64_t)gm * sAm + (int64_t)gk * sAk] : T(0);
+            int nn, kb;
+            if (b_kfast) { kb = tid % GBK; nn = tid / GBK + 16 * r; } else { nn = tid % GBN; kb = tid / GBN + 4 * r; }
+            int gn = n0 + nn, gkb = k0 + kb;
+            Bs[kb][nn] = (gn < N && gkb < kend) ? B[(int64_t)gkb * sBk + (int64_t)gn * sBn] : T(0);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < GBK; ++kk) {
+            T a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+        }
+        __syncthreads();
+    }
+    T* Cz = C + (int64_t)blockIdx.z * sCz;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int gm = m0 + ty * 4 + i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int gn = n0 + tx * 4 + j;
+            if (gn < N) Cz[(int64_t)gm * sCm + (int64_t)gn * sCn] = acc[i][j];
+        }
+    }
+}
+
+template <typename T>
+__global__ void reduce_splits_kernel(int M, int N, int splits, const T* __restrict__ part, T* __restrict__ C, int64_t sCm,
+                                     int64_t sCn) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)M * N) return;
+    T s = T(0);
+    for (int z = 0; z < splits; ++z) s += part[(int64_t)z * M * N + idx];
+    int m = idx / N, nn = idx % N;
+    C[(int64_t)m * sCm + (int64_t)nn * sCn] = s;
+}
+
+// ---- MU-MSE ratio: F[i] *= max(0, Num[i]-lambda) / (Den[i]+delta)   (multupd.jl:101-103, :112-114)
+template <typename T>
+__global__ void mu_mse_ratio_kernel(T* __restrict__ F, const T* __restrict__ Num, const T* __restrict__ Den, int64_t len,
+                                    T lambda, T delta) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        T num = sub_rn(Num[i], lambda);
+        if (!(num > T(0))) num = (num != num) ? num : T(0);
+        F[i] = mul_rn(F[i], div_rn(num, add_rn(Den[i], delta)));
+    }
+}
+
+// ---- MU-Div pieces (multupd.jl:172-179, :184-191)
+template <typename T>
+__global__ void mu_div_quot_kernel(T* __restrict__ Q, const T* __restrict__ X, int64_t p, int64_t n, int64_t ldx,
+                                   const T* __restrict__ WH, T delta) {
+    int64_t len = p * n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i % p, c = i / p;
+        Q[i] = div_rn(X[r + c * ldx], add_rn(WH[i], delta));
+    }
+}
+
+// out[j] = sum_i A[i*sI + j*sJ], one block per j (double accumulation, fixed order => deterministic)
+template <typename T>
+__global__ void strided_sum_kernel(const T* __restrict__ A, int64_t len, int64_t sI, int64_t sJ, T* __restrict__ out) {
+    __shared__ double red[256];
+    const T* a = A + (int64_t)blockIdx.x * sJ;
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < len; i += blockDim.x) s += (double)a[i * sI];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = (T)red[0];
+}
+
+// H[i,j] *= WtQ[i,j] / (sW[i] + lambda)  (k x n col-major)   /   W[i,j] *= QHt[i,j] / (sH[j] + lambda) (p x k)
+template <typename T>
+__global__ void mu_div_scale_kernel(T* __restrict__ F, const T* __restrict__ Num, const T* __restrict__ s, int64_t rows,
+                                    int64_t cols, int s_along_rows, T lambda) {
+    int64_t len = rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i % rows, c = i / rows;
+        T d = add_rn(s_along_rows ? s[r] : s[c], lambda);
+        F[i] = mul_rn(F[i], div_rn(Num[i], d));
+    }
+}
+
+// ---- stop_condition partial sums (common.jl:92-111).  One block per component j:
+// acc[4*j..] = {dev_w, sum_w, dev_h, sum_h} as doubles.  W p x k (col j contiguous), H k x n (row j, stride k).
+template <typename T>
+__global__ void stop_partials_kernel(const T* __restrict__ W, const T* __restrict__ preW, int64_t p, const T* __restrict__ H,
+                                     const T* __restrict__ preH, int64_t n, int64_t k, double* __restrict__ acc) {
+    __shared__ double red[4][256];
+    const int j = blockIdx.x;
+    double dw = 0, sw = 0, dh = 0, sh = 0;
+    for (int64_t i = threadIdx.x; i < p; i += blockDim.x) {
+        T a = W[i + j * p], b = preW[i + j * p];
+        T d = sub_rn(a, b), s = add_rn(a, b);
+        dw += (double)mul_rn(d, d);
+        sw += (double)mul_rn(s, s);
+    }
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        T a = H[j + i * k], b = preH[j + i * k];
+        T d = sub_rn(a, b), s = add_rn(a, b);
+        dh += (double)mul_rn(d, d);
+        sh += (double)mul_rn(s, s);
+    }
+    red[0][threadIdx.x] = dw; red[1][threadIdx.x] = sw; red[2][threadIdx.x] = dh; red[3][threadIdx.x] = sh;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o)
+            for (int q = 0; q < 4; ++q) red[q][threadIdx.x] += red[q][threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x < 4) acc[4 * j + threadIdx.x] = red[threadIdx.x][0];
+}
+
+// Final decision, one thread: flag[0] = converged, dev[0] = devmax over all components (comparisons in T)
+template <typename T>
+__global__ void stop_final_kernel(const double* __restrict__ acc, int64_t k, T tol, int* __restrict__ flag, double* __restrict__ dev) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    bool conv = true;
+    T devmax = T(0);
+    for (int64_t j = 0; j < k; ++j) {
+        T dw = (T)acc[4 * j], sw = (T)acc[4 * j + 1], dh = (T)acc[4 * j + 2], sh = (T)acc[4 * j + 3];
+        T rw = dw / sw, rh = dh / sh;
+        T m = (rw != rw) ? rw : ((rh != rh) ? rh : (rw > rh ? rw : rh));
+        T sq = sqrt(m);
+        devmax = (devmax != devmax) ? devmax : ((sq != sq) ? sq : (sq > devmax ? sq : devmax));
+        if (sqrt(dw) > tol * sqrt(sw) || sqrt(dh) > tol * sqrt(sh)) conv = false;
+    }
+    flag[0] = conv ? 1 : 0;
+    dev[0] = (double)devmax;
+}
+
+// ---- objectives (StatsBase.sqL2dist / gkldiv semantics: differences in T, Float64 accumulator)
+template <typename T, int MODE>  // MODE 0: sum (x-y)^2, 1: gkldiv, 2: sum |y| (x ignored)
+__global__ void objective_partials_kernel(const T* __restrict__ X, int64_t p, int64_t n, int64_t ldx, const T* __restrict__ Y,
+                                          double* __restrict__ part) {
+    __shared__ double red[256];
+    int64_t len = p * n;
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        if (MODE == 2) {
+            s += (double)fabs(Y[i]);
+        } else {
+            int64_t r = i % p, c = i / p;
+            T a = X[r + c * ldx], b = Y[i];
+            if (MODE == 0) {
+                T d = sub_rn(a, b);
+                s += (double)mul_rn(d, d);
+            } else {
+                if (a > T(0)) {
+                    T t = mul_rn(a, (T)log(div_rn(a, b)));
+                    t = sub_rn(t, a);
+                    t = add_rn(t, b);
+                    s += (double)t;
+                } else {
+                    s += (double)b;
+                }
+            }
+        }
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part[blockIdx.x] = red[0];
+}
+
+__global__ void sum_partials_kernel(const double* __restrict__ part, int nparts, double* __restrict__ out) {
+    __shared__ double red[256];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += part[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = red[0];
+}
+
+// ---- GreedyCD (greedycd.jl:94-166) ---------------------------------------------------------------
+// G[i][r] (row-major rows x k) <- (F P)[i][r] - Z[i][r] (+ lambda); FP and Z are row-major rows x k.
+template <typename T>
+__global__ void gcd_form_g_kernel(T* __restrict__ G, const T* __restrict__ Z, int64_t len, T lambda, int add_lambda) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        T g = sub_rn(G[i], Z[i]);
+        if (add_lambda) g = add_rn(g, lambda);
+        G[i] = g;
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void gcd_sd(T w, T g, T prr, T& s, T& d) {
+    // S = max(0, W - G/(eps(T)+P[r,r])) - W ; D = -G*S - 0.5*P[r,r]*S^2   (greedycd.jl:127-128, :155-156)
+    T t = sub_rn(w, div_rn(g, add_rn(eps_of<T>(), prr)));
+    s = sub_rn(t > T(0) ? t : T(0), w);
+    d = sub_rn(mul_rn(-g, s), mul_rn(mul_rn(T(0.5), prr), mul_rn(s, s)));
+}
+
+// warp-level (value, index) arg-max with first-max tie-break
+template <typename T>
+__device__ __forceinline__ void warp_argmax(T& v, int& idx) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        T ov = __shfl_xor_sync(0xffffffffu, v, o);
+        int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+}
+
+constexpr int GCD_WARPS = 4;
+
+// pass 1: per-row max_r D[i,r]  -> per-block max (greedycd.jl:132-137)
+template <typename T>
+__global__ void __launch_bounds__(GCD_WARPS * 32) gcd_rowmax_kernel(const T* __restrict__ F, int64_t sFr, int64_t sFc,
+                                                                   const T* __restrict__ G, const T* __restrict__ P,
+                                                                   int64_t rows, int k, T* __restrict__ blockmax) {
+    __shared__ T wmax[GCD_WARPS];
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    int64_t i = (int64_t)blockIdx.x * GCD_WARPS + warp;
+    T best = T(-1.0);
+    if (i < rows) {
+        int bi = 0x7fffffff;
+        T bv = (T)(-INFINITY);
+        for (int r = lane; r < k; r += 32) {
+            T s, d;
+            gcd_sd(F[i * sFr + r * sFc], G[i * k + r], P[r + (int64_t)r * k], s, d);
+            if (d > bv) { bv = d; bi = r; }
+        }
+        warp_argmax(bv, bi);
+        best = bv;
+    }
+    if (lane == 0) wmax[warp] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        T m = T(-1.0);
+        for (int w = 0; w < GCD_WARPS; ++w) m = wmax[w] > m ? wmax[w] : m;
+        blockmax[blockIdx.x] = m;
+    }
+}
+
+template <typename T>
+__global__ void max_partials_kernel(const T* __restrict__ part, int nparts, T* __restrict__ out) {
+    __shared__ T red[256];
+    T m = T(-1.0);
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) m = part[i] > m ? part[i] : m;
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] = red[threadIdx.x + o] > red[threadIdx.x] ? red[threadIdx.x + o] : red[threadIdx.x];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = red[0];
+}
+
+// pass 2: the per-row greedy coordinate loop, one warp per row, row state in shared memory
+// (greedycd.jl:139-165).  smem per warp: g[k], f[k], fnew[k]; per block: pdiag[k].
+template <typename T>
+__global__ void __launch_bounds__(GCD_WARPS * 32) gcd_rows_kernel(T* __restrict__ F, int64_t sFr, int64_t sFc,
+                                                                 const T* __restrict__ G, const T* __restrict__ P,
+                                                                 int64_t rows, int k, const T* __restrict__ p_init_ptr,
+                                                                 unsigned long long* __restrict__ updates) {
+    extern __shared__ unsigned char smem_raw[];
+    T* pdiag = (T*)smem_raw;
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    T* g = pdiag + k + (size_t)warp * 3 * k;
+    T* f = g + k;
+    T* fnew = f + k;
+    for (int r = threadIdx.x; r < k; r += blockDim.x) pdiag[r] = P[r + (int64_t)r * k];
+    __syncthreads();
+    int64_t i = (int64_t)blockIdx.x * GCD_WARPS + warp;
+    if (i >= rows) return;
+    for (int r = lane; r < k; r += 32) {
+        g[r] = G[i * k + r];
+        f[r] = F[i * sFr + r * sFc];
+        fnew[r] = T(0);
+    }
+    __syncwarp();
+    const T thresh = mul_rn(T(0.001), p_init_ptr[0]);
+    const int64_t maxsteps = (int64_t)k * k;
+    unsigned long long nupd = 0;
+    for (int64_t it = 0; it < maxsteps; ++it) {
+        int bi = 0x7fffffff;
+        T bv = (T)(-INFINITY);
+        for (int r = lane; r < k; r += 32) {
+            T s, d;
+            gcd_sd(f[r], g[r], pdiag[r], s, d);
+            if (d > bv) { bv = d; bi = r; }
+        }
+        warp_argmax(bv, bi);
+        if (bv < thresh) break;
+        T sq, dq;
+        gcd_sd(f[bi], g[bi], pdiag[bi], sq, dq);
+        __syncwarp();
+        if (lane == 0) fnew[bi] = add_rn(fnew[bi], sq);
+        const T* prow = P + (int64_t)bi;  // P[qi, r] = P[qi + r*k]
+        for (int r = lane; r < k; r += 32) g[r] = add_rn(g[r], mul_rn(sq, prow[(int64_t)r * k]));
+        __syncwarp();
+        ++nupd;
+    }
+    for (int r = lane; r < k; r += 32) {
+        T v = add_rn(f[r], fnew[r]);
+        if (v < T(0)) v = T(0);  // projectnn! (utils.jl:34-41)
+        F[i * sFr + r * sFc] = v;
+    }
+    if (lane == 0 && nupd) atomicAdd(updates, nupd);
+}
+
+// strided copy (2D) for packing caller matrices with ld != rows
+template <typename T>
+__global__ void copy2d_kernel(T* __restrict__ dst, int64_t ldd, const T* __restrict__ src, int64_t lds, int64_t rows, int64_t cols) {
+    int64_t len = rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i % rows, c = i / rows;
+        dst[r + c * ldd] = src[r + c * lds];
+    }
+}
+
+inline int ew_blocks(int64_t len) { return (int)std::min<int64_t>(ceil_div(len, 256), 148 * 16); }
+
+template <typename T>
+struct Simt {
+    nmfb200_handle* h;
+    cudaStream_t st;
+    int64_t p, n, k;
+    const T* X;
+    int64_t ldx;
+
+    void gemm(int M, int N, int K, const T* A, int64_t sAm, int64_t sAk, const T* B, int64_t sBk, int64_t sBn, T* C, int64_t sCm,
+              int64_t sCn) {
+        int tiles = (int)(ceil_div(M, GBM) * ceil_div(N, GBN));
+        int splits = 1;
+        if (tiles < 148 && K >= 4096) splits = (int)std::min<int64_t>(std::max<int64_t>(1, 296 / tiles), ceil_div(K, 1024));
+        int kchunk = (int)(ceil_div(ceil_div(K, splits), GBK) * GBK);
+        splits = (int)ceil_div(K, kchunk);
+        dim3 grid((unsigned)ceil_div(N, GBN), (unsigned)ceil_div(M, GBM), (unsigned)splits);
+        if (splits == 1) {
+            gemm_kernel<T><<<grid, 256, 0, st>>>(M, N, K, A, sAm, sAk, B, sBk, sBn, C, sCm, sCn, 0, kchunk);
+            h->launches += 1;
+        } else {
+            T* part = h->buf_t<T>("simt.gemm_part", (size_t)splits * M * N);
+            gemm_kernel<T><<<grid, 256, 0, st>>>(M, N, K, A, sAm, sAk, B, sBk, sBn, part, N, 1, (int64_t)M * N, kchunk);
+            reduce_splits_kernel<T><<<(unsigned)ceil_div((int64_t)M * N, 256), 256, 0, st>>>(M, N, splits, part, C, sCm, sCn);
+            h->launches += 2;
+        }
+        NMF_CUDA(cudaGetLastError());
+    }
+
+    double reduce_objective(int mode, const T* Xp, int64_t rows, int64_t cols, int64_t ld, const T* Y) {
+        int nb = ew_blocks(rows * cols);
+        double* part = h->buf_t<double>("simt.obj_part", (size_t)nb + 1);
+        if (mode == 0) objective_partials_kernel<T, 0><<<nb, 256, 0, st>>>(Xp, rows, cols, ld, Y, part);
+        else if (mode == 1) objective_partials_kernel<T, 1><<<nb, 256, 0, st>>>(Xp, rows, cols, ld, Y, part);
+        else objective_partials_kernel<T, 2><<<nb, 256, 0, st>>>(Xp, rows, cols, ld, Y, part);
+        sum_partials_kernel<<<1, 256, 0, st>>>(part, nb, part + nb);
+        h->launches += 2;
+        h->allreduce_sum(part + nb, 1);  // row-sharded X: partial objective per rank
+        double v = 0;
+        NMF_CUDA(cudaMemcpyAsync(&v, part + nb, sizeof(double), cudaMemcpyDeviceToHost, st));
+        NMF_CUDA(cudaStreamSynchronize(st));
+        return v;
+    }
+
+    // objective with W (p x k), H (k x n) column-major compact
+    double objective(int alg, const T* W, const T* H, double lambda_w, double lambda_h) {
+        T* WH = h->buf_t<T>("simt.WH", (size_t)p * n);
+        gemm((int)p, (int)n, (int)k, W, 1, p, H, 1, k, WH, 1, p);
+        if (alg == 1) return (double)(T)reduce_objective(1, X, p, n, ldx, WH);  // gkldiv, Result converts to T
+        T r = mul_rn_host(T(0.5), (T)reduce_objective(0, X, p, n, ldx, WH));
+        if (alg == 2) {  // greedycd.jl:85-90
+            if (lambda_w > 0) {
+                double l1 = reduce_objective(2, nullptr, p, k, p, W);
+                r = (T)(r + (T)lambda_w * (T)l1);
+            }
+            if (lambda_h > 0) {
+                // H is replicated across ranks: undo the allreduce multiplication
+                double l1 = reduce_objective(2, nullptr, k, n, k, H) / (h->comm ? h->nranks : 1);
+                r = (T)(r + (T)lambda_h * (T)l1);
+            }
+        }
+        return (double)r;
+    }
+    static T mul_rn_host(T a, T b) { return a * b; }
+
+    // one call of stop_condition; returns converged and dev
+    bool stop(const T* W, const T* preW, const T* H, const T* preH, T tol, double* dev_out) {
+        double* acc = h->buf_t<double>("simt.stop_acc", (size_t)4 * k + 2);
+        int* flag = (int*)h->buf("simt.stop_flag", 16);
+        stop_partials_kernel<T><<<(unsigned)k, 256, 0, st>>>(W, preW, p, H, preH, n, k, acc);
+        h->launches += 1;
+        if (h->comm) {
+            // W rows are sharded: sum dev_w/sum_w over ranks; H sums are replicated -> divide back
+            h->allreduce_sum(acc, (size_t)4 * k);
+            // (the H entries were multiplied by nranks; stop_final works on ratios dev_h/sum_h and on
+            //  sqrt(dev_h) > tol*sqrt(sum_h), both invariant under a common positive factor.)
+        }
+        stop_final_kernel<T><<<1, 32, 0, st>>>(acc, k, tol, flag, acc + 4 * k);
+        h->launches += 1;
+        int hflag = 0;
+        double hdev = 0;
+        NMF_CUDA(cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        NMF_CUDA(cudaMemcpyAsync(&hdev, acc + 4 * k, sizeof(double), cudaMemcpyDeviceToHost, st));
+        NMF_CUDA(cudaStreamSynchronize(st));
+        *dev_out = hdev;
+        return hflag != 0;
+    }
+
+    // ---- MU-MSE iteration (multupd.jl:83-116) in Gram form
+    void iter_multmse(T* W, T* H, bool update_H, T lw, T lh, T delta) {
+        T* num_h = h->buf_t<T>("simt.num_h", (size_t)k * n + (size_t)k * k);  // [A (k x n) | G (k x k)] packed for one allreduce
+        T* gram = num_h + (size_t)k * n;
+        T* den_h = h->buf_t<T>("simt.den_h", (size_t)k * n);
+        T* num_w = h->buf_t<T>("simt.num_w", (size_t)p * k);
+        T* den_w = h->buf_t<T>("simt.den_w", (size_t)p * k);
+        if (update_H) {
+            gemm((int)k, (int)n, (int)p, W, p, 1, X, 1, ldx, num_h, 1, k);  // W'X (k x n)
+            gemm((int)k, (int)k, (int)p, W, p, 1, W, 1, p, gram, 1, k);    // W'W
+            h->allreduce_sum(num_h, (size_t)k * n + (size_t)k * k);
+            gemm((int)k, (int)n, (int)k, gram, 1, k, H, 1, k, den_h, 1, k);  // (W'W) H
+            mu_mse_ratio_kernel<T><<<ew_blocks(k * n), 256, 0, st>>>(H, num_h, den_h, k * n, lh, delta);
+            h->launches += 1;
+        }
+        T* gramh = h->buf_t<T>("simt.gramh", (size_t)k * k);
+        gemm((int)p, (int)k, (int)n, X, 1, ldx, H, k, 1, num_w, 1, p);      // X H' (p x k)
+        gemm((int)k, (int)k, (int)n, H, 1, k, H, k, 1, gramh, 1, k);        // H H'
+        gemm((int)p, (int)k, (int)k, W, 1, p, gramh, 1, k, den_w, 1, p);    // W (H H')
+        mu_mse_ratio_kernel<T><<<ew_blocks(p * k), 256, 0, st>>>(W, num_w, den_w, p * k, lw, delta);
+        h->launches += 1;
+        NMF_CUDA(cudaGetLastError());
+    }
+
+    // ---- MU-Div iteration (multupd.jl:150-193), as written with materialised WH and Q
+    void iter_multdiv(T* W, T* H, bool update_H, T lw, T lh, T delta, bool first) {
+        T* WH = h->buf_t<T>("simt.WH", (size_t)p * n);
+        T* Q = h->buf_t<T>("simt.Q", (size_t)p * n);
+        if (first) gemm((int)p, (int)n, (int)k, W, 1, p, H, 1, k, WH, 1, p);  // prepare_state (multupd.jl:138)
+        if (update_H) {
+            T* wtq = h->buf_t<T>("simt.num_h", (size_t)k * n + (size_t)k * k);  // [W'Q | sW] packed
+            T* sW = wtq + (size_t)k * n;
+            mu_div_quot_kernel<T><<<ew_blocks(p * n), 256, 0, st>>>(Q, X, p, n, ldx, WH, delta);
+            h->launches += 1;
+            gemm((int)k, (int)n, (int)p, W, p, 1, Q, 1, p, wtq, 1, k);
+            strided_sum_kernel<T><<<(unsigned)k, 256, 0, st>>>(W, p, 1, p, sW);
+            h->launches += 1;
+            h->allreduce_sum(wtq, (size_t)k * n + (size_t)k);
+            mu_div_scale_kernel<T><<<ew_blocks(k * n), 256, 0, st>>>(H, wtq, sW, k, n, 1, lh);
+            h->launches += 1;
+            gemm((int)p, (int)n, (int)k, W, 1, p, H, 1, k, WH, 1, p);
+        }
+        T* qht = h->buf_t<T>("simt.num_w", (size_t)p * k);
+        T* sH = h->buf_t<T>("simt.sH", (size_t)k);
+        mu_div_quot_kernel<T><<<ew_blocks(p * n), 256, 0, st>>>(Q, X, p, n, ldx, WH, delta);
+        gemm((int)p, (int)k, (int)n, Q, 1, p, H, k, 1, qht, 1, p);
+        strided_sum_kernel<T><<<(unsigned)k, 256, 0, st>>>(H, n, k, 1, sH);
+        mu_div_scale_kernel<T><<<ew_blocks(p * k), 256, 0, st>>>(W, qht, sH, p, k, 0, lw);
+        h->launches += 3;
+        gemm((int)p, (int)n, (int)k, W, 1, p, H, 1, k, WH, 1, p);
+        NMF_CUDA(cudaGetLastError());
+    }
+
+    // ---- GreedyCD half-step (greedycd.jl:94-166) for factor F (rows x k, element strides sFr/sFc)
+    // against O (cols x k, strides sOr/sOc); Xv(r, c) = Xp[r*sXr + c*sXc].
+    void gcd_half(T* F, int64_t sFr, int64_t sFc, const T* O, int64_t sOr, int64_t sOc, int64_t rows, int64_t cols, int64_t sXr,
+                  int64_t sXc, T lambda, bool rows_sharded, unsigned long long* d_updates) {
+        // packed [Z (rows x k row-major) | P (k x k)]: when the contraction dim is sharded both are allreduced
+        T* Z = h->buf_t<T>("simt.gcd_Z", (size_t)std::max(p, n) * k + (size_t)k * k);
+        T* P = Z + (size_t)rows * k;
+        T* G = h->buf_t<T>("simt.gcd_G", (size_t)std::max(p, n) * k);
+        gemm((int)k, (int)k, (int)cols, O, sOc, sOr, O, sOr, sOc, P, 1, k);          // P = O'O   (:117)
+        gemm((int)rows, (int)k, (int)cols, X, sXr, sXc, O, sOr, sOc, Z, k, 1);      // Z = X O   (:118)
+        if (!rows_sharded) h->allreduce_sum(Z, (size_t)rows * k + (size_t)k * k);   // H-step under row sharding
+        gemm((int)rows, (int)k, (int)k, F, sFr, sFc, P, 1, k, G, k, 1);              // G = F P   (:119)
+        gcd_form_g_kernel<T><<<ew_blocks(rows * k), 256, 0, st>>>(G, Z, rows * k, lambda, lambda > T(0) ? 1 : 0);  // :120-123
+        int nb = (int)ceil_div(rows, GCD_WARPS);
+        T* bmax = h->buf_t<T>("simt.gcd_bmax", (size_t)nb + 1);
+        gcd_rowmax_kernel<T><<<nb, GCD_WARPS * 32, 0, st>>>(F, sFr, sFc, G, P, rows, (int)k, bmax);
+        max_partials_kernel<T><<<1, 256, 0, st>>>(bmax, nb, bmax + nb);
+        if (rows_sharded) h->allreduce_max(bmax + nb, 1);  // p_init is a max over ALL rows (:132-137)
+        size_t smem = ((size_t)k + (size_t)GCD_WARPS * 3 * k) * sizeof(T);
+        NMF_CUDA(cudaFuncSetAttribute(gcd_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gcd_rows_kernel<T><<<nb, GCD_WARPS * 32, smem, st>>>(F, sFr, sFc, G, P, rows, (int)k, bmax + nb, d_updates);
+        h->launches += 4;
+        NMF_CUDA(cudaGetLastError());
+    }
+
+    void iter_greedycd(T* W, T* H, bool update_H, T lw, T lh, unsigned long long* d_updates) {
+        // W-step: F = W (p x k), O = H' (n x k): O(c, a) = H[a + c*k]; X(r, c) = X[r + c*ldx]
+        gcd_half(W, 1, p, H, k, 1, p, n, 1, ldx, lw, /*rows_sharded=*/h->comm != nullptr, d_updates);
+        if (update_H) {
+            // H-step: F = H' (n x k): F(j, a) = H[a + j*k]; O = W (p x k); X'(j, i) = X[i + j*ldx]
+            gcd_half(H, k, 1, W, 1, p, n, p, ldx, 1, lh, /*rows_sharded=*/false, d_updates);
+        }
+    }
+};
+
+}  // namespace
+
+template <typename T>
+void simt_solve(nmfb200_handle* h, const SolveArgs& a, T* Wc, int64_t ldw, T* Hc, int64_t ldh, nmfb200_result* out) {
+    NMF_REQUIRE(h->x_elt == (int)sizeof(T), NMFB200_ESTATE, "set_X with the same element type must precede solve");
+    Simt<T> s{h, h->stream, h->p, h->n, a.k, (const T*)h->dX, h->ldx};
+    cudaStream_t st = h->stream;
+    const int64_t p = h->p, n = h->n, k = a.k;
+    NMF_REQUIRE(ldw >= p && ldh >= k, NMFB200_EDIM, "Dimensions of X, W, and H are inconsistent.");
+    const T eps = std::numeric_limits<T>::epsilon();
+    const T delta = std::sqrt(eps);
+    T lw = (T)a.lambda_w, lh = (T)a.lambda_h;
+    if (a.alg == 1) {  // multupd.jl:37-40
+        lw = std::max(lw, delta);
+        lh = std::max(lh, delta);
+    }
+    const T tol = (T)a.tol;
+
+    cudaEvent_t e0, e1, e2;
+    NMF_CUDA(cudaEventCreate(&e0));
+    NMF_CUDA(cudaEventCreate(&e1));
+    NMF_CUDA(cudaEventCreate(&e2));
+    NMF_CUDA(cudaEventRecord(e0, st));
+
+    // stage W, H into compact device buffers
+    T* W = h->buf_t<T>("simt.W", (size_t)p * k);
+    T* H = h->buf_t<T>("simt.H", (size_t)k * n);
+    T* preW = h->buf_t<T>("simt.preW", (size_t)p * k);
+    T* preH = h->buf_t<T>("simt.preH", (size_t)k * n);
+    if (a.on_device) {
+        copy2d_kernel<T><<<ew_blocks(p * k), 256, 0, st>>>(W, p, Wc, ldw, p, k);
+        copy2d_kernel<T><<<ew_blocks(k * n), 256, 0, st>>>(H, k, Hc, ldh, k, n);
+    } else {
+        NMF_CUDA(cudaMemcpy2DAsync(W, p * sizeof(T), Wc, ldw * sizeof(T), p * sizeof(T), k, cudaMemcpyHostToDevice, st));
+        NMF_CUDA(cudaMemcpy2DAsync(H, k * sizeof(T), Hc, ldh * sizeof(T), k * sizeof(T), n, cudaMemcpyHostToDevice, st));
+    }
+    unsigned long long* d_updates = (unsigned long long*)h->buf("simt.gcd_updates", 16);
+    NMF_CUDA(cudaMemsetAsync(d_updates, 0, sizeof(unsigned long long), st));
+    NMF_CUDA(cudaEventRecord(e1, st));
+
+    double objv = std::numeric_limits<double>::quiet_NaN();
+    double t_start = 0;
+    auto now = []() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec + 1e-9 * ts.tv_nsec;
+    };
+    if (a.verbose) {  // common.jl:54-59
+        t_start = now();
+        objv = s.objective(a.alg, W, H, lw, lh);
+        if (h->trace) h->trace(h->trace_user, 0, 0.0, objv, NAN, NAN);
+    }
+    bool converged = false;
+    int64_t t = 0;
+    double dev = 0;
+    while (!converged && t < a.maxiter) {  // common.jl:64-83
+        ++t;
+        NMF_CUDA(cudaMemcpyAsync(preW, W, (size_t)p * k * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        NMF_CUDA(cudaMemcpyAsync(preH, H, (size_t)k * n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        if (a.alg == 0) s.iter_multmse(W, H, a.update_H != 0, lw, lh, delta);
+        else if (a.alg == 1) s.iter_multdiv(W, H, a.update_H != 0, lw, lh, delta, t == 1);
+        else s.iter_greedycd(W, H, a.update_H != 0, lw, lh, d_updates);
+        converged = s.stop(W, preW, H, preH, tol, &dev);
+        if (a.verbose) {
+            double pre = objv;
+            objv = s.objective(a.alg, W, H, lw, lh);
+            if (h->trace) h->trace(h->trace_user, t, now() - t_start, objv, objv - pre, dev);
+        }
+    }
+    NMF_CUDA(cudaEventRecord(e2, st));
+    if (!a.verbose) objv = s.objective(a.alg, W, H, lw, lh);  // common.jl:85-87
+
+    if (a.on_device) {
+        copy2d_kernel<T><<<ew_blocks(p * k), 256, 0, st>>>(Wc, ldw, W, p, p, k);
+        copy2d_kernel<T><<<ew_blocks(k * n), 256, 0, st>>>(Hc, ldh, H, k, k, n);
+    } else {
+        NMF_CUDA(cudaMemcpy2DAsync(Wc, ldw * sizeof(T), W, p * sizeof(T), p * sizeof(T), k, cudaMemcpyDeviceToHost, st));
+        NMF_CUDA(cudaMemcpy2DAsync(Hc, ldh * sizeof(T), H, k * sizeof(T), k * sizeof(T), n, cudaMemcpyDeviceToHost, st));
+    }
+    unsigned long long upd = 0;
+    NMF_CUDA(cudaMemcpyAsync(&upd, d_updates, sizeof(upd), cudaMemcpyDeviceToHost, st));
+    NMF_CUDA(cudaStreamSynchronize(st));
+    float ms_up = 0, ms_loop = 0;
+    cudaEventElapsedTime(&ms_up, e0, e1);
+    cudaEventElapsedTime(&ms_loop, e1, e2);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaEventDestroy(e2);
+    out->niters = t;
+    out->converged = converged ? 1 : 0;
+    out->engine = 0;
+    out->objvalue = objv;
+    out->last_dev = dev;
+    out->solve_ms = ms_loop;
+    out->upload_ms = ms_up;
+    out->coordinate_updates = (int64_t)upd;
+    out->kernel_launches = h->launches;
+}
+
+template void simt_solve<float>(nmfb200_handle*, const SolveArgs&, float*, int64_t, float*, int64_t, nmfb200_result*);
+template void simt_solve<double>(nmfb200_handle*, const SolveArgs&, double*, int64_t, double*, int64_t, nmfb200_result*);
+
+}  // namespace nmfb200

@@ -1,0 +1,57 @@
+"""Generates the committed golden fixtures tests/golden/*.npz.
+
+The reference (Julia) cannot run in the build image and holds no golden vectors of its own, so these
+are produced by the oracle restatement (oracle/nmf_oracle.py) on seeded inputs.  Each file stores the
+inputs (X, W0, H0, options) and the oracle outputs (W, H, niters, converged, objvalue).
+Run from the repo root:  python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import nmf_oracle as O  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def planted(rng, p, n, k, T):
+    # test/interf.jl:7-9 recipe
+    Wg = np.maximum(rng.random((p, k)) - 0.3, 0)
+    Hg = np.maximum(rng.random((k, n)) - 0.3, 0)
+    return np.asfortranarray(Wg @ Hg, dtype=T)
+
+
+def case(name, alg, T, p, n, k, maxiter, tol, seed, data="uniform", **kw):
+    rng = np.random.default_rng(seed)
+    T = np.dtype(T)
+    X = np.asfortranarray(rng.random((p, n)), dtype=T) if data == "uniform" else planted(rng, p, n, k, T)
+    W0, H0 = O.randinit(p, n, k, T, rng, normalize=True)
+    W, H = W0.copy(order="F"), H0.copy(order="F")
+    if alg in ("multmse", "multdiv"):
+        inst = O.MultUpdate(T, obj=alg[4:], maxiter=maxiter, tol=tol, **kw)
+    else:
+        inst = O.GreedyCD(T, maxiter=maxiter, tol=tol, **kw)
+    r = O.solve(inst, X, W, H)
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"), X=X, W0=W0, H0=H0, W=W, H=H, niters=r.niters, converged=r.converged,
+        objvalue=float(r.objvalue), alg=alg, maxiter=maxiter, tol=float(tol), k=k,
+        lambda_w=float(kw.get("lambda_w", 0.0)), lambda_h=float(kw.get("lambda_h", 0.0)),
+        update_H=bool(kw.get("update_H", True)),
+    )
+    print(f"{name}: niters={r.niters} converged={r.converged} objvalue={float(r.objvalue):.9g}")
+
+
+if __name__ == "__main__":
+    # BASELINE config 1: nnmf(rand(200,150), 5; alg=:multmse, init=:random, maxiter=50), Float64,
+    # tol = cbrt(eps/100) as nnmf passes it (interf.jl:8)
+    case("cfg1_multmse_f64", "multmse", np.float64, 200, 150, 5, 50, np.cbrt(np.finfo(np.float64).eps / 100), 0)
+    case("multmse_f32_uniform", "multmse", np.float32, 96, 80, 8, 30, 1e-9, 1)
+    case("multmse_f32_planted_reg", "multmse", np.float32, 64, 72, 6, 40, 1e-9, 2, data="planted", lambda_w=1e-3, lambda_h=2e-3)
+    case("multmse_f64_noH", "multmse", np.float64, 40, 56, 4, 25, 1e-12, 3, update_H=False)
+    case("multdiv_f64_uniform", "multdiv", np.float64, 72, 60, 5, 30, 1e-12, 4)
+    case("multdiv_f32_planted", "multdiv", np.float32, 64, 48, 4, 30, 1e-9, 5, data="planted")
+    case("greedycd_f64_uniform", "greedycd", np.float64, 60, 50, 4, 12, 1e-12, 6)
+    case("greedycd_f32_planted_reg", "greedycd", np.float32, 48, 40, 4, 12, 1e-9, 7, data="planted", lambda_w=1e-4, lambda_h=1e-4)

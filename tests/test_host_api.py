@@ -1,0 +1,141 @@
+"""Host-side mirror of the reference API (no GPU needed): option types, validation order/messages,
+Result semantics, and that the C-ABI library loads and exports every symbol include/nmfb200.h declares."""
+import os
+import re
+import subprocess
+import warnings
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_exported_and_bound(NMF):
+    hdr = open(os.path.join(ROOT, "include", "nmfb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(nmfb200_[A-Za-z0-9_]+)\s*\(", hdr)) - {"nmfb200_trace_fn"}
+    assert len(declared) >= 21
+    NMF.build.build_library()
+    lib = NMF._lib.load()  # resolves every bound symbol or raises
+    assert declared == set(NMF._lib.SIGNATURES), (declared ^ set(NMF._lib.SIGNATURES))
+    out = subprocess.check_output(["nm", "-D", "--defined-only", NMF._lib.LIB_PATH], text=True)
+    exported = set(re.findall(r" T (nmfb200_[A-Za-z0-9_]+)", out))
+    assert declared <= exported, declared - exported
+    assert lib.nmfb200_version() == 100
+    assert lib.nmfb200_status_string(1) == b"invalid argument"
+    assert lib.nmfb200_status_string(2) == b"dimension mismatch"
+
+
+def test_result_struct_matches_header(NMF):
+    import ctypes
+    # int64, int32, int32, 4 doubles, 2 int64 -> 64 bytes, no padding surprises
+    assert ctypes.sizeof(NMF._lib.NmfResult) == 8 + 4 + 4 + 8 * 4 + 8 * 2
+
+
+def test_library_built_for_sm100a_only(NMF):
+    NMF.build.build_library()
+    out = subprocess.check_output(["cuobjdump", "-lelf", NMF._lib.LIB_PATH], text=True)
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_multupdate_ctor(NMF):
+    a = NMF.MultUpdate(np.float32)
+    assert (a.obj, a.maxiter, a.verbose, a.update_H) == ("mse", 100, False, True)
+    assert a.tol == np.float32(np.cbrt(np.finfo(np.float32).eps))
+    assert a.lambda_w == 0 and a.lambda_h == 0
+    for bad in (dict(obj="kl"), dict(maxiter=1), dict(tol=0), dict(lambda_w=-1e-3), dict(lambda_h=-1e-3)):
+        with pytest.raises(NMF.ArgumentError):
+            NMF.MultUpdate(np.float64, **bad)
+    d = NMF.MultUpdate(np.float64, obj="div", lambda_w=1e-3)
+    assert d.lambda_w == 1e-3 and d.lambda_h == np.sqrt(np.finfo(np.float64).eps)
+    with pytest.warns(UserWarning, match="deprecated"):
+        l = NMF.MultUpdate(np.float64, lambda_=0.5, lambda_h=0.25)
+    assert l.lambda_w == 0.5 and l.lambda_h == 0.25
+
+
+def test_greedycd_ctor(NMF):
+    a = NMF.GreedyCD(np.float64)
+    assert (a.maxiter, a.verbose, a.update_H, a.lambda_w, a.lambda_h) == (100, False, True, 0, 0)
+    assert a.tol == np.cbrt(np.finfo(np.float64).eps)
+    for bad in (dict(maxiter=1), dict(tol=0), dict(lambda_w=-1), dict(lambda_h=-1)):
+        with pytest.raises(NMF.ArgumentError):
+            NMF.GreedyCD(np.float32, **bad)
+
+
+def test_other_algorithm_types_exist(NMF):
+    assert NMF.ProjectedALS(np.float32).lambda_w == np.float32(np.cbrt(np.finfo(np.float32).eps))
+    assert NMF.ALSPGrad(np.float64).maxsubiter == 200
+    assert NMF.CoordinateDescent(np.float64, alpha=1e-4, l1ratio=0.5, shuffle=True).shuffle
+    assert NMF.SPA(np.float64).obj == "mse"
+    with pytest.raises(NMF.ArgumentError):
+        NMF.SPA(np.float64, obj="x")
+
+
+def test_result_eq_hash(NMF):  # test/utils.jl:65-69
+    W, H = np.ones((3, 2)), np.ones((2, 4))
+    a, b = NMF.Result(W, H, 3, True, 0.5), NMF.Result(W.copy(), H.copy(), 3, True, 0.5)
+    assert a == b and hash(a) == hash(b)
+    assert a != NMF.Result(W, H, 4, True, 0.5)
+    with pytest.raises(NMF.DimensionMismatch):
+        NMF.Result(np.ones((3, 2)), np.ones((3, 4)), 1, False, 0.0)
+    assert isinstance(NMF.Result(W.astype(np.float32), H.astype(np.float32), 1, False, 0.1).objvalue, np.float32)
+
+
+def test_nnmf_validation_before_gpu(NMF):
+    """interf.jl:15-36, :55, :74-79 -- all raised before any device work."""
+    X = np.random.default_rng(0).random((6, 5))
+    with pytest.raises(NMF.ArgumentError, match="non-negative"):
+        NMF.nnmf(X - 1.0, 2, alg="multmse", init="random")
+    with pytest.raises(NMF.ArgumentError, match="should not exceed"):
+        NMF.nnmf(X, 6, alg="multmse", init="random")
+    with pytest.raises(NMF.ArgumentError, match="replicates"):
+        NMF.nnmf(X, 2, alg="multmse", init="random", replicates=0)
+    with pytest.raises(NMF.ArgumentError, match="set W0 and H0"):
+        NMF.nnmf(X, 2, alg="multmse", init="custom")
+    W0, H0 = np.ones((6, 2)), np.ones((2, 5))
+    with pytest.raises(NMF.ArgumentError, match="W0 must be non-negative"):
+        NMF.nnmf(X, 2, alg="multmse", init="custom", W0=-W0, H0=H0)
+    with pytest.raises(NMF.ArgumentError, match="Invalid size for W0"):
+        NMF.nnmf(X, 2, alg="multmse", init="custom", W0=np.ones((5, 2)), H0=H0)
+    with pytest.raises(NMF.ArgumentError, match="H0 must be non-negative"):
+        NMF.nnmf(X, 2, alg="multmse", init="custom", W0=W0, H0=-H0)
+    with pytest.raises(NMF.ArgumentError, match="Invalid size for H0"):
+        NMF.nnmf(X, 2, alg="multmse", init="custom", W0=W0, H0=np.ones((2, 4)))
+    with pytest.raises(NMF.ArgumentError, match="Invalid value for init"):
+        NMF.nnmf(X, 2, alg="multmse", init="bogus")
+    with pytest.raises(NMF.ArgumentError, match="Invalid algorithm"):
+        NMF.nnmf(X, 2, alg="bogus", init="random")
+    with pytest.raises(NMF.ArgumentError, match="use :spa instead"):
+        NMF.nnmf(X, 2, alg="spa", init="random")
+    with pytest.raises(NMF.ArgumentError, match="maxiter must be greater than 1"):
+        NMF.nnmf(X, 2, alg="multmse", init="random", maxiter=1)
+    with pytest.raises(NotImplementedError):
+        NMF.nnmf(X, 2, alg="projals", init="random")
+    with pytest.raises(NotImplementedError):
+        NMF.nnmf(X, 2)  # default init=:nndsvdar is a "next" row
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        with pytest.raises(NMF.ArgumentError):
+            NMF.nnmf(X, 2, alg="bogus", init="random", W0=W0, update_H=False)
+    msgs = " ".join(str(x.message) for x in w)
+    assert "Only W will be updated." in msgs and "Ignore W0 and H0" in msgs
+
+
+def test_randinit(NMF):  # test/initialization.jl:4-27
+    W, H = NMF.randinit(10, 7, 3, np.float32, normalize=True, rng=np.random.default_rng(1))
+    assert W.dtype == np.float32 and W.flags.f_contiguous and H.flags.f_contiguous
+    np.testing.assert_allclose(W.sum(axis=0), 1.0, rtol=1e-6)
+    W, H = NMF.randinit(10, 7, 3, np.float64, zeroh=True)
+    assert (H == 0).all() and H.shape == (3, 7)
+
+
+def test_no_gpu_fails_loudly(NMF):
+    """Without a CUDA device the product must raise, never fall back to a CPU path."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    X = np.random.default_rng(0).random((6, 5))
+    with pytest.raises(NMF.NmfB200Error):
+        NMF.nnmf(X, 2, alg="multmse", init="random")

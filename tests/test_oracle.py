@@ -1,0 +1,133 @@
+"""The oracle against every fixture / known-answer test the reference holds for the hot path
+ and against the committed golden vectors.  CPU only."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def _start(oracle, T, rng):
+    X, Wg, Hg = oracle.laurberg6x3(0.3, T)
+    W = np.asfortranarray(Wg + rng.random(Wg.shape).astype(T) * T(0.1))
+    return X, W, Hg.copy(order="F")
+
+
+# test/multupd.jl:4-21
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+@pytest.mark.parametrize("obj", ["mse", "div"])
+@pytest.mark.parametrize("lw", [0.0, 1e-4])
+@pytest.mark.parametrize("lh", [0.0, 1e-4])
+def test_reference_kat_multupd(oracle, T, obj, lw, lh):
+    X, W, H = _start(oracle, T, np.random.default_rng(11))
+    oracle.solve(oracle.MultUpdate(T, obj=obj, maxiter=5000, tol=1e-9, lambda_w=lw, lambda_h=lh), X, W, H)
+    assert (W >= 0).all() and (H >= 0).all()
+    assert not np.isnan(W).any() and not np.isnan(H).any()
+    assert np.linalg.norm(X - W @ H) <= 1e-2  # `X ≈ W*Hg atol=1e-2`
+
+
+# test/greedycd.jl:5-20
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+@pytest.mark.parametrize("lw", [0.0, 1e-5])
+@pytest.mark.parametrize("lh", [0.0, 1e-5])
+def test_reference_kat_greedycd(oracle, T, lw, lh):
+    X, W, H = _start(oracle, T, np.random.default_rng(12))
+    oracle.solve(oracle.GreedyCD(T, maxiter=1000, tol=1e-9, lambda_w=lw, lambda_h=lh), X, W, H)
+    assert (W >= 0).all() and (H >= 0).all()
+    assert not np.isnan(W).any() and not np.isnan(H).any()
+    assert np.linalg.norm(X - W @ H) <= 1e-3
+
+
+# test/interf.jl:31-37: update_H=false leaves H bit-identical and changes W
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+@pytest.mark.parametrize("alg", ["multmse", "multdiv", "greedycd"])
+def test_reference_kat_update_H_false(oracle, T, alg):
+    rng = np.random.default_rng(13)
+    p, n, k = 5, 8, 3
+    Wg = np.maximum(rng.random((p, k)) - 0.3, 0)
+    Hg = np.maximum(rng.random((k, n)) - 0.3, 0)
+    X = np.asfortranarray(Wg @ Hg, dtype=T)
+    W = np.asfortranarray(np.maximum(rng.random((p, k)) - 0.3, 0), dtype=T)
+    H = np.asfortranarray(np.maximum(rng.random((k, n)) - 0.3, 0), dtype=T)
+    with pytest.warns(UserWarning) if False else _nullcontext():
+        ret = oracle.nnmf(X, k, alg=alg, init="custom", W0=W.copy(order="F"), H0=H.copy(order="F"), update_H=False)
+    assert (ret.H == H).all()
+    assert (ret.W != W).any()
+
+
+class _nullcontext:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+# test/initialization.jl:22-27
+def test_randinit_normalize(oracle):
+    rng = np.random.default_rng(3)
+    W, H = oracle.randinit(12, 9, 4, np.float64, rng, normalize=True)
+    assert W.shape == (12, 4) and H.shape == (4, 9)
+    np.testing.assert_allclose(W.sum(axis=0), 1.0, rtol=1e-12)
+    assert (W >= 0).all() and (H >= 0).all()
+    W, H = oracle.randinit(12, 9, 4, np.float32, rng, zeroh=True)
+    assert (H == 0).all()
+
+
+def test_stop_condition_semantics(oracle):
+    """common.jl:92-111: early exit at the first failing component, all-zero component counts as converged."""
+    T = np.float64
+    W = np.asfortranarray(np.array([[1.0, 0.0], [2.0, 0.0]]))
+    H = np.asfortranarray(np.array([[1.0, 1.0, 1.0], [0.0, 0.0, 0.0]]))
+    conv, dev = oracle.stop_condition(W, W.copy(order="F"), H, H.copy(order="F"), 1e-6)
+    assert conv  # 0/0 = NaN ratios never trip `>`
+    W2 = W.copy(order="F")
+    W2[0, 0] = 1.1
+    conv, dev = oracle.stop_condition(W2, W, H, H.copy(order="F"), 1e-6)
+    assert not conv
+    want = np.sqrt(0.1 ** 2 / (2.1 ** 2 + 4.0 ** 2))
+    assert abs(dev - want) < 1e-12
+
+
+def test_constructor_validation(oracle):
+    for bad in (dict(obj="l1"), dict(maxiter=1), dict(tol=0.0), dict(lambda_w=-1.0), dict(lambda_h=-1.0)):
+        with pytest.raises(oracle.ArgumentError):
+            oracle.MultUpdate(np.float64, **bad)
+    for bad in (dict(maxiter=1), dict(tol=-1.0), dict(lambda_w=-1.0), dict(lambda_h=-1.0)):
+        with pytest.raises(oracle.ArgumentError):
+            oracle.GreedyCD(np.float32, **bad)
+    a = oracle.MultUpdate(np.float32, obj="div")  # multupd.jl:37-40
+    assert a.lambda_w == np.float32(np.sqrt(np.finfo(np.float32).eps)) == a.lambda_h
+
+
+def test_objective_definitions(oracle):
+    rng = np.random.default_rng(5)
+    a = rng.random(1000).astype(np.float32)
+    b = rng.random(1000).astype(np.float32) + np.float32(0.1)
+    a[::7] = 0
+    np.testing.assert_allclose(oracle.sqL2dist(a, b), np.sum((a.astype(np.float64) - b) ** 2), rtol=1e-6)
+    a64, b64 = a.astype(np.float64), b.astype(np.float64)
+    want = np.where(a64 > 0, a64 * np.log(np.where(a64 > 0, a64, 1) / b64) - a64 + b64, b64).sum()
+    np.testing.assert_allclose(oracle.gkldiv(a, b), want, rtol=1e-5)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(g)[:-4] for g in GOLDEN])
+def test_oracle_reproduces_golden(oracle, path):
+    g = np.load(path)
+    T = g["X"].dtype
+    alg = str(g["alg"])
+    kw = dict(maxiter=int(g["maxiter"]), tol=float(g["tol"]), lambda_w=float(g["lambda_w"]), lambda_h=float(g["lambda_h"]),
+              update_H=bool(g["update_H"]))
+    inst = oracle.MultUpdate(T, obj=alg[4:], **kw) if alg.startswith("mult") else oracle.GreedyCD(T, **kw)
+    W, H = np.asfortranarray(g["W0"]), np.asfortranarray(g["H0"])
+    r = oracle.solve(inst, np.asfortranarray(g["X"]), W, H)
+    rtol = 1e-9 if T == np.float64 else 2e-4
+    if alg == "greedycd":  # discrete coordinate choices: only the objective is stable across BLAS thread counts
+        rtol = 1e-6 if T == np.float64 else 1e-3
+    assert r.niters == int(g["niters"]) and r.converged == bool(g["converged"])
+    np.testing.assert_allclose(float(r.objvalue), float(g["objvalue"]), rtol=rtol)
+    if alg != "greedycd":
+        np.testing.assert_allclose(W, g["W"], rtol=rtol, atol=rtol)
+        np.testing.assert_allclose(H, g["H"], rtol=rtol, atol=rtol)
