@@ -160,8 +160,9 @@ def test_abi_errors(NMF):
     rng = np.random.default_rng(28)
     X = np.asfortranarray(rng.random((10, 8)))
     with NMF.Session() as s:
+        Wd, Hd = NMF.randinit(10, 8, 2, np.float64, rng=rng)
         with pytest.raises(NMF.NmfB200Error):  # solve before set_X
-            s.solve_raw("multmse", np.float64, 0, 10, 0, 2, 2, 10, 1e-3, 0, 0, True, False, False)
+            s.solve_raw("multmse", np.float64, Wd.ctypes.data, 10, Hd.ctypes.data, 2, 2, 10, 1e-3, 0, 0, True, False, False)
         Xn = X.copy(order="F")
         Xn[3, 4] = -0.5
         with pytest.raises(NMF.ArgumentError, match="non-negative"):
@@ -174,8 +175,6 @@ def test_abi_errors(NMF):
             s.solve(NMF.MultUpdate(np.float32), W, H)
         with pytest.raises(NotImplementedError):
             s.solve(NMF.ProjectedALS(np.float64), W, H)
-        r = s.solve_raw("multmse", np.float64, W.ctypes.data, 10, H.ctypes.data, 2, 2, 1, 1e-3, 0, 0, True, False, False) \
-            if False else None
         import ctypes
         res = NMF._lib.NmfResult()
         st = s._lib.nmfb200_solve_multmse_f64(s._h, W.ctypes.data_as(ctypes.c_void_p), 10, H.ctypes.data_as(ctypes.c_void_p), 2, 2,
