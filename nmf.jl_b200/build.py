@@ -15,7 +15,7 @@ NVCC_FLAGS = [
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
 ]
-LINK = ["-lcudart_static", "-ldl", "-lrt", "-lpthread", "-lcuda"]
+LINK = ["-lcudart_static", "-ldl", "-lrt", "-lpthread"]
 
 
 def sources():

@@ -160,6 +160,8 @@ struct SolveArgs {
 // engines (one translation unit each)
 template <typename T>
 void simt_solve(nmfb200_handle* h, const SolveArgs& a, T* W, int64_t ldw, T* H, int64_t ldh, nmfb200_result* out);
+double simt_objective_f32(nmfb200_handle* h, int alg, const float* W, int64_t ldw, const float* H, int64_t ldh, int64_t k,
+                          double lambda_w, double lambda_h);
 bool tc_supported(const nmfb200_handle* h, const SolveArgs& a);
 void tc_solve(nmfb200_handle* h, const SolveArgs& a, float* W, int64_t ldw, float* H, int64_t ldh, nmfb200_result* out);
 void tc_release(nmfb200_handle* h);

@@ -428,9 +428,11 @@ struct Simt {
     }
 
     // objective with W (p x k), H (k x n) column-major compact
-    double objective(int alg, const T* W, const T* H, double lambda_w, double lambda_h) {
+    double objective(int alg, const T* W, const T* H, double lambda_w, double lambda_h, int64_t ldw = 0, int64_t ldh = 0) {
+        if (ldw == 0) ldw = p;
+        if (ldh == 0) ldh = k;
         T* WH = h->buf_t<T>("simt.WH", (size_t)p * n);
-        gemm((int)p, (int)n, (int)k, W, 1, p, H, 1, k, WH, 1, p);
+        gemm((int)p, (int)n, (int)k, W, 1, ldw, H, 1, ldh, WH, 1, p);
         if (alg == 1) return (double)(T)reduce_objective(1, X, p, n, ldx, WH);  // gkldiv, Result converts to T
         T r = mul_rn_host(T(0.5), (T)reduce_objective(0, X, p, n, ldx, WH));
         if (alg == 2) {  // greedycd.jl:85-90
@@ -656,6 +658,13 @@ void simt_solve(nmfb200_handle* h, const SolveArgs& a, T* Wc, int64_t ldw, T* Hc
     out->upload_ms = ms_up;
     out->coordinate_updates = (int64_t)upd;
     out->kernel_launches = h->launches;
+}
+
+double simt_objective_f32(nmfb200_handle* h, int alg, const float* W, int64_t ldw, const float* H, int64_t ldh, int64_t k,
+                          double lambda_w, double lambda_h) {
+    NMF_REQUIRE(alg != 2 || (ldw == h->p && ldh == k), NMFB200_EINVAL, "compact factors required for the L1 terms");
+    Simt<float> s{h, h->stream, h->p, h->n, k, (const float*)h->dX, h->ldx};
+    return s.objective(alg, W, H, lambda_w, lambda_h, ldw, ldh);
 }
 
 template void simt_solve<float>(nmfb200_handle*, const SolveArgs&, float*, int64_t, float*, int64_t, nmfb200_result*);

@@ -1,0 +1,97 @@
+"""Tensor-core engine (tcgen05 bf16 operands, fp32 accumulate) vs the oracle, through the C ABI.
+Tolerances: X and the B operand are rounded to bf16 (2^-9 relative per element), sums over >= 200
+terms average that down to ~1e-4 per numerator; the denominators use a bf16 hi/lo split (~2^-17).
+Stated bars: objvalue 1e-4 relative (north-star), W/H relative Frobenius 5e-3."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _relerr(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def _problem(NMF, p, n, k, seed, planted=False):
+    rng = np.random.default_rng(seed)
+    if planted:
+        X = np.maximum(rng.random((p, k)) - 0.3, 0) @ np.maximum(rng.random((k, n)) - 0.3, 0)
+    else:
+        X = rng.random((p, n))
+    X = np.asfortranarray(X, dtype=np.float32)
+    W0, H0 = NMF.randinit(p, n, k, np.float32, normalize=True, rng=rng)
+    return X, W0, H0
+
+
+@pytest.mark.parametrize("p,n,k,iters", [
+    (256, 384, 64, 2),      # one CTA pair of tiles, KP = 64, a single iteration pair
+    (256, 384, 64, 10),
+    (300, 200, 5, 10),      # ragged rows (tail tile), k padded 5 -> 64
+    (1024, 768, 128, 10),   # KP = 128
+    (515, 1030, 100, 8),    # ragged, k padded 100 -> 128
+    (640, 512, 200, 6),     # KP = 256
+    (2048, 1536, 128, 20),
+])
+def test_tc_multmse_vs_oracle(NMF, oracle, p, n, k, iters):
+    X, W0, H0 = _problem(NMF, p, n, k, seed=p + n + k)
+    Wg, Hg, Wo, Ho = W0.copy(order="F"), H0.copy(order="F"), W0.copy(order="F"), H0.copy(order="F")
+    r = NMF.solve(NMF.MultUpdate(np.float32, obj="mse", maxiter=iters, tol=1e-9), X, Wg, Hg, engine="tc")
+    ro = oracle.solve(oracle.MultUpdate(np.float32, obj="mse", maxiter=iters, tol=1e-9), X, Wo, Ho)
+    assert r.info["engine"] == "tc" and r.info["kernel_launches"] >= 5 * iters
+    assert r.niters == ro.niters == iters and not r.converged
+    assert np.isfinite(Wg).all() and np.isfinite(Hg).all() and (Wg >= 0).all() and (Hg >= 0).all()
+    ew, eh = _relerr(Wg, Wo), _relerr(Hg, Ho)
+    eo = abs(float(r.objvalue) - float(ro.objvalue)) / float(ro.objvalue)
+    print(f"tc p={p} n={n} k={k} it={iters}: errW={ew:.2e} errH={eh:.2e} errObj={eo:.2e}")
+    assert ew <= 5e-3 and eh <= 5e-3
+    assert eo <= 1e-4
+
+
+def test_tc_regularised_and_planted(NMF, oracle):
+    X, W0, H0 = _problem(NMF, 512, 384, 32, seed=7, planted=True)
+    Wg, Hg, Wo, Ho = W0.copy(order="F"), H0.copy(order="F"), W0.copy(order="F"), H0.copy(order="F")
+    kw = dict(obj="mse", maxiter=30, tol=1e-9, lambda_w=1e-3, lambda_h=2e-3)
+    r = NMF.solve(NMF.MultUpdate(np.float32, **kw), X, Wg, Hg, engine="tc")
+    ro = oracle.solve(oracle.MultUpdate(np.float32, **kw), X, Wo, Ho)
+    assert r.niters == ro.niters == 30
+    # low-residual problem: the objective is small, so compare reconstructions rather than objvalue ratio
+    assert _relerr(Wg @ Hg, Wo @ Ho) <= 5e-3
+    assert abs(float(r.objvalue) - float(ro.objvalue)) <= 2e-2 * float(ro.objvalue) + 1e-6 * float(np.sum(X * X))
+
+
+def test_tc_update_H_false_bit_identical(NMF):
+    X, W0, H0 = _problem(NMF, 256, 256, 16, seed=9)
+    Wg, Hg = W0.copy(order="F"), H0.copy(order="F")
+    r = NMF.solve(NMF.MultUpdate(np.float32, maxiter=5, tol=1e-9, update_H=False), X, Wg, Hg, engine="tc")
+    assert r.info["engine"] == "tc"
+    assert (Hg == H0).all()       # test/interf.jl:35
+    assert (Wg != W0).any()
+
+
+def test_tc_convergence_matches_oracle_iteration(NMF, oracle):
+    X, W0, H0 = _problem(NMF, 384, 256, 8, seed=11)
+    Wg, Hg, Wo, Ho = W0.copy(order="F"), H0.copy(order="F"), W0.copy(order="F"), H0.copy(order="F")
+    tol = 3e-3
+    with NMF.Session(engine="tc") as s:
+        s.set_option("check_every", 5)
+        s.set_X(X)
+        r = s.solve(NMF.MultUpdate(np.float32, maxiter=2000, tol=tol), Wg, Hg)
+    ro = oracle.solve(oracle.MultUpdate(np.float32, maxiter=2000, tol=tol), X, Wo, Ho)
+    assert ro.converged and r.converged
+    # near the threshold the stopping iteration may move by a few steps (bf16 numerators)
+    assert abs(r.niters - ro.niters) <= max(3, ro.niters // 20), (r.niters, ro.niters)
+    assert abs(float(r.objvalue) - float(ro.objvalue)) <= 1e-4 * float(ro.objvalue)
+
+
+def test_tc_session_reuse_and_auto_engine(NMF, oracle):
+    """X stays resident (bf16 caches built once); auto picks tc for Float32 multmse."""
+    X, W0, H0 = _problem(NMF, 256, 320, 24, seed=13)
+    with NMF.Session(engine="auto") as s:
+        s.set_X(X)
+        outs = []
+        for _ in range(2):
+            Wg, Hg = W0.copy(order="F"), H0.copy(order="F")
+            r = s.solve(NMF.MultUpdate(np.float32, maxiter=6, tol=1e-9), Wg, Hg)
+            assert r.info["engine"] == "tc"
+            outs.append((Wg, Hg, float(r.objvalue)))
+        assert (outs[0][0] == outs[1][0]).all() and (outs[0][1] == outs[1][1]).all()  # deterministic
