@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- NMF iteration throughput on B200 (BASELINE.json metric), one JSON line on stdout.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is ONE NMF iteration (H half-step + W half-step + stop_condition) of MultUpdate(:mse).
+Workload (synthetic, numpy default_rng, X ~ U[0,1), W0 column-sum-1, H0 ~ U[0,1)):
+  N = 1 : BASELINE.json configs[1]  -- dense fp32 X 16384 x 16384, k = 128
+  N > 1 : configs[4] family         -- X (16384*N) x 16384 row-sharded, 16384 rows per GPU (weak
+          scaling; N = 8 is exactly configs[4]), one NCCL all-reduce of [W'W | W'X] per iteration.
+value  = cells*iters/s = p_total * n * K / t  with t = device time of exactly K iterations, inputs
+         resident in HBM (CUDA events on the solver's stream, max over ranks).
+e2e    = the same metric through the public host API (NMF.solve with HOST buffers): includes the
+         H2D copy of X, W0, H0 from pinned memory, the bf16 cache build, K iterations, the final
+         objective and the D2H copy of W, H.
+--impl reference: NMF.jl cannot run here (no Julia); the reference arm times the NumPy/OpenBLAS
+         restatement of NMF.jl's update_wh! as written (oracle/, 6 sgemm + ratio loops) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+ROWS_PER_GPU = 16384
+NCOLS = 16384
+K = 128
+METRIC = "NMF cells*iters/sec, MultUpdate(:mse) k=128 (iterations/sec in iters_per_sec)"
+UNIT = "cells*iters/s"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), float(d["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.004):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        self.period = period_s
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {}
+        for nm in dir(nv):
+            if nm.startswith("nvmlClocksThrottleReason") or nm.startswith("nvmlClocksEventReason"):
+                v = getattr(nv, nm)
+                if isinstance(v, int) and v not in (0,) and "All" not in nm and "None" not in nm:
+                    names[v] = nm.replace("nvmlClocksThrottleReason", "").replace("nvmlClocksEventReason", "")
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit and nm not in ("GpuIdle", "ApplicationsClocksSetting"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def __enter__(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def make_problem(rows: int, n: int, k: int, seed: int, pinned: bool):
+    """X (rows x n), W0 (rows x k), H0 (k x n): column-major float32 (returned as Julia-layout arrays)."""
+    import torch
+    rng = np.random.default_rng(seed)
+
+    def alloc(shape_f):  # column-major array of shape (r, c) == C-order (c, r)
+        r, c = shape_f
+        t = torch.empty((c, r), dtype=torch.float32, pin_memory=pinned)
+        return t, t.numpy().T
+
+    tx, X = alloc((rows, n))
+    for j0 in range(0, n, 1024):  # chunked fill keeps the float64 temporary small
+        j1 = min(n, j0 + 1024)
+        X[:, j0:j1] = rng.random((rows, j1 - j0), dtype=np.float32)
+    tw, W = alloc((rows, k))
+    W[...] = rng.random((rows, k), dtype=np.float32)
+    W /= W.sum(axis=0, keepdims=True)  # normalize1_cols! (utils.jl:28-32), as nnmf's :random init does
+    th, H = alloc((k, n))
+    H[...] = np.random.default_rng(12345).random((k, n), dtype=np.float32)  # H0 identical on every rank
+    return (tx, tw, th), X, W, H
+
+
+def cpu_reference_rate(rows: int, n: int, k: int, steps: int, warmup: int, budget_s: float = 60.0):
+    """NumPy/OpenBLAS restatement of update_wh!(::MultUpdMSE) (multupd.jl:83-116) timed on the host.
+    Bounded sample: at most `rows` <= 16384 rows are used and at most `budget_s` seconds of timed work."""
+    import nmf_oracle as O
+    from threadpoolctl import threadpool_info
+    rng = np.random.default_rng(0)
+    X = np.asfortranarray(rng.random((rows, n), dtype=np.float32))
+    W, H = O.randinit(rows, n, k, np.float32, rng, normalize=True)
+    upd = O.MultUpdMSE(np.float32, True, np.float32(0), np.float32(0), np.float32(np.sqrt(np.finfo(np.float32).eps)))
+    st = upd.prepare_state(X, W, H)
+    preW, preH = np.empty_like(W), np.empty_like(H)
+
+    def one():  # one trip of the loop body of nmf_skeleton! (common.jl:64-74)
+        np.copyto(preW, W)
+        np.copyto(preH, H)
+        upd.update_wh(st, X, W, H)
+        O.stop_condition(W, preW, H, preH, 1e-9)
+
+    for _ in range(max(1, min(warmup, 1))):
+        one()
+    t0 = time.perf_counter()
+    done = 0
+    while done < steps and (time.perf_counter() - t0) < budget_s:
+        one()
+        done += 1
+    dt = time.perf_counter() - t0
+    threads = max([d.get("num_threads", 1) for d in threadpool_info() if d.get("user_api") == "blas"] or [os.cpu_count()])
+    return done / dt, done, threads
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    n_gpus = args.gpus
+    p_total = ROWS_PER_GPU * n_gpus
+    # bounded sample: the reference's cost is linear in the number of rows -> time 16384 rows, scale by 1/N
+    its, done, threads = cpu_reference_rate(ROWS_PER_GPU, NCOLS, K, args.steps, args.warmup)
+    it_full = its / n_gpus
+    value = p_total * NCOLS * it_full
+    sample = (f"{done} full iterations of the as-written MultUpdMSE update (6 sgemm + 2 ratio loops + stop_condition) on "
+              f"{ROWS_PER_GPU}x{NCOLS}, k={K}" + (f"; rows scaled x{n_gpus} (cost linear in p)" if n_gpus > 1 else ""))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "iters_per_sec": it_full, "n_gpus": n_gpus,
+        "steps": done, "warmup": 1, "ms_per_step": 1e3 / it_full, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"MultUpdate(:mse) dense fp32 X {p_total}x{NCOLS}, k={K}", "rows_per_gpu": ROWS_PER_GPU,
+                   "note": "NMF.jl itself cannot run here (no Julia): NumPy/OpenBLAS restatement of its CPU path"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank: int, world: int, local_rank: int):
+    import torch
+    import nmf_jl_b200 as NMF
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_gpus = world
+    rows, n, k = ROWS_PER_GPU, NCOLS, K
+    p_total = rows * n_gpus
+    hbm_peak, tf_peak, peak_src = peaks()
+
+    keep, X, W0, H0 = make_problem(rows, n, k, seed=1000 + rank, pinned=True)
+    tx, tw, th = keep
+    dX = tx.cuda(non_blocking=True)
+    dW = torch.empty_like(tw, device="cuda")
+    dH = torch.empty_like(th, device="cuda")
+    torch.cuda.synchronize()
+
+    sess = NMF.Session(device=local_rank, engine="tc")
+    if world > 1:
+        uid = [NMF.Session.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        sess.comm_init(rank, world, uid[0])
+    sess.set_X_device(dX.data_ptr(), rows, n, rows, np.float32, keepalive=dX)
+    sess.set_option("check_every", max(args.steps, args.warmup, 1))  # no host round trip inside the timed loop
+
+    def device_solve(iters, timed):
+        dW.copy_(tw, non_blocking=True)
+        dH.copy_(th, non_blocking=True)
+        torch.cuda.synchronize()
+        sess.set_option("time_kernels", 1 if timed else 0)
+        return sess.solve_raw("multmse", np.float32, dW.data_ptr(), rows, dH.data_ptr(), k, k, max(iters, 2), 1e-30, 0.0, 0.0,
+                              True, False, True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident number: W warm-up iterations, then exactly K timed iterations
+    device_solve(max(args.warmup, 3), timed=False)
+    barrier()
+    with ClockSampler(local_rank) as clk:
+        res = device_solve(args.steps, timed=True)
+        barrier()
+    assert res.niters == max(args.steps, 2) and res.engine == 1, "tensor-core engine did not run the requested iterations"
+    loop_ms = torch.tensor([res.solve_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(loop_ms, op=dist.ReduceOp.MAX)
+    loop_ms = float(loop_ms.item())
+    iters = res.niters
+    it_per_s = iters / (loop_ms * 1e-3)
+    value = p_total * n * it_per_s
+
+    # ---- end-to-end through the host API (host buffers in pinned memory)
+    e2e_iters = iters
+    Wh, Hh = W0.copy(order="F"), H0.copy(order="F")
+    sess2 = NMF.Session(device=local_rank, engine="tc")
+    if world > 1:
+        uid = [NMF.Session.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        sess2.comm_init(rank, world, uid[0])
+    sess2.set_option("check_every", max(e2e_iters, 1))
+    alg = NMF.MultUpdate(np.float32, obj="mse", maxiter=max(e2e_iters, 2), tol=1e-30)
+    for rep in range(2):  # first pass warms allocations, second is timed
+        Wh[...] = W0
+        Hh[...] = H0
+        barrier()
+        t0 = time.perf_counter()
+        sess2.set_X(X)
+        r2 = sess2.solve(alg, Wh, Hh)
+        torch.cuda.synchronize()
+        t_e2e = time.perf_counter() - t0
+    t_e2e_t = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_e2e_t, op=dist.ReduceOp.MAX)
+    t_e2e = float(t_e2e_t.item())
+    e2e_value = p_total * n * r2.niters / t_e2e
+    h2d = (X.nbytes + W0.nbytes + H0.nbytes) / r2.niters
+    d2h = (W0.nbytes + H0.nbytes + 8) / r2.niters
+    objv = float(r2.objvalue)
+    sess2.close()
+
+    # ---- roofline of the dominant kernel (mu_update_kernel: one launch per half-step)
+    launches = max(int(res.hot_kernel_launches), 1)
+    kern_ms = res.hot_kernel_ms / launches
+    # algorithmic bytes per launch: the bf16 X panel once + the factor read & written in fp32
+    alg_bytes = rows * n * 2 + 2 * ((rows + n) / 2) * k * 4
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
+    flops_iter = 4.0 * rows * n * k + 4.0 * k * k * (rows + n)
+    tflops = flops_iter * it_per_s / 1e12
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "iters_per_sec": it_per_s, "n_gpus": n_gpus, "steps": iters,
+            "warmup": max(args.warmup, 3), "ms_per_step": loop_ms / iters, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16 operands, f32 accumulate/state", "data": "synthetic",
+            "config": {"workload": f"MultUpdate(:mse) dense fp32 X {p_total}x{n}, k={k}" +
+                       (f" row-sharded over {n_gpus} GPUs" if n_gpus > 1 else " (BASELINE configs[1])"),
+                       "rows_per_gpu": rows, "tol": 1e-30, "lambda": 0.0,
+                       "l2": "inputs larger than L2: two 512 MiB bf16 X panels per iteration vs 126 MB L2, no flush needed",
+                       "engine": "tc", "objvalue_e2e": objv},
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "iters_per_sec": r2.niters / t_e2e, "seconds": t_e2e, "iters": r2.niters,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(res.kernel_launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": None, "kernel": "mu_update_kernel<128,0>", "kernel_ms": kern_ms, "launches_timed": launches,
+                         "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                         "tensor_tflops_whole_iteration": tflops, "tensor_frac_of_sustained_bf16": tflops / tf_peak},
+        }
+        # CPU baseline on rank 0 at N = 1 only (bounded sample, ~10-30 s)
+        if n_gpus == 1 and not args.no_cpu:
+            its, done, threads = cpu_reference_rate(rows, n, k, steps=6, warmup=1, budget_s=25.0)
+            line["cpu_baseline"] = {"value": p_total * n * its, "unit": UNIT, "iters_per_sec": its, "cores": threads, "kind": "port",
+                                    "sample": f"{done} full-size iterations of the NumPy/OpenBLAS restatement of NMF.jl's "
+                                              f"MultUpdMSE update_wh! (as written, 6 sgemm) on {rows}x{n}, k={k}"}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    sess.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus:
+        if args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} processes (WORLD_SIZE={world})")
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -55,6 +55,8 @@ typedef struct nmfb200_result {
     double upload_ms;           /* host->device time of W/H (and X if passed through solve) */
     int64_t coordinate_updates; /* GreedyCD only: inner coordinate steps taken (greedycd.jl:144-162) */
     int64_t kernel_launches;    /* number of library kernels launched by this call */
+    double hot_kernel_ms;       /* option "time_kernels"=1: summed device time of the dominant kernel's launches */
+    int64_t hot_kernel_launches;/*   ... and how many launches that sum covers (0 when the option is off) */
 } nmfb200_result;
 
 typedef struct nmfb200_handle nmfb200_handle;
@@ -78,7 +80,9 @@ int nmfb200_set_stream(nmfb200_handle* h, void* stream);
  *                                               tc: tcgen05 bf16-operand / fp32-accumulate kernels
  *                                               (Float32 only); auto = tc when shape allows.
  *   "check_every" = "<int>"                  -- host polls the device convergence flag every N
- *                                               iterations (results are independent of N). */
+ *                                               iterations (results are independent of N).
+ *   "time_kernels" = "0" | "1"               -- bracket every launch of the dominant kernel with
+ *                                               CUDA events and report the sum in nmfb200_result. */
 int nmfb200_set_option(nmfb200_handle* h, const char* key, const char* value);
 int nmfb200_set_trace(nmfb200_handle* h, nmfb200_trace_fn fn, void* user);
 

@@ -23,6 +23,8 @@ class NmfResult(ctypes.Structure):
         ("upload_ms", ctypes.c_double),
         ("coordinate_updates", ctypes.c_int64),
         ("kernel_launches", ctypes.c_int64),
+        ("hot_kernel_ms", ctypes.c_double),
+        ("hot_kernel_launches", ctypes.c_int64),
     ]
 
 

@@ -312,7 +312,8 @@ class Session:
         if Hf is not H:
             H[...] = Hf
         info = {"engine": "tc" if r.engine == 1 else "simt", "solve_ms": r.solve_ms, "upload_ms": r.upload_ms,
-                "last_dev": r.last_dev, "coordinate_updates": r.coordinate_updates, "kernel_launches": r.kernel_launches}
+                "last_dev": r.last_dev, "coordinate_updates": r.coordinate_updates, "kernel_launches": r.kernel_launches,
+                "hot_kernel_ms": r.hot_kernel_ms, "hot_kernel_launches": r.hot_kernel_launches}
         return Result(W, H, r.niters, bool(r.converged), r.objvalue, info)
 
 

@@ -177,6 +177,8 @@ int nmfb200_set_option(nmfb200_handle* h, const char* key, const char* value) {
             int c = atoi(value);
             NMF_REQUIRE(c >= 1, NMFB200_EINVAL, "check_every must be >= 1");
             h->check_every = c;
+        } else if (k == "time_kernels") {
+            h->time_kernels = atoi(value) != 0;
         } else {
             throw Error{NMFB200_EINVAL, "unknown option " + k};
         }

@@ -93,6 +93,9 @@ struct nmfb200_handle {
     // options
     int engine_opt = 0;  // 0 auto, 1 simt, 2 tc
     int check_every = 8;
+    int time_kernels = 0;
+    std::vector<cudaEvent_t> ev_pool;  // events for time_kernels
+    size_t ev_used = 0;
     nmfb200_trace_fn trace = nullptr;
     void* trace_user = nullptr;
 
@@ -131,7 +134,30 @@ struct nmfb200_handle {
             bufs.erase(it);
         }
     }
+    cudaEvent_t next_event() {
+        if (ev_used == ev_pool.size()) {
+            cudaEvent_t e;
+            NMF_CUDA(cudaEventCreate(&e));
+            ev_pool.push_back(e);
+        }
+        return ev_pool[ev_used++];
+    }
+    // sum of (ev[2i+1] - ev[2i]) over the events handed out since ev_used was reset; stream must be idle
+    double drain_event_pairs(int64_t* npairs) {
+        double ms = 0;
+        for (size_t i = 0; i + 1 < ev_used; i += 2) {
+            float t = 0;
+            cudaEventElapsedTime(&t, ev_pool[i], ev_pool[i + 1]);
+            ms += t;
+        }
+        *npairs = (int64_t)(ev_used / 2);
+        ev_used = 0;
+        return ms;
+    }
     void free_all() {
+        for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
+        ev_pool.clear();
+        ev_used = 0;
         for (auto& kv : bufs)
             if (kv.second.ptr) cudaFree(kv.second.ptr);
         bufs.clear();

@@ -602,9 +602,12 @@ struct TcSolver {
         prm.state = state;
         prm.R = F.R; prm.Kdim = Kdim; prm.lambda = lambda; prm.delta = delta;
         const int smem = UpdCfg<KP>::SMEM_BYTES;
+        const bool timed = h->time_kernels && mode != 2;
+        if (timed) NMF_CUDA(cudaEventRecord(h->next_event(), st));
         if (mode == 0) mu_update_kernel<KP, 0><<<F.tiles, 192, smem, st>>>(prm);
         else if (mode == 1) mu_update_kernel<KP, 1><<<F.tiles, 192, smem, st>>>(prm);
         else mu_update_kernel<KP, 2><<<F.tiles, 192, smem, st>>>(prm);
+        if (timed) NMF_CUDA(cudaEventRecord(h->next_event(), st));
         h->launches += 1;
     }
 
@@ -707,6 +710,7 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
     if (!a.update_H) s.launch_gram(H, true);  // H never changes: P_H once
     NMF_CUDA(cudaEventRecord(e1, st));
 
+    h->ev_used = 0;
     int64_t enq = 0;
     bool converged = false;
     int64_t iters = 0;
@@ -764,6 +768,7 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
     out->upload_ms = ms_up;
     out->coordinate_updates = 0;
     out->kernel_launches = h->launches;
+    out->hot_kernel_ms = h->drain_event_pairs(&out->hot_kernel_launches);
 }
 
 }  // namespace

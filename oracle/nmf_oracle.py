@@ -100,6 +100,12 @@ def _isF(a: np.ndarray) -> bool:
     return a.flags.f_contiguous
 
 
+def _mm(A: np.ndarray, B: np.ndarray) -> np.ndarray:
+    """A @ B returned column-major without a layout copy: (B' A')' -- the same sgemm/dgemm call
+    LinearAlgebra.mul! makes on column-major operands."""
+    return (B.T @ A.T).T
+
+
 # --------------------------------------------------------------------------------------------------
 # common.jl
 # --------------------------------------------------------------------------------------------------
@@ -237,7 +243,7 @@ class MultUpdMSE:
 
     def prepare_state(self, X, W, H):  # :70-80
         p, n, k = nmf_checksize(X, W, H)
-        return {"WH": _F(W @ H)}
+        return {"WH": _mm(W, H)}
 
     def evaluate_objv(self, s, X, W, H):  # :81
         return self.T.type(0.5) * self.T.type(sqL2dist(X, s["WH"]))
@@ -247,14 +253,14 @@ class MultUpdMSE:
         ratio = _fn("oracle_mu_mse_ratio", T)
         WH = s["WH"]
         if self.update_H:
-            WtX = _F(W.T @ X)                       # :98
-            WtWH = _F(W.T @ WH)                     # :99
+            WtX = _mm(W.T, X)                       # :98
+            WtWH = _mm(W.T, WH)                     # :99
             ratio(_p(H), _p(WtX), _p(WtWH), H.size, T.type(self.lambda_h), T.type(self.delta))  # :101-103
-            WH = s["WH"] = _F(W @ H)                # :104
-        XHt = _F(X @ H.T)                           # :109
-        WHHt = _F(WH @ H.T)                         # :110
+            WH = s["WH"] = _mm(W, H)                # :104
+        XHt = _mm(X, H.T)                           # :109
+        WHHt = _mm(WH, H.T)                         # :110
         ratio(_p(W), _p(XHt), _p(WHHt), W.size, T.type(self.lambda_w), T.type(self.delta))      # :112-114
-        s["WH"] = _F(W @ H)                         # :115
+        s["WH"] = _mm(W, H)                         # :115
 
 
 class MultUpdDiv:
@@ -265,7 +271,7 @@ class MultUpdDiv:
 
     def prepare_state(self, X, W, H):  # :136-147
         nmf_checksize(X, W, H)
-        return {"WH": _F(W @ H), "Q": np.empty(X.shape, dtype=self.T, order="F")}
+        return {"WH": _mm(W, H), "Q": np.empty(X.shape, dtype=self.T, order="F")}
 
     def evaluate_objv(self, s, X, W, H):  # :148 (gkldiv returns Float64; Result converts to T)
         return gkldiv(X, s["WH"])
@@ -278,15 +284,15 @@ class MultUpdDiv:
         quot = _fn("oracle_mu_div_quot", T)
         if self.update_H:
             quot(_p(Q), _p(X), _p(s["WH"]), X.size, T.type(self.delta))            # :172-174
-            WtQ = _F(W.T @ Q)                                                      # :175
+            WtQ = _mm(W.T, Q)                                                      # :175
             sW = np.ascontiguousarray(W.sum(axis=0, dtype=T))                      # :176
             _fn("oracle_mu_div_scale_h", T)(_p(H), _p(WtQ), _p(sW), k, n, T.type(self.lambda_h))  # :177-179
-            s["WH"] = _F(W @ H)                                                    # :180
+            s["WH"] = _mm(W, H)                                                    # :180
         quot(_p(Q), _p(X), _p(s["WH"]), X.size, T.type(self.delta))                # :184-186
-        QHt = _F(Q @ H.T)                                                          # :187
+        QHt = _mm(Q, H.T)                                                          # :187
         sH = np.ascontiguousarray(H.sum(axis=1, dtype=T))                          # :188
         _fn("oracle_mu_div_scale_w", T)(_p(W), _p(QHt), _p(sH), p, k, T.type(self.lambda_w))      # :189-191
-        s["WH"] = _F(W @ H)                                                        # :192
+        s["WH"] = _mm(W, H)                                                        # :192
 
 
 def solve_multupdate(alg: MultUpdate, X, W, H, log=None) -> Result:
@@ -351,7 +357,7 @@ class GreedyCDUpd:
 
     def evaluate_objv(self, s, X, W, H):  # :82-92
         T = self.T
-        WH = _F(W @ H)
+        WH = _mm(W, H)
         r = T.type(0.5) * T.type(sqL2dist(X, WH))
         if self.lambda_w > 0:
             r = T.type(r + self.lambda_w * T.type(np.abs(W).sum(dtype=T)))
@@ -362,9 +368,9 @@ class GreedyCDUpd:
     def _update(self, X, F, Ot, lam):
         """_update_GreedyCD! :94-166 for factor F (rows x k) against Ot (cols x k): X is rows x cols."""
         T = self.T
-        P = _F(Ot.T @ Ot)                 # :117
-        Z = X @ Ot                        # :118
-        G = _F(F @ P)                     # :119
+        P = _mm(Ot.T, Ot)                 # :117
+        Z = _mm(X, Ot)                    # :118
+        G = _mm(F, P)                     # :119
         G -= Z                            # :120
         if lam > 0:
             G += T.type(lam)              # :121-123

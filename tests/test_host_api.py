@@ -29,8 +29,8 @@ def test_header_symbols_exported_and_bound(NMF):
 
 def test_result_struct_matches_header(NMF):
     import ctypes
-    # int64, int32, int32, 4 doubles, 2 int64 -> 64 bytes, no padding surprises
-    assert ctypes.sizeof(NMF._lib.NmfResult) == 8 + 4 + 4 + 8 * 4 + 8 * 2
+    # int64, int32, int32, 4 doubles, 2 int64, double, int64 -> 80 bytes, no padding surprises
+    assert ctypes.sizeof(NMF._lib.NmfResult) == 8 + 4 + 4 + 8 * 4 + 8 * 2 + 8 + 8
 
 
 def test_library_built_for_sm100a_only(NMF):
