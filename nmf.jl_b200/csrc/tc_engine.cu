@@ -32,7 +32,7 @@ struct TcState {
     int converged;
     int iters;
     float devmax;
-    unsigned int gram_ctr;
+    int pad;
 };
 
 // ---- kernel parameter block (tensor maps must live in __grid_constant__ param space) ---------------
@@ -289,12 +289,9 @@ __global__ void __launch_bounds__(192, 1) mu_update_kernel(const __grid_constant
 // ---- Gram: P += T T'  for T = FbT ([KP][R] bf16, rows of length R contiguous) ------------------------
 struct GramParams {
     CUtensorMap tmT;  // bf16 [KP][R], box 64 x 128
-    float* P;         // [KP][KP] fp32 accumulator (zero on entry of the first CTA, re-zeroed by the finalizer)
-    bf16* Phi;
-    bf16* Plo;
-    TcState* state;
+    float* part;      // [gridDim.x][KP][KP] fp32 partial Grams (plain stores, reduced by gram_reduce_kernel)
+    const TcState* state;
     int R, chunk;     // rows (K extent) per CTA, multiple of 64
-    int finalize;     // 1: last CTA splits P into Phi/Plo and zeroes P
 };
 
 template <int KP>
@@ -307,13 +304,6 @@ struct GramCfg {
 };
 
 template <int KP>
-__device__ __forceinline__ void split_store(float v, bf16* Phi, bf16* Plo, int idx) {
-    bf16 hi = __float2bfloat16_rn(v);
-    Phi[idx] = hi;
-    Plo[idx] = __float2bfloat16_rn(v - __bfloat162float(hi));
-}
-
-template <int KP>
 __global__ void __launch_bounds__(192, 1) gram_kernel(const __grid_constant__ GramParams prm) {
     using C = GramCfg<KP>;
     if (prm.state->converged) return;
@@ -323,7 +313,6 @@ __global__ void __launch_bounds__(192, 1) gram_kernel(const __grid_constant__ Gr
     uint64_t* empty_bar = full_bar + C::STAGES;
     uint64_t* tmem_full = empty_bar + C::STAGES;
     uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
-    uint32_t* last_flag = tmem_slot + 1;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int k_begin = blockIdx.x * prm.chunk;
@@ -385,6 +374,7 @@ __global__ void __launch_bounds__(192, 1) gram_kernel(const __grid_constant__ Gr
         const int q = warp & 3;
         mbar_wait(tmem_full, 0);
         tc_fence_after();
+        float* part = prm.part + (size_t)blockIdx.x * KP * KP;
 #pragma unroll 1
         for (int m = 0; m < C::MT; ++m) {
             const int a = 128 * m + 32 * q + lane;
@@ -394,31 +384,15 @@ __global__ void __launch_bounds__(192, 1) gram_kernel(const __grid_constant__ Gr
                 tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + m * KP + c0, v);
                 tmem_ld_wait();
                 if (a < KP) {
-                    float* dst = prm.P + (size_t)a * KP + c0;
+                    float4* dst = (float4*)(part + (size_t)a * KP + c0);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
+                    for (int j = 0; j < 8; ++j)
+                        dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                             __uint_as_float(v[4 * j + 3]));
                 }
             }
         }
         tc_fence_before();
-        if (prm.finalize) {
-            __threadfence();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (threadIdx.x == 64) {
-                unsigned int prev = atomicAdd(&prm.state->gram_ctr, 1u);
-                *last_flag = (prev == gridDim.x - 1) ? 1u : 0u;
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (*last_flag) {
-                __threadfence();
-                for (int i = threadIdx.x - 64; i < KP * KP; i += 128) {
-                    float v = __ldcg(prm.P + i);
-                    split_store<KP>(v, prm.Phi, prm.Plo, i);
-                    prm.P[i] = 0.f;
-                }
-                if (threadIdx.x == 64) prm.state->gram_ctr = 0u;
-            }
-        }
     }
     __syncthreads();
     if (warp == 1) {
@@ -427,15 +401,39 @@ __global__ void __launch_bounds__(192, 1) gram_kernel(const __grid_constant__ Gr
     }
 }
 
-// multi-GPU: split an all-reduced fp32 Gram into bf16 hi/lo and clear the accumulator
-__global__ void gram_split_kernel(float* P, bf16* Phi, bf16* Plo, int n, const TcState* st) {
+// P[e] = sum_g part[g][e]; writes the fp32 Gram and (do_split) its bf16 hi/lo split.  One element per thread.
+__global__ void __launch_bounds__(256) gram_reduce_kernel(const float* __restrict__ part, int nparts, int nelem, float* __restrict__ P,
+                                                          bf16* __restrict__ Phi, bf16* __restrict__ Plo, int do_split,
+                                                          const TcState* st) {
+    if (st->converged) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nelem) return;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int g = 0;
+    for (; g + 4 <= nparts; g += 4) {
+        s0 += part[(size_t)g * nelem + i];
+        s1 += part[(size_t)(g + 1) * nelem + i];
+        s2 += part[(size_t)(g + 2) * nelem + i];
+        s3 += part[(size_t)(g + 3) * nelem + i];
+    }
+    for (; g < nparts; ++g) s0 += part[(size_t)g * nelem + i];
+    const float v = (s0 + s1) + (s2 + s3);
+    P[i] = v;
+    if (do_split) {
+        bf16 hi = __float2bfloat16_rn(v);
+        Phi[i] = hi;
+        Plo[i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+}
+
+// multi-GPU: split an all-reduced fp32 Gram into bf16 hi/lo
+__global__ void gram_split_kernel(const float* __restrict__ P, bf16* __restrict__ Phi, bf16* __restrict__ Plo, int n, const TcState* st) {
     if (st->converged) return;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float v = P[i];
         bf16 hi = __float2bfloat16_rn(v);
         Phi[i] = hi;
         Plo[i] = __float2bfloat16_rn(v - __bfloat162float(hi));
-        P[i] = 0.f;
     }
 }
 
@@ -446,25 +444,35 @@ __global__ void conv_kernel(const float* __restrict__ partW, int tilesW, const f
     if (st->converged) return;
     __shared__ int fail;
     __shared__ float devs[256];
+    __shared__ double red[4][1024];
     const int a = threadIdx.x;
     if (a == 0) fail = 0;
     __syncthreads();
-    if (do_reduce && a < KP) {
+    if (do_reduce) {
+        // blockDim.x = 1024: KP components x (1024 / KP) tile groups, then a shared-memory pass over the groups
+        const int groups = blockDim.x / KP;
+        const int g = threadIdx.x / KP, c = threadIdx.x % KP;
         double dw = 0, sw = 0, dh = 0, sh = 0;
-        for (int t = 0; t < tilesW; ++t) {
-            dw += (double)partW[(size_t)t * 2 * KP + a];
-            sw += (double)partW[(size_t)t * 2 * KP + KP + a];
-        }
-        if (update_H) {
-            for (int t = 0; t < tilesH; ++t) {
-                dh += (double)partH[(size_t)t * 2 * KP + a];
-                sh += (double)partH[(size_t)t * 2 * KP + KP + a];
+        if (g < groups) {
+            for (int t = g; t < tilesW; t += groups) {
+                dw += (double)partW[(size_t)t * 2 * KP + c];
+                sw += (double)partW[(size_t)t * 2 * KP + KP + c];
             }
-        } else {
-            dh = 0;
-            sh = 1;
+            if (update_H)
+                for (int t = g; t < tilesH; t += groups) {
+                    dh += (double)partH[(size_t)t * 2 * KP + c];
+                    sh += (double)partH[(size_t)t * 2 * KP + KP + c];
+                }
         }
-        acc[a] = dw; acc[KP + a] = sw; acc[2 * KP + a] = dh; acc[3 * KP + a] = sh;
+        red[0][threadIdx.x] = dw; red[1][threadIdx.x] = sw; red[2][threadIdx.x] = dh; red[3][threadIdx.x] = sh;
+        __syncthreads();
+        if (threadIdx.x < KP) {
+            for (int gg = 1; gg < groups; ++gg) {
+                dw += red[0][gg * KP + c]; sw += red[1][gg * KP + c]; dh += red[2][gg * KP + c]; sh += red[3][gg * KP + c];
+            }
+            if (!update_H) { dh = 0; sh = 1; }
+            acc[c] = dw; acc[KP + c] = sw; acc[2 * KP + c] = dh; acc[3 * KP + c] = sh;
+        }
     }
     if (!do_decide) return;
     __syncthreads();
@@ -476,7 +484,7 @@ __global__ void conv_kernel(const float* __restrict__ partW, int tilesW, const f
         dev = sqrtf(m);
         if (sqrtf(dw) > tol * sqrtf(sw) || sqrtf(dh) > tol * sqrtf(sh)) atomicExch(&fail, 1);
     }
-    devs[a] = dev;
+    if (a < 256) devs[a] = dev;
     __syncthreads();
     if (a == 0) {
         float dm = 0.f;
@@ -611,15 +619,18 @@ struct TcSolver {
         h->launches += 1;
     }
 
-    void launch_gram(const Factor& F, bool finalize) {
+    void launch_gram(const Factor& F, bool split) {
         GramParams g;
         g.tmT = make_tmap_bf16(F.bT, (uint64_t)F.R, (uint64_t)F.rowsT, (uint64_t)F.ldT, 128);
-        g.P = F.P; g.Phi = F.Phi; g.Plo = F.Plo; g.state = state; g.R = F.R;
-        g.chunk = 512;
-        g.finalize = finalize ? 1 : 0;
-        int grid = (int)ceil_div(F.R, g.chunk);
+        // ~128 CTAs at most, each a multiple of 64 rows and at least 256
+        g.chunk = (int)std::max<int64_t>(256, round_up(ceil_div(F.R, 128), 64));
+        const int grid = (int)ceil_div(F.R, g.chunk);
+        g.part = h->buf_t<float>("tc.gram_part", (size_t)grid * KP * KP);
+        g.state = state;
+        g.R = F.R;
         gram_kernel<KP><<<grid, 192, GramCfg<KP>::SMEM_BYTES, st>>>(g);
-        h->launches += 1;
+        gram_reduce_kernel<<<(KP * KP + 255) / 256, 256, 0, st>>>(g.part, grid, KP * KP, F.P, F.Phi, F.Plo, split ? 1 : 0, state);
+        h->launches += 2;
     }
 
     static void set_attrs() {
@@ -682,8 +693,6 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
     TcState* state = (TcState*)h->buf("tc.state", sizeof(TcState));
     double* acc = h->buf_t<double>("tc.acc", 4 * KP);
     NMF_CUDA(cudaMemsetAsync(state, 0, sizeof(TcState), st));
-    NMF_CUDA(cudaMemsetAsync(W.P, 0, (size_t)KP * KP * sizeof(float), st));
-    NMF_CUDA(cudaMemsetAsync(H.P, 0, (size_t)KP * KP * sizeof(float), st));
     NMF_CUDA(cudaMemsetAsync(W.bT, 0, (size_t)W.rowsT * W.ldT * sizeof(bf16), st));
     NMF_CUDA(cudaMemsetAsync(H.bT, 0, (size_t)H.rowsT * H.ldT * sizeof(bf16), st));
 
@@ -725,7 +734,7 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
             }
             s.launch_update(0, W, H, Xc, ldn, (int)n, lw, delta, nullptr);      // W-step
             s.launch_gram(W, true);
-            conv_kernel<<<1, 256, 0, st>>>(W.conv, W.tiles, H.conv, H.tiles, KP, (int)k, a.update_H, acc, tol, state, 1, 1);
+            conv_kernel<<<1, 1024, 0, st>>>(W.conv, W.tiles, H.conv, H.tiles, KP, (int)k, a.update_H, acc, tol, state, 1, 1);
             h->launches += 1;
         }
         enq += batch;
