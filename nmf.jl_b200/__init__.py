@@ -21,6 +21,6 @@ from .api import (  # noqa: F401
     solve,
     solve_replicates,
 )
-from . import _lib, build  # noqa: F401
+from . import _lib, build, dist  # noqa: F401
 
 __version__ = "0.1.0"

@@ -619,7 +619,7 @@ struct TcSolver {
         h->launches += 1;
     }
 
-    void launch_gram(const Factor& F, bool split) {
+    void launch_gram(const Factor& F, bool split, float* P_dst = nullptr) {
         GramParams g;
         g.tmT = make_tmap_bf16(F.bT, (uint64_t)F.R, (uint64_t)F.rowsT, (uint64_t)F.ldT, 128);
         // ~128 CTAs at most, each a multiple of 64 rows and at least 256
@@ -629,7 +629,7 @@ struct TcSolver {
         g.state = state;
         g.R = F.R;
         gram_kernel<KP><<<grid, 192, GramCfg<KP>::SMEM_BYTES, st>>>(g);
-        gram_reduce_kernel<<<(KP * KP + 255) / 256, 256, 0, st>>>(g.part, grid, KP * KP, F.P, F.Phi, F.Plo, split ? 1 : 0, state);
+        gram_reduce_kernel<<<(KP * KP + 255) / 256, 256, 0, st>>>(g.part, grid, KP * KP, P_dst ? P_dst : F.P, F.Phi, F.Plo, split ? 1 : 0, state);
         h->launches += 2;
     }
 
@@ -714,8 +714,10 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
 
     TcSolver<KP> s{h, st, state};
     const bool multi = h->comm != nullptr;
-    NMF_REQUIRE(!multi, NMFB200_ENOTSUP, "tensor-core engine: multi-GPU path not wired yet");
-    s.launch_gram(W, true);                 // P_W = W'W for the first H-step
+    // multi-GPU (rows of X, W sharded; H replicated): packed all-reduce buffer [ (W_g' X_g)' : n x KP | W_g' W_g : KP x KP ]
+    float* packed = multi ? h->buf_t<float>("tc.packed", (size_t)n * KP + (size_t)KP * KP) : nullptr;
+    float* packed_P = multi ? packed + (size_t)n * KP : nullptr;
+    s.launch_gram(W, !multi, packed_P);       // P_W = W'W for the first H-step (partial per rank when sharded)
     if (!a.update_H) s.launch_gram(H, true);  // H never changes: P_H once
     NMF_CUDA(cudaEventRecord(e1, st));
 
@@ -729,13 +731,28 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
         int64_t batch = std::min<int64_t>(h->check_every, a.maxiter - enq);
         for (int64_t i = 0; i < batch; ++i) {
             if (a.update_H) {
-                s.launch_update(0, H, W, Xr, ldp, (int)p, lh, delta, nullptr);  // H-step: rows of H' against W
+                if (!multi) {
+                    s.launch_update(0, H, W, Xr, ldp, (int)p, lh, delta, nullptr);  // H-step: rows of H' against W
+                } else {
+                    s.launch_update(1, H, W, Xr, ldp, (int)p, lh, delta, packed);   // partial numerators of this shard
+                    h->allreduce_sum(packed, (size_t)n * KP + (size_t)KP * KP);     // THE exchange step of the iteration
+                    gram_split_kernel<<<(KP * KP + 255) / 256, 256, 0, st>>>(packed_P, W.Phi, W.Plo, KP * KP, state);
+                    h->launches += 1;
+                    s.launch_update(2, H, W, Xr, ldp, (int)p, lh, delta, packed);   // ratio with the reduced numerators
+                }
                 s.launch_gram(H, true);
             }
-            s.launch_update(0, W, H, Xc, ldn, (int)n, lw, delta, nullptr);      // W-step
-            s.launch_gram(W, true);
-            conv_kernel<<<1, 1024, 0, st>>>(W.conv, W.tiles, H.conv, H.tiles, KP, (int)k, a.update_H, acc, tol, state, 1, 1);
-            h->launches += 1;
+            s.launch_update(0, W, H, Xc, ldn, (int)n, lw, delta, nullptr);          // W-step (local rows)
+            s.launch_gram(W, !multi, packed_P);
+            if (!multi) {
+                conv_kernel<<<1, 1024, 0, st>>>(W.conv, W.tiles, H.conv, H.tiles, KP, (int)k, a.update_H, acc, tol, state, 1, 1);
+                h->launches += 1;
+            } else {
+                conv_kernel<<<1, 1024, 0, st>>>(W.conv, W.tiles, H.conv, H.tiles, KP, (int)k, a.update_H, acc, tol, state, 1, 0);
+                h->allreduce_sum(acc, (size_t)2 * KP);  // dev_w, sum_w over all row shards; the H sums are replicated
+                conv_kernel<<<1, 1024, 0, st>>>(W.conv, W.tiles, H.conv, H.tiles, KP, (int)k, a.update_H, acc, tol, state, 0, 1);
+                h->launches += 2;
+            }
         }
         enq += batch;
         NMF_CUDA(cudaGetLastError());
@@ -785,7 +802,6 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
 bool tc_supported(const nmfb200_handle* h, const SolveArgs& a) {
     if (a.alg != 0) return false;         // MultUpdate(:mse) only, so far
     if (a.verbose) return false;          // per-iteration objective: exact engine
-    if (h->comm != nullptr) return false;  // multi-GPU: exact engine until MODE 1/2 are wired
     if (pick_kp(a.k) == 0) return false;
     if (h->p > (int64_t)INT32_MAX / 256 || h->n > (int64_t)INT32_MAX / 256) return false;
     return true;

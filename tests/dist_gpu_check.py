@@ -1,0 +1,76 @@
+"""Run under torchrun on >= 2 GPUs: the row-sharded solve must reproduce the single-GPU / oracle result.
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_gpu_check.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    sys.path.insert(0, p)
+import nmf_jl_b200 as NMF  # noqa: E402
+import nmf_oracle as O  # noqa: E402
+
+
+def relerr(a, b):
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ok = True
+    cases = [("multmse", "tc", 1000, 768, 96, 12, np.float32), ("multmse", "simt", 301, 200, 7, 10, np.float64),
+             ("multdiv", "simt", 257, 190, 6, 8, np.float64), ("greedycd", "simt", 120, 90, 5, 4, np.float64),
+             ("multmse", "tc", 515, 640, 32, 400, np.float32)]
+    for (algname, engine, p, n, k, iters, T) in cases:
+        rng = np.random.default_rng(42)
+        X = np.asfortranarray(rng.random((p, n)), dtype=T)
+        W0, H0 = NMF.randinit(p, n, k, T, normalize=True, rng=rng)
+        tol = 1e-9 if iters < 100 else 2e-3
+        if algname == "greedycd":
+            alg, oalg = NMF.GreedyCD(T, maxiter=iters, tol=tol), O.GreedyCD(T, maxiter=iters, tol=tol)
+        else:
+            alg = NMF.MultUpdate(T, obj=algname[4:], maxiter=iters, tol=tol)
+            oalg = O.MultUpdate(T, obj=algname[4:], maxiter=iters, tol=tol)
+        lo, hi = NMF.dist.row_shard(p, rank, world)
+        Wl, Hl = np.asfortranarray(W0[lo:hi]), H0.copy(order="F")
+        with NMF.Session(device=local, engine=engine) as s:
+            s.set_option("check_every", 7)
+            NMF.dist.init_comm(s)
+            r = NMF.dist.solve_sharded(alg, s, np.asfortranarray(X[lo:hi]), Wl, Hl)
+        Wo, Ho = W0.copy(order="F"), H0.copy(order="F")
+        ro = O.solve(oalg, X, Wo, Ho)
+        ew, eh = relerr(Wl, Wo[lo:hi]), relerr(Hl, Ho)
+        eo = abs(float(r.objvalue) - float(ro.objvalue)) / float(ro.objvalue)
+        wtol = 5e-3 if engine == "tc" else (1e-8 if algname != "greedycd" else 1e-5)
+        good = (eo <= 1e-4 and (algname == "greedycd" or (ew <= wtol and eh <= wtol)) and r.info["engine"] == engine)
+        if iters < 100:
+            good = good and r.niters == ro.niters
+        else:
+            good = good and r.converged and ro.converged and abs(r.niters - ro.niters) <= max(3, ro.niters // 20)
+        # H must be bit-identical on every rank (replicated state)
+        Ht = torch.from_numpy(np.ascontiguousarray(Hl)).cuda()
+        Hmax, Hmin = Ht.clone(), Ht.clone()
+        dist.all_reduce(Hmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(Hmin, op=dist.ReduceOp.MIN)
+        same = bool((Hmax == Hmin).all().item())
+        print(f"[rank {rank}/{world}] {algname}/{engine} p={p} n={n} k={k}: niters={r.niters}/{ro.niters} conv={r.converged} errW={ew:.2e} "
+              f"errH={eh:.2e} errObj={eo:.2e} H_replicated_identical={same} -> {'ok' if good and same else 'FAIL'}", flush=True)
+        ok = ok and good and same
+    flag = torch.tensor([0 if ok else 1], device="cuda")
+    dist.all_reduce(flag)
+    dist.barrier()
+    dist.destroy_process_group()
+    if flag.item() != 0:
+        sys.exit(1)
+    if rank == 0:
+        print("dist_gpu_check ok")
+
+
+if __name__ == "__main__":
+    main()
