@@ -1,0 +1,213 @@
+# NMFB200.jl -- thin Julia front-end of libnmfb200.so (include/nmfb200.h).
+#
+# Keeps the reference's API for the accelerated path: `nnmf`, `NMFB200.solve!`, `NMFB200.Result{T}`,
+# and the option types `MultUpdate{T}`, `GreedyCD{T}` (same keyword names, defaults and validation as
+# NMF.jl src/multupd.jl:9-43, src/greedycd.jl:10-31, src/interf.jl:3-101), so existing code can do
+#     const NMF = NMFB200
+# All numerics live behind the C ABI; this file only validates, ccalls and maps status -> exception.
+# NOTE: Julia is not installed in the build image of this repository, so this file is written against
+# the header but has not been executed there; the tested binding is nmf.jl_b200/_lib.py (same calls).
+module NMFB200
+
+export nnmf
+
+const libnmfb200 = get(ENV, "NMFB200_LIB", joinpath(@__DIR__, "..", "libnmfb200.so"))
+
+# ---- status codes (include/nmfb200.h) ----------------------------------------------------------------
+const OK, EINVAL, EDIM, ECUDA, ENCCL, ENOMEM, ESTATE, ENOTSUP = 0:7
+
+struct CResult            # nmfb200_result
+    niters::Int64
+    converged::Int32
+    engine::Int32
+    objvalue::Float64
+    last_dev::Float64
+    solve_ms::Float64
+    upload_ms::Float64
+    coordinate_updates::Int64
+    kernel_launches::Int64
+    hot_kernel_ms::Float64
+    hot_kernel_launches::Int64
+end
+
+mutable struct Handle
+    ptr::Ptr{Cvoid}
+    function Handle(device::Integer=0)
+        ref = Ref{Ptr{Cvoid}}(C_NULL)
+        st = ccall((:nmfb200_create, libnmfb200), Cint, (Ref{Ptr{Cvoid}}, Cint, Cint), ref, device, 0)
+        st == OK || error("nmfb200_create failed: ", unsafe_string(ccall((:nmfb200_status_string, libnmfb200), Cstring, (Cint,), st)))
+        h = new(ref[])
+        finalizer(x -> (x.ptr != C_NULL && ccall((:nmfb200_destroy, libnmfb200), Cint, (Ptr{Cvoid},), x.ptr); x.ptr = C_NULL), h)
+        return h
+    end
+end
+
+function check(h::Handle, st::Integer)
+    st == OK && return
+    msg = unsafe_string(ccall((:nmfb200_last_error, libnmfb200), Cstring, (Ptr{Cvoid},), h.ptr))
+    st == EINVAL && throw(ArgumentError(msg))
+    st == EDIM && throw(DimensionMismatch(msg))
+    error("libnmfb200 [", unsafe_string(ccall((:nmfb200_status_string, libnmfb200), Cstring, (Cint,), st)), "] ", msg)
+end
+
+set_option!(h::Handle, key::AbstractString, value) =
+    check(h, ccall((:nmfb200_set_option, libnmfb200), Cint, (Ptr{Cvoid}, Cstring, Cstring), h.ptr, key, string(value)))
+
+# ---- Result (src/common.jl:21-38) ----------------------------------------------------------------------
+struct Result{T}
+    W::Matrix{T}
+    H::Matrix{T}
+    niters::Int
+    converged::Bool
+    objvalue::T
+    function Result{T}(W::Matrix{T}, H::Matrix{T}, niters::Int, converged::Bool, objv) where T
+        size(W, 2) == size(H, 1) || throw(DimensionMismatch("Inner dimensions of W and H mismatch."))
+        new{T}(W, H, niters, converged, objv)
+    end
+end
+Base.:(==)(A::Result, B::Result) = A.W == B.W && A.H == B.H && A.niters == B.niters && A.converged == B.converged && A.objvalue == B.objvalue
+Base.hash(s::Result, h::UInt) = hash(s.objvalue, hash(s.converged, hash(s.niters, hash(s.H, hash(s.W, h + (0x09c9f08cfcba6de3 % UInt))))))
+
+# ---- option types --------------------------------------------------------------------------------------
+mutable struct MultUpdate{T}            # src/multupd.jl:9-43
+    obj::Symbol
+    maxiter::Int
+    verbose::Bool
+    tol::T
+    update_H::Bool
+    lambda_w::T
+    lambda_h::T
+    function MultUpdate{T}(; obj::Symbol=:mse, maxiter::Integer=100, verbose::Bool=false, tol::Real=cbrt(eps(T)),
+                           update_H::Bool=true, lambda_w::Real=zero(T), lambda_h::Real=zero(T),
+                           lambda::Union{Real,Nothing}=nothing) where T
+        obj == :mse || obj == :div || throw(ArgumentError("Invalid value for obj."))
+        maxiter > 1 || throw(ArgumentError("maxiter must be greater than 1."))
+        tol > 0 || throw(ArgumentError("tol must be positive."))
+        lambda_w >= 0 || throw(ArgumentError("lambda_w must be non-negative."))
+        lambda_h >= 0 || throw(ArgumentError("lambda_h must be non-negative."))
+        if lambda !== nothing && lambda >= 0
+            @warn "lambda is deprecated, use lambda_w and lambda_h instead."
+            lambda_w = iszero(lambda_w) ? lambda : lambda_w
+            lambda_h = iszero(lambda_h) ? lambda : lambda_h
+        end
+        if obj == :div
+            lambda_w = max(lambda_w, sqrt(eps(T)))
+            lambda_h = max(lambda_h, sqrt(eps(T)))
+        end
+        new{T}(obj, maxiter, verbose, tol, update_H, lambda_w, lambda_h)
+    end
+end
+
+mutable struct GreedyCD{T}              # src/greedycd.jl:10-31
+    maxiter::Int
+    verbose::Bool
+    tol::T
+    update_H::Bool
+    lambda_w::T
+    lambda_h::T
+    function GreedyCD{T}(; maxiter::Integer=100, verbose::Bool=false, tol::Real=cbrt(eps(T)), update_H::Bool=true,
+                         lambda_w::Real=zero(T), lambda_h::Real=zero(T)) where T
+        maxiter > 1 || throw(ArgumentError("maxiter must be greater than 1."))
+        tol > 0 || throw(ArgumentError("tol must be positive."))
+        lambda_w >= 0 || throw(ArgumentError("lambda_w must be non-negative."))
+        lambda_h >= 0 || throw(ArgumentError("lambda_h must be non-negative."))
+        new{T}(maxiter, verbose, tol, update_H, lambda_w, lambda_h)
+    end
+end
+
+# ---- set_X / solve! ---------------------------------------------------------------------------------------
+for (T, sfx) in ((Float32, "f32"), (Float64, "f64"))
+    setx = Symbol("nmfb200_set_X_", sfx)
+    @eval function set_X!(h::Handle, X::Matrix{$T}; check_nonneg::Bool=false)
+        GC.@preserve X check(h, ccall(($(QuoteNode(setx)), libnmfb200), Cint,
+            (Ptr{Cvoid}, Ptr{$T}, Int64, Int64, Int64, Cint), h.ptr, X, size(X, 1), size(X, 2), stride(X, 2), check_nonneg))
+    end
+    for (alg, name) in ((:multmse, "multmse"), (:multdiv, "multdiv"), (:greedycd, "greedycd"))
+        cname = Symbol("nmfb200_solve_", name, "_", sfx)
+        fname = Symbol("_solve_", name)
+        @eval function $fname(h::Handle, W::Matrix{$T}, H::Matrix{$T}, maxiter, tol, lw, lh, update_H, verbose)
+            res = Ref{CResult}()
+            GC.@preserve W H check(h, ccall(($(QuoteNode(cname)), libnmfb200), Cint,
+                (Ptr{Cvoid}, Ptr{$T}, Int64, Ptr{$T}, Int64, Int64, Int64, $T, $T, $T, Cint, Cint, Cint, Ref{CResult}),
+                h.ptr, W, stride(W, 2), H, stride(H, 2), size(W, 2), maxiter, tol, lw, lh, update_H, verbose, 0, res))
+            r = res[]
+            return Result{$T}(W, H, Int(r.niters), r.converged != 0, $T(r.objvalue))   # aliases the caller's W, H like the reference
+        end
+    end
+end
+
+function nmf_checksize(X, W::AbstractMatrix, H::AbstractMatrix)   # src/common.jl:5-16
+    p, n = size(X); k = size(W, 2)
+    (size(W, 1) == p && size(H) == (k, n)) || throw(DimensionMismatch("Dimensions of X, W, and H are inconsistent."))
+    return (p, n, k)
+end
+
+"""    solve!(alg, X, W, H; handle=Handle()) -> Result{T}   (NMF.solve!, src/multupd.jl:45, src/greedycd.jl:33)"""
+function solve!(alg::MultUpdate{T}, X::Matrix{T}, W::Matrix{T}, H::Matrix{T}; handle::Handle=Handle(), x_resident::Bool=false) where T
+    nmf_checksize(X, W, H)
+    x_resident || set_X!(handle, X)
+    f = alg.obj == :mse ? _solve_multmse : _solve_multdiv
+    f(handle, W, H, alg.maxiter, alg.tol, alg.lambda_w, alg.lambda_h, alg.update_H, alg.verbose)
+end
+function solve!(alg::GreedyCD{T}, X::Matrix{T}, W::Matrix{T}, H::Matrix{T}; handle::Handle=Handle(), x_resident::Bool=false) where T
+    nmf_checksize(X, W, H)
+    x_resident || set_X!(handle, X)
+    _solve_greedycd(handle, W, H, alg.maxiter, alg.tol, alg.lambda_w, alg.lambda_h, alg.update_H, alg.verbose)
+end
+
+# ---- randinit (src/initialization.jl:4-17, src/utils.jl:26-32) and nnmf (src/interf.jl:3-101) -------------------
+function randinit(p::Integer, n::Integer, k::Integer, T::DataType; normalize::Bool=false, zeroh::Bool=false)
+    W = rand(T, p, k)
+    if normalize
+        for j in 1:k
+            W[:, j] .*= 1 / sum(view(W, :, j))
+        end
+    end
+    H = zeroh ? zeros(T, k, n) : rand(T, k, n)
+    return W, H
+end
+
+function nnmf(X::AbstractMatrix{T}, k::Integer; init::Symbol=:nndsvdar, initdata=nothing, alg::Symbol=:greedycd,
+              maxiter::Integer=100, tol::Real=cbrt(eps(T) / 100), replicates::Integer=1,
+              W0::Union{AbstractMatrix{T},Nothing}=nothing, H0::Union{AbstractMatrix{T},Nothing}=nothing,
+              update_H::Bool=true, verbose::Bool=false, device::Integer=0) where T
+    eltype(X) <: Number && all(t -> t >= zero(T), X) || throw(ArgumentError("The elements of X must be non-negative."))
+    p, n = size(X)
+    k <= min(p, n) || throw(ArgumentError("The value of k should not exceed min(size(X))."))
+    replicates >= 1 || throw(ArgumentError("The value of replicates must be positive."))
+    if !update_H && init != :custom
+        @warn "Only W will be updated."
+    end
+    if init == :custom
+        W0 !== nothing && H0 !== nothing || throw(ArgumentError("To use :custom initialization, set W0 and H0."))
+        all(t -> t >= zero(T), W0) || throw(ArgumentError("The elements of W0 must be non-negative."))
+        size(W0) == (p, k) || throw(ArgumentError("Invalid size for W0."))
+        all(t -> t >= zero(T), H0) || throw(ArgumentError("The elements of H0 must be non-negative."))
+        size(H0) == (k, n) || throw(ArgumentError("Invalid size for H0."))
+    else
+        W0 === nothing && H0 === nothing || @warn "Ignore W0 and H0 except for :custom initialization."
+    end
+    W, H = init == :random ? randinit(p, n, k, T; normalize=true) :
+           init == :custom ? (Matrix{T}(W0), Matrix{T}(H0)) :
+           init in (:nndsvd, :nndsvda, :nndsvdar, :spa) ? error("init=:$init is not on the accelerated path yet; use :random or :custom") :
+           throw(ArgumentError("Invalid value for init."))
+    inst = alg == :multmse ? MultUpdate{T}(obj=:mse, maxiter=maxiter, tol=tol, verbose=verbose, update_H=update_H) :
+           alg == :multdiv ? MultUpdate{T}(obj=:div, maxiter=maxiter, tol=tol, verbose=verbose, update_H=update_H) :
+           alg == :greedycd ? GreedyCD{T}(maxiter=maxiter, tol=tol, verbose=verbose, update_H=update_H) :
+           alg in (:projals, :alspgrad, :cd, :spa) ? error("alg=:$alg is not on the accelerated path yet") :
+           throw(ArgumentError("Invalid algorithm."))
+    h = Handle(device)
+    Xm = Matrix{T}(X)
+    set_X!(h, Xm)                                      # X stays resident on the GPU across replicates
+    ret = solve!(inst, Xm, W, H; handle=h, x_resident=true)
+    for _ in 2:replicates                              # src/interf.jl:91-98
+        Wr, Hr = randinit(p, n, k, T; normalize=true)
+        tmp = solve!(inst, Xm, Wr, Hr; handle=h, x_resident=true)
+        if ret.objvalue > tmp.objvalue
+            ret = tmp
+        end
+    end
+    return ret
+end
+
+end # module
