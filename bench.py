@@ -208,6 +208,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         sess.comm_init(rank, world, uid[0])
     sess.set_X_device(dX.data_ptr(), rows, n, rows, np.float32, keepalive=dX)
     sess.set_option("check_every", max(args.steps, args.warmup, 1))  # no host round trip inside the timed loop
+    for kv in args.opt:
+        key, val = kv.split("=")
+        sess.set_option(key, val)
 
     def device_solve(iters, timed):
         dW.copy_(tw, non_blocking=True)
@@ -317,6 +320,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--opt", action="append", default=[], help="library option key=value for experiments (device-resident leg)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -81,6 +81,9 @@ int nmfb200_set_stream(nmfb200_handle* h, void* stream);
  *                                               (Float32 only); auto = tc when shape allows.
  *   "check_every" = "<int>"                  -- host polls the device convergence flag every N
  *                                               iterations (results are independent of N).
+ *   "tc_tile_rows" = "<int>"                 -- rows of a factor owned by one CTA of the tensor-core
+ *                                               update kernel (multiple of 8 in [8,128]; 0 = auto).
+ *   "tc_debug"     = "<int>"                 -- diagnostics for profiling experiments, 0 in production.
  *   "time_kernels" = "0" | "1"               -- bracket every launch of the dominant kernel with
  *                                               CUDA events and report the sum in nmfb200_result. */
 int nmfb200_set_option(nmfb200_handle* h, const char* key, const char* value);

@@ -177,6 +177,14 @@ int nmfb200_set_option(nmfb200_handle* h, const char* key, const char* value) {
             int c = atoi(value);
             NMF_REQUIRE(c >= 1, NMFB200_EINVAL, "check_every must be >= 1");
             h->check_every = c;
+        } else if (k == "tc_tile_rows") {
+            h->tc_tile_rows = atoi(value);
+        } else if (k == "tc_sa") {
+            h->tc_sa = atoi(value);
+        } else if (k == "tc_sb") {
+            h->tc_sb = atoi(value);
+        } else if (k == "tc_debug") {
+            h->tc_debug = atoi(value);
         } else if (k == "time_kernels") {
             h->time_kernels = atoi(value) != 0;
         } else {

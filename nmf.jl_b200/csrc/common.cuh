@@ -94,6 +94,9 @@ struct nmfb200_handle {
     int engine_opt = 0;  // 0 auto, 1 simt, 2 tc
     int check_every = 8;
     int time_kernels = 0;
+    int tc_tile_rows = 0;  // 0 = auto
+    int tc_debug = 0;      // diagnostics (see UpdateParams::debug)
+    int tc_sa = 0, tc_sb = 0;  // ring depth overrides (experiments)
     std::vector<cudaEvent_t> ev_pool;  // events for time_kernels
     size_t ev_used = 0;
     nmfb200_trace_fn trace = nullptr;
@@ -106,6 +109,7 @@ struct nmfb200_handle {
     bool x_owned = false;
     uint64_t x_epoch = 0;     // bumped on every set_X; engines key their derived caches on it
     uint64_t tc_x_epoch = 0;  // epoch the bf16 caches were built for
+    int tc_x_trH = 0, tc_x_trW = 0;  // ... and their tile heights
 
     // multi-GPU
     ncclComm_t comm = nullptr;

@@ -14,7 +14,7 @@
 //
 // The k x k Gram P = F'F of the freshly updated factor is a second small tcgen05 kernel
 // (gram_kernel, split over row chunks, fp32 red.add into P, last CTA converts to bf16 hi/lo).
-// stop_condition is finished by conv_kernel (one block).  The iteration loop is enqueued without
+// stop_condition is finished by conv_reduce_kernel (last block decides).  The loop is enqueued without
 // host round trips: every kernel exits immediately once the device-side `converged` flag is set, and
 // the host polls that flag every `check_every` iterations.
 #include <cuda_bf16.h>
@@ -32,12 +32,12 @@ struct TcState {
     int converged;
     int iters;
     float devmax;
-    int pad;
+    unsigned int ticket;
 };
 
 // ---- kernel parameter block (tensor maps must live in __grid_constant__ param space) ---------------
 struct UpdateParams {
-    CUtensorMap tmA;    // Xs   bf16 [R][Kdim]     box 64 x 128
+    CUtensorMap tmA;    // Xs   bf16 tile-contiguous [tiles*nkb*tile_rows][64], box 64 x tile_rows
     CUtensorMap tmB;    // O^T  bf16 [KP][Kdim]    box 64 x KP
     CUtensorMap tmFhi;  // F hi bf16 [R][KP]       box 64 x 128
     CUtensorMap tmFlo;  // F lo
@@ -52,19 +52,26 @@ struct UpdateParams {
     const TcState* state;
     int64_t ldT;
     int R, Kdim;
+    int rotate;         // 1: CTA c walks the k-blocks starting at a hashed offset (wrap-around)
+    int tile_rows;      // rows of F owned by one CTA (<= 128, multiple of 8); the TMA boxes of A / Fhi / Flo have this many rows
+    int debug;          // diagnostics only: bit 0 = load the B operand for the first k-block only (WRONG results)
     float lambda, delta;
 };
 
 template <int KP>
 struct UpdCfg {
-    static constexpr int A_BYTES = 128 * 128;
-    static constexpr int B_BYTES = KP * 128;
+    static constexpr int A_BYTES = 128 * 128;   // A part of a stage: up to 128 rows x 64 bf16
+    static constexpr int B_BYTES = KP * 128;    // B part: KP rows x 64 bf16
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    // One ring, A and B of a k-block travel together (one wait + one commit per block on the MMA thread).
+    // Deeper / split rings were measured and bought nothing (profiles/r1b_pipeline_experiments.md).
     static constexpr int STAGES = KP == 256 ? 4 : (KP == 128 ? 6 : 8);
+    static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
     static constexpr int CONV_BYTES = 4 * 2 * KP * 4;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + CONV_BYTES + 256 + 1024;
+    static constexpr int SMEM_BYTES = RING_BYTES + CONV_BYTES + 1024 + 1024;  // ring | barriers (1 KB) | conv scratch | align slack
     static constexpr int TMEM_COLS = 2 * KP;
     static constexpr int NSLAB = KP / 64;
+    static constexpr int THREADS = 192;  // w0 TMA producer, w1 MMA issuer, w2-5 epilogue
 };
 
 // sum v[j] over the 32 lanes of the warp; afterwards v[0] on lane l holds the total of column l
@@ -88,23 +95,29 @@ __device__ __forceinline__ uint32_t pack_bf16x2(bf16 lo, bf16 hi) {
 // MODE 0: fused (single GPU).  MODE 1: numerators only -> num_io (row-sharded H-step, before the
 // all-reduce).  MODE 2: no main loop, numerators read from num_io (after the all-reduce).
 template <int KP, int MODE>
-__global__ void __launch_bounds__(192, 1) mu_update_kernel(const __grid_constant__ UpdateParams prm) {
+__global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const __grid_constant__ UpdateParams prm) {
     using C = UpdCfg<KP>;
     if (prm.state->converged) return;  // uniform: the loop has already met stop_condition
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* full_bar = (uint64_t*)(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t* full_bar = (uint64_t*)(smem + C::RING_BYTES);
     uint64_t* empty_bar = full_bar + C::STAGES;
     uint64_t* tmem_full = empty_bar + C::STAGES;
     uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
-    float* conv_s = (float*)(smem + C::STAGES * C::STAGE_BYTES + 256);  // [4 warps][2][KP]
+    float* conv_s = (float*)(smem + C::RING_BYTES + 1024);  // [4 warps][2][KP]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int r0 = blockIdx.x * 128;
+    const int tile_rows = prm.tile_rows;
+    const int r0 = blockIdx.x * tile_rows;
+    const uint32_t a_bytes = (uint32_t)tile_rows * 128u;
     const int nkb = (MODE == 2) ? 0 : (prm.Kdim + 63) / 64;
     constexpr int NPRE = (MODE == 1) ? 0 : 3 * C::NSLAB;
     const int total = NPRE + nkb;
+    // De-correlate the CTAs: they all stream panels whose bases differ by exact multiples of the tile size
+    // (4 MiB at config 2) in lockstep.  CTA c starts its k-loop at a hashed block and wraps around (the sum
+    // over k is order independent; the order is fixed per CTA, so results stay deterministic).
+    const int kb_start = (prm.rotate && nkb > 0) ? (int)(((uint32_t)blockIdx.x * 0x9E3779B1u >> 8) % (uint32_t)nkb) : 0;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&prm.tmA);
@@ -131,22 +144,27 @@ __global__ void __launch_bounds__(192, 1) mu_update_kernel(const __grid_constant
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
+            int s = 0, kb = kb_start;
+            uint32_t ph = 0;
+            uint8_t* dst = smem;
+            const int arow0 = blockIdx.x * nkb * tile_rows;
+            const bool dbg_noB = (prm.debug & 1) != 0;
             for (int b = 0; b < total; ++b) {
-                const int s = b % C::STAGES;
-                const uint32_t ph = (uint32_t)(b / C::STAGES) & 1u;
                 mbar_wait(&empty_bar[s], ph ^ 1u);
-                mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
-                uint8_t* a_dst = smem + s * C::STAGE_BYTES;
-                uint8_t* b_dst = a_dst + C::A_BYTES;
                 if (b < NPRE) {  // Den = Fhi*Phi + Fhi*Plo + Flo*Phi
+                    mbar_arrive_expect_tx(&full_bar[s], a_bytes + C::B_BYTES);
                     const int t = b / C::NSLAB, sl = b % C::NSLAB;
-                    tma_load_2d(a_dst, t == 2 ? &prm.tmFlo : &prm.tmFhi, &full_bar[s], 64 * sl, r0);
-                    tma_load_2d(b_dst, t == 1 ? &prm.tmPlo : &prm.tmPhi, &full_bar[s], 64 * sl, 0);
+                    tma_load_2d(dst, t == 2 ? &prm.tmFlo : &prm.tmFhi, &full_bar[s], 64 * sl, r0);
+                    tma_load_2d(dst + C::A_BYTES, t == 1 ? &prm.tmPlo : &prm.tmPhi, &full_bar[s], 64 * sl, 0);
                 } else {
-                    const int kb = b - NPRE;
-                    tma_load_2d(a_dst, &prm.tmA, &full_bar[s], 64 * kb, r0);
-                    tma_load_2d(b_dst, &prm.tmB, &full_bar[s], 64 * kb, 0);
+                    const bool skipB = dbg_noB && b >= NPRE + C::STAGES;  // diagnostic: stale B after the first ring fill
+                    mbar_arrive_expect_tx(&full_bar[s], a_bytes + (skipB ? 0u : (uint32_t)C::B_BYTES));
+                    tma_load_2d(dst, &prm.tmA, &full_bar[s], 0, arow0 + kb * tile_rows);  // tile-contiguous X
+                    if (!skipB) tma_load_2d(dst + C::A_BYTES, &prm.tmB, &full_bar[s], 64 * kb, 0);
+                    if (++kb == nkb) kb = 0;
                 }
+                dst += C::STAGE_BYTES;
+                if (++s == C::STAGES) { s = 0; ph ^= 1u; dst = smem; }
             }
         }
         __syncwarp();
@@ -154,14 +172,14 @@ __global__ void __launch_bounds__(192, 1) mu_update_kernel(const __grid_constant
         // ===== MMA issuer =====
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(FMT_BF16, 128, KP);
+            int s = 0;
+            uint32_t ph = 0;
+            const uint64_t adesc0 = make_kmajor_sw128_desc(smem_u32(smem));
+            const uint64_t bdesc0 = make_kmajor_sw128_desc(smem_u32(smem + C::A_BYTES));
+            uint64_t adesc = adesc0, bdesc = bdesc0;
             for (int b = 0; b < total; ++b) {
-                const int s = b % C::STAGES;
-                const uint32_t ph = (uint32_t)(b / C::STAGES) & 1u;
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem + s * C::STAGE_BYTES);
-                const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
-                const uint64_t bdesc = make_kmajor_sw128_desc(a_addr + C::A_BYTES);
                 const bool pre = b < NPRE;
                 const uint32_t d = pre ? tmem_base + KP : tmem_base;
                 const bool first = pre ? (b == 0) : (b == NPRE);
@@ -169,15 +187,18 @@ __global__ void __launch_bounds__(192, 1) mu_update_kernel(const __grid_constant
                 for (int kk = 0; kk < 4; ++kk)  // 4 x (K = 16 bf16 = 32 B) per 128-B swizzle row
                     umma_bf16(d, adesc + 2 * kk, bdesc + 2 * kk, idesc, (!first || kk > 0) ? 1u : 0u);
                 umma_commit(&empty_bar[s]);  // frees the stage when these MMAs have read it
+                adesc += C::STAGE_BYTES >> 4;  // descriptor start address is in 16-byte units
+                bdesc += C::STAGE_BYTES >> 4;
+                if (++s == C::STAGES) { s = 0; ph ^= 1u; adesc = adesc0; bdesc = bdesc0; }
             }
             umma_commit(tmem_full);
         }
         __syncwarp();
-    } else {
+    } else if (warp >= 2 && warp <= 5) {
         // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
         const int q = warp & 3;
         const int row = r0 + 32 * q + lane;
-        const bool valid = row < prm.R;
+        const bool valid = (32 * q + lane) < tile_rows && row < prm.R;
         const uint32_t t_lane = tmem_base + ((uint32_t)(32 * q) << 16);
         mbar_wait(tmem_full, 0);
         tc_fence_after();
@@ -401,28 +422,35 @@ __global__ void __launch_bounds__(192, 1) gram_kernel(const __grid_constant__ Gr
     }
 }
 
-// P[e] = sum_g part[g][e]; writes the fp32 Gram and (do_split) its bf16 hi/lo split.  One element per thread.
+// P[e] = sum_g part[g][e]; writes the fp32 Gram and (do_split) its bf16 hi/lo split.  Four lanes per element
+// (each sums every 4th partial with 8 loads in flight), combined with two shuffles: fixed order => deterministic.
 __global__ void __launch_bounds__(256) gram_reduce_kernel(const float* __restrict__ part, int nparts, int nelem, float* __restrict__ P,
                                                           bf16* __restrict__ Phi, bf16* __restrict__ Plo, int do_split,
                                                           const TcState* st) {
     if (st->converged) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nelem) return;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int g = 0;
-    for (; g + 4 <= nparts; g += 4) {
-        s0 += part[(size_t)g * nelem + i];
-        s1 += part[(size_t)(g + 1) * nelem + i];
-        s2 += part[(size_t)(g + 2) * nelem + i];
-        s3 += part[(size_t)(g + 3) * nelem + i];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int sub = t & 3;
+    const int i = t >> 2;
+    float acc = 0.f;
+    if (i < nelem) {
+        int g = sub;
+        for (; g + 28 < nparts; g += 32) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(part + (size_t)(g + 4 * u) * nelem + i);
+            acc += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+        }
+        for (; g < nparts; g += 4) acc += __ldcg(part + (size_t)g * nelem + i);
     }
-    for (; g < nparts; ++g) s0 += part[(size_t)g * nelem + i];
-    const float v = (s0 + s1) + (s2 + s3);
-    P[i] = v;
-    if (do_split) {
-        bf16 hi = __float2bfloat16_rn(v);
-        Phi[i] = hi;
-        Plo[i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (i < nelem && sub == 0) {
+        P[i] = acc;
+        if (do_split) {
+            bf16 hi = __float2bfloat16_rn(acc);
+            Phi[i] = hi;
+            Plo[i] = __float2bfloat16_rn(acc - __bfloat162float(hi));
+        }
     }
 }
 
@@ -437,52 +465,24 @@ __global__ void gram_split_kernel(const float* __restrict__ P, bf16* __restrict_
     }
 }
 
-// ---- stop_condition finish (common.jl:92-111): one block, thread a owns component a ---------------
-// acc (double [4][KP]) = {dev_w, sum_w, dev_h, sum_h}; stage 0 = reduce tiles into acc, stage 1 = decide.
-__global__ void conv_kernel(const float* __restrict__ partW, int tilesW, const float* __restrict__ partH, int tilesH, int KP, int k,
-                            int update_H, double* __restrict__ acc, float tol, TcState* st, int do_reduce, int do_decide) {
-    if (st->converged) return;
-    __shared__ int fail;
-    __shared__ float devs[256];
-    __shared__ double red[4][1024];
+// ---- stop_condition finish (common.jl:92-111) ---------------------------------------------------------
+// acc (double [4][KP]) = {dev_w, sum_w, dev_h, sum_h}.  conv_reduce_kernel: grid = 4 * KP/32 blocks of 8 warps;
+// block (q, cb) sums quantity q of components [32cb, 32cb+32) over all tiles (warp w takes tiles w, w+8, ...;
+// 8 loads in flight; fixed combination order => deterministic).  With do_decide the last block to finish
+// (atomic ticket) applies the reference's test; multi-GPU runs the decision as a separate launch after the
+// all-reduce of the W-side sums (conv_decide_kernel).
+__device__ void conv_decide(const double* acc, int KP, int k, float tol, TcState* st, float* devs, int* fail) {
     const int a = threadIdx.x;
-    if (a == 0) fail = 0;
-    __syncthreads();
-    if (do_reduce) {
-        // blockDim.x = 1024: KP components x (1024 / KP) tile groups, then a shared-memory pass over the groups
-        const int groups = blockDim.x / KP;
-        const int g = threadIdx.x / KP, c = threadIdx.x % KP;
-        double dw = 0, sw = 0, dh = 0, sh = 0;
-        if (g < groups) {
-            for (int t = g; t < tilesW; t += groups) {
-                dw += (double)partW[(size_t)t * 2 * KP + c];
-                sw += (double)partW[(size_t)t * 2 * KP + KP + c];
-            }
-            if (update_H)
-                for (int t = g; t < tilesH; t += groups) {
-                    dh += (double)partH[(size_t)t * 2 * KP + c];
-                    sh += (double)partH[(size_t)t * 2 * KP + KP + c];
-                }
-        }
-        red[0][threadIdx.x] = dw; red[1][threadIdx.x] = sw; red[2][threadIdx.x] = dh; red[3][threadIdx.x] = sh;
-        __syncthreads();
-        if (threadIdx.x < KP) {
-            for (int gg = 1; gg < groups; ++gg) {
-                dw += red[0][gg * KP + c]; sw += red[1][gg * KP + c]; dh += red[2][gg * KP + c]; sh += red[3][gg * KP + c];
-            }
-            if (!update_H) { dh = 0; sh = 1; }
-            acc[c] = dw; acc[KP + c] = sw; acc[2 * KP + c] = dh; acc[3 * KP + c] = sh;
-        }
-    }
-    if (!do_decide) return;
+    if (a == 0) *fail = 0;
     __syncthreads();
     float dev = 0.f;
     if (a < k) {
-        float dw = (float)acc[a], sw = (float)acc[KP + a], dh = (float)acc[2 * KP + a], sh = (float)acc[3 * KP + a];
+        float dw = (float)__ldcg(acc + a), sw = (float)__ldcg(acc + KP + a), dh = (float)__ldcg(acc + 2 * KP + a),
+              sh = (float)__ldcg(acc + 3 * KP + a);
         float rw = dw / sw, rh = dh / sh;
-        float m = (rw != rw) ? rw : ((rh != rh) ? rh : fmaxf(rw, rh));
+        float m = (rw != rw) ? rw : ((rh != rh) ? rh : fmaxf(rw, rh));  // Julia max(): NaN propagates (common.jl:105)
         dev = sqrtf(m);
-        if (sqrtf(dw) > tol * sqrtf(sw) || sqrtf(dh) > tol * sqrtf(sh)) atomicExch(&fail, 1);
+        if (sqrtf(dw) > tol * sqrtf(sw) || sqrtf(dh) > tol * sqrtf(sh)) atomicExch(fail, 1);  // common.jl:106
     }
     if (a < 256) devs[a] = dev;
     __syncthreads();
@@ -491,29 +491,101 @@ __global__ void conv_kernel(const float* __restrict__ partW, int tilesW, const f
         for (int i = 0; i < k; ++i) dm = (dm != dm) ? dm : ((devs[i] != devs[i]) ? devs[i] : fmaxf(dm, devs[i]));
         st->devmax = dm;
         st->iters += 1;
-        if (!fail) st->converged = 1;
+        if (!*fail) st->converged = 1;
     }
 }
 
-// ---- X caches ---------------------------------------------------------------------------------------
-// Xr[j][i] = bf16(X[i + j*ldx])  (same orientation as the caller's column-major X)
-__global__ void cvt_rows_kernel(const float* __restrict__ X, int64_t p, int64_t n, int64_t ldx, bf16* __restrict__ Xr, int64_t ldp) {
-    const int64_t j = blockIdx.y;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ldp; i += (int64_t)gridDim.x * blockDim.x)
-        Xr[j * ldp + i] = __float2bfloat16_rn(i < p ? X[i + j * ldx] : 0.f);
-}
-// Xc[i][j] = bf16(X[i + j*ldx])  (transposed), 32x32 tiles through shared memory
-__global__ void cvt_transpose_kernel(const float* __restrict__ X, int64_t p, int64_t n, int64_t ldx, bf16* __restrict__ Xc, int64_t ldn) {
-    __shared__ float tile[32][33];
-    const int64_t i0 = (int64_t)blockIdx.x * 32, j0 = (int64_t)blockIdx.y * 32;
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        int64_t i = i0 + threadIdx.x, j = j0 + r;
-        tile[r][threadIdx.x] = (i < p && j < n) ? X[i + j * ldx] : 0.f;
+__global__ void __launch_bounds__(256) conv_reduce_kernel(const float* __restrict__ partW, int tilesW, const float* __restrict__ partH,
+                                                          int tilesH, int KP, int k, int update_H, double* __restrict__ acc, float tol,
+                                                          TcState* st, int do_decide) {
+    if (st->converged) return;
+    __shared__ double red[8][32];
+    __shared__ float devs[256];
+    __shared__ int fail, is_last;
+    const int cbs = KP / 32;
+    const int q = blockIdx.x / cbs, cb = blockIdx.x % cbs;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = cb * 32 + lane;
+    const float* part = (q < 2 ? partW : partH) + (size_t)(q & 1) * KP + c;
+    const int tiles = q < 2 ? tilesW : (update_H ? tilesH : 0);
+    double s = 0.0;
+    int t = w;
+    for (; t + 56 < tiles; t += 64) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcg(part + (size_t)(t + 8 * u) * 2 * KP);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += (double)v[u];
+    }
+    for (; t < tiles; t += 8) s += (double)__ldcg(part + (size_t)t * 2 * KP);
+    red[w][lane] = s;
+    __syncthreads();
+    if (w == 0) {
+        double tot = red[0][lane];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) tot += red[i][lane];
+        if (q >= 2 && !update_H) tot = (q == 2) ? 0.0 : 1.0;  // H untouched: dev_h = 0 (sum_h only scales a ratio of 0)
+        acc[(size_t)q * KP + c] = tot;
+    }
+    if (!do_decide) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int prev = atomicAdd(&st->ticket, 1u);
+        is_last = (prev == gridDim.x - 1) ? 1 : 0;
     }
     __syncthreads();
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        int64_t i = i0 + r, j = j0 + threadIdx.x;
-        if (i < p && j < ldn) Xc[i * ldn + j] = __float2bfloat16_rn(tile[threadIdx.x][r]);
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) st->ticket = 0u;
+    conv_decide(acc, KP, k, tol, st, devs, &fail);
+}
+
+__global__ void __launch_bounds__(256) conv_decide_kernel(const double* __restrict__ acc, int KP, int k, float tol, TcState* st) {
+    if (st->converged) return;
+    __shared__ float devs[256];
+    __shared__ int fail;
+    conv_decide(acc, KP, k, tol, st, devs, &fail);
+}
+
+// ---- X caches: bf16, TILE-CONTIGUOUS ---------------------------------------------------------------------
+// A panel with R rows and contraction length Kdim is stored as [tile][kb][TR rows][64 cols] (TR = rows per
+// CTA, kb = 64-wide k-block): one TMA box = one contiguous TR*128-byte burst and a CTA streams one
+// sequential region of HBM (instead of gathering 128-B segments from TR rows a full row pitch apart).
+// Padding rows / columns are written as zeros.  element(r, c) = X[r*sr + c*sc].
+// (a) contraction index contiguous in the source (sc == 1): direct
+__global__ void cvt_tiled_direct_kernel(const float* __restrict__ X, int64_t sr, int R, int Kdim, int TR, int nkb,
+                                        bf16* __restrict__ dst) {
+    const int64_t row_slot = blockIdx.y;            // tile * TR + row-in-tile
+    const int tile = (int)(row_slot / TR), rr = (int)(row_slot % TR);
+    const int64_t r = (int64_t)tile * TR + rr;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nkb * 64; c += gridDim.x * blockDim.x) {
+        float v = (r < R && c < Kdim) ? X[r * sr + c] : 0.f;
+        const int kb = c >> 6, cc = c & 63;
+        dst[(((int64_t)tile * nkb + kb) * TR + rr) * 64 + cc] = __float2bfloat16_rn(v);
+    }
+}
+// (b) row index contiguous in the source (sr == 1): 64 x 64 transpose through shared memory
+__global__ void cvt_tiled_transpose_kernel(const float* __restrict__ X, int64_t sc, int R, int Kdim, int TR, int nkb, int tiles,
+                                           bf16* __restrict__ dst) {
+    __shared__ float tile_s[64][65];
+    const int kb = blockIdx.x;
+    const int64_t r_base = (int64_t)blockIdx.y * 64;   // 64 consecutive logical rows
+    for (int y = threadIdx.y; y < 64; y += blockDim.y) {  // y: column within the k-block, x: row (contiguous in X)
+        int64_t r = r_base + threadIdx.x * 2;
+        int c = kb * 64 + y;
+        float v0 = (r < R && c < Kdim) ? X[r + (int64_t)c * sc] : 0.f;
+        float v1 = (r + 1 < R && c < Kdim) ? X[r + 1 + (int64_t)c * sc] : 0.f;
+        tile_s[threadIdx.x * 2][y] = v0;
+        tile_s[threadIdx.x * 2 + 1][y] = v1;
+    }
+    __syncthreads();
+    for (int y = threadIdx.y; y < 64; y += blockDim.y) {  // y: row within the 64-row group, x: column pair
+        int64_t r = r_base + y;
+        const int tile = (int)(r / TR), rr = (int)(r % TR);
+        if (tile >= tiles) continue;  // the grid is rounded up to 64-row groups
+        __nv_bfloat162 pk = __floats2bfloat162_rn(tile_s[y][threadIdx.x * 2], tile_s[y][threadIdx.x * 2 + 1]);
+        *(__nv_bfloat162*)(dst + (((int64_t)tile * nkb + kb) * TR + rr) * 64 + threadIdx.x * 2) = pk;
     }
 }
 
@@ -587,6 +659,7 @@ struct Factor {  // one factor in row-factor layout
     bf16 *Phi = nullptr, *Plo = nullptr;
     float* conv = nullptr;
     int tiles = 0;
+    int tile_rows = 128;
 };
 
 template <int KP>
@@ -595,13 +668,17 @@ struct TcSolver {
     cudaStream_t st;
     TcState* state;
 
-    void launch_update(int mode, const Factor& F, const Factor& O, const bf16* Xs, int64_t ldX, int Kdim, float lambda, float delta,
+    void launch_update(int mode, const Factor& F, const Factor& O, const bf16* Xs, int Kdim, float lambda, float delta,
                        float* num_io) {
         UpdateParams prm;
-        prm.tmA = make_tmap_bf16(Xs, (uint64_t)Kdim, (uint64_t)F.R, (uint64_t)ldX, 128);
+        prm.tile_rows = F.tile_rows;
+        prm.debug = h->tc_debug;
+        prm.rotate = (h->tc_debug & 4) ? 1 : 0;  // measured: lockstep CTAs share each B tile in L2; rotation costs ~4%
+        const uint64_t nkb = (uint64_t)ceil_div(Kdim, 64);
+        prm.tmA = make_tmap_bf16(Xs, 64, (uint64_t)F.tiles * nkb * F.tile_rows, 64, (uint32_t)F.tile_rows);
         prm.tmB = make_tmap_bf16(O.bT, (uint64_t)Kdim, KP, (uint64_t)O.ldT, KP);
-        prm.tmFhi = make_tmap_bf16(F.hi, KP, (uint64_t)F.R, KP, 128);
-        prm.tmFlo = make_tmap_bf16(F.lo, KP, (uint64_t)F.R, KP, 128);
+        prm.tmFhi = make_tmap_bf16(F.hi, KP, (uint64_t)F.R, KP, (uint32_t)F.tile_rows);
+        prm.tmFlo = make_tmap_bf16(F.lo, KP, (uint64_t)F.R, KP, (uint32_t)F.tile_rows);
         prm.tmPhi = make_tmap_bf16(O.Phi, KP, KP, KP, KP);
         prm.tmPlo = make_tmap_bf16(O.Plo, KP, KP, KP, KP);
         prm.F = F.m; prm.Fhi = F.hi; prm.Flo = F.lo; prm.FbT = F.bT; prm.ldT = F.ldT;
@@ -612,9 +689,9 @@ struct TcSolver {
         const int smem = UpdCfg<KP>::SMEM_BYTES;
         const bool timed = h->time_kernels && mode != 2;
         if (timed) NMF_CUDA(cudaEventRecord(h->next_event(), st));
-        if (mode == 0) mu_update_kernel<KP, 0><<<F.tiles, 192, smem, st>>>(prm);
-        else if (mode == 1) mu_update_kernel<KP, 1><<<F.tiles, 192, smem, st>>>(prm);
-        else mu_update_kernel<KP, 2><<<F.tiles, 192, smem, st>>>(prm);
+        if (mode == 0) mu_update_kernel<KP, 0><<<F.tiles, UpdCfg<KP>::THREADS, smem, st>>>(prm);
+        else if (mode == 1) mu_update_kernel<KP, 1><<<F.tiles, UpdCfg<KP>::THREADS, smem, st>>>(prm);
+        else mu_update_kernel<KP, 2><<<F.tiles, UpdCfg<KP>::THREADS, smem, st>>>(prm);
         if (timed) NMF_CUDA(cudaEventRecord(h->next_event(), st));
         h->launches += 1;
     }
@@ -629,7 +706,7 @@ struct TcSolver {
         g.state = state;
         g.R = F.R;
         gram_kernel<KP><<<grid, 192, GramCfg<KP>::SMEM_BYTES, st>>>(g);
-        gram_reduce_kernel<<<(KP * KP + 255) / 256, 256, 0, st>>>(g.part, grid, KP * KP, P_dst ? P_dst : F.P, F.Phi, F.Plo, split ? 1 : 0, state);
+        gram_reduce_kernel<<<(4 * KP * KP + 255) / 256, 256, 0, st>>>(g.part, grid, KP * KP, P_dst ? P_dst : F.P, F.Phi, F.Plo, split ? 1 : 0, state);
         h->launches += 2;
     }
 
@@ -644,12 +721,21 @@ struct TcSolver {
     }
 };
 
+// Rows of a factor per CTA of the update kernel (multiple of 8, <= 128).
+int pick_tile_rows(int R, int forced) {
+    if (forced >= 8 && forced <= 128 && forced % 8 == 0) return forced;
+    // Measured (profiles/r1b_pipeline_experiments.md): the time per k-block does not shrink with the box height,
+    // so full 128-row boxes always win, even when that leaves SMs idle (128 CTAs at 16384 rows).
+    return R >= 128 ? 128 : (int)round_up(std::max(R, 8), 8);
+}
+
 Factor alloc_factor(nmfb200_handle* h, const char* tag, int R, int KP) {
     Factor f;
     std::string t(tag);
     f.R = R;
     f.ldT = round_up(R, 64);
-    f.tiles = (int)ceil_div(R, 128);
+    f.tile_rows = pick_tile_rows(R, h->tc_tile_rows);
+    f.tiles = (int)ceil_div(R, f.tile_rows);
     f.m = h->buf_t<float>("tc." + t + ".m", (size_t)R * KP);
     f.hi = h->buf_t<bf16>("tc." + t + ".hi", (size_t)R * KP);
     f.lo = h->buf_t<bf16>("tc." + t + ".lo", (size_t)R * KP);
@@ -667,7 +753,6 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
     TcSolver<KP>::set_attrs();
     cudaStream_t st = h->stream;
     const int64_t p = h->p, n = h->n, k = a.k;
-    const int64_t ldp = round_up(p, 64), ldn = round_up(n, 64);
     const float delta = std::sqrt(std::numeric_limits<float>::epsilon());
     const float lw = (float)a.lambda_w, lh = (float)a.lambda_h, tol = (float)a.tol;
 
@@ -676,16 +761,25 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
     NMF_CUDA(cudaEventCreate(&e1));
     NMF_CUDA(cudaEventCreate(&e2));
 
-    // bf16 caches of X in both orientations (built once per set_X)
-    bf16* Xr = h->buf_t<bf16>("tc.Xr", (size_t)n * ldp);
-    bf16* Xc = h->buf_t<bf16>("tc.Xc", (size_t)p * ldn);
-    if (h->tc_x_epoch != h->x_epoch) {
+    // bf16 tile-contiguous caches of X in both orientations (built once per set_X / tile shape)
+    const int trH = pick_tile_rows((int)n, h->tc_tile_rows), trW = pick_tile_rows((int)p, h->tc_tile_rows);
+    const int64_t tilesH = ceil_div(n, trH), tilesW = ceil_div(p, trW);
+    const int nkbH = (int)ceil_div(p, 64), nkbW = (int)ceil_div(n, 64);
+    bf16* Xr = h->buf_t<bf16>("tc.Xr", (size_t)tilesH * nkbH * trH * 64);  // rows = columns of X, contraction over p
+    bf16* Xc = h->buf_t<bf16>("tc.Xc", (size_t)tilesW * nkbW * trW * 64);  // rows = rows of X, contraction over n
+    if (h->tc_x_epoch != h->x_epoch || h->tc_x_trH != trH || h->tc_x_trW != trW) {
         const float* X = (const float*)h->dX;
-        cvt_rows_kernel<<<dim3((unsigned)std::min<int64_t>(ceil_div(ldp, 256), 64), (unsigned)n), 256, 0, st>>>(X, p, n, h->ldx, Xr, ldp);
-        cvt_transpose_kernel<<<dim3((unsigned)ceil_div(p, 32), (unsigned)ceil_div(ldn, 32)), dim3(32, 8), 0, st>>>(X, p, n, h->ldx, Xc, ldn);
+        cvt_tiled_direct_kernel<<<dim3((unsigned)std::min<int64_t>(ceil_div((int64_t)nkbH * 64, 256), 64), (unsigned)(tilesH * trH)), 256, 0, st>>>(
+            X, h->ldx, (int)n, (int)p, trH, nkbH, Xr);
+        NMF_REQUIRE(trW % 8 == 0, NMFB200_EINVAL, "tile rows must be a multiple of 8");
+        // the transpose kernel walks 64 logical rows per block; cover the padded row range of the last tile too
+        cvt_tiled_transpose_kernel<<<dim3((unsigned)nkbW, (unsigned)ceil_div(tilesW * trW, 64)), dim3(32, 8), 0, st>>>(
+            X, h->ldx, (int)p, (int)n, trW, nkbW, (int)tilesW, Xc);
         h->launches += 2;
         NMF_CUDA(cudaGetLastError());
         h->tc_x_epoch = h->x_epoch;
+        h->tc_x_trH = trH;
+        h->tc_x_trW = trW;
     }
     NMF_CUDA(cudaEventRecord(e0, st));
 
@@ -732,25 +826,25 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
         for (int64_t i = 0; i < batch; ++i) {
             if (a.update_H) {
                 if (!multi) {
-                    s.launch_update(0, H, W, Xr, ldp, (int)p, lh, delta, nullptr);  // H-step: rows of H' against W
+                    s.launch_update(0, H, W, Xr, (int)p, lh, delta, nullptr);  // H-step: rows of H' against W
                 } else {
-                    s.launch_update(1, H, W, Xr, ldp, (int)p, lh, delta, packed);   // partial numerators of this shard
+                    s.launch_update(1, H, W, Xr, (int)p, lh, delta, packed);   // partial numerators of this shard
                     h->allreduce_sum(packed, (size_t)n * KP + (size_t)KP * KP);     // THE exchange step of the iteration
                     gram_split_kernel<<<(KP * KP + 255) / 256, 256, 0, st>>>(packed_P, W.Phi, W.Plo, KP * KP, state);
                     h->launches += 1;
-                    s.launch_update(2, H, W, Xr, ldp, (int)p, lh, delta, packed);   // ratio with the reduced numerators
+                    s.launch_update(2, H, W, Xr, (int)p, lh, delta, packed);   // ratio with the reduced numerators
                 }
                 s.launch_gram(H, true);
             }
-            s.launch_update(0, W, H, Xc, ldn, (int)n, lw, delta, nullptr);          // W-step (local rows)
+            s.launch_update(0, W, H, Xc, (int)n, lw, delta, nullptr);          // W-step (local rows)
             s.launch_gram(W, !multi, packed_P);
             if (!multi) {
-                conv_kernel<<<1, 1024, 0, st>>>(W.conv, W.tiles, H.conv, H.tiles, KP, (int)k, a.update_H, acc, tol, state, 1, 1);
+                conv_reduce_kernel<<<4 * (KP / 32), 256, 0, st>>>(W.conv, W.tiles, H.conv, H.tiles, KP, (int)k, a.update_H, acc, tol, state, 1);
                 h->launches += 1;
             } else {
-                conv_kernel<<<1, 1024, 0, st>>>(W.conv, W.tiles, H.conv, H.tiles, KP, (int)k, a.update_H, acc, tol, state, 1, 0);
+                conv_reduce_kernel<<<4 * (KP / 32), 256, 0, st>>>(W.conv, W.tiles, H.conv, H.tiles, KP, (int)k, a.update_H, acc, tol, state, 0);
                 h->allreduce_sum(acc, (size_t)2 * KP);  // dev_w, sum_w over all row shards; the H sums are replicated
-                conv_kernel<<<1, 1024, 0, st>>>(W.conv, W.tiles, H.conv, H.tiles, KP, (int)k, a.update_H, acc, tol, state, 0, 1);
+                conv_decide_kernel<<<1, 256, 0, st>>>(acc, KP, (int)k, tol, state);
                 h->launches += 2;
             }
         }
