@@ -454,23 +454,12 @@ __global__ void __launch_bounds__(256) gram_reduce_kernel(const float* __restric
     }
 }
 
-// multi-GPU: split an all-reduced fp32 Gram into bf16 hi/lo
-__global__ void gram_split_kernel(const float* __restrict__ P, bf16* __restrict__ Phi, bf16* __restrict__ Plo, int n, const TcState* st) {
-    if (st->converged) return;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float v = P[i];
-        bf16 hi = __float2bfloat16_rn(v);
-        Phi[i] = hi;
-        Plo[i] = __float2bfloat16_rn(v - __bfloat162float(hi));
-    }
-}
-
 // ---- stop_condition finish (common.jl:92-111) ---------------------------------------------------------
 // acc (double [4][KP]) = {dev_w, sum_w, dev_h, sum_h}.  conv_reduce_kernel: grid = 4 * KP/32 blocks of 8 warps;
 // block (q, cb) sums quantity q of components [32cb, 32cb+32) over all tiles (warp w takes tiles w, w+8, ...;
 // 8 loads in flight; fixed combination order => deterministic).  With do_decide the last block to finish
 // (atomic ticket) applies the reference's test; multi-GPU runs the decision as a separate launch after the
-// all-reduce of the W-side sums (conv_decide_kernel).
+// packed all-reduce (post_allreduce_kernel).
 __device__ void conv_decide(const double* acc, int KP, int k, float tol, TcState* st, float* devs, int* fail) {
     const int a = threadIdx.x;
     if (a == 0) *fail = 0;
@@ -497,7 +486,7 @@ __device__ void conv_decide(const double* acc, int KP, int k, float tol, TcState
 
 __global__ void __launch_bounds__(256) conv_reduce_kernel(const float* __restrict__ partW, int tilesW, const float* __restrict__ partH,
                                                           int tilesH, int KP, int k, int update_H, double* __restrict__ acc, float tol,
-                                                          TcState* st, int do_decide) {
+                                                          TcState* st, int do_decide, float* __restrict__ wsums_f32) {
     if (st->converged) return;
     __shared__ double red[8][32];
     __shared__ float devs[256];
@@ -526,6 +515,7 @@ __global__ void __launch_bounds__(256) conv_reduce_kernel(const float* __restric
         for (int i = 1; i < 8; ++i) tot += red[i][lane];
         if (q >= 2 && !update_H) tot = (q == 2) ? 0.0 : 1.0;  // H untouched: dev_h = 0 (sum_h only scales a ratio of 0)
         acc[(size_t)q * KP + c] = tot;
+        if (wsums_f32 && q < 2) wsums_f32[(size_t)q * KP + c] = (float)tot;  // multi-GPU: rides in the packed all-reduce
     }
     if (!do_decide) return;
     __threadfence();
@@ -541,11 +531,30 @@ __global__ void __launch_bounds__(256) conv_reduce_kernel(const float* __restric
     conv_decide(acc, KP, k, tol, st, devs, &fail);
 }
 
-__global__ void __launch_bounds__(256) conv_decide_kernel(const double* __restrict__ acc, int KP, int k, float tol, TcState* st) {
+// multi-GPU, after the packed all-reduce: block 0 finishes stop_condition of the PREVIOUS iteration (its W-side
+// sums travelled in the tail of the packed buffer; nothing of the current iteration has touched W or H yet),
+// the other blocks split the reduced Gram W'W into bf16 hi/lo.
+__global__ void __launch_bounds__(256) post_allreduce_kernel(double* __restrict__ acc, const float* __restrict__ wsums_f32, int has_prev,
+                                                             int KP, int k, float tol, TcState* st, const float* __restrict__ P,
+                                                             bf16* __restrict__ Phi, bf16* __restrict__ Plo) {
     if (st->converged) return;
     __shared__ float devs[256];
     __shared__ int fail;
-    conv_decide(acc, KP, k, tol, st, devs, &fail);
+    if (blockIdx.x == 0) {
+        if (!has_prev) return;
+        for (int i = threadIdx.x; i < 2 * KP; i += blockDim.x) acc[i] = (double)wsums_f32[i];
+        __syncthreads();
+        conv_decide(acc, KP, k, tol, st, devs, &fail);
+        return;
+    }
+    if (P == nullptr) return;
+    const int i = (blockIdx.x - 1) * blockDim.x + threadIdx.x;
+    if (i < KP * KP) {
+        float v = P[i];
+        bf16 hi = __float2bfloat16_rn(v);
+        Phi[i] = hi;
+        Plo[i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
 }
 
 // ---- X caches: bf16, TILE-CONTIGUOUS ---------------------------------------------------------------------
@@ -809,8 +818,10 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
     TcSolver<KP> s{h, st, state};
     const bool multi = h->comm != nullptr;
     // multi-GPU (rows of X, W sharded; H replicated): packed all-reduce buffer [ (W_g' X_g)' : n x KP | W_g' W_g : KP x KP ]
-    float* packed = multi ? h->buf_t<float>("tc.packed", (size_t)n * KP + (size_t)KP * KP) : nullptr;
+    float* packed = multi ? h->buf_t<float>("tc.packed", (size_t)n * KP + (size_t)KP * KP + 2 * KP) : nullptr;
     float* packed_P = multi ? packed + (size_t)n * KP : nullptr;
+    float* packed_ws = multi ? packed_P + (size_t)KP * KP : nullptr;  // W-side stop_condition sums of the previous iteration
+    if (multi) NMF_CUDA(cudaMemsetAsync(packed_ws, 0, 2 * KP * sizeof(float), st));
     s.launch_gram(W, !multi, packed_P);       // P_W = W'W for the first H-step (partial per rank when sharded)
     if (!a.update_H) s.launch_gram(H, true);  // H never changes: P_H once
     NMF_CUDA(cudaEventRecord(e1, st));
@@ -821,32 +832,41 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
     int64_t iters = 0;
     float devmax = 0.f;
     TcState hs;
+    const int post_blocks = 1 + (KP * KP + 255) / 256;
     while (enq < a.maxiter) {
         int64_t batch = std::min<int64_t>(h->check_every, a.maxiter - enq);
         for (int64_t i = 0; i < batch; ++i) {
+            bool pending = multi && i > 0;  // the previous iteration of this batch still awaits its decision
             if (a.update_H) {
                 if (!multi) {
                     s.launch_update(0, H, W, Xr, (int)p, lh, delta, nullptr);  // H-step: rows of H' against W
                 } else {
                     s.launch_update(1, H, W, Xr, (int)p, lh, delta, packed);   // partial numerators of this shard
-                    h->allreduce_sum(packed, (size_t)n * KP + (size_t)KP * KP);     // THE exchange step of the iteration
-                    gram_split_kernel<<<(KP * KP + 255) / 256, 256, 0, st>>>(packed_P, W.Phi, W.Plo, KP * KP, state);
+                    // THE exchange step: [numerators | W'W | W-side stop sums of the previous iteration]
+                    h->allreduce_sum(packed, (size_t)n * KP + (size_t)KP * KP + 2 * KP);
+                    post_allreduce_kernel<<<post_blocks, 256, 0, st>>>(acc, packed_ws, pending ? 1 : 0, KP, (int)k, tol, state, packed_P,
+                                                                       W.Phi, W.Plo);
                     h->launches += 1;
+                    pending = false;
                     s.launch_update(2, H, W, Xr, (int)p, lh, delta, packed);   // ratio with the reduced numerators
                 }
                 s.launch_gram(H, true);
             }
-            s.launch_update(0, W, H, Xc, (int)n, lw, delta, nullptr);          // W-step (local rows)
-            s.launch_gram(W, !multi, packed_P);
-            if (!multi) {
-                conv_reduce_kernel<<<4 * (KP / 32), 256, 0, st>>>(W.conv, W.tiles, H.conv, H.tiles, KP, (int)k, a.update_H, acc, tol, state, 1);
+            if (pending) {  // update_H = false: no packed exchange to ride on
+                h->allreduce_sum(packed_ws, (size_t)2 * KP);
+                post_allreduce_kernel<<<1, 256, 0, st>>>(acc, packed_ws, 1, KP, (int)k, tol, state, nullptr, nullptr, nullptr);
                 h->launches += 1;
-            } else {
-                conv_reduce_kernel<<<4 * (KP / 32), 256, 0, st>>>(W.conv, W.tiles, H.conv, H.tiles, KP, (int)k, a.update_H, acc, tol, state, 0);
-                h->allreduce_sum(acc, (size_t)2 * KP);  // dev_w, sum_w over all row shards; the H sums are replicated
-                conv_decide_kernel<<<1, 256, 0, st>>>(acc, KP, (int)k, tol, state);
-                h->launches += 2;
             }
+            s.launch_update(0, W, H, Xc, (int)n, lw, delta, nullptr);          // W-step (local rows)
+            if (a.update_H || !multi) s.launch_gram(W, !multi, packed_P);
+            conv_reduce_kernel<<<4 * (KP / 32), 256, 0, st>>>(W.conv, W.tiles, H.conv, H.tiles, KP, (int)k, a.update_H, acc, tol, state,
+                                                              multi ? 0 : 1, packed_ws);
+            h->launches += 1;
+        }
+        if (multi) {  // decision of the last iteration of the batch
+            h->allreduce_sum(packed_ws, (size_t)2 * KP);
+            post_allreduce_kernel<<<1, 256, 0, st>>>(acc, packed_ws, 1, KP, (int)k, tol, state, nullptr, nullptr, nullptr);
+            h->launches += 1;
         }
         enq += batch;
         NMF_CUDA(cudaGetLastError());
