@@ -216,7 +216,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         dW.copy_(tw, non_blocking=True)
         dH.copy_(th, non_blocking=True)
         torch.cuda.synchronize()
-        sess.set_option("time_kernels", 1 if timed else 0)
+        sess.set_option("time_kernels", (2 if args.timeline else 1) if timed else 0)
         return sess.solve_raw("multmse", np.float32, dW.data_ptr(), rows, dH.data_ptr(), k, k, max(iters, 2), 1e-30, 0.0, 0.0,
                               True, False, True)
 
@@ -272,7 +272,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     # ---- roofline of the dominant kernel (mu_update_kernel: one launch per half-step)
     launches = max(int(res.hot_kernel_launches), 1)
-    kern_ms = res.hot_kernel_ms / launches
+    kern_ms = res.hot_kernel_ms / launches if res.hot_kernel_launches else float("nan")
     # algorithmic bytes per launch: the bf16 X panel once + the factor read & written in fp32
     alg_bytes = rows * n * 2 + 2 * ((rows + n) / 2) * k * 4
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
@@ -320,6 +320,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--timeline", action="store_true", help="print the per-phase event timeline of the iteration (stderr)")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value for experiments (device-resident leg)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -83,6 +83,8 @@ int nmfb200_set_stream(nmfb200_handle* h, void* stream);
  *                                               iterations (results are independent of N).
  *   "tc_tile_rows" = "<int>"                 -- rows of a factor owned by one CTA of the tensor-core
  *                                               update kernel (multiple of 8 in [8,128]; 0 = auto).
+ *   "tc_xchg"      = "p2p" | "nccl"          -- multi-GPU exchange of the tensor-core engine: fused peer-memory
+ *                                               reduce-scatter/all-gather over NVLink (default) or ncclAllReduce.
  *   "tc_debug"     = "<int>"                 -- diagnostics for profiling experiments, 0 in production.
  *   "time_kernels" = "0" | "1"               -- bracket every launch of the dominant kernel with
  *                                               CUDA events and report the sum in nmfb200_result. */

@@ -183,10 +183,14 @@ int nmfb200_set_option(nmfb200_handle* h, const char* key, const char* value) {
             h->tc_sa = atoi(value);
         } else if (k == "tc_sb") {
             h->tc_sb = atoi(value);
+        } else if (k == "tc_xchg") {
+            if (v == "p2p") h->tc_xchg = 1;
+            else if (v == "nccl") h->tc_xchg = 0;
+            else throw Error{NMFB200_EINVAL, "tc_xchg must be p2p|nccl"};
         } else if (k == "tc_debug") {
             h->tc_debug = atoi(value);
         } else if (k == "time_kernels") {
-            h->time_kernels = atoi(value) != 0;
+            h->time_kernels = atoi(value);
         } else {
             throw Error{NMFB200_EINVAL, "unknown option " + k};
         }

@@ -45,6 +45,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     static NcclApi& get() {
         static NcclApi api;
@@ -56,8 +57,9 @@ struct NcclApi {
             api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
             api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
             api.AllReduce = (decltype(api.AllReduce))dlsym(api.lib, "ncclAllReduce");
+            api.AllGather = (decltype(api.AllGather))dlsym(api.lib, "ncclAllGather");
             api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
-            NMF_REQUIRE(api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString,
+            NMF_REQUIRE(api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.AllGather && api.GetErrorString,
                         NMFB200_ENCCL, "libnccl.so.2 lacks a required symbol");
         }
         return api;
@@ -83,6 +85,21 @@ template <> struct NcclType<double> { static constexpr ncclDataType_t v = ncclFl
 
 }  // namespace nmfb200
 
+namespace nmfb200 {
+constexpr int XCHG_MAX_RANKS = 8;
+// Peer-memory exchange arena (one per rank, mapped into every peer through CUDA IPC): the fused
+// reduce-scatter / all-gather of the row-sharded H-step writes straight into the peers' HBM over NVLink.
+struct Xchg {
+    bool ready = false;
+    int G = 0, rank = 0;
+    size_t rows_per_seg = 0, row_floats = 0;  // segment geometry the arena was built for
+    void* arena_local = nullptr;
+    size_t arena_bytes = 0;
+    void* arena_peer[XCHG_MAX_RANKS] = {};    // [rank] -> mapped base (own entry = arena_local)
+    unsigned int epoch = 0;
+};
+}  // namespace nmfb200
+
 // The opaque handle of the C ABI.
 struct nmfb200_handle {
     int device = 0;
@@ -96,6 +113,8 @@ struct nmfb200_handle {
     int time_kernels = 0;
     int tc_tile_rows = 0;  // 0 = auto
     int tc_debug = 0;      // diagnostics (see UpdateParams::debug)
+    int tc_xchg = 1;       // multi-GPU exchange: 1 = fused peer-memory reduce-scatter/all-gather, 0 = ncclAllReduce
+    nmfb200::Xchg xchg;
     int tc_sa = 0, tc_sb = 0;  // ring depth overrides (experiments)
     std::vector<cudaEvent_t> ev_pool;  // events for time_kernels
     size_t ev_used = 0;
@@ -137,6 +156,34 @@ struct nmfb200_handle {
             if (it->second.ptr) cudaFree(it->second.ptr);
             bufs.erase(it);
         }
+    }
+    // phase timeline (option time_kernels = 2): mark(label) records an event; the time since the previous mark is
+    // charged to `label`.  Printed to stderr at the end of the solve (diagnostics for multi-GPU runs).
+    std::vector<std::pair<const char*, cudaEvent_t>> marks;
+    void mark(const char* label) {
+        if (time_kernels != 2) return;
+        cudaEvent_t e;
+        NMF_CUDA(cudaEventCreate(&e));
+        NMF_CUDA(cudaEventRecord(e, stream));
+        marks.emplace_back(label, e);
+    }
+    void report_marks(int64_t iters) {
+        if (marks.empty()) return;
+        std::map<std::string, std::pair<double, int>> agg;
+        std::vector<std::string> order;
+        for (size_t i = 1; i < marks.size(); ++i) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+            auto& a = agg[marks[i].first];
+            if (a.second == 0) order.push_back(marks[i].first);
+            a.first += ms;
+            a.second += 1;
+        }
+        fprintf(stderr, "[nmfb200 rank %d] phase timeline over %lld iterations (us per iteration):", rank, (long long)iters);
+        for (auto& name : order) fprintf(stderr, "  %s=%.1f", name.c_str(), agg[name].first * 1e3 / (double)std::max<int64_t>(iters, 1));
+        fprintf(stderr, "\n");
+        for (auto& m : marks) cudaEventDestroy(m.second);
+        marks.clear();
     }
     cudaEvent_t next_event() {
         if (ev_used == ev_pool.size()) {

@@ -35,6 +35,19 @@ struct TcState {
     unsigned int ticket;
 };
 
+// ---- peer-memory exchange (multi-GPU) ---------------------------------------------------------------
+// The packed vector [numerators n x KP | W'W KP x KP | W-side stop sums 2 x KP] is treated as Rtot = n+KP+2
+// rows of KP floats, cut into G contiguous segments of RS rows; rank j owns (reduces) segment j.
+// Arena of every rank (IPC-mapped into all peers): flags | packed [G*RS][KP].  A rank's kernels write their
+// partial sums into its own `packed`; the exchange kernel PULLS its segment from every peer over NVLink, sums
+// in rank order and PUSHES the reduced segment into every peer's `packed` (reduce-scatter + all-gather fused).
+struct XchgDev {
+    float* packed[XCHG_MAX_RANKS];        // packed[j] = rank j's packed vector (mapped peer memory)
+    unsigned int* flags[XCHG_MAX_RANKS];  // flags[j][phase * XCHG_MAX_RANKS + src]: "src reached epoch in phase"
+    unsigned int* ticket;                 // local counter for the last-block pattern
+    int G, rank, RS;
+};
+
 // ---- kernel parameter block (tensor maps must live in __grid_constant__ param space) ---------------
 struct UpdateParams {
     CUtensorMap tmA;    // Xs   bf16 tile-contiguous [tiles*nkb*tile_rows][64], box 64 x tile_rows
@@ -454,6 +467,84 @@ __global__ void __launch_bounds__(256) gram_reduce_kernel(const float* __restric
     }
 }
 
+// ---- exchange kernels -----------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Wait until every rank has published `epoch` in this rank's flag row of `phase` (local memory poll, bounded).
+__device__ __forceinline__ void xchg_wait_all(const XchgDev& x, int phase, unsigned int epoch) {
+    if ((int)threadIdx.x < x.G) {
+        const unsigned int* f = x.flags[x.rank] + phase * XCHG_MAX_RANKS + threadIdx.x;
+        const long long t0 = clock64();
+        while ((int)(ld_acquire_sys(f) - epoch) < 0) {
+            if (clock64() - t0 > 20000000000LL) {  // ~10 s
+                printf("nmfb200: peer barrier timed out (rank %d waiting for %d, phase %d, epoch %u)\n", x.rank, (int)threadIdx.x, phase, epoch);
+                __trap();
+            }
+        }
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void xchg_signal_all(const XchgDev& x, int phase, unsigned int epoch) {  // call from < G threads
+    if ((int)threadIdx.x < x.G) {
+        __threadfence_system();
+        st_release_sys(x.flags[threadIdx.x] + phase * XCHG_MAX_RANKS + x.rank, epoch);
+    }
+}
+
+// Fused reduce-scatter + all-gather over NVLink peer memory, one launch:
+//   (1) block 0 publishes "my partial sums are complete" (true by stream order: the producing kernels ran before);
+//   (2) every block waits for all ranks, then pulls its share of this rank's segment from all ranks' packed vectors
+//       (coalesced 16-byte peer loads), sums in rank order (=> bit-identical on every rank) and pushes the result
+//       into every rank's packed vector (peer stores);
+//   (3) the last block to finish publishes "my reduced segment is in place" (phase 1); consumers wait on that.
+__global__ void __launch_bounds__(256) xchg_reduce_gather_kernel(XchgDev x, int KP, unsigned int epoch) {
+    __shared__ int is_last;
+    if (blockIdx.x == 0) xchg_signal_all(x, 0, epoch);
+    xchg_wait_all(x, 0, epoch);
+    const size_t seg4 = (size_t)x.RS * KP / 4;  // float4 elements per segment
+    const size_t off = (size_t)x.rank * seg4;
+    // U independent elements per thread and trip: G*U 16-byte peer loads in flight hide the ~2-3 us NVLink latency
+    constexpr int U = 4;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < seg4; i0 += U * stride) {
+        float4 v[U][XCHG_MAX_RANKS];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const size_t i = i0 + u * stride;
+#pragma unroll
+            for (int src = 0; src < XCHG_MAX_RANKS; ++src)
+                if (src < x.G && i < seg4) v[u][src] = __ldcg((const float4*)x.packed[src] + off + i);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const size_t i = i0 + u * stride;
+            if (i >= seg4) break;
+            float4 s = v[u][0];
+#pragma unroll
+            for (int src = 1; src < XCHG_MAX_RANKS; ++src)
+                if (src < x.G) { s.x += v[u][src].x; s.y += v[u][src].y; s.z += v[u][src].z; s.w += v[u][src].w; }
+#pragma unroll
+            for (int dst = 0; dst < XCHG_MAX_RANKS; ++dst)
+                if (dst < x.G) ((float4*)x.packed[dst])[off + i] = s;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(x.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (is_last) {
+        if (threadIdx.x == 0) *x.ticket = 0u;
+        xchg_signal_all(x, 1, epoch);
+    }
+}
+
 // ---- stop_condition finish (common.jl:92-111) ---------------------------------------------------------
 // acc (double [4][KP]) = {dev_w, sum_w, dev_h, sum_h}.  conv_reduce_kernel: grid = 4 * KP/32 blocks of 8 warps;
 // block (q, cb) sums quantity q of components [32cb, 32cb+32) over all tiles (warp w takes tiles w, w+8, ...;
@@ -536,13 +627,14 @@ __global__ void __launch_bounds__(256) conv_reduce_kernel(const float* __restric
 // the other blocks split the reduced Gram W'W into bf16 hi/lo.
 __global__ void __launch_bounds__(256) post_allreduce_kernel(double* __restrict__ acc, const float* __restrict__ wsums_f32, int has_prev,
                                                              int KP, int k, float tol, TcState* st, const float* __restrict__ P,
-                                                             bf16* __restrict__ Phi, bf16* __restrict__ Plo) {
+                                                             bf16* __restrict__ Phi, bf16* __restrict__ Plo, XchgDev x, unsigned int epoch) {
+    if (x.G > 0) xchg_wait_all(x, 1, epoch);  // peer-memory exchange: every rank's reduced segment has landed here
     if (st->converged) return;
     __shared__ float devs[256];
     __shared__ int fail;
     if (blockIdx.x == 0) {
         if (!has_prev) return;
-        for (int i = threadIdx.x; i < 2 * KP; i += blockDim.x) acc[i] = (double)wsums_f32[i];
+        for (int i = threadIdx.x; i < 2 * KP; i += blockDim.x) acc[i] = (double)__ldcg(wsums_f32 + i);
         __syncthreads();
         conv_decide(acc, KP, k, tol, st, devs, &fail);
         return;
@@ -696,7 +788,7 @@ struct TcSolver {
         prm.state = state;
         prm.R = F.R; prm.Kdim = Kdim; prm.lambda = lambda; prm.delta = delta;
         const int smem = UpdCfg<KP>::SMEM_BYTES;
-        const bool timed = h->time_kernels && mode != 2;
+        const bool timed = h->time_kernels == 1 && mode != 2;
         if (timed) NMF_CUDA(cudaEventRecord(h->next_event(), st));
         if (mode == 0) mu_update_kernel<KP, 0><<<F.tiles, UpdCfg<KP>::THREADS, smem, st>>>(prm);
         else if (mode == 1) mu_update_kernel<KP, 1><<<F.tiles, UpdCfg<KP>::THREADS, smem, st>>>(prm);
@@ -729,6 +821,88 @@ struct TcSolver {
         done = true;
     }
 };
+
+// ---- peer-memory exchange arena: allocate, export through CUDA IPC, import every peer's ------------------
+void xchg_teardown(nmfb200_handle* h) {
+    Xchg& x = h->xchg;
+    for (int j = 0; j < XCHG_MAX_RANKS; ++j) {
+        if (x.arena_peer[j] && j != x.rank) cudaIpcCloseMemHandle(x.arena_peer[j]);
+        x.arena_peer[j] = nullptr;
+    }
+    if (x.arena_local) cudaFree(x.arena_local);
+    x.arena_local = nullptr;
+    x.ready = false;
+}
+
+constexpr size_t XCHG_FLAG_BYTES = 256;
+
+// Collective over the communicator: every rank calls it with the same (n, KP).  Returns false (and leaves the
+// NCCL path in charge) if peer mapping is not possible on this machine.
+bool xchg_setup(nmfb200_handle* h, int64_t n, int KP, XchgDev* out) {
+    Xchg& x = h->xchg;
+    const int G = h->nranks;
+    if (!h->tc_xchg || G > XCHG_MAX_RANKS || G < 2) return false;
+    const size_t rtot = (size_t)n + KP + 2;
+    const size_t RS = (rtot + G - 1) / G;
+    if (!(x.ready && x.G == G && x.rank == h->rank && x.rows_per_seg == RS && x.row_floats == (size_t)KP)) {
+        xchg_teardown(h);
+        x.G = G;
+        x.rank = h->rank;
+        x.rows_per_seg = RS;
+        x.row_floats = (size_t)KP;
+        const size_t region = (size_t)G * RS * KP * sizeof(float);
+        x.arena_bytes = XCHG_FLAG_BYTES + region;
+        NMF_CUDA(cudaMalloc(&x.arena_local, x.arena_bytes));
+        NMF_CUDA(cudaMemsetAsync(x.arena_local, 0, x.arena_bytes, h->stream));
+        cudaIpcMemHandle_t mine;
+        NMF_CUDA(cudaIpcGetMemHandle(&mine, x.arena_local));
+        char* dsend = (char*)h->buf("tc.xchg_ipc_send", sizeof(mine));
+        char* drecv = (char*)h->buf("tc.xchg_ipc_recv", sizeof(mine) * XCHG_MAX_RANKS);
+        NMF_CUDA(cudaMemcpyAsync(dsend, &mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream));
+        NMF_NCCL(NcclApi::get().AllGather(dsend, drecv, sizeof(mine), ncclChar, h->comm, h->stream));
+        std::vector<cudaIpcMemHandle_t> all(G);
+        NMF_CUDA(cudaMemcpyAsync(all.data(), drecv, sizeof(mine) * G, cudaMemcpyDeviceToHost, h->stream));
+        NMF_CUDA(cudaStreamSynchronize(h->stream));
+        int ok = 1;
+        for (int j = 0; j < G; ++j) {
+            if (j == x.rank) {
+                x.arena_peer[j] = x.arena_local;
+                continue;
+            }
+            void* p = nullptr;
+            cudaError_t err = cudaIpcOpenMemHandle(&p, all[j], cudaIpcMemLazyEnablePeerAccess);
+            if (err != cudaSuccess) {
+                cudaGetLastError();
+                ok = 0;
+                break;
+            }
+            x.arena_peer[j] = p;
+        }
+        // agree on the outcome: everybody falls back to NCCL if anybody could not map a peer
+        int* dok = (int*)h->buf("tc.xchg_ok", sizeof(int));
+        NMF_CUDA(cudaMemcpyAsync(dok, &ok, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        NMF_NCCL(NcclApi::get().AllReduce(dok, dok, 1, ncclInt32, ncclMin, h->comm, h->stream));
+        NMF_CUDA(cudaMemcpyAsync(&ok, dok, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        NMF_CUDA(cudaStreamSynchronize(h->stream));
+        if (!ok) {
+            xchg_teardown(h);
+            h->tc_xchg = 0;
+            return false;
+        }
+        x.epoch = 0;
+        x.ready = true;
+    }
+    out->G = G;
+    out->rank = x.rank;
+    out->RS = (int)RS;
+    out->ticket = (unsigned int*)((char*)x.arena_local + 128);
+    for (int j = 0; j < XCHG_MAX_RANKS; ++j) {
+        char* base = (char*)x.arena_peer[j];
+        out->flags[j] = base ? (unsigned int*)base : nullptr;
+        out->packed[j] = base ? (float*)(base + XCHG_FLAG_BYTES) : nullptr;
+    }
+    return true;
+}
 
 // Rows of a factor per CTA of the update kernel (multiple of 8, <= 128).
 int pick_tile_rows(int R, int forced) {
@@ -818,10 +992,21 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
     TcSolver<KP> s{h, st, state};
     const bool multi = h->comm != nullptr;
     // multi-GPU (rows of X, W sharded; H replicated): packed all-reduce buffer [ (W_g' X_g)' : n x KP | W_g' W_g : KP x KP ]
-    float* packed = multi ? h->buf_t<float>("tc.packed", (size_t)n * KP + (size_t)KP * KP + 2 * KP) : nullptr;
-    float* packed_P = multi ? packed + (size_t)n * KP : nullptr;
-    float* packed_ws = multi ? packed_P + (size_t)KP * KP : nullptr;  // W-side stop_condition sums of the previous iteration
+    // multi-GPU exchange of the packed vector [numerators n x KP | W'W | W-side stop sums]:
+    //   p2p  : MODE 1 stores its rows into the owner rank's HBM, reduce + all-gather kernel, flag barriers (NVLink)
+    //   nccl : ncclAllReduce on a local packed buffer
+    XchgDev xd;
+    std::memset(&xd, 0, sizeof(xd));
+    const bool p2p = multi && xchg_setup(h, n, KP, &xd);
+    if (!p2p) std::memset(&xd, 0, sizeof(xd));  // G = 0: consumers do not wait on peer flags
+    const size_t packed_len = (size_t)n * KP + (size_t)KP * KP + 2 * KP;
+    float* packed = !multi ? nullptr : (p2p ? xd.packed[xd.rank] : h->buf_t<float>("tc.packed", packed_len));
+    float* packed_P = multi ? packed + (size_t)n * KP : nullptr;   // gram_reduce writes the local Gram partial here
+    float* packed_ws = multi ? packed_P + (size_t)KP * KP : nullptr;  // conv_reduce writes the local W-side stop sums here
+    float* ws_small = multi ? h->buf_t<float>("tc.ws_small", 2 * KP) : nullptr;  // stand-alone decision (end of batch)
     if (multi) NMF_CUDA(cudaMemsetAsync(packed_ws, 0, 2 * KP * sizeof(float), st));
+    XchgDev xnone;
+    std::memset(&xnone, 0, sizeof(xnone));
     s.launch_gram(W, !multi, packed_P);       // P_W = W'W for the first H-step (partial per rank when sharded)
     if (!a.update_H) s.launch_gram(H, true);  // H never changes: P_H once
     NMF_CUDA(cudaEventRecord(e1, st));
@@ -837,35 +1022,55 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
         int64_t batch = std::min<int64_t>(h->check_every, a.maxiter - enq);
         for (int64_t i = 0; i < batch; ++i) {
             bool pending = multi && i > 0;  // the previous iteration of this batch still awaits its decision
+            h->mark("start");
             if (a.update_H) {
                 if (!multi) {
                     s.launch_update(0, H, W, Xr, (int)p, lh, delta, nullptr);  // H-step: rows of H' against W
+                    h->mark("updH");
                 } else {
-                    s.launch_update(1, H, W, Xr, (int)p, lh, delta, packed);   // partial numerators of this shard
+                    s.launch_update(1, H, W, Xr, (int)p, lh, delta, packed);  // partial numerators of this shard
+                    h->mark("mode1");
                     // THE exchange step: [numerators | W'W | W-side stop sums of the previous iteration]
-                    h->allreduce_sum(packed, (size_t)n * KP + (size_t)KP * KP + 2 * KP);
+                    unsigned int ep = 0;
+                    if (p2p) {
+                        ep = ++h->xchg.epoch;
+                        xchg_reduce_gather_kernel<<<148, 256, 0, st>>>(xd, KP, ep);  // NVLink peer memory, one launch
+                        h->launches += 1;
+                        h->mark("xchg");
+                    } else {
+                        h->allreduce_sum(packed, packed_len);
+                        h->mark("nccl");
+                    }
                     post_allreduce_kernel<<<post_blocks, 256, 0, st>>>(acc, packed_ws, pending ? 1 : 0, KP, (int)k, tol, state, packed_P,
-                                                                       W.Phi, W.Plo);
+                                                                       W.Phi, W.Plo, xd, ep);
                     h->launches += 1;
                     pending = false;
+                    h->mark("post");
                     s.launch_update(2, H, W, Xr, (int)p, lh, delta, packed);   // ratio with the reduced numerators
+                    h->mark("mode2");
                 }
                 s.launch_gram(H, true);
+                h->mark("gramH");
             }
             if (pending) {  // update_H = false: no packed exchange to ride on
-                h->allreduce_sum(packed_ws, (size_t)2 * KP);
-                post_allreduce_kernel<<<1, 256, 0, st>>>(acc, packed_ws, 1, KP, (int)k, tol, state, nullptr, nullptr, nullptr);
+                NMF_CUDA(cudaMemcpyAsync(ws_small, packed_ws, 2 * KP * sizeof(float), cudaMemcpyDeviceToDevice, st));
+                h->allreduce_sum(ws_small, (size_t)2 * KP);
+                post_allreduce_kernel<<<1, 256, 0, st>>>(acc, ws_small, 1, KP, (int)k, tol, state, nullptr, nullptr, nullptr, xnone, 0u);
                 h->launches += 1;
             }
             s.launch_update(0, W, H, Xc, (int)n, lw, delta, nullptr);          // W-step (local rows)
+            h->mark("updW");
             if (a.update_H || !multi) s.launch_gram(W, !multi, packed_P);
+            h->mark("gramW");
             conv_reduce_kernel<<<4 * (KP / 32), 256, 0, st>>>(W.conv, W.tiles, H.conv, H.tiles, KP, (int)k, a.update_H, acc, tol, state,
                                                               multi ? 0 : 1, packed_ws);
             h->launches += 1;
+            h->mark("conv");
         }
         if (multi) {  // decision of the last iteration of the batch
-            h->allreduce_sum(packed_ws, (size_t)2 * KP);
-            post_allreduce_kernel<<<1, 256, 0, st>>>(acc, packed_ws, 1, KP, (int)k, tol, state, nullptr, nullptr, nullptr);
+            NMF_CUDA(cudaMemcpyAsync(ws_small, packed_ws, 2 * KP * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            h->allreduce_sum(ws_small, (size_t)2 * KP);
+            post_allreduce_kernel<<<1, 256, 0, st>>>(acc, ws_small, 1, KP, (int)k, tol, state, nullptr, nullptr, nullptr, xnone, 0u);
             h->launches += 1;
         }
         enq += batch;
@@ -909,6 +1114,7 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
     out->coordinate_updates = 0;
     out->kernel_launches = h->launches;
     out->hot_kernel_ms = h->drain_event_pairs(&out->hot_kernel_launches);
+    h->report_marks(iters);
 }
 
 }  // namespace
@@ -930,6 +1136,6 @@ void tc_solve(nmfb200_handle* h, const SolveArgs& a, float* W, int64_t ldw, floa
     }
 }
 
-void tc_release(nmfb200_handle*) {}
+void tc_release(nmfb200_handle* h) { xchg_teardown(h); }
 
 }  // namespace nmfb200
