@@ -313,6 +313,49 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         dist.destroy_process_group()
 
 
+def run_secondary(args):
+    """BASELINE configs[2] (MultUpdate :div, X 8192x65536, k=64) and configs[3] (GreedyCD, X 32768x32768, k=256):
+    device-resident iteration rate through the C ABI.  Not the driver's headline line; recorded in profiles/."""
+    import torch
+    import nmf_jl_b200 as NMF
+    cfg = {"cfg3": ("multdiv", 8192, 65536, 64), "cfg4": ("greedycd", 32768, 32768, 256)}[args.workload]
+    alg, p, n, k = cfg
+    torch.cuda.set_device(0)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(0)
+    dX = torch.rand((n, p), device="cuda", generator=g)            # column-major p x n
+    dW = torch.rand((k, p), device="cuda", generator=g)
+    dW /= dW.sum(dim=1, keepdim=True)                               # columns of W sum to 1
+    dH = torch.rand((n, k), device="cuda", generator=g)
+    W0, H0 = dW.clone(), dH.clone()
+    sess = NMF.Session(device=0, engine=args.engine)
+    sess.set_X_device(dX.data_ptr(), p, n, p, np.float32, keepalive=dX)
+    sess.set_option("check_every", max(args.steps, 1))
+    out = {}
+    for iters, tag in ((max(args.warmup, 2), "warm"), (max(args.steps, 2), "timed")):
+        dW.copy_(W0)
+        dH.copy_(H0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = sess.solve_raw(alg, np.float32, dW.data_ptr(), p, dH.data_ptr(), k, k, iters, 1e-30, 0.0, 0.0, True, False, True)
+        torch.cuda.synchronize()
+        out[tag] = (r, time.perf_counter() - t0)
+    r, wall = out["timed"]
+    it_s = r.niters / (r.solve_ms * 1e-3)
+    flops = (8.0 * p * n * k) if alg == "multdiv" else (4.0 * p * n * k + 4.0 * k * k * (p + n))
+    alg_bytes = 2.0 * p * n * 4
+    hbm_peak, tf_peak, src = peaks()
+    line = {"metric": METRIC.replace("MultUpdate(:mse) k=128", f"{alg} k={k}"), "value": p * n * it_s, "unit": UNIT, "iters_per_sec": it_s,
+            "n_gpus": 1, "steps": int(r.niters), "ms_per_step": r.solve_ms / r.niters, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {alg} dense fp32 X {p}x{n}, k={k}", "engine": "tc" if r.engine == 1 else "simt"},
+            "objvalue": r.objvalue, "coordinate_updates": int(r.coordinate_updates), "gpu_launches": int(r.kernel_launches),
+            "roofline": {"bound": "hbm", "achieved": alg_bytes * it_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": alg_bytes * it_s / 1e9 / hbm_peak, "note": "whole iteration vs 2 fp32 passes over X", "peak_source": src,
+                         "tflops": flops * it_s / 1e12}}
+    print(json.dumps(line), flush=True)
+    sess.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -320,6 +363,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4"], help="cfg2 = headline (default); cfg3/cfg4 = secondary")
+    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc"])
     ap.add_argument("--timeline", action="store_true", help="print the per-phase event timeline of the iteration (stderr)")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value for experiments (device-resident leg)")
     args = ap.parse_args()
@@ -329,6 +374,9 @@ def main():
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload != "cfg2":
+        run_secondary(args)
         return
     if world != args.gpus:
         if args.gpus > 1:

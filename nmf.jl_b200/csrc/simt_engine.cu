@@ -7,22 +7,10 @@
 //   * reductions run in parallel (pairwise order) instead of Julia's sequential order.
 // Layouts on device are the caller's: column-major X (p x n), W (p x k), H (k x n).
 #include "common.cuh"
+#include "gcd_kernels.cuh"
 
 namespace nmfb200 {
 namespace {
-
-// ---- un-fused arithmetic helpers (the reference's scalar loops are not FMA-contracted) ----------
-__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
-__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
-__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
-__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
-__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
-__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
-template <typename T> __device__ __forceinline__ T eps_of();
-template <> __device__ __forceinline__ float eps_of<float>() { return 1.1920928955078125e-07f; }
-template <> __device__ __forceinline__ double eps_of<double>() { return 2.220446049250313e-16; }
 
 // ---- generic strided GEMM: C(m,n) = sum_k A(m,k) B(k,n); 64x64x16 tiles, 256 threads, 4x4 per thread
 constexpr int GBM = 64, GBN = 64, GBK = 16;
@@ -253,123 +241,6 @@ __global__ void gcd_form_g_kernel(T* __restrict__ G, const T* __restrict__ Z, in
         if (add_lambda) g = add_rn(g, lambda);
         G[i] = g;
     }
-}
-
-template <typename T>
-__device__ __forceinline__ void gcd_sd(T w, T g, T prr, T& s, T& d) {
-    // S = max(0, W - G/(eps(T)+P[r,r])) - W ; D = -G*S - 0.5*P[r,r]*S^2   (greedycd.jl:127-128, :155-156)
-    T t = sub_rn(w, div_rn(g, add_rn(eps_of<T>(), prr)));
-    s = sub_rn(t > T(0) ? t : T(0), w);
-    d = sub_rn(mul_rn(-g, s), mul_rn(mul_rn(T(0.5), prr), mul_rn(s, s)));
-}
-
-// warp-level (value, index) arg-max with first-max tie-break
-template <typename T>
-__device__ __forceinline__ void warp_argmax(T& v, int& idx) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        T ov = __shfl_xor_sync(0xffffffffu, v, o);
-        int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-        if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
-    }
-}
-
-constexpr int GCD_WARPS = 4;
-
-// pass 1: per-row max_r D[i,r]  -> per-block max (greedycd.jl:132-137)
-template <typename T>
-__global__ void __launch_bounds__(GCD_WARPS * 32) gcd_rowmax_kernel(const T* __restrict__ F, int64_t sFr, int64_t sFc,
-                                                                   const T* __restrict__ G, const T* __restrict__ P,
-                                                                   int64_t rows, int k, T* __restrict__ blockmax) {
-    __shared__ T wmax[GCD_WARPS];
-    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    int64_t i = (int64_t)blockIdx.x * GCD_WARPS + warp;
-    T best = T(-1.0);
-    if (i < rows) {
-        int bi = 0x7fffffff;
-        T bv = (T)(-INFINITY);
-        for (int r = lane; r < k; r += 32) {
-            T s, d;
-            gcd_sd(F[i * sFr + r * sFc], G[i * k + r], P[r + (int64_t)r * k], s, d);
-            if (d > bv) { bv = d; bi = r; }
-        }
-        warp_argmax(bv, bi);
-        best = bv;
-    }
-    if (lane == 0) wmax[warp] = best;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        T m = T(-1.0);
-        for (int w = 0; w < GCD_WARPS; ++w) m = wmax[w] > m ? wmax[w] : m;
-        blockmax[blockIdx.x] = m;
-    }
-}
-
-template <typename T>
-__global__ void max_partials_kernel(const T* __restrict__ part, int nparts, T* __restrict__ out) {
-    __shared__ T red[256];
-    T m = T(-1.0);
-    for (int i = threadIdx.x; i < nparts; i += blockDim.x) m = part[i] > m ? part[i] : m;
-    red[threadIdx.x] = m;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if ((int)threadIdx.x < o) red[threadIdx.x] = red[threadIdx.x + o] > red[threadIdx.x] ? red[threadIdx.x + o] : red[threadIdx.x];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) out[0] = red[0];
-}
-
-// pass 2: the per-row greedy coordinate loop, one warp per row, row state in shared memory
-// (greedycd.jl:139-165).  smem per warp: g[k], f[k], fnew[k]; per block: pdiag[k].
-template <typename T>
-__global__ void __launch_bounds__(GCD_WARPS * 32) gcd_rows_kernel(T* __restrict__ F, int64_t sFr, int64_t sFc,
-                                                                 const T* __restrict__ G, const T* __restrict__ P,
-                                                                 int64_t rows, int k, const T* __restrict__ p_init_ptr,
-                                                                 unsigned long long* __restrict__ updates) {
-    extern __shared__ unsigned char smem_raw[];
-    T* pdiag = (T*)smem_raw;
-    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    T* g = pdiag + k + (size_t)warp * 3 * k;
-    T* f = g + k;
-    T* fnew = f + k;
-    for (int r = threadIdx.x; r < k; r += blockDim.x) pdiag[r] = P[r + (int64_t)r * k];
-    __syncthreads();
-    int64_t i = (int64_t)blockIdx.x * GCD_WARPS + warp;
-    if (i >= rows) return;
-    for (int r = lane; r < k; r += 32) {
-        g[r] = G[i * k + r];
-        f[r] = F[i * sFr + r * sFc];
-        fnew[r] = T(0);
-    }
-    __syncwarp();
-    const T thresh = mul_rn(T(0.001), p_init_ptr[0]);
-    const int64_t maxsteps = (int64_t)k * k;
-    unsigned long long nupd = 0;
-    for (int64_t it = 0; it < maxsteps; ++it) {
-        int bi = 0x7fffffff;
-        T bv = (T)(-INFINITY);
-        for (int r = lane; r < k; r += 32) {
-            T s, d;
-            gcd_sd(f[r], g[r], pdiag[r], s, d);
-            if (d > bv) { bv = d; bi = r; }
-        }
-        warp_argmax(bv, bi);
-        if (bv < thresh) break;
-        T sq, dq;
-        gcd_sd(f[bi], g[bi], pdiag[bi], sq, dq);
-        __syncwarp();
-        if (lane == 0) fnew[bi] = add_rn(fnew[bi], sq);
-        const T* prow = P + (int64_t)bi;  // P[qi, r] = P[qi + r*k]
-        for (int r = lane; r < k; r += 32) g[r] = add_rn(g[r], mul_rn(sq, prow[(int64_t)r * k]));
-        __syncwarp();
-        ++nupd;
-    }
-    for (int r = lane; r < k; r += 32) {
-        T v = add_rn(f[r], fnew[r]);
-        if (v < T(0)) v = T(0);  // projectnn! (utils.jl:34-41)
-        F[i * sFr + r * sFc] = v;
-    }
-    if (lane == 0 && nupd) atomicAdd(updates, nupd);
 }
 
 // strided copy (2D) for packing caller matrices with ld != rows

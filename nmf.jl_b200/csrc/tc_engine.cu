@@ -20,6 +20,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "gcd_kernels.cuh"
 #include "tc_ptx.cuh"
 
 namespace nmfb200 {
@@ -61,7 +62,8 @@ struct UpdateParams {
     bf16* Flo;          // [R][KP]
     bf16* FbT;          // [KP][ldT] transposed bf16 copy
     float* num_io;      // MODE 1: raw numerators out, MODE 2: reduced numerators in ([R][KP])
-    float* conv_part;   // [tiles][2][KP]
+    float* conv_part;   // [tiles][2][KP]   (MODE 3: [tiles] per-CTA max of D, greedycd.jl:132-137)
+    const float* Pfull; // MODE 3: fp32 Gram of the other factor ([KP][KP]); its diagonal enters S and D
     const TcState* state;
     int64_t ldT;
     int R, Kdim;
@@ -107,6 +109,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(bf16 lo, bf16 hi) {
 
 // MODE 0: fused (single GPU).  MODE 1: numerators only -> num_io (row-sharded H-step, before the
 // all-reduce).  MODE 2: no main loop, numerators read from num_io (after the all-reduce).
+// MODE 3: GreedyCD gradient: G = F*P - Xs*O (+lambda) -> num_io, per-CTA max_r D[i,r] -> conv_part (greedycd.jl:117-137).
 template <int KP, int MODE>
 __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const __grid_constant__ UpdateParams prm) {
     using C = UpdCfg<KP>;
@@ -217,6 +220,11 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
         tc_fence_after();
         float* convw = conv_s + q * 2 * KP;
         const float lambda = prm.lambda, delta = prm.delta;
+        float gcd_rowmax = -1.0f;
+        if (MODE == 3) {  // diagonal of P into shared memory (conv scratch is free in this mode)
+            for (int i = threadIdx.x - 64; i < KP; i += 128) conv_s[i] = prm.Pfull[(size_t)i * KP + i];
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
 #pragma unroll 1
         for (int c0 = 0; c0 < KP; c0 += 32) {
             uint32_t num_u[32], den_u[32];
@@ -255,6 +263,27 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                 for (int j = 0; j < 32; ++j) { f[j] = 0.f; if (MODE == 2) num_u[j] = 0u; }
             }
             tmem_ld_wait();
+            if (MODE == 3) {
+                float g[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float gv = __uint_as_float(den_u[j]) - __uint_as_float(num_u[j]);       // G = F P - Z   (greedycd.jl:119-120)
+                    if (lambda > 0.f) gv += lambda;                                           // :121-123
+                    g[j] = gv;
+                    const float prr = conv_s[c0 + j];
+                    const float w = f[j];
+                    const float t = w - gv / (1.1920928955078125e-07f + prr);                 // :127
+                    const float sv = fmaxf(t, 0.f) - w;
+                    const float dv = -gv * sv - 0.5f * prr * sv * sv;                         // :128
+                    if (valid) gcd_rowmax = fmaxf(gcd_rowmax, dv);
+                }
+                if (valid) {
+                    float4* dst = (float4*)(prm.num_io + (size_t)row * KP + c0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dst[j] = make_float4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
+                }
+                continue;
+            }
             float d2[32], s2[32];
             uint32_t hi_p[16], lo_p[16];
 #pragma unroll
@@ -302,7 +331,14 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
             convw[c0 + lane] = d2[0];
             convw[KP + c0 + lane] = s2[0];
         }
-        if (MODE != 1) {
+        if (MODE == 3) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) gcd_rowmax = fmaxf(gcd_rowmax, __shfl_xor_sync(0xffffffffu, gcd_rowmax, o));
+            asm volatile("bar.sync 1, 128;" ::: "memory");   // everybody is done reading the diagonal
+            if (lane == 0) conv_s[q] = gcd_rowmax;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (threadIdx.x == 64) prm.conv_part[blockIdx.x] = fmaxf(fmaxf(conv_s[0], conv_s[1]), fmaxf(conv_s[2], conv_s[3]));
+        } else if (MODE != 1) {
             // combine the four lane quarters: named barrier over the 128 epilogue threads
             asm volatile("bar.sync 1, 128;" ::: "memory");
             const int t = threadIdx.x - 64;  // 0..127
@@ -770,7 +806,7 @@ struct TcSolver {
     TcState* state;
 
     void launch_update(int mode, const Factor& F, const Factor& O, const bf16* Xs, int Kdim, float lambda, float delta,
-                       float* num_io) {
+                       float* num_io, float* conv_override = nullptr) {
         UpdateParams prm;
         prm.tile_rows = F.tile_rows;
         prm.debug = h->tc_debug;
@@ -784,7 +820,8 @@ struct TcSolver {
         prm.tmPlo = make_tmap_bf16(O.Plo, KP, KP, KP, KP);
         prm.F = F.m; prm.Fhi = F.hi; prm.Flo = F.lo; prm.FbT = F.bT; prm.ldT = F.ldT;
         prm.num_io = num_io;
-        prm.conv_part = F.conv;
+        prm.conv_part = conv_override ? conv_override : F.conv;
+        prm.Pfull = O.P;
         prm.state = state;
         prm.R = F.R; prm.Kdim = Kdim; prm.lambda = lambda; prm.delta = delta;
         const int smem = UpdCfg<KP>::SMEM_BYTES;
@@ -792,7 +829,8 @@ struct TcSolver {
         if (timed) NMF_CUDA(cudaEventRecord(h->next_event(), st));
         if (mode == 0) mu_update_kernel<KP, 0><<<F.tiles, UpdCfg<KP>::THREADS, smem, st>>>(prm);
         else if (mode == 1) mu_update_kernel<KP, 1><<<F.tiles, UpdCfg<KP>::THREADS, smem, st>>>(prm);
-        else mu_update_kernel<KP, 2><<<F.tiles, UpdCfg<KP>::THREADS, smem, st>>>(prm);
+        else if (mode == 2) mu_update_kernel<KP, 2><<<F.tiles, UpdCfg<KP>::THREADS, smem, st>>>(prm);
+        else mu_update_kernel<KP, 3><<<F.tiles, UpdCfg<KP>::THREADS, smem, st>>>(prm);
         if (timed) NMF_CUDA(cudaEventRecord(h->next_event(), st));
         h->launches += 1;
     }
@@ -817,6 +855,7 @@ struct TcSolver {
         NMF_CUDA(cudaFuncSetAttribute(mu_update_kernel<KP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, UpdCfg<KP>::SMEM_BYTES));
         NMF_CUDA(cudaFuncSetAttribute(mu_update_kernel<KP, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, UpdCfg<KP>::SMEM_BYTES));
         NMF_CUDA(cudaFuncSetAttribute(mu_update_kernel<KP, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, UpdCfg<KP>::SMEM_BYTES));
+        NMF_CUDA(cudaFuncSetAttribute(mu_update_kernel<KP, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, UpdCfg<KP>::SMEM_BYTES));
         NMF_CUDA(cudaFuncSetAttribute(gram_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, GramCfg<KP>::SMEM_BYTES));
         done = true;
     }
@@ -931,6 +970,33 @@ Factor alloc_factor(nmfb200_handle* h, const char* tag, int R, int KP) {
     return f;
 }
 
+// bf16 tile-contiguous caches of X in both orientations (built once per set_X / tile shape)
+void build_x_caches(nmfb200_handle* h, bf16** Xr_out, bf16** Xc_out) {
+    cudaStream_t st = h->stream;
+    const int64_t p = h->p, n = h->n;
+    const int trH = pick_tile_rows((int)n, h->tc_tile_rows), trW = pick_tile_rows((int)p, h->tc_tile_rows);
+    const int64_t tilesH = ceil_div(n, trH), tilesW = ceil_div(p, trW);
+    const int nkbH = (int)ceil_div(p, 64), nkbW = (int)ceil_div(n, 64);
+    bf16* Xr_ = h->buf_t<bf16>("tc.Xr", (size_t)tilesH * nkbH * trH * 64);  // rows = columns of X, contraction over p
+    bf16* Xc_ = h->buf_t<bf16>("tc.Xc", (size_t)tilesW * nkbW * trW * 64);  // rows = rows of X, contraction over n
+    if (h->tc_x_epoch != h->x_epoch || h->tc_x_trH != trH || h->tc_x_trW != trW) {
+        const float* X = (const float*)h->dX;
+        cvt_tiled_direct_kernel<<<dim3((unsigned)std::min<int64_t>(ceil_div((int64_t)nkbH * 64, 256), 64), (unsigned)(tilesH * trH)), 256, 0, st>>>(
+            X, h->ldx, (int)n, (int)p, trH, nkbH, Xr_);
+        NMF_REQUIRE(trW % 8 == 0, NMFB200_EINVAL, "tile rows must be a multiple of 8");
+        // the transpose kernel walks 64 logical rows per block; cover the padded row range of the last tile too
+        cvt_tiled_transpose_kernel<<<dim3((unsigned)nkbW, (unsigned)ceil_div(tilesW * trW, 64)), dim3(32, 8), 0, st>>>(
+            X, h->ldx, (int)p, (int)n, trW, nkbW, (int)tilesW, Xc_);
+        h->launches += 2;
+        NMF_CUDA(cudaGetLastError());
+        h->tc_x_epoch = h->x_epoch;
+        h->tc_x_trH = trH;
+        h->tc_x_trW = trW;
+    }
+    *Xr_out = Xr_;
+    *Xc_out = Xc_;
+}
+
 template <int KP>
 void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, float* Hc, int64_t ldh, nmfb200_result* out) {
     TcSolver<KP>::set_attrs();
@@ -944,26 +1010,8 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
     NMF_CUDA(cudaEventCreate(&e1));
     NMF_CUDA(cudaEventCreate(&e2));
 
-    // bf16 tile-contiguous caches of X in both orientations (built once per set_X / tile shape)
-    const int trH = pick_tile_rows((int)n, h->tc_tile_rows), trW = pick_tile_rows((int)p, h->tc_tile_rows);
-    const int64_t tilesH = ceil_div(n, trH), tilesW = ceil_div(p, trW);
-    const int nkbH = (int)ceil_div(p, 64), nkbW = (int)ceil_div(n, 64);
-    bf16* Xr = h->buf_t<bf16>("tc.Xr", (size_t)tilesH * nkbH * trH * 64);  // rows = columns of X, contraction over p
-    bf16* Xc = h->buf_t<bf16>("tc.Xc", (size_t)tilesW * nkbW * trW * 64);  // rows = rows of X, contraction over n
-    if (h->tc_x_epoch != h->x_epoch || h->tc_x_trH != trH || h->tc_x_trW != trW) {
-        const float* X = (const float*)h->dX;
-        cvt_tiled_direct_kernel<<<dim3((unsigned)std::min<int64_t>(ceil_div((int64_t)nkbH * 64, 256), 64), (unsigned)(tilesH * trH)), 256, 0, st>>>(
-            X, h->ldx, (int)n, (int)p, trH, nkbH, Xr);
-        NMF_REQUIRE(trW % 8 == 0, NMFB200_EINVAL, "tile rows must be a multiple of 8");
-        // the transpose kernel walks 64 logical rows per block; cover the padded row range of the last tile too
-        cvt_tiled_transpose_kernel<<<dim3((unsigned)nkbW, (unsigned)ceil_div(tilesW * trW, 64)), dim3(32, 8), 0, st>>>(
-            X, h->ldx, (int)p, (int)n, trW, nkbW, (int)tilesW, Xc);
-        h->launches += 2;
-        NMF_CUDA(cudaGetLastError());
-        h->tc_x_epoch = h->x_epoch;
-        h->tc_x_trH = trH;
-        h->tc_x_trW = trW;
-    }
+    bf16 *Xr = nullptr, *Xc = nullptr;
+    build_x_caches(h, &Xr, &Xc);
     NMF_CUDA(cudaEventRecord(e0, st));
 
     Factor W = alloc_factor(h, "W", (int)p, KP), H = alloc_factor(h, "H", (int)n, KP);
@@ -1117,10 +1165,160 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
     h->report_marks(iters);
 }
 
+// ---- GreedyCD on the tensor-core engine (greedycd.jl:94-178) ---------------------------------------------------
+// After the per-row coordinate kernel has rewritten the fp32 master, rebuild the bf16 operand forms of the factor
+// and the stop_condition partial sums against the copy taken before the half-step.  One block per 128-row tile.
+__global__ void __launch_bounds__(256) gcd_repack_kernel(const float* __restrict__ Fm, const float* __restrict__ Fprev, int R, int KP,
+                                                         bf16* __restrict__ Fhi, bf16* __restrict__ Flo, bf16* __restrict__ FbT, int64_t ldT,
+                                                         float* __restrict__ conv_part) {
+    __shared__ float red[2][256];
+    const int groups = 256 / KP > 0 ? 256 / KP : 1;
+    const int cols_per_thread = KP > 256 ? 0 : 1;
+    (void)cols_per_thread;
+    const int g = threadIdx.x / KP, a = threadIdx.x % KP;
+    const int r0 = blockIdx.x * 128;
+    float d2 = 0.f, s2 = 0.f;
+    if (g < groups) {
+        for (int rr = g; rr < 128; rr += groups) {
+            const int r = r0 + rr;
+            if (r >= R) break;
+            const size_t idx = (size_t)r * KP + a;
+            const float v = Fm[idx], o = Fprev[idx];
+            const bf16 hi = __float2bfloat16_rn(v);
+            Fhi[idx] = hi;
+            Flo[idx] = __float2bfloat16_rn(v - __bfloat162float(hi));
+            FbT[(size_t)a * ldT + r] = hi;
+            const float dd = v - o, ss = v + o;
+            d2 += dd * dd;
+            s2 += ss * ss;
+        }
+    }
+    red[0][threadIdx.x] = d2;
+    red[1][threadIdx.x] = s2;
+    __syncthreads();
+    if (threadIdx.x < KP) {
+        for (int gg = 1; gg < groups; ++gg) { d2 += red[0][gg * KP + a]; s2 += red[1][gg * KP + a]; }
+        conv_part[(size_t)blockIdx.x * 2 * KP + a] = d2;
+        conv_part[(size_t)blockIdx.x * 2 * KP + KP + a] = s2;
+    }
+}
+
+template <int KP>
+void tc_solve_gcd_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, float* Hc, int64_t ldh, nmfb200_result* out) {
+    TcSolver<KP>::set_attrs();
+    cudaStream_t st = h->stream;
+    const int64_t p = h->p, n = h->n, k = a.k;
+    const float lw = (float)a.lambda_w, lh = (float)a.lambda_h, tol = (float)a.tol;
+    cudaEvent_t e0, e1, e2;
+    NMF_CUDA(cudaEventCreate(&e0));
+    NMF_CUDA(cudaEventCreate(&e1));
+    NMF_CUDA(cudaEventCreate(&e2));
+    bf16 *Xr = nullptr, *Xc = nullptr;
+    build_x_caches(h, &Xr, &Xc);
+    NMF_CUDA(cudaEventRecord(e0, st));
+
+    Factor W = alloc_factor(h, "W", (int)p, KP), H = alloc_factor(h, "H", (int)n, KP);
+    // conv partials here are per 128-row tile of the repack kernel
+    const int tilesW = (int)ceil_div(p, 128), tilesH = (int)ceil_div(n, 128);
+    W.conv = h->buf_t<float>("tc.W.conv", (size_t)std::max(tilesW, W.tiles) * 2 * KP);
+    H.conv = h->buf_t<float>("tc.H.conv", (size_t)std::max(tilesH, H.tiles) * 2 * KP);
+    TcState* state = (TcState*)h->buf("tc.state", sizeof(TcState));
+    double* acc = h->buf_t<double>("tc.acc", 4 * KP);
+    const size_t rmax = (size_t)std::max(p, n);
+    float* G = h->buf_t<float>("tc.gcd_G", rmax * KP);
+    float* prev = h->buf_t<float>("tc.gcd_prev", rmax * KP);
+    const int maxtiles = std::max(W.tiles, H.tiles);
+    float* bmax = h->buf_t<float>("tc.gcd_bmax", (size_t)maxtiles + 1);
+    unsigned long long* d_updates = (unsigned long long*)h->buf("tc.gcd_updates", 16);
+    NMF_CUDA(cudaMemsetAsync(state, 0, sizeof(TcState), st));
+    NMF_CUDA(cudaMemsetAsync(d_updates, 0, sizeof(unsigned long long), st));
+    NMF_CUDA(cudaMemsetAsync(W.bT, 0, (size_t)W.rowsT * W.ldT * sizeof(bf16), st));
+    NMF_CUDA(cudaMemsetAsync(H.bT, 0, (size_t)H.rowsT * H.ldT * sizeof(bf16), st));
+
+    float *Wd = Wc, *Hd = Hc;
+    int64_t ldwd = ldw, ldhd = ldh;
+    if (!a.on_device) {
+        Wd = h->buf_t<float>("tc.Wstage", (size_t)p * k);
+        Hd = h->buf_t<float>("tc.Hstage", (size_t)k * n);
+        ldwd = p;
+        ldhd = k;
+        NMF_CUDA(cudaMemcpy2DAsync(Wd, p * sizeof(float), Wc, ldw * sizeof(float), p * sizeof(float), k, cudaMemcpyHostToDevice, st));
+        NMF_CUDA(cudaMemcpy2DAsync(Hd, k * sizeof(float), Hc, ldh * sizeof(float), k * sizeof(float), n, cudaMemcpyHostToDevice, st));
+    }
+    pack_factor_kernel<<<ew_grid(p * KP), 256, 0, st>>>(Wd, 1, ldwd, (int)p, (int)k, KP, W.m, W.hi, W.lo, W.bT, W.ldT);
+    pack_factor_kernel<<<ew_grid(n * KP), 256, 0, st>>>(Hd, ldhd, 1, (int)n, (int)k, KP, H.m, H.hi, H.lo, H.bT, H.ldT);
+    h->launches += 2;
+    TcSolver<KP> s{h, st, state};
+    s.launch_gram(H, true);  // P = HH' for the first W-step (greedycd.jl:117)
+    NMF_CUDA(cudaEventRecord(e1, st));
+
+    const size_t rows_smem = ((size_t)KP + (size_t)GCD_WARPS * 3 * KP) * sizeof(float);
+    NMF_CUDA(cudaFuncSetAttribute(gcd_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem));
+    auto half_step = [&](Factor& F, Factor& O, const bf16* Xs, int Kdim, float lambda, int tiles128) {
+        NMF_CUDA(cudaMemcpyAsync(prev, F.m, (size_t)F.R * KP * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        s.launch_update(3, F, O, Xs, Kdim, lambda, 0.f, G, bmax);                                  // G = F P - X O (+lambda), per-CTA max D
+        max_partials_kernel<float><<<1, 256, 0, st>>>(bmax, F.tiles, bmax + maxtiles);            // p_init (:132-137)
+        gcd_rows_kernel<float><<<(unsigned)ceil_div(F.R, GCD_WARPS), GCD_WARPS * 32, rows_smem, st>>>(
+            F.m, KP, 1, G, O.P, F.R, KP, bmax + maxtiles, d_updates);                             // :139-165
+        gcd_repack_kernel<<<tiles128, 256, 0, st>>>(F.m, prev, F.R, KP, F.hi, F.lo, F.bT, F.ldT, F.conv);
+        h->launches += 3;
+        s.launch_gram(F, true);                                                                   // Gram of the updated factor
+    };
+
+    bool converged = false;
+    int64_t iters = 0;
+    float devmax = 0.f;
+    TcState hs;
+    while (iters < a.maxiter && !converged) {  // one host check per iteration: the row kernel has no early-exit flag
+        half_step(W, H, Xc, (int)n, lw, tilesW);                                                   // W first (greedycd.jl:169-171)
+        if (a.update_H) half_step(H, W, Xr, (int)p, lh, tilesH);                                   // then H (:173-177)
+        conv_reduce_kernel<<<4 * (KP / 32), 256, 0, st>>>(W.conv, tilesW, H.conv, tilesH, KP, (int)k, a.update_H, acc, tol, state, 1, nullptr);
+        h->launches += 1;
+        NMF_CUDA(cudaGetLastError());
+        NMF_CUDA(cudaMemcpyAsync(&hs, state, sizeof(TcState), cudaMemcpyDeviceToHost, st));
+        NMF_CUDA(cudaStreamSynchronize(st));
+        iters = hs.iters;
+        devmax = hs.devmax;
+        converged = hs.converged != 0;
+    }
+    NMF_CUDA(cudaEventRecord(e2, st));
+    unpack_factor_kernel<<<ew_grid(p * k), 256, 0, st>>>(W.m, (int)p, (int)k, KP, Wd, 1, ldwd);
+    unpack_factor_kernel<<<ew_grid(n * k), 256, 0, st>>>(H.m, (int)n, (int)k, KP, Hd, ldhd, 1);
+    h->launches += 2;
+    double objv = simt_objective_f32(h, 2, Wd, ldwd, Hd, ldhd, k, a.lambda_w, a.lambda_h);  // greedycd.jl:82-92
+    unsigned long long upd = 0;
+    NMF_CUDA(cudaMemcpyAsync(&upd, d_updates, sizeof(upd), cudaMemcpyDeviceToHost, st));
+    if (!a.on_device) {
+        NMF_CUDA(cudaMemcpy2DAsync(Wc, ldw * sizeof(float), Wd, p * sizeof(float), p * sizeof(float), k, cudaMemcpyDeviceToHost, st));
+        NMF_CUDA(cudaMemcpy2DAsync(Hc, ldh * sizeof(float), Hd, k * sizeof(float), k * sizeof(float), n, cudaMemcpyDeviceToHost, st));
+    }
+    NMF_CUDA(cudaStreamSynchronize(st));
+    float ms_up = 0, ms_loop = 0;
+    cudaEventElapsedTime(&ms_up, e0, e1);
+    cudaEventElapsedTime(&ms_loop, e1, e2);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaEventDestroy(e2);
+    out->niters = iters;
+    out->converged = converged ? 1 : 0;
+    out->engine = 1;
+    out->objvalue = objv;
+    out->last_dev = devmax;
+    out->solve_ms = ms_loop;
+    out->upload_ms = ms_up;
+    out->coordinate_updates = (int64_t)upd;
+    out->kernel_launches = h->launches;
+    out->hot_kernel_ms = h->drain_event_pairs(&out->hot_kernel_launches);
+}
+
 }  // namespace
 
 bool tc_supported(const nmfb200_handle* h, const SolveArgs& a) {
-    if (a.alg != 0) return false;         // MultUpdate(:mse) only, so far
+    if (a.alg == 1) return false;         // MultUpdate(:div): exact engine (fused quotient chain = next)
+    if (a.alg == 2) {                     // GreedyCD: bf16 gradients; single GPU; auto-selected for large problems only
+        if (h->comm != nullptr) return false;
+        if (h->engine_opt != 2 && h->p * h->n < ((int64_t)1 << 24)) return false;
+    }
     if (a.verbose) return false;          // per-iteration objective: exact engine
     if (pick_kp(a.k) == 0) return false;
     if (h->p > (int64_t)INT32_MAX / 256 || h->n > (int64_t)INT32_MAX / 256) return false;
@@ -1128,6 +1326,14 @@ bool tc_supported(const nmfb200_handle* h, const SolveArgs& a) {
 }
 
 void tc_solve(nmfb200_handle* h, const SolveArgs& a, float* W, int64_t ldw, float* H, int64_t ldh, nmfb200_result* out) {
+    if (a.alg == 2) {
+        switch (pick_kp(a.k)) {
+            case 64: tc_solve_gcd_kp<64>(h, a, W, ldw, H, ldh, out); return;
+            case 128: tc_solve_gcd_kp<128>(h, a, W, ldw, H, ldh, out); return;
+            case 256: tc_solve_gcd_kp<256>(h, a, W, ldw, H, ldh, out); return;
+            default: throw Error{NMFB200_ENOTSUP, "k > 256 is not covered by the tensor-core engine"};
+        }
+    }
     switch (pick_kp(a.k)) {
         case 64: tc_solve_kp<64>(h, a, W, ldw, H, ldh, out); break;
         case 128: tc_solve_kp<128>(h, a, W, ldw, H, ldh, out); break;

@@ -95,3 +95,24 @@ def test_tc_session_reuse_and_auto_engine(NMF, oracle):
             assert r.info["engine"] == "tc"
             outs.append((Wg, Hg, float(r.objvalue)))
         assert (outs[0][0] == outs[1][0]).all() and (outs[0][1] == outs[1][1]).all()  # deterministic
+
+
+@pytest.mark.parametrize("p,n,k,iters,lam", [(512, 384, 16, 6, 0.0), (700, 900, 100, 4, 0.0), (384, 512, 200, 3, 1e-3)])
+def test_tc_greedycd_vs_oracle(NMF, oracle, p, n, k, iters, lam):
+    """GreedyCD with tensor-core gradients (bf16 X / factor operands).  Coordinate choices are discrete, so W/H
+    trajectories are not comparable element-wise; the bar is the objective (north-star 1e-4 is for MU; here the
+    gradient carries ~1e-4 relative noise per entry, stated bar 2e-3) plus the invariants the reference tests."""
+    X, W0, H0 = _problem(NMF, p, n, k, seed=p + k)
+    Wg, Hg, Wo, Ho = W0.copy(order="F"), H0.copy(order="F"), W0.copy(order="F"), H0.copy(order="F")
+    kw = dict(maxiter=iters, tol=1e-9, lambda_w=lam, lambda_h=lam)
+    r = NMF.solve(NMF.GreedyCD(np.float32, **kw), X, Wg, Hg, engine="tc")
+    ro = oracle.solve(oracle.GreedyCD(np.float32, **kw), X, Wo, Ho)
+    assert r.info["engine"] == "tc" and r.niters == ro.niters == iters
+    assert (Wg >= 0).all() and (Hg >= 0).all() and np.isfinite(Wg).all() and np.isfinite(Hg).all()
+    eo = abs(float(r.objvalue) - float(ro.objvalue)) / float(ro.objvalue)
+    obj0 = 0.5 * float(np.sum((X - W0 @ H0) ** 2))
+    print(f"tc greedycd p={p} n={n} k={k}: obj={float(r.objvalue):.6g} oracle={float(ro.objvalue):.6g} rel={eo:.2e} "
+          f"updates={r.info['coordinate_updates']}/{ro.coordinate_updates}")
+    assert float(r.objvalue) < obj0
+    assert eo <= 2e-3
+    assert abs(r.info["coordinate_updates"] - ro.coordinate_updates) <= 0.05 * ro.coordinate_updates
