@@ -124,8 +124,10 @@ __global__ void __launch_bounds__(GCD_WARPS * 32) gcd_rows_kernel(T* __restrict_
         gcd_sd(f[bi], g[bi], pdiag[bi], sq, dq);
         __syncwarp();
         if (lane == 0) fnew[bi] = add_rn(fnew[bi], sq);
-        const T* prow = P + (int64_t)bi;  // P[qi, r] = P[qi + r*k]
-        for (int r = lane; r < k; r += 32) g[r] = add_rn(g[r], mul_rn(sq, prow[(int64_t)r * k]));
+        // P[qi, r] (greedycd.jl:151).  P = O'O is symmetric (bit-for-bit: both triangles are the same sums of the same
+        // products), so read the contiguous column P[:, qi] = P[r + qi*k] -- coalesced across the warp.
+        const T* prow = P + (int64_t)bi * k;
+        for (int r = lane; r < k; r += 32) g[r] = add_rn(g[r], mul_rn(sq, prow[r]));
         __syncwarp();
         ++nupd;
     }
@@ -137,6 +139,61 @@ __global__ void __launch_bounds__(GCD_WARPS * 32) gcd_rows_kernel(T* __restrict_
     if (lane == 0 && nupd) atomicAdd(updates, nupd);
 }
 
+
+// Register-resident variant for the tensor-core engine: factor F and gradient G are row-major [R][KP], KP is a
+// compile-time multiple of 32, every lane owns KP/32 components of its row in registers; the only memory traffic
+// of a coordinate step is the contiguous row P[q, :] (KP/32 independent, coalesced loads per lane).
+// 1/(eps + P[r,r]) is hoisted out of the loop (multiply instead of divide: the gradients are bf16-derived anyway).
+template <int KP>
+__global__ void __launch_bounds__(256) gcd_rows_tc_kernel(float* __restrict__ F, const float* __restrict__ G, const float* __restrict__ P,
+                                                          int R, const float* __restrict__ p_init_ptr,
+                                                          unsigned long long* __restrict__ updates) {
+    constexpr int NE = KP / 32;
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= R) return;
+    float g[NE], f[NE], fn[NE], prr[NE], rinv[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        const int r = lane + 32 * e;
+        g[e] = G[row * KP + r];
+        f[e] = F[row * KP + r];
+        fn[e] = 0.f;
+        prr[e] = P[(size_t)r * KP + r];
+        rinv[e] = 1.0f / (1.1920928955078125e-07f + prr[e]);
+    }
+    const float thresh = 0.001f * p_init_ptr[0];       // nu * p_init (greedycd.jl:140,145)
+    unsigned long long nupd = 0;
+    for (int it = 0; it < KP * KP; ++it) {             // at most k^2 coordinate steps per row (:144)
+        float bv = -INFINITY, bs = 0.f;
+        int bi = 0x7fffffff;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {                 // S, D and the first arg-max (:153-158)
+            const float t = f[e] - g[e] * rinv[e];
+            const float s = fmaxf(t, 0.f) - f[e];
+            const float d = -g[e] * s - 0.5f * prr[e] * s * s;
+            if (d > bv) { bv = d; bi = lane + 32 * e; bs = s; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; bs = os; }
+        }
+        if (bv < thresh) break;                        // :145-147
+        const float* prow = P + (size_t)bi * KP;       // symmetric P: row q contiguous
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            if (bi == lane + 32 * e) fn[e] += bs;      // Wnew[i,q] += S[i,q] (:149)
+            g[e] += bs * __ldg(prow + lane + 32 * e);  // G[i,:] += S[i,q] P[q,:] (:151)
+        }
+        ++nupd;
+    }
+#pragma unroll
+    for (int e = 0; e < NE; ++e) F[row * KP + lane + 32 * e] = fmaxf(f[e] + fn[e], 0.f);  // :164-165
+    if (lane == 0 && nupd) atomicAdd(updates, nupd);
+}
 
 }  // namespace
 }  // namespace nmfb200

@@ -1252,14 +1252,11 @@ void tc_solve_gcd_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t l
     s.launch_gram(H, true);  // P = HH' for the first W-step (greedycd.jl:117)
     NMF_CUDA(cudaEventRecord(e1, st));
 
-    const size_t rows_smem = ((size_t)KP + (size_t)GCD_WARPS * 3 * KP) * sizeof(float);
-    NMF_CUDA(cudaFuncSetAttribute(gcd_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem));
     auto half_step = [&](Factor& F, Factor& O, const bf16* Xs, int Kdim, float lambda, int tiles128) {
         NMF_CUDA(cudaMemcpyAsync(prev, F.m, (size_t)F.R * KP * sizeof(float), cudaMemcpyDeviceToDevice, st));
         s.launch_update(3, F, O, Xs, Kdim, lambda, 0.f, G, bmax);                                  // G = F P - X O (+lambda), per-CTA max D
         max_partials_kernel<float><<<1, 256, 0, st>>>(bmax, F.tiles, bmax + maxtiles);            // p_init (:132-137)
-        gcd_rows_kernel<float><<<(unsigned)ceil_div(F.R, GCD_WARPS), GCD_WARPS * 32, rows_smem, st>>>(
-            F.m, KP, 1, G, O.P, F.R, KP, bmax + maxtiles, d_updates);                             // :139-165
+        gcd_rows_tc_kernel<KP><<<(unsigned)ceil_div(F.R, 8), 256, 0, st>>>(F.m, G, O.P, F.R, bmax + maxtiles, d_updates);  // :139-165
         gcd_repack_kernel<<<tiles128, 256, 0, st>>>(F.m, prev, F.R, KP, F.hi, F.lo, F.bT, F.ldT, F.conv);
         h->launches += 3;
         s.launch_gram(F, true);                                                                   // Gram of the updated factor
