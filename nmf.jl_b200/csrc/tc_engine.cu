@@ -64,6 +64,7 @@ struct UpdateParams {
     float* num_io;      // MODE 1: raw numerators out, MODE 2: reduced numerators in ([R][KP])
     float* conv_part;   // [tiles][2][KP]   (MODE 3: [tiles] per-CTA max of D, greedycd.jl:132-137)
     const float* Pfull; // MODE 3: fp32 Gram of the other factor ([KP][KP]); its diagonal enters S and D
+    const float* colsum; // MODE 4: column sums of the other factor (sW / sH of multupd.jl:176,188), [KP]
     const TcState* state;
     int64_t ldT;
     int R, Kdim;
@@ -109,6 +110,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(bf16 lo, bf16 hi) {
 
 // MODE 0: fused (single GPU).  MODE 1: numerators only -> num_io (row-sharded H-step, before the
 // all-reduce).  MODE 2: no main loop, numerators read from num_io (after the all-reduce).
+// MODE 4: MultUpdate(:div): Xs is the quotient panel Q, no denominator MMAs; F <- F * Num / (colsum + lambda) (multupd.jl:177-179,189-191).
 // MODE 3: GreedyCD gradient: G = F*P - Xs*O (+lambda) -> num_io, per-CTA max_r D[i,r] -> conv_part (greedycd.jl:117-137).
 template <int KP, int MODE>
 __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const __grid_constant__ UpdateParams prm) {
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
     const int r0 = blockIdx.x * tile_rows;
     const uint32_t a_bytes = (uint32_t)tile_rows * 128u;
     const int nkb = (MODE == 2) ? 0 : (prm.Kdim + 63) / 64;
-    constexpr int NPRE = (MODE == 1) ? 0 : 3 * C::NSLAB;
+    constexpr int NPRE = (MODE == 1 || MODE == 4) ? 0 : 3 * C::NSLAB;
     const int total = NPRE + nkb;
     // De-correlate the CTAs: they all stream panels whose bases differ by exact multiples of the tile size
     // (4 MiB at config 2) in lockstep.  CTA c starts its k-loop at a hashed block and wraps around (the sum
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&prm.tmA);
         prefetch_tmap(&prm.tmB);
-        if (MODE != 1) {
+        if (MODE != 1 && MODE != 4) {
             prefetch_tmap(&prm.tmFhi);
             prefetch_tmap(&prm.tmFlo);
             prefetch_tmap(&prm.tmPhi);
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
             uint32_t num_u[32], den_u[32];
             float f[32];
             if (MODE != 2) tmem_ld32(t_lane + c0, num_u);
-            if (MODE != 1) tmem_ld32(t_lane + KP + c0, den_u);
+            if (MODE != 1 && MODE != 4) tmem_ld32(t_lane + KP + c0, den_u);
             if (MODE == 1) {
                 tmem_ld_wait();
                 if (valid) {
@@ -291,10 +293,15 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                 float fn[2];
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    float num = __uint_as_float(num_u[j + e]) - lambda;
-                    num = (num > 0.f || num != num) ? num : 0.f;             // Julia max(0, x): NaN propagates
-                    float den = __uint_as_float(den_u[j + e]) + delta;
-                    float v = f[j + e] * __fdiv_rn(num, den);                // multupd.jl:102 / :113
+                    float v;
+                    if (MODE == 4) {
+                        v = f[j + e] * __fdiv_rn(__uint_as_float(num_u[j + e]), prm.colsum[c0 + j + e] + lambda);  // multupd.jl:178 / :190
+                    } else {
+                        float num = __uint_as_float(num_u[j + e]) - lambda;
+                        num = (num > 0.f || num != num) ? num : 0.f;         // Julia max(0, x): NaN propagates
+                        float den = __uint_as_float(den_u[j + e]) + delta;
+                        v = f[j + e] * __fdiv_rn(num, den);                  // multupd.jl:102 / :113
+                    }
                     fn[e] = valid ? v : 0.f;
                     float dd = fn[e] - f[j + e], ss = fn[e] + f[j + e];      // common.jl:98-99 / :103-104
                     d2[j + e] = dd * dd;
@@ -795,6 +802,7 @@ struct Factor {  // one factor in row-factor layout
     float* P = nullptr;  // Gram of THIS factor (k x k), fp32 accumulator
     bf16 *Phi = nullptr, *Plo = nullptr;
     float* conv = nullptr;
+    float* colsum = nullptr;  // [KP] column sums (MultUpdate :div)
     int tiles = 0;
     int tile_rows = 128;
 };
@@ -822,6 +830,7 @@ struct TcSolver {
         prm.num_io = num_io;
         prm.conv_part = conv_override ? conv_override : F.conv;
         prm.Pfull = O.P;
+        prm.colsum = O.colsum;
         prm.state = state;
         prm.R = F.R; prm.Kdim = Kdim; prm.lambda = lambda; prm.delta = delta;
         const int smem = UpdCfg<KP>::SMEM_BYTES;
@@ -830,7 +839,8 @@ struct TcSolver {
         if (mode == 0) mu_update_kernel<KP, 0><<<F.tiles, UpdCfg<KP>::THREADS, smem, st>>>(prm);
         else if (mode == 1) mu_update_kernel<KP, 1><<<F.tiles, UpdCfg<KP>::THREADS, smem, st>>>(prm);
         else if (mode == 2) mu_update_kernel<KP, 2><<<F.tiles, UpdCfg<KP>::THREADS, smem, st>>>(prm);
-        else mu_update_kernel<KP, 3><<<F.tiles, UpdCfg<KP>::THREADS, smem, st>>>(prm);
+        else if (mode == 3) mu_update_kernel<KP, 3><<<F.tiles, UpdCfg<KP>::THREADS, smem, st>>>(prm);
+        else mu_update_kernel<KP, 4><<<F.tiles, UpdCfg<KP>::THREADS, smem, st>>>(prm);
         if (timed) NMF_CUDA(cudaEventRecord(h->next_event(), st));
         h->launches += 1;
     }
@@ -856,6 +866,7 @@ struct TcSolver {
         NMF_CUDA(cudaFuncSetAttribute(mu_update_kernel<KP, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, UpdCfg<KP>::SMEM_BYTES));
         NMF_CUDA(cudaFuncSetAttribute(mu_update_kernel<KP, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, UpdCfg<KP>::SMEM_BYTES));
         NMF_CUDA(cudaFuncSetAttribute(mu_update_kernel<KP, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, UpdCfg<KP>::SMEM_BYTES));
+        NMF_CUDA(cudaFuncSetAttribute(mu_update_kernel<KP, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, UpdCfg<KP>::SMEM_BYTES));
         NMF_CUDA(cudaFuncSetAttribute(gram_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, GramCfg<KP>::SMEM_BYTES));
         done = true;
     }
@@ -967,6 +978,7 @@ Factor alloc_factor(nmfb200_handle* h, const char* tag, int R, int KP) {
     f.Phi = h->buf_t<bf16>("tc." + t + ".Phi", (size_t)KP * KP);
     f.Plo = h->buf_t<bf16>("tc." + t + ".Plo", (size_t)KP * KP);
     f.conv = h->buf_t<float>("tc." + t + ".conv", (size_t)f.tiles * 2 * KP);
+    f.colsum = h->buf_t<float>("tc." + t + ".colsum", (size_t)KP);
     return f;
 }
 
@@ -1165,6 +1177,341 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
     h->report_marks(iters);
 }
 
+// ---- MultUpdate(:div) on the tensor-core engine (multupd.jl:150-193) ----------------------------------------------
+// Quotient kernel: Q = X ./ (W H + delta) (multupd.jl:172-174 / :184-186) produced tile by tile, never via a
+// p x n fp32 intermediate: a CTA owns 128 rows of the "row factor" Rf (resident in smem), walks the k-blocks of
+// its tile-contiguous X panel, and per 128 x 64 tile
+//   MMA warp:      D[128 x 64] = Rf_tile * Cf_tile'   (tcgen05, K = KP, bf16 operands) into one of two TMEM buffers,
+//   8 epilogue warps: Q = X_tile / (D + delta) from the X tile in smem (swizzled) -> bf16 Q tile in smem ->
+//                  TMA store into the Q panel (same tile-contiguous layout as the X panel),
+// so the update kernel (MODE 4) can stream Q exactly like it streams X.  HBM traffic: read X (2 B) + write Q (2 B).
+struct QuotParams {
+    CUtensorMap tmX;   // X panel  bf16 tile-contiguous [tiles*nkb*128][64], box 64 x 128 (load)
+    CUtensorMap tmQ;   // Q panel, same geometry (store)
+    CUtensorMap tmR;   // row factor hi  bf16 [R][KP],  box 64 x 128
+    CUtensorMap tmC;   // col factor hi  bf16 [C][KP],  box 64 x 64
+    const TcState* state;
+    int nkb;           // k-blocks per tile = ceil(C / 64)
+    float delta;
+};
+
+template <int KP>
+struct QuotCfg {
+    static constexpr int NSLAB = KP / 64;
+    static constexpr int RF_BYTES = NSLAB * 128 * 128;   // resident row-factor tile
+    static constexpr int C_BYTES = NSLAB * 64 * 128;     // one stage of the column factor: 64 rows x KP
+    static constexpr int X_BYTES = 128 * 128;
+    static constexpr int SC = 4, SX = 4, SO = 2;
+    static constexpr int OFF_C = RF_BYTES;
+    static constexpr int OFF_X = OFF_C + SC * C_BYTES;
+    static constexpr int OFF_O = OFF_X + SX * X_BYTES;
+    static constexpr int OFF_BAR = OFF_O + SO * X_BYTES;
+    static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
+    static constexpr int THREADS = 320;                  // w0 producer, w1 MMA, w2..w9 epilogue
+    static constexpr int TMEM_COLS = 128;                // 2 buffers x 64 fp32 columns
+};
+
+template <int KP>
+__global__ void __launch_bounds__(QuotCfg<KP>::THREADS, 1) div_quot_kernel(const __grid_constant__ QuotParams prm) {
+    using C = QuotCfg<KP>;
+    if (prm.state->converged) return;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* fullC = (uint64_t*)(smem + C::OFF_BAR);
+    uint64_t* emptyC = fullC + C::SC;
+    uint64_t* fullX = emptyC + C::SC;
+    uint64_t* emptyX = fullX + C::SX;
+    uint64_t* tfull = emptyX + C::SX;    // [2]
+    uint64_t* tempty = tfull + 2;        // [2]
+    uint64_t* rf_full = tempty + 2;
+    uint32_t* tmem_slot = (uint32_t*)(rf_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = prm.nkb;
+    const int row0 = blockIdx.x * 128;
+    const int prow0 = blockIdx.x * nkb * 128;  // first panel row of this tile
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&prm.tmX);
+        prefetch_tmap(&prm.tmQ);
+        prefetch_tmap(&prm.tmR);
+        prefetch_tmap(&prm.tmC);
+        for (int s = 0; s < C::SC; ++s) { mbar_init(&fullC[s], 1); mbar_init(&emptyC[s], 1); }
+        for (int s = 0; s < C::SX; ++s) { mbar_init(&fullX[s], 1); mbar_init(&emptyX[s], 8); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8); }
+        mbar_init(rf_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer: resident row-factor tile, then per k-block the X tile and the column-factor rows =====
+        if (lane == 0) {
+            mbar_arrive_expect_tx(rf_full, C::RF_BYTES);
+            for (int sl = 0; sl < C::NSLAB; ++sl) tma_load_2d(smem + sl * 128 * 128, &prm.tmR, rf_full, 64 * sl, row0);
+            int sc = 0, sx = 0;
+            uint32_t phc = 0, phx = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(&emptyX[sx], phx ^ 1u);
+                mbar_arrive_expect_tx(&fullX[sx], C::X_BYTES);
+                tma_load_2d(smem + C::OFF_X + sx * C::X_BYTES, &prm.tmX, &fullX[sx], 0, prow0 + kb * 128);
+                mbar_wait(&emptyC[sc], phc ^ 1u);
+                mbar_arrive_expect_tx(&fullC[sc], C::C_BYTES);
+                for (int sl = 0; sl < C::NSLAB; ++sl)
+                    tma_load_2d(smem + C::OFF_C + sc * C::C_BYTES + sl * 64 * 128, &prm.tmC, &fullC[sc], 64 * sl, 64 * kb);
+                if (++sx == C::SX) { sx = 0; phx ^= 1u; }
+                if (++sc == C::SC) { sc = 0; phc ^= 1u; }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer: D = Rf * Cf' for every k-block, alternating TMEM buffers =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(FMT_BF16, 128, 64);
+            mbar_wait(rf_full, 0);
+            int sc = 0;
+            uint32_t phc = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int b = kb & 1;
+                mbar_wait(&tempty[b], (((uint32_t)kb >> 1) & 1u) ^ 1u);  // epilogue has drained this TMEM buffer
+                mbar_wait(&fullC[sc], phc);
+                tc_fence_after();
+                const uint32_t cbase = smem_u32(smem + C::OFF_C + sc * C::C_BYTES);
+#pragma unroll
+                for (int sl = 0; sl < C::NSLAB; ++sl) {
+                    const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(smem + sl * 128 * 128));
+                    const uint64_t bdesc = make_kmajor_sw128_desc(cbase + sl * 64 * 128);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_bf16(tmem_base + b * 64, adesc + 2 * kk, bdesc + 2 * kk, idesc, (sl > 0 || kk > 0) ? 1u : 0u);
+                }
+                umma_commit(&emptyC[sc]);
+                umma_commit(&tfull[b]);
+                if (++sc == C::SC) { sc = 0; phc ^= 1u; }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue: 8 warps; warp e handles TMEM lane quarter (warp % 4) and column half e / 4 =====
+        const int e = warp - 2;
+        const int q = warp & 3, hf = e >> 2;
+        const int r = 32 * q + lane;                 // row inside the tile
+        const float delta = prm.delta;
+        int sx = 0;
+        uint32_t phx = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int b = kb & 1, ob = kb & 1;
+            mbar_wait(&tfull[b], ((uint32_t)kb >> 1) & 1u);
+            tc_fence_after();
+            uint32_t d[32];
+            tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + b * 64 + 32 * hf, d);
+            mbar_wait(&fullX[sx], phx);
+            const uint8_t* xt = smem + C::OFF_X + sx * C::X_BYTES + r * 128;
+            uint4 xv[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) xv[c] = *(const uint4*)(xt + (((4 * hf + c) ^ (r & 7)) << 4));
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&tempty[b]);             // TMEM buffer b may be overwritten
+                mbar_arrive(&emptyX[sx]);            // X stage may be refilled
+            }
+            uint4 qv[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint32_t xin[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w};
+                uint32_t qo[4];
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const float x0 = __uint_as_float(xin[w] << 16), x1 = __uint_as_float(xin[w] & 0xffff0000u);
+                    const float d0 = __uint_as_float(d[8 * c + 2 * w]) + delta, d1 = __uint_as_float(d[8 * c + 2 * w + 1]) + delta;
+                    qo[w] = pack_bf16x2(__float2bfloat16_rn(__fdividef(x0, d0)), __float2bfloat16_rn(__fdividef(x1, d1)));
+                }
+                qv[c] = make_uint4(qo[0], qo[1], qo[2], qo[3]);
+            }
+            // output staging buffer ob: its previous TMA store (two k-blocks ago) must have finished reading smem
+            if (threadIdx.x == 64) tma_store_wait_read<1>();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            uint8_t* ot = smem + C::OFF_O + ob * C::X_BYTES + r * 128;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) *(uint4*)(ot + (((4 * hf + c) ^ (r & 7)) << 4)) = qv[c];
+            fence_proxy_async();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (threadIdx.x == 64) {
+                tma_store_2d(&prm.tmQ, smem + C::OFF_O + ob * C::X_BYTES, 0, prow0 + kb * 128);
+                tma_store_commit();
+            }
+            if (++sx == C::SX) { sx = 0; phx ^= 1u; }
+        }
+        if (threadIdx.x == 64) tma_store_wait_all<0>();
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// column sums of a row-factor [R][KP] (sW = sum(W,1), sH = sum(H,2): multupd.jl:176,188): per 128-row tile, then reduced
+__global__ void __launch_bounds__(256) colsum_tiles_kernel(const float* __restrict__ Fm, int R, int KP, float* __restrict__ part,
+                                                           const TcState* st) {
+    if (st->converged) return;
+    __shared__ float red[256];
+    const int groups = 256 / KP > 0 ? 256 / KP : 1;
+    const int g = threadIdx.x / KP, a = threadIdx.x % KP;
+    const int r0 = blockIdx.x * 128;
+    float s = 0.f;
+    if (g < groups)
+        for (int rr = g; rr < 128 && r0 + rr < R; rr += groups) s += Fm[(size_t)(r0 + rr) * KP + a];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x < KP) {
+        for (int gg = 1; gg < groups; ++gg) s += red[gg * KP + a];
+        part[(size_t)blockIdx.x * KP + a] = s;
+    }
+}
+__global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restrict__ part, int tiles, int KP, float* __restrict__ out,
+                                                            const TcState* st) {
+    if (st->converged) return;
+    __shared__ double red[8][32];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * 32 + lane;
+    double s = 0.0;
+    for (int t = w; t < tiles; t += 8) s += (double)__ldcg(part + (size_t)t * KP + c);
+    red[w][lane] = s;
+    __syncthreads();
+    if (w == 0) {
+        double tot = red[0][lane];
+        for (int i = 1; i < 8; ++i) tot += red[i][lane];
+        out[c] = (float)tot;
+    }
+}
+
+template <int KP>
+void tc_solve_div_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, float* Hc, int64_t ldh, nmfb200_result* out) {
+    TcSolver<KP>::set_attrs();
+    static bool quot_attr = false;
+    if (!quot_attr) {
+        NMF_CUDA(cudaFuncSetAttribute(div_quot_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, QuotCfg<KP>::SMEM_BYTES));
+        quot_attr = true;
+    }
+    cudaStream_t st = h->stream;
+    const int64_t p = h->p, n = h->n, k = a.k;
+    const float delta = std::sqrt(std::numeric_limits<float>::epsilon());
+    const float lw = std::max((float)a.lambda_w, delta), lh = std::max((float)a.lambda_h, delta);  // multupd.jl:37-40
+    const float tol = (float)a.tol;
+    cudaEvent_t e0, e1, e2;
+    NMF_CUDA(cudaEventCreate(&e0));
+    NMF_CUDA(cudaEventCreate(&e1));
+    NMF_CUDA(cudaEventCreate(&e2));
+    bf16 *Xr = nullptr, *Xc = nullptr;
+    build_x_caches(h, &Xr, &Xc);
+    NMF_CUDA(cudaEventRecord(e0, st));
+
+    Factor W = alloc_factor(h, "W", (int)p, KP), H = alloc_factor(h, "H", (int)n, KP);
+    NMF_REQUIRE(W.tile_rows == 128 && H.tile_rows == 128, NMFB200_ENOTSUP, "tensor-core :div path needs 128-row tiles");
+    TcState* state = (TcState*)h->buf("tc.state", sizeof(TcState));
+    double* acc = h->buf_t<double>("tc.acc", 4 * KP);
+    const int nkbH = (int)ceil_div(p, 64), nkbW = (int)ceil_div(n, 64);
+    const size_t q_elems = std::max((size_t)H.tiles * nkbH, (size_t)W.tiles * nkbW) * 128 * 64;
+    bf16* Q = h->buf_t<bf16>("tc.Q", q_elems);
+    float* cs_part = h->buf_t<float>("tc.colsum_part", (size_t)std::max(W.tiles, H.tiles) * KP);
+    NMF_CUDA(cudaMemsetAsync(state, 0, sizeof(TcState), st));
+    NMF_CUDA(cudaMemsetAsync(W.bT, 0, (size_t)W.rowsT * W.ldT * sizeof(bf16), st));
+    NMF_CUDA(cudaMemsetAsync(H.bT, 0, (size_t)H.rowsT * H.ldT * sizeof(bf16), st));
+
+    float *Wd = Wc, *Hd = Hc;
+    int64_t ldwd = ldw, ldhd = ldh;
+    if (!a.on_device) {
+        Wd = h->buf_t<float>("tc.Wstage", (size_t)p * k);
+        Hd = h->buf_t<float>("tc.Hstage", (size_t)k * n);
+        ldwd = p;
+        ldhd = k;
+        NMF_CUDA(cudaMemcpy2DAsync(Wd, p * sizeof(float), Wc, ldw * sizeof(float), p * sizeof(float), k, cudaMemcpyHostToDevice, st));
+        NMF_CUDA(cudaMemcpy2DAsync(Hd, k * sizeof(float), Hc, ldh * sizeof(float), k * sizeof(float), n, cudaMemcpyHostToDevice, st));
+    }
+    pack_factor_kernel<<<ew_grid(p * KP), 256, 0, st>>>(Wd, 1, ldwd, (int)p, (int)k, KP, W.m, W.hi, W.lo, W.bT, W.ldT);
+    pack_factor_kernel<<<ew_grid(n * KP), 256, 0, st>>>(Hd, ldhd, 1, (int)n, (int)k, KP, H.m, H.hi, H.lo, H.bT, H.ldT);
+    h->launches += 2;
+    TcSolver<KP> s{h, st, state};
+    NMF_CUDA(cudaEventRecord(e1, st));
+
+    // one half-step: Q = X ./ (Rf Cf' + delta) over Rf's panel, column sums of Cf, then Rf <- Rf .* (Q Cf) ./ (colsum + lambda)
+    auto half_step = [&](Factor& Rf, Factor& Cf, const bf16* Xs, int nkb, int Kdim, float lambda) {
+        QuotParams qp;
+        const uint64_t prow = (uint64_t)Rf.tiles * nkb * 128;
+        qp.tmX = make_tmap_bf16(Xs, 64, prow, 64, 128);
+        qp.tmQ = make_tmap_bf16(Q, 64, prow, 64, 128);
+        qp.tmR = make_tmap_bf16(Rf.hi, KP, (uint64_t)Rf.R, KP, 128);
+        qp.tmC = make_tmap_bf16(Cf.hi, KP, (uint64_t)Cf.R, KP, 64);
+        qp.state = state;
+        qp.nkb = nkb;
+        qp.delta = delta;
+        div_quot_kernel<KP><<<Rf.tiles, QuotCfg<KP>::THREADS, QuotCfg<KP>::SMEM_BYTES, st>>>(qp);
+        colsum_tiles_kernel<<<Cf.tiles, 256, 0, st>>>(Cf.m, Cf.R, KP, cs_part, state);
+        colsum_reduce_kernel<<<KP / 32, 256, 0, st>>>(cs_part, Cf.tiles, KP, Cf.colsum, state);
+        h->launches += 3;
+        s.launch_update(4, Rf, Cf, Q, Kdim, lambda, delta, nullptr);
+    };
+
+    h->ev_used = 0;
+    int64_t enq = 0;
+    bool converged = false;
+    int64_t iters = 0;
+    float devmax = 0.f;
+    TcState hs;
+    while (enq < a.maxiter) {
+        int64_t batch = std::min<int64_t>(h->check_every, a.maxiter - enq);
+        for (int64_t i = 0; i < batch; ++i) {
+            if (a.update_H) half_step(H, W, Xr, nkbH, (int)p, lh);   // multupd.jl:171-181
+            half_step(W, H, Xc, nkbW, (int)n, lw);                    // :183-192
+            conv_reduce_kernel<<<4 * (KP / 32), 256, 0, st>>>(W.conv, W.tiles, H.conv, H.tiles, KP, (int)k, a.update_H, acc, tol, state, 1, nullptr);
+            h->launches += 1;
+        }
+        enq += batch;
+        NMF_CUDA(cudaGetLastError());
+        NMF_CUDA(cudaMemcpyAsync(&hs, state, sizeof(TcState), cudaMemcpyDeviceToHost, st));
+        NMF_CUDA(cudaStreamSynchronize(st));
+        iters = hs.iters;
+        devmax = hs.devmax;
+        if (hs.converged) {
+            converged = true;
+            break;
+        }
+    }
+    NMF_CUDA(cudaEventRecord(e2, st));
+    unpack_factor_kernel<<<ew_grid(p * k), 256, 0, st>>>(W.m, (int)p, (int)k, KP, Wd, 1, ldwd);
+    unpack_factor_kernel<<<ew_grid(n * k), 256, 0, st>>>(H.m, (int)n, (int)k, KP, Hd, ldhd, 1);
+    h->launches += 2;
+    double objv = simt_objective_f32(h, 1, Wd, ldwd, Hd, ldhd, k, 0.0, 0.0);  // gkldiv (multupd.jl:148)
+    if (!a.on_device) {
+        NMF_CUDA(cudaMemcpy2DAsync(Wc, ldw * sizeof(float), Wd, p * sizeof(float), p * sizeof(float), k, cudaMemcpyDeviceToHost, st));
+        NMF_CUDA(cudaMemcpy2DAsync(Hc, ldh * sizeof(float), Hd, k * sizeof(float), k * sizeof(float), n, cudaMemcpyDeviceToHost, st));
+    }
+    NMF_CUDA(cudaStreamSynchronize(st));
+    float ms_up = 0, ms_loop = 0;
+    cudaEventElapsedTime(&ms_up, e0, e1);
+    cudaEventElapsedTime(&ms_loop, e1, e2);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaEventDestroy(e2);
+    out->niters = iters;
+    out->converged = converged ? 1 : 0;
+    out->engine = 1;
+    out->objvalue = objv;
+    out->last_dev = devmax;
+    out->solve_ms = ms_loop;
+    out->upload_ms = ms_up;
+    out->coordinate_updates = 0;
+    out->kernel_launches = h->launches;
+    out->hot_kernel_ms = h->drain_event_pairs(&out->hot_kernel_launches);
+}
+
 // ---- GreedyCD on the tensor-core engine (greedycd.jl:94-178) ---------------------------------------------------
 // After the per-row coordinate kernel has rewritten the fp32 master, rebuild the bf16 operand forms of the factor
 // and the stop_condition partial sums against the copy taken before the half-step.  One block per 128-row tile.
@@ -1311,7 +1658,10 @@ void tc_solve_gcd_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t l
 }  // namespace
 
 bool tc_supported(const nmfb200_handle* h, const SolveArgs& a) {
-    if (a.alg == 1) return false;         // MultUpdate(:div): exact engine (fused quotient chain = next)
+    if (a.alg == 1) {                     // MultUpdate(:div): quotient kernel + update kernel; k <= 128, single GPU
+        if (h->comm != nullptr || a.k > 128 || h->p < 128 || h->n < 128) return false;
+        if (h->engine_opt != 2 && h->p * h->n < ((int64_t)1 << 20)) return false;
+    }
     if (a.alg == 2) {                     // GreedyCD: bf16 gradients; single GPU; auto-selected for large problems only
         if (h->comm != nullptr) return false;
         if (h->engine_opt != 2 && h->p * h->n < ((int64_t)1 << 24)) return false;
@@ -1323,6 +1673,13 @@ bool tc_supported(const nmfb200_handle* h, const SolveArgs& a) {
 }
 
 void tc_solve(nmfb200_handle* h, const SolveArgs& a, float* W, int64_t ldw, float* H, int64_t ldh, nmfb200_result* out) {
+    if (a.alg == 1) {
+        switch (pick_kp(a.k)) {
+            case 64: tc_solve_div_kp<64>(h, a, W, ldw, H, ldh, out); return;
+            case 128: tc_solve_div_kp<128>(h, a, W, ldw, H, ldh, out); return;
+            default: throw Error{NMFB200_ENOTSUP, "k > 128 is not covered by the tensor-core :div path"};
+        }
+    }
     if (a.alg == 2) {
         switch (pick_kp(a.k)) {
             case 64: tc_solve_gcd_kp<64>(h, a, W, ldw, H, ldh, out); return;

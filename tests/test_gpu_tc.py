@@ -118,3 +118,32 @@ def test_tc_greedycd_vs_oracle(NMF, oracle, p, n, k, iters, lam):
     # the number of coordinate steps is NOT comparable: once D falls to the bf16 noise floor of the gradient
     # (~P s^2/2 with s ~ 1e-4) the nu*p_init threshold (greedycd.jl:145) is crossed by noise
     assert r.info["coordinate_updates"] > 0
+
+
+@pytest.mark.parametrize("p,n,k,iters", [
+    (512, 640, 32, 10),     # KP = 64
+    (384, 257, 20, 10),     # ragged tails in both directions
+    (1024, 1280, 64, 8),
+    (640, 512, 100, 6),     # KP = 128
+])
+def test_tc_multdiv_vs_oracle(NMF, oracle, p, n, k, iters):
+    """MultUpdate(:div) on the tensor-core engine: Q = X ./ (WH + delta) is formed tile-wise (bf16 WH operands, Q
+    rounded to bf16) and streamed into the second GEMM.  Bars: objvalue 1e-4 relative, W/H relative Frobenius 5e-3."""
+    X, W0, H0 = _problem(NMF, p, n, k, seed=3 * p + k)
+    Wg, Hg, Wo, Ho = W0.copy(order="F"), H0.copy(order="F"), W0.copy(order="F"), H0.copy(order="F")
+    r = NMF.solve(NMF.MultUpdate(np.float32, obj="div", maxiter=iters, tol=1e-9), X, Wg, Hg, engine="tc")
+    ro = oracle.solve(oracle.MultUpdate(np.float32, obj="div", maxiter=iters, tol=1e-9), X, Wo, Ho)
+    assert r.info["engine"] == "tc" and r.niters == ro.niters == iters
+    assert np.isfinite(Wg).all() and np.isfinite(Hg).all() and (Wg >= 0).all() and (Hg >= 0).all()
+    ew, eh = _relerr(Wg, Wo), _relerr(Hg, Ho)
+    eo = abs(float(r.objvalue) - float(ro.objvalue)) / float(ro.objvalue)
+    print(f"tc multdiv p={p} n={n} k={k} it={iters}: errW={ew:.2e} errH={eh:.2e} errObj={eo:.2e}")
+    assert ew <= 5e-3 and eh <= 5e-3
+    assert eo <= 1e-4
+
+
+def test_tc_multdiv_update_H_false(NMF):
+    X, W0, H0 = _problem(NMF, 256, 384, 16, seed=17)
+    Wg, Hg = W0.copy(order="F"), H0.copy(order="F")
+    r = NMF.solve(NMF.MultUpdate(np.float32, obj="div", maxiter=4, tol=1e-9, update_H=False), X, Wg, Hg, engine="tc")
+    assert r.info["engine"] == "tc" and (Hg == H0).all() and (Wg != W0).any()
