@@ -700,10 +700,10 @@ __global__ void __launch_bounds__(256) post_allreduce_kernel(double* __restrict_
 // (a) contraction index contiguous in the source (sc == 1): direct
 __global__ void cvt_tiled_direct_kernel(const float* __restrict__ X, int64_t sr, int R, int Kdim, int TR, int nkb,
                                         bf16* __restrict__ dst) {
-    const int64_t row_slot = blockIdx.y;            // tile * TR + row-in-tile
+    const int64_t row_slot = blockIdx.x;            // tile * TR + row-in-tile (x: up to 2^31-1 rows)
     const int tile = (int)(row_slot / TR), rr = (int)(row_slot % TR);
     const int64_t r = (int64_t)tile * TR + rr;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nkb * 64; c += gridDim.x * blockDim.x) {
+    for (int c = blockIdx.y * blockDim.x + threadIdx.x; c < nkb * 64; c += gridDim.y * blockDim.x) {
         float v = (r < R && c < Kdim) ? X[r * sr + c] : 0.f;
         const int kb = c >> 6, cc = c & 63;
         dst[(((int64_t)tile * nkb + kb) * TR + rr) * 64 + cc] = __float2bfloat16_rn(v);
@@ -993,7 +993,7 @@ void build_x_caches(nmfb200_handle* h, bf16** Xr_out, bf16** Xc_out) {
     bf16* Xc_ = h->buf_t<bf16>("tc.Xc", (size_t)tilesW * nkbW * trW * 64);  // rows = rows of X, contraction over n
     if (h->tc_x_epoch != h->x_epoch || h->tc_x_trH != trH || h->tc_x_trW != trW) {
         const float* X = (const float*)h->dX;
-        cvt_tiled_direct_kernel<<<dim3((unsigned)std::min<int64_t>(ceil_div((int64_t)nkbH * 64, 256), 64), (unsigned)(tilesH * trH)), 256, 0, st>>>(
+        cvt_tiled_direct_kernel<<<dim3((unsigned)(tilesH * trH), (unsigned)std::min<int64_t>(ceil_div((int64_t)nkbH * 64, 256), 64)), 256, 0, st>>>(
             X, h->ldx, (int)n, (int)p, trH, nkbH, Xr_);
         NMF_REQUIRE(trW % 8 == 0, NMFB200_EINVAL, "tile rows must be a multiple of 8");
         // the transpose kernel walks 64 logical rows per block; cover the padded row range of the last tile too
@@ -1192,6 +1192,7 @@ struct QuotParams {
     CUtensorMap tmC;   // col factor hi  bf16 [C][KP],  box 64 x 64
     const TcState* state;
     int nkb;           // k-blocks per tile = ceil(C / 64)
+    int kchunk;        // k-blocks handled by one CTA: blockIdx.y walks [y*kchunk, min(nkb, (y+1)*kchunk))
     float delta;
 };
 
@@ -1226,9 +1227,10 @@ __global__ void __launch_bounds__(QuotCfg<KP>::THREADS, 1) div_quot_kernel(const
     uint64_t* rf_full = tempty + 2;
     uint32_t* tmem_slot = (uint32_t*)(rf_full + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nkb = prm.nkb;
+    const int kb0 = blockIdx.y * prm.kchunk;                      // quotient tiles are independent: split k freely
+    const int nkb = min(prm.nkb, kb0 + prm.kchunk) - kb0;         // k-blocks of this CTA
     const int row0 = blockIdx.x * 128;
-    const int prow0 = blockIdx.x * nkb * 128;  // first panel row of this tile
+    const int prow0 = (blockIdx.x * prm.nkb + kb0) * 128;         // first panel row of this CTA's first tile
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&prm.tmX);
@@ -1261,7 +1263,7 @@ __global__ void __launch_bounds__(QuotCfg<KP>::THREADS, 1) div_quot_kernel(const
                 mbar_wait(&emptyC[sc], phc ^ 1u);
                 mbar_arrive_expect_tx(&fullC[sc], C::C_BYTES);
                 for (int sl = 0; sl < C::NSLAB; ++sl)
-                    tma_load_2d(smem + C::OFF_C + sc * C::C_BYTES + sl * 64 * 128, &prm.tmC, &fullC[sc], 64 * sl, 64 * kb);
+                    tma_load_2d(smem + C::OFF_C + sc * C::C_BYTES + sl * 64 * 128, &prm.tmC, &fullC[sc], 64 * sl, 64 * (kb0 + kb));
                 if (++sx == C::SX) { sx = 0; phx ^= 1u; }
                 if (++sc == C::SC) { sc = 0; phc ^= 1u; }
             }
@@ -1451,8 +1453,12 @@ void tc_solve_div_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t l
         qp.tmC = make_tmap_bf16(Cf.hi, KP, (uint64_t)Cf.R, KP, 64);
         qp.state = state;
         qp.nkb = nkb;
+        // enough CTAs for ~2 waves, at least 32 k-blocks each
+        int ksplit = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(296, Rf.tiles), nkb / 32));
+        qp.kchunk = (int)ceil_div(nkb, ksplit);
+        ksplit = (int)ceil_div(nkb, qp.kchunk);
         qp.delta = delta;
-        div_quot_kernel<KP><<<Rf.tiles, QuotCfg<KP>::THREADS, QuotCfg<KP>::SMEM_BYTES, st>>>(qp);
+        div_quot_kernel<KP><<<dim3(Rf.tiles, ksplit), QuotCfg<KP>::THREADS, QuotCfg<KP>::SMEM_BYTES, st>>>(qp);
         colsum_tiles_kernel<<<Cf.tiles, 256, 0, st>>>(Cf.m, Cf.R, KP, cs_part, state);
         colsum_reduce_kernel<<<KP / 32, 256, 0, st>>>(cs_part, Cf.tiles, KP, Cf.colsum, state);
         h->launches += 3;
