@@ -57,6 +57,9 @@ struct UpdateParams {
     CUtensorMap tmFlo;  // F lo
     CUtensorMap tmPhi;  // P hi bf16 [KP][KP]      box 64 x KP
     CUtensorMap tmPlo;  // P lo
+    CUtensorMap tmF32;  // F fp32 [R][KP]          box 32 x tile_rows (staged epilogue store)
+    CUtensorMap tmT;    // F^T bf16 [KP][R]        box 64 x KP        (staged epilogue store of the transposed copy)
+    float* gram_part;   // staged epilogue: [tiles][KP][KP] fp32 Gram contribution of each tile (nullptr = skip)
     float* F;           // [R][KP] fp32 master, updated in place
     bf16* Fhi;          // [R][KP]
     bf16* Flo;          // [R][KP]
@@ -87,7 +90,7 @@ struct UpdCfg {
     static constexpr int SMEM_BYTES = RING_BYTES + CONV_BYTES + 1024 + 1024;  // ring | barriers (1 KB) | conv scratch | align slack
     static constexpr int TMEM_COLS = 2 * KP;
     static constexpr int NSLAB = KP / 64;
-    static constexpr int THREADS = 192;  // w0 TMA producer, w1 MMA issuer, w2-5 epilogue
+    static constexpr int THREADS = 320;  // w0 TMA producer, w1 MMA issuer, w2-9 epilogue (lane quarter = warp % 4, column half = (warp-2)/4)
 };
 
 // sum v[j] over the 32 lanes of the warp; afterwards v[0] on lane l holds the total of column l
@@ -122,8 +125,16 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
     uint64_t* full_bar = (uint64_t*)(smem + C::RING_BYTES);
     uint64_t* empty_bar = full_bar + C::STAGES;
     uint64_t* tmem_full = empty_bar + C::STAGES;
-    uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+    uint64_t* gram_bar = tmem_full + 1;
+    uint32_t* tmem_slot = (uint32_t*)(gram_bar + 1);
     float* conv_s = (float*)(smem + C::RING_BYTES + 1024);  // [4 warps][2][KP]
+    // Staged epilogue (KP <= 128, modes that write the factor): the ring is idle once the accumulators are complete
+    constexpr bool STAGED = (KP <= 128) && (MODE == 0 || MODE == 2 || MODE == 4);
+    uint8_t* const SF = smem;                              // fp32 tile:  KP/32 boxes of 128 rows x 128 B
+    uint8_t* const SH = SF + (KP / 32) * 16384;            // bf16 hi:    KP/64 boxes
+    uint8_t* const SL = SH + (KP / 64) * 16384;            // bf16 lo
+    uint8_t* const ST = SL + (KP / 64) * 16384;            // transposed: 2 boxes of KP rows x 128 B (64 tile rows each)
+    static_assert(!STAGED || (KP / 32 + 2 * (KP / 64)) * 16384 + 2 * KP * 128 <= C::RING_BYTES, "staging does not fit in the ring");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile_rows = prm.tile_rows;
@@ -151,6 +162,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(tmem_full, 1);
+        mbar_init(gram_bar, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
@@ -212,9 +224,10 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
             umma_commit(tmem_full);
         }
         __syncwarp();
-    } else if (warp >= 2 && warp <= 5) {
-        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+    } else if (warp >= 2) {
+        // ===== epilogue: warps 2..9, TMEM lane quarter = warp % 4, columns [chalf*KP/2, (chalf+1)*KP/2) =====
         const int q = warp & 3;
+        const int chalf = (warp - 2) >> 2;
         const int row = r0 + 32 * q + lane;
         const bool valid = (32 * q + lane) < tile_rows && row < prm.R;
         const uint32_t t_lane = tmem_base + ((uint32_t)(32 * q) << 16);
@@ -224,11 +237,11 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
         const float lambda = prm.lambda, delta = prm.delta;
         float gcd_rowmax = -1.0f;
         if (MODE == 3) {  // diagonal of P into shared memory (conv scratch is free in this mode)
-            for (int i = threadIdx.x - 64; i < KP; i += 128) conv_s[i] = prm.Pfull[(size_t)i * KP + i];
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int i = threadIdx.x - 64; i < KP; i += 256) conv_s[i] = prm.Pfull[(size_t)i * KP + i];
+            asm volatile("bar.sync 1, 256;" ::: "memory");
         }
 #pragma unroll 1
-        for (int c0 = 0; c0 < KP; c0 += 32) {
+        for (int c0 = chalf * (KP / 2); c0 < (chalf + 1) * (KP / 2); c0 += 32) {
             uint32_t num_u[32], den_u[32];
             float f[32];
             if (MODE != 2) tmem_ld32(t_lane + c0, num_u);
@@ -295,12 +308,12 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                 for (int e = 0; e < 2; ++e) {
                     float v;
                     if (MODE == 4) {
-                        v = f[j + e] * __fdiv_rn(__uint_as_float(num_u[j + e]), prm.colsum[c0 + j + e] + lambda);  // multupd.jl:178 / :190
+                        v = f[j + e] * __fdividef(__uint_as_float(num_u[j + e]), prm.colsum[c0 + j + e] + lambda);  // multupd.jl:178 / :190
                     } else {
                         float num = __uint_as_float(num_u[j + e]) - lambda;
                         num = (num > 0.f || num != num) ? num : 0.f;         // Julia max(0, x): NaN propagates
                         float den = __uint_as_float(den_u[j + e]) + delta;
-                        v = f[j + e] * __fdiv_rn(num, den);                  // multupd.jl:102 / :113
+                        v = f[j + e] * __fdividef(num, den);                 // multupd.jl:102 / :113 (2-ulp divide; operands are bf16-derived)
                     }
                     fn[e] = valid ? v : 0.f;
                     float dd = fn[e] - f[j + e], ss = fn[e] + f[j + e];      // common.jl:98-99 / :103-104
@@ -314,7 +327,30 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                 hi_p[j / 2] = pack_bf16x2(h0, h1);
                 lo_p[j / 2] = pack_bf16x2(l0, l1);
             }
-            if (valid) {
+            if constexpr (STAGED) {
+                // stage the four forms of the new tile in the (idle) ring, in the swizzled images the TMA stores expect
+                const int rr = 32 * q + lane;
+                uint8_t* sf = SF + (c0 >> 5) * 16384 + rr * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *(float4*)(sf + ((j ^ (rr & 7)) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                uint8_t* sh = SH + (c0 >> 6) * 16384 + rr * 128;
+                uint8_t* sl = SL + (c0 >> 6) * 16384 + rr * 128;
+                const int cb = (c0 & 63) >> 3;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    *(uint4*)(sh + (((cb + j) ^ (rr & 7)) << 4)) = make_uint4(hi_p[4 * j], hi_p[4 * j + 1], hi_p[4 * j + 2], hi_p[4 * j + 3]);
+                    *(uint4*)(sl + (((cb + j) ^ (rr & 7)) << 4)) = make_uint4(lo_p[4 * j], lo_p[4 * j + 1], lo_p[4 * j + 2], lo_p[4 * j + 3]);
+                }
+                uint8_t* st = ST + (rr >> 6) * (KP * 128) + ((rr & 7) << 1);
+                const int rch = (rr & 63) >> 3;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int a = c0 + j;
+                    const uint32_t pk = hi_p[j / 2];
+                    *(unsigned short*)(st + a * 128 + ((rch ^ (a & 7)) << 4)) = (unsigned short)((j & 1) ? (pk >> 16) : (pk & 0xffffu));
+                }
+            } else if (valid) {
                 float4* dst = (float4*)(prm.F + (size_t)row * KP + c0);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
@@ -341,17 +377,71 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
         if (MODE == 3) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) gcd_rowmax = fmaxf(gcd_rowmax, __shfl_xor_sync(0xffffffffu, gcd_rowmax, o));
-            asm volatile("bar.sync 1, 128;" ::: "memory");   // everybody is done reading the diagonal
-            if (lane == 0) conv_s[q] = gcd_rowmax;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (threadIdx.x == 64) prm.conv_part[blockIdx.x] = fmaxf(fmaxf(conv_s[0], conv_s[1]), fmaxf(conv_s[2], conv_s[3]));
+            asm volatile("bar.sync 1, 256;" ::: "memory");   // everybody is done reading the diagonal
+            if (lane == 0) conv_s[warp - 2] = gcd_rowmax;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (threadIdx.x == 64) {
+                float m = conv_s[0];
+                for (int i = 1; i < 8; ++i) m = fmaxf(m, conv_s[i]);
+                prm.conv_part[blockIdx.x] = m;
+            }
         } else if (MODE != 1) {
-            // combine the four lane quarters: named barrier over the 128 epilogue threads
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            const int t = threadIdx.x - 64;  // 0..127
-            for (int i = t; i < 2 * KP; i += 128) {
+            if constexpr (STAGED) {
+                fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA / tensor-core (async) proxy
+                tc_fence_before();     // our TMEM reads are complete (the Gram below reuses the Num columns)
+            }
+            // combine the four lane quarters: named barrier over the 256 epilogue threads
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if constexpr (STAGED) {
+                if (threadIdx.x == 64) {
+#pragma unroll
+                    for (int b = 0; b < KP / 32; ++b) tma_store_2d(&prm.tmF32, SF + b * 16384, 32 * b, r0);
+#pragma unroll
+                    for (int b = 0; b < KP / 64; ++b) {
+                        tma_store_2d(&prm.tmFhi, SH + b * 16384, 64 * b, r0);
+                        tma_store_2d(&prm.tmFlo, SL + b * 16384, 64 * b, r0);
+                    }
+                    tma_store_2d(&prm.tmT, ST, r0, 0);
+                    if (tile_rows > 64) tma_store_2d(&prm.tmT, ST + KP * 128, r0 + 64, 0);
+                    tma_store_commit();
+                    if (prm.gram_part != nullptr) {  // Gram contribution of this tile: T T' (K = 128 rows), into the Num columns
+                        tc_fence_after();
+                        constexpr uint32_t gdesc_i = make_idesc(FMT_BF16, 128, KP);
+#pragma unroll
+                        for (int hb = 0; hb < 2; ++hb) {
+                            const uint64_t td = make_kmajor_sw128_desc(smem_u32(ST + hb * KP * 128));
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) umma_bf16(tmem_base, td + 2 * kk, td + 2 * kk, gdesc_i, (hb > 0 || kk > 0) ? 1u : 0u);
+                        }
+                        umma_commit(gram_bar);
+                    }
+                }
+            }
+            const int t = threadIdx.x - 64;  // 0..255
+            for (int i = t; i < 2 * KP; i += 256) {
                 float s = conv_s[i] + conv_s[2 * KP + i] + conv_s[4 * KP + i] + conv_s[6 * KP + i];
                 prm.conv_part[(size_t)blockIdx.x * 2 * KP + i] = s;
+            }
+            if constexpr (STAGED) {
+                if (prm.gram_part != nullptr) {
+                    mbar_wait(gram_bar, 0);
+                    tc_fence_after();
+                    const int a = 32 * q + lane;
+                    float* gp = prm.gram_part + ((size_t)blockIdx.x * KP + a) * KP;
+#pragma unroll 1
+                    for (int c0 = chalf * (KP / 2); c0 < (chalf + 1) * (KP / 2); c0 += 32) {
+                        uint32_t v[32];
+                        tmem_ld32(t_lane + c0, v);
+                        tmem_ld_wait();
+                        if (a < KP) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                ((float4*)(gp + c0))[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                        }
+                    }
+                }
+                if (threadIdx.x == 64) tma_store_wait_all<0>();  // smem must stay valid until the bulk stores have drained
             }
         }
         tc_fence_before();
@@ -789,6 +879,20 @@ CUtensorMap make_tmap_bf16(const void* ptr, uint64_t inner, uint64_t rows, uint6
     return m;
 }
 
+// fp32 matrix [rows][inner] with row pitch ld (elements); box = 32 (128 B) x box_rows, SWIZZLE_128B
+CUtensorMap make_tmap_f32(const void* ptr, uint64_t inner, uint64_t rows, uint64_t ld, uint32_t box_rows) {
+    CUtensorMap m;
+    cuuint64_t dims[2] = {inner, rows};
+    cuuint64_t strides[1] = {ld * sizeof(float)};
+    cuuint32_t box[2] = {32, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    NMF_REQUIRE(r == CUDA_SUCCESS, NMFB200_ECUDA, "cuTensorMapEncodeTiled(f32) failed with code " + std::to_string((int)r));
+    return m;
+}
+
 inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 inline int pick_kp(int64_t k) { return k <= 64 ? 64 : (k <= 128 ? 128 : (k <= 256 ? 256 : 0)); }
 inline int ew_grid(int64_t len) { return (int)std::min<int64_t>(ceil_div(len, 256), 148 * 16); }
@@ -813,9 +917,16 @@ struct TcSolver {
     cudaStream_t st;
     TcState* state;
 
+    // gram: -1 = no Gram of the updated factor wanted; 0 / 1 = wanted, without / with the bf16 hi-lo split;
+    // gram_dst = where the fp32 Gram goes (default F.P).  KP <= 128: the update kernel's staged epilogue produces the
+    // per-tile contributions itself (only a reduce launch follows); KP = 256: separate gram_kernel pass.
     void launch_update(int mode, const Factor& F, const Factor& O, const bf16* Xs, int Kdim, float lambda, float delta,
-                       float* num_io, float* conv_override = nullptr) {
+                       float* num_io, float* conv_override = nullptr, int gram = -1, float* gram_dst = nullptr) {
         UpdateParams prm;
+        const bool fused_gram = gram >= 0 && KP <= 128 && (mode == 0 || mode == 2);
+        prm.gram_part = fused_gram ? h->buf_t<float>("tc.gram_part", (size_t)std::max(F.tiles, 1) * KP * KP) : nullptr;
+        prm.tmF32 = make_tmap_f32(F.m, KP, (uint64_t)F.R, KP, (uint32_t)F.tile_rows);
+        prm.tmT = make_tmap_bf16(F.bT, (uint64_t)F.R, (uint64_t)F.rowsT, (uint64_t)F.ldT, KP);
         prm.tile_rows = F.tile_rows;
         prm.debug = h->tc_debug;
         prm.rotate = (h->tc_debug & 4) ? 1 : 0;  // measured: lockstep CTAs share each B tile in L2; rotation costs ~4%
@@ -843,6 +954,13 @@ struct TcSolver {
         else mu_update_kernel<KP, 4><<<F.tiles, UpdCfg<KP>::THREADS, smem, st>>>(prm);
         if (timed) NMF_CUDA(cudaEventRecord(h->next_event(), st));
         h->launches += 1;
+        if (fused_gram) {
+            gram_reduce_kernel<<<(4 * KP * KP + 255) / 256, 256, 0, st>>>(prm.gram_part, F.tiles, KP * KP, gram_dst ? gram_dst : F.P, F.Phi,
+                                                                           F.Plo, gram, state);
+            h->launches += 1;
+        } else if (gram >= 0) {
+            launch_gram(F, gram != 0, gram_dst);
+        }
     }
 
     void launch_gram(const Factor& F, bool split, float* P_dst = nullptr) {
@@ -1085,7 +1203,7 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
             h->mark("start");
             if (a.update_H) {
                 if (!multi) {
-                    s.launch_update(0, H, W, Xr, (int)p, lh, delta, nullptr);  // H-step: rows of H' against W
+                    s.launch_update(0, H, W, Xr, (int)p, lh, delta, nullptr, nullptr, 1);  // H-step (+ tile Grams of the new H)
                     h->mark("updH");
                 } else {
                     s.launch_update(1, H, W, Xr, (int)p, lh, delta, packed);  // partial numerators of this shard
@@ -1106,10 +1224,9 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
                     h->launches += 1;
                     pending = false;
                     h->mark("post");
-                    s.launch_update(2, H, W, Xr, (int)p, lh, delta, packed);   // ratio with the reduced numerators
+                    s.launch_update(2, H, W, Xr, (int)p, lh, delta, packed, nullptr, 1);   // ratio with the reduced numerators
                     h->mark("mode2");
                 }
-                s.launch_gram(H, true);
                 h->mark("gramH");
             }
             if (pending) {  // update_H = false: no packed exchange to ride on
@@ -1118,10 +1235,9 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
                 post_allreduce_kernel<<<1, 256, 0, st>>>(acc, ws_small, 1, KP, (int)k, tol, state, nullptr, nullptr, nullptr, xnone, 0u);
                 h->launches += 1;
             }
-            s.launch_update(0, W, H, Xc, (int)n, lw, delta, nullptr);          // W-step (local rows)
+            // W-step (local rows) + W'W for the next H-step (partial per rank when sharded; not needed if H is fixed)
+            s.launch_update(0, W, H, Xc, (int)n, lw, delta, nullptr, nullptr, (a.update_H || !multi) ? (multi ? 0 : 1) : -1, packed_P);
             h->mark("updW");
-            if (a.update_H || !multi) s.launch_gram(W, !multi, packed_P);
-            h->mark("gramW");
             conv_reduce_kernel<<<4 * (KP / 32), 256, 0, st>>>(W.conv, W.tiles, H.conv, H.tiles, KP, (int)k, a.update_H, acc, tol, state,
                                                               multi ? 0 : 1, packed_ws);
             h->launches += 1;
