@@ -755,6 +755,91 @@ __global__ void __launch_bounds__(256) conv_reduce_kernel(const float* __restric
     conv_decide(acc, KP, k, tol, st, devs, &fail);
 }
 
+// One launch for the two small reductions that follow the W-step: blocks [0, gram_blocks) reduce the per-tile Gram
+// contributions (gram_reduce_kernel's work), the remaining 4*KP/32 blocks reduce the stop_condition partial sums and the
+// last of them decides (conv_reduce_kernel's work).
+__device__ __forceinline__ void gram_reduce_body(const float* __restrict__ part, int nparts, int nelem, float* __restrict__ P,
+                                                 bf16* __restrict__ Phi, bf16* __restrict__ Plo, int do_split, int block) {
+    const int t = block * blockDim.x + threadIdx.x;
+    const int sub = t & 3;
+    const int i = t >> 2;
+    float acc = 0.f;
+    if (i < nelem) {
+        int g = sub;
+        for (; g + 28 < nparts; g += 32) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(part + (size_t)(g + 4 * u) * nelem + i);
+            acc += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+        }
+        for (; g < nparts; g += 4) acc += __ldcg(part + (size_t)g * nelem + i);
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (i < nelem && sub == 0) {
+        P[i] = acc;
+        if (do_split) {
+            bf16 hi = __float2bfloat16_rn(acc);
+            Phi[i] = hi;
+            Plo[i] = __float2bfloat16_rn(acc - __bfloat162float(hi));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) gram_conv_reduce_kernel(const float* __restrict__ gpart, int nparts, int nelem, float* __restrict__ P,
+                                                               bf16* __restrict__ Phi, bf16* __restrict__ Plo, int do_split, int gram_blocks,
+                                                               const float* __restrict__ partW, int tilesW, const float* __restrict__ partH,
+                                                               int tilesH, int KP, int k, int update_H, double* __restrict__ acc, float tol,
+                                                               TcState* st, int do_decide, float* __restrict__ wsums_f32) {
+    if (st->converged) return;
+    if ((int)blockIdx.x < gram_blocks) {
+        gram_reduce_body(gpart, nparts, nelem, P, Phi, Plo, do_split, blockIdx.x);
+        return;
+    }
+    __shared__ double red[8][32];
+    __shared__ float devs[256];
+    __shared__ int fail, is_last;
+    const int cblock = blockIdx.x - gram_blocks, nconv = gridDim.x - gram_blocks;
+    const int cbs = KP / 32;
+    const int q = cblock / cbs, cb = cblock % cbs;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = cb * 32 + lane;
+    const float* part = (q < 2 ? partW : partH) + (size_t)(q & 1) * KP + c;
+    const int tiles = q < 2 ? tilesW : (update_H ? tilesH : 0);
+    double s = 0.0;
+    int t = w;
+    for (; t + 56 < tiles; t += 64) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcg(part + (size_t)(t + 8 * u) * 2 * KP);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += (double)v[u];
+    }
+    for (; t < tiles; t += 8) s += (double)__ldcg(part + (size_t)t * 2 * KP);
+    red[w][lane] = s;
+    __syncthreads();
+    if (w == 0) {
+        double tot = red[0][lane];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) tot += red[i][lane];
+        if (q >= 2 && !update_H) tot = (q == 2) ? 0.0 : 1.0;
+        acc[(size_t)q * KP + c] = tot;
+        if (wsums_f32 && q < 2) wsums_f32[(size_t)q * KP + c] = (float)tot;
+    }
+    if (!do_decide) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int prev = atomicAdd(&st->ticket, 1u);
+        is_last = (prev == (unsigned)nconv - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) st->ticket = 0u;
+    conv_decide(acc, KP, k, tol, st, devs, &fail);
+}
+
 // multi-GPU, after the packed all-reduce: block 0 finishes stop_condition of the PREVIOUS iteration (its W-side
 // sums travelled in the tail of the packed buffer; nothing of the current iteration has touched W or H yet),
 // the other blocks split the reduced Gram W'W into bf16 hi/lo.
@@ -916,6 +1001,9 @@ struct TcSolver {
     nmfb200_handle* h;
     cudaStream_t st;
     TcState* state;
+    bool defer_gram_reduce = false;  // the caller will run gram_conv_reduce_kernel itself
+    bool last_fused_gram = false;
+    float* last_gram_part = nullptr;
 
     // gram: -1 = no Gram of the updated factor wanted; 0 / 1 = wanted, without / with the bf16 hi-lo split;
     // gram_dst = where the fp32 Gram goes (default F.P).  KP <= 128: the update kernel's staged epilogue produces the
@@ -954,11 +1042,13 @@ struct TcSolver {
         else mu_update_kernel<KP, 4><<<F.tiles, UpdCfg<KP>::THREADS, smem, st>>>(prm);
         if (timed) NMF_CUDA(cudaEventRecord(h->next_event(), st));
         h->launches += 1;
-        if (fused_gram) {
+        last_fused_gram = fused_gram;
+        last_gram_part = prm.gram_part;
+        if (fused_gram && !defer_gram_reduce) {
             gram_reduce_kernel<<<(4 * KP * KP + 255) / 256, 256, 0, st>>>(prm.gram_part, F.tiles, KP * KP, gram_dst ? gram_dst : F.P, F.Phi,
                                                                            F.Plo, gram, state);
             h->launches += 1;
-        } else if (gram >= 0) {
+        } else if (gram >= 0 && !fused_gram) {
             launch_gram(F, gram != 0, gram_dst);
         }
     }
@@ -1236,10 +1326,16 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
                 h->launches += 1;
             }
             // W-step (local rows) + W'W for the next H-step (partial per rank when sharded; not needed if H is fixed)
-            s.launch_update(0, W, H, Xc, (int)n, lw, delta, nullptr, nullptr, (a.update_H || !multi) ? (multi ? 0 : 1) : -1, packed_P);
+            const int gramW = (a.update_H || !multi) ? (multi ? 0 : 1) : -1;
+            s.defer_gram_reduce = true;
+            s.launch_update(0, W, H, Xc, (int)n, lw, delta, nullptr, nullptr, gramW, packed_P);
+            s.defer_gram_reduce = false;
             h->mark("updW");
-            conv_reduce_kernel<<<4 * (KP / 32), 256, 0, st>>>(W.conv, W.tiles, H.conv, H.tiles, KP, (int)k, a.update_H, acc, tol, state,
-                                                              multi ? 0 : 1, packed_ws);
+            const int gram_blocks = (s.last_fused_gram && gramW >= 0) ? (4 * KP * KP + 255) / 256 : 0;
+            // one launch: Gram reduce (if produced by the staged epilogue) + stop_condition reduce / decision
+            gram_conv_reduce_kernel<<<gram_blocks + 4 * (KP / 32), 256, 0, st>>>(
+                s.last_gram_part, W.tiles, KP * KP, packed_P ? packed_P : W.P, W.Phi, W.Plo, gramW > 0 ? 1 : 0, gram_blocks, W.conv, W.tiles,
+                H.conv, H.tiles, KP, (int)k, a.update_H, acc, tol, state, multi ? 0 : 1, packed_ws);
             h->launches += 1;
             h->mark("conv");
         }

@@ -37,7 +37,7 @@ def test_tc_multmse_vs_oracle(NMF, oracle, p, n, k, iters):
     Wg, Hg, Wo, Ho = W0.copy(order="F"), H0.copy(order="F"), W0.copy(order="F"), H0.copy(order="F")
     r = NMF.solve(NMF.MultUpdate(np.float32, obj="mse", maxiter=iters, tol=1e-9), X, Wg, Hg, engine="tc")
     ro = oracle.solve(oracle.MultUpdate(np.float32, obj="mse", maxiter=iters, tol=1e-9), X, Wo, Ho)
-    assert r.info["engine"] == "tc" and r.info["kernel_launches"] >= 5 * iters
+    assert r.info["engine"] == "tc" and r.info["kernel_launches"] >= 4 * iters  # update_H, reduce, update_W, reduce+stop per iteration
     assert r.niters == ro.niters == iters and not r.converged
     assert np.isfinite(Wg).all() and np.isfinite(Hg).all() and (Wg >= 0).all() and (Hg >= 0).all()
     ew, eh = _relerr(Wg, Wo), _relerr(Hg, Ho)
