@@ -276,6 +276,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     # algorithmic bytes per launch: the bf16 X panel once + the factor read & written in fp32
     alg_bytes = rows * n * 2 + 2 * ((rows + n) / 2) * k * 4
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
+    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "update_kernel_traffic.json")) as f:
+            traffic = float(json.load(f)["dram_bytes_per_launch"])
+    except Exception:
+        pass
     flops_iter = 4.0 * rows * n * k + 4.0 * k * k * (rows + n)
     tflops = flops_iter * it_per_s / 1e12
 
@@ -294,7 +300,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(res.kernel_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "kernel": "mu_update_kernel<128,0>", "kernel_ms": kern_ms, "launches_timed": launches,
+                         "traffic": traffic, "traffic_source": "profiles/r1f_update_kernel_ncu_full.md (ncu --set full, same workload)",
+                         "kernel": "mu_update_kernel<128,0>", "kernel_ms": kern_ms, "launches_timed": launches,
                          "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                          "tensor_tflops_whole_iteration": tflops, "tensor_frac_of_sustained_bf16": tflops / tf_peak},
         }
