@@ -115,7 +115,7 @@ struct nmfb200_handle {
     int tc_debug = 0;      // diagnostics (see UpdateParams::debug)
     int tc_xchg = 1;       // multi-GPU exchange: 1 = fused peer-memory reduce-scatter/all-gather, 0 = ncclAllReduce
     nmfb200::Xchg xchg;
-    int tc_sa = 0, tc_sb = 0;  // ring depth overrides (experiments)
+    int tc_prefetch = 0;   // L2 prefetch distance of the X panel in k-blocks (0 = off)
     std::vector<cudaEvent_t> ev_pool;  // events for time_kernels
     size_t ev_used = 0;
     nmfb200_trace_fn trace = nullptr;

@@ -72,6 +72,7 @@ struct UpdateParams {
     int64_t ldT;
     int R, Kdim;
     int rotate;         // 1: CTA c walks the k-blocks starting at a hashed offset (wrap-around)
+    int prefetch;       // > 0: issue an L2 prefetch of the X tile `prefetch` k-blocks ahead of the ring
     int tile_rows;      // rows of F owned by one CTA (<= 128, multiple of 8); the TMA boxes of A / Fhi / Flo have this many rows
     int debug;          // diagnostics only: bit 0 = load the B operand for the first k-block only (WRONG results)
     float lambda, delta;
@@ -191,6 +192,11 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                     mbar_arrive_expect_tx(&full_bar[s], a_bytes + (skipB ? 0u : (uint32_t)C::B_BYTES));
                     tma_load_2d(dst, &prm.tmA, &full_bar[s], 0, arow0 + kb * tile_rows);  // tile-contiguous X
                     if (!skipB) tma_load_2d(dst + C::A_BYTES, &prm.tmB, &full_bar[s], 64 * kb, 0);
+                    if (prm.prefetch > 0 && (b - NPRE) + prm.prefetch < nkb) {
+                        int kp = kb + prm.prefetch;
+                        if (kp >= nkb) kp -= nkb;
+                        tma_prefetch_2d(&prm.tmA, 0, arow0 + kp * tile_rows);
+                    }
                     if (++kb == nkb) kb = 0;
                 }
                 dst += C::STAGE_BYTES;
@@ -1017,7 +1023,8 @@ struct TcSolver {
         prm.tmT = make_tmap_bf16(F.bT, (uint64_t)F.R, (uint64_t)F.rowsT, (uint64_t)F.ldT, KP);
         prm.tile_rows = F.tile_rows;
         prm.debug = h->tc_debug;
-        prm.rotate = (h->tc_debug & 4) ? 1 : 0;  // measured: lockstep CTAs share each B tile in L2; rotation costs ~4%
+        prm.rotate = (h->tc_debug & 4) ? 1 : 0;
+        prm.prefetch = h->tc_prefetch;  // measured: lockstep CTAs share each B tile in L2; rotation costs ~4%
         const uint64_t nkb = (uint64_t)ceil_div(Kdim, 64);
         prm.tmA = make_tmap_bf16(Xs, 64, (uint64_t)F.tiles * nkb * F.tile_rows, 64, (uint32_t)F.tile_rows);
         prm.tmB = make_tmap_bf16(O.bT, (uint64_t)Kdim, KP, (uint64_t)O.ldT, KP);
