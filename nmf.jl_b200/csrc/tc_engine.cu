@@ -1564,8 +1564,25 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
     float devmax = 0.f;
     TcState hs;
     const int post_blocks = 1 + (KP * KP + 255) / 256;
+    // verbose (common.jl:54-59, 76-82): objective before the loop and after every iteration, through the trace callback
+    double v_objv = std::numeric_limits<double>::quiet_NaN(), v_t0 = 0;
+    auto wall = []() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec + 1e-9 * ts.tv_nsec;
+    };
+    auto objective_now = [&]() {
+        double v = 0;
+        NMF_REQUIRE(tc_objective<KP>(h, 0, W, H, 0.0, 0.0, &v), NMFB200_ENOTSUP, "verbose on the tensor-core engine needs the tensor-core objective");
+        return v;
+    };
+    if (a.verbose) {
+        v_t0 = wall();
+        v_objv = objective_now();
+        if (h->trace) h->trace(h->trace_user, 0, 0.0, v_objv, NAN, NAN);
+    }
     while (enq < a.maxiter) {
-        int64_t batch = std::min<int64_t>(h->check_every, a.maxiter - enq);
+        int64_t batch = a.verbose ? 1 : std::min<int64_t>(h->check_every, a.maxiter - enq);
         for (int64_t i = 0; i < batch; ++i) {
             bool pending = multi && i > 0;  // the previous iteration of this batch still awaits its decision
             h->mark("start");
@@ -1629,6 +1646,11 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
         NMF_CUDA(cudaStreamSynchronize(st));
         iters = hs.iters;
         devmax = hs.devmax;
+        if (a.verbose) {
+            const double pre = v_objv;
+            v_objv = objective_now();
+            if (h->trace) h->trace(h->trace_user, iters, wall() - v_t0, v_objv, v_objv - pre, (double)devmax);
+        }
         if (hs.converged) {
             converged = true;
             break;
@@ -1642,8 +1664,8 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
     h->launches += 2;
     NMF_CUDA(cudaGetLastError());
     // objective 0.5*||X - WH||^2 (multupd.jl:81): exact fp32 GEMM + fp64 reduction from the SIMT engine
-    double objv = 0;
-    if (!tc_objective<KP>(h, 0, W, H, 0.0, 0.0, &objv)) objv = simt_objective_f32(h, 0, Wd, ldwd, Hd, ldhd, k, 0.0, 0.0);
+    double objv = v_objv;
+    if (!a.verbose && !tc_objective<KP>(h, 0, W, H, 0.0, 0.0, &objv)) objv = simt_objective_f32(h, 0, Wd, ldwd, Hd, ldhd, k, 0.0, 0.0);
     if (!a.on_device) {
         NMF_CUDA(cudaMemcpy2DAsync(Wc, ldw * sizeof(float), Wd, p * sizeof(float), p * sizeof(float), k, cudaMemcpyDeviceToHost, st));
         NMF_CUDA(cudaMemcpy2DAsync(Hc, ldh * sizeof(float), Hd, k * sizeof(float), k * sizeof(float), n, cudaMemcpyDeviceToHost, st));
@@ -2166,7 +2188,7 @@ bool tc_supported(const nmfb200_handle* h, const SolveArgs& a) {
         if (h->comm != nullptr) return false;
         if (h->engine_opt != 2 && h->p * h->n < ((int64_t)1 << 24)) return false;
     }
-    if (a.verbose) return false;          // per-iteration objective: exact engine
+    if (a.verbose && (a.alg != 0 || h->n < 128 || h->p < 64 || (h->ldx % 4) != 0)) return false;  // per-iteration objective: MU-MSE only
     if (pick_kp(a.k) == 0) return false;
     if (h->p > (int64_t)INT32_MAX / 256 || h->n > (int64_t)INT32_MAX / 256) return false;
     return true;

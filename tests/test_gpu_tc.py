@@ -147,3 +147,24 @@ def test_tc_multdiv_update_H_false(NMF):
     Wg, Hg = W0.copy(order="F"), H0.copy(order="F")
     r = NMF.solve(NMF.MultUpdate(np.float32, obj="div", maxiter=4, tol=1e-9, update_H=False), X, Wg, Hg, engine="tc")
     assert r.info["engine"] == "tc" and (Hg == H0).all() and (Wg != W0).any()
+
+
+def test_tc_verbose_trace_matches_oracle_objective(NMF, oracle):
+    """verbose=true (common.jl:54-59, 76-82) on the tensor-core engine: objective before the loop and after every
+    iteration through the trace callback; the last line's objective is Result.objvalue."""
+    X, W0, H0 = _problem(NMF, 512, 384, 24, seed=19)
+    Wg, Hg, Wo, Ho = W0.copy(order="F"), H0.copy(order="F"), W0.copy(order="F"), H0.copy(order="F")
+    lines = []
+    with NMF.Session(engine="tc") as s:
+        s.set_X(X)
+        s.set_trace(lambda it, el, ob, ch, dv: lines.append((it, el, ob, ch, dv)))
+        r = s.solve(NMF.MultUpdate(np.float32, maxiter=6, tol=1e-9, verbose=True), Wg, Hg)
+    assert r.info["engine"] == "tc"
+    assert [l[0] for l in lines] == list(range(0, 7))
+    obj0 = 0.5 * float(np.sum((X.astype(np.float64) - W0.astype(np.float64) @ H0.astype(np.float64)) ** 2))
+    assert abs(lines[0][2] - obj0) <= 1e-4 * obj0 and np.isnan(lines[0][3]) and np.isnan(lines[0][4])
+    assert all(lines[i + 1][2] <= lines[i][2] * (1 + 1e-6) for i in range(6))      # MU-MSE is monotone
+    assert all(abs(lines[i + 1][3] - (lines[i + 1][2] - lines[i][2])) <= 1e-6 * obj0 for i in range(6))
+    assert lines[-1][2] == float(r.objvalue)
+    ro = oracle.solve(oracle.MultUpdate(np.float32, maxiter=6, tol=1e-9), X, Wo, Ho)
+    assert abs(float(r.objvalue) - float(ro.objvalue)) <= 1e-4 * float(ro.objvalue)
