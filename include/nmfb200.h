@@ -57,6 +57,8 @@ typedef struct nmfb200_result {
     int64_t kernel_launches;    /* number of library kernels launched by this call */
     double hot_kernel_ms;       /* option "time_kernels"=1: summed device time of the dominant kernel's launches */
     int64_t hot_kernel_launches;/*   ... and how many launches that sum covers (0 when the option is off) */
+    int64_t sub_iterations;     /* ALSPGrad only: projected-gradient sub-iterations summed over both factors (alspgrad.jl:114,270) */
+    double tolg_final;          /* ALSPGrad only: the updater's tolg after its x0.1 decays (alspgrad.jl:409-411,419-421) */
 } nmfb200_result;
 
 typedef struct nmfb200_handle nmfb200_handle;
@@ -104,7 +106,8 @@ int nmfb200_set_X_dev_f64(nmfb200_handle* h, const double* dX, int64_t p, int64_
  * Common arguments: W (p x k, ldw), H (k x n, ldh) initialised by the caller, updated in place.
  * `on_device` != 0: W and H are device pointers on this handle's GPU (no PCIe traffic).
  * maxiter/tol/lambda_w/lambda_h/update_H/verbose: the fields of the algorithm struct.  Validation
- * is the constructor's (EINVAL): maxiter > 1, tol > 0, lambda >= 0.  niters/converged/objvalue
+ * is the constructor's (EINVAL): maxiter > 1, tol > 0, lambda >= 0 for MultUpdate and GreedyCD; the
+ * ProjectedALS / CoordinateDescent / ALSPGrad constructors of the reference validate nothing.  niters/converged/objvalue
  * follow nmf_skeleton! (common.jl:45-89) and stop_condition (common.jl:92-111). */
 
 /* NMF.solve!(::MultUpdate{T} with obj=:mse, X, W, H)  -- multupd.jl:45-48, :83-116 */
@@ -128,6 +131,35 @@ int nmfb200_solve_greedycd_f32(nmfb200_handle* h, float* W, int64_t ldw, float* 
                                int verbose, int on_device, nmfb200_result* out);
 int nmfb200_solve_greedycd_f64(nmfb200_handle* h, double* W, int64_t ldw, double* H, int64_t ldh, int64_t k,
                                int64_t maxiter, double tol, double lambda_w, double lambda_h, int update_H,
+                               int verbose, int on_device, nmfb200_result* out);
+
+/* NMF.solve!(::ProjectedALS{T}, X, W, H)  -- projals.jl:37-39, :77-107.  lambda_w / lambda_h are the L2 weights
+ * (the constructor validates nothing: maxiter = 1 is accepted, projals.jl:26-34).  The k x k normal equations are
+ * solved on the GPU (Gauss-Jordan inverse of the SPD Gram in Float64, one CTA); a Gram that is not positive definite
+ * returns NMFB200_EINVAL (Julia: PosDefException from potrf!, utils.jl:68,78). */
+int nmfb200_solve_projals_f32(nmfb200_handle* h, float* W, int64_t ldw, float* H, int64_t ldh, int64_t k,
+                              int64_t maxiter, float tol, float lambda_w, float lambda_h, int update_H,
+                              int verbose, int on_device, nmfb200_result* out);
+int nmfb200_solve_projals_f64(nmfb200_handle* h, double* W, int64_t ldw, double* H, int64_t ldh, int64_t k,
+                              int64_t maxiter, double tol, double lambda_w, double lambda_h, int update_H,
+                              int verbose, int on_device, nmfb200_result* out);
+/* NMF.solve!(::CoordinateDescent{T}, X, W, H)  -- coorddesc.jl:49-51, :108-181.
+ * regularization: 0 :both, 1 :components, 2 :transformation, 3 :none (coorddesc.jl:65-71).
+ * shuffle != 0 draws one permutation of the components per half-step (coorddesc.jl:131-132) from a splitmix64 /
+ * Fisher-Yates generator seeded with `seed` (Julia's global RNG has no counterpart outside Julia). */
+int nmfb200_solve_cd_f32(nmfb200_handle* h, float* W, int64_t ldw, float* H, int64_t ldh, int64_t k,
+                         int64_t maxiter, float tol, float alpha, float l1ratio, int regularization, int shuffle,
+                         uint64_t seed, int update_H, int verbose, int on_device, nmfb200_result* out);
+int nmfb200_solve_cd_f64(nmfb200_handle* h, double* W, int64_t ldw, double* H, int64_t ldh, int64_t k,
+                         int64_t maxiter, double tol, double alpha, double l1ratio, int regularization, int shuffle,
+                         uint64_t seed, int update_H, int verbose, int on_device, nmfb200_result* out);
+/* NMF.solve!(::ALSPGrad{T}, X, W, H)  -- alspgrad.jl:381-383, :400-425 with the sub-solvers :86-191 / :242-347
+ * (traceiter = 20, beta = 0.2, sigma = 0.01 as hard-wired at alspgrad.jl:405-406,415-416). */
+int nmfb200_solve_alspgrad_f32(nmfb200_handle* h, float* W, int64_t ldw, float* H, int64_t ldh, int64_t k,
+                               int64_t maxiter, int64_t maxsubiter, float tol, float tolg, int update_H,
+                               int verbose, int on_device, nmfb200_result* out);
+int nmfb200_solve_alspgrad_f64(nmfb200_handle* h, double* W, int64_t ldw, double* H, int64_t ldh, int64_t k,
+                               int64_t maxiter, int64_t maxsubiter, double tol, double tolg, int update_H,
                                int verbose, int on_device, nmfb200_result* out);
 
 /* ---- multi-GPU: rows of X / W sharded over ranks, H replicated -----------

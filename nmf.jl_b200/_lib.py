@@ -25,6 +25,8 @@ class NmfResult(ctypes.Structure):
         ("kernel_launches", ctypes.c_int64),
         ("hot_kernel_ms", ctypes.c_double),
         ("hot_kernel_launches", ctypes.c_int64),
+        ("sub_iterations", ctypes.c_int64),
+        ("tolg_final", ctypes.c_double),
     ]
 
 
@@ -33,10 +35,19 @@ TRACE_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int64, ctypes.c_doub
 
 # name -> (restype, argtypes); kept in one table so tests can check it against the header
 _vp, _i, _i64, _f, _d, _cp = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double, ctypes.c_char_p
+_u64 = ctypes.c_uint64
 
 
 def _solve_sig(ct):
     return (_i, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, ct, ct, ct, _i, _i, _i, ctypes.POINTER(NmfResult)])
+
+
+def _solve_cd_sig(ct):
+    return (_i, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, ct, ct, ct, _i, _i, _u64, _i, _i, _i, ctypes.POINTER(NmfResult)])
+
+
+def _solve_alspgrad_sig(ct):
+    return (_i, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, ct, ct, _i, _i, _i, ctypes.POINTER(NmfResult)])
 
 
 SIGNATURES = {
@@ -58,6 +69,12 @@ SIGNATURES = {
     "nmfb200_solve_multdiv_f64": _solve_sig(_d),
     "nmfb200_solve_greedycd_f32": _solve_sig(_f),
     "nmfb200_solve_greedycd_f64": _solve_sig(_d),
+    "nmfb200_solve_projals_f32": _solve_sig(_f),
+    "nmfb200_solve_projals_f64": _solve_sig(_d),
+    "nmfb200_solve_cd_f32": _solve_cd_sig(_f),
+    "nmfb200_solve_cd_f64": _solve_cd_sig(_d),
+    "nmfb200_solve_alspgrad_f32": _solve_alspgrad_sig(_f),
+    "nmfb200_solve_alspgrad_f64": _solve_alspgrad_sig(_d),
     "nmfb200_comm_unique_id": (_i, [_vp]),
     "nmfb200_comm_init": (_i, [_vp, _i, _i, _vp]),
     "nmfb200_comm_destroy": (_i, [_vp]),

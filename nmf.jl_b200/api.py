@@ -8,9 +8,10 @@ Same names, argument meaning, defaults and error behaviour as the reference:
   MultUpdate        multupd.jl:9-43        solve_replicates   interf.jl:85-101
   GreedyCD          greedycd.jl:10-31      randinit           initialization.jl:4-17
   solve             multupd.jl:45 / greedycd.jl:33  (`NMF.solve!(alg, X, W, H)`)
-ProjectedALS / ALSPGrad / CoordinateDescent / SPA exist as option types (projals.jl:18-35,
-alspgrad.jl:352-373, coorddesc.jl:24-46, spa.jl:8-15) but are not on the accelerated path; solve()
-raises NotImplementedError for them rather than falling back to a CPU implementation.
+  ProjectedALS      projals.jl:18-39       CoordinateDescent  coorddesc.jl:24-51
+  ALSPGrad          alspgrad.jl:352-383
+SPA exists as an option type (spa.jl:8-15) but is not on the accelerated path; solve() raises
+NotImplementedError for it rather than falling back to a CPU implementation.
 
 Arrays: NumPy, shapes as in Julia (X p x n, W p x k, H k x n).  Column-major (Fortran-order) arrays
 are passed to the library without a copy and updated in place; other layouts are staged through a
@@ -132,7 +133,7 @@ class GreedyCD:
 
 
 class ProjectedALS:
-    """projals.jl:18-35 (no validation in the reference constructor).  Not accelerated yet."""
+    """projals.jl:18-35 (no validation in the reference constructor)."""
 
     def __init__(self, T=np.float64, *, maxiter=100, verbose=False, tol=None, update_H=True, lambda_w=None, lambda_h=None):
         T = np.dtype(T)
@@ -145,7 +146,7 @@ class ProjectedALS:
 
 
 class ALSPGrad:
-    """alspgrad.jl:352-373.  Not accelerated yet."""
+    """alspgrad.jl:352-373."""
 
     def __init__(self, T=np.float64, *, maxiter=100, maxsubiter=200, tol=None, tolg=None, update_H=True, verbose=False):
         T = np.dtype(T)
@@ -155,17 +156,23 @@ class ALSPGrad:
         self.update_H, self.verbose = bool(update_H), bool(verbose)
 
 
+_CD_REG = {"both": 0, "components": 1, "transformation": 2, "none": 3}
+
+
 class CoordinateDescent:
-    """coorddesc.jl:24-46.  Not accelerated yet."""
+    """coorddesc.jl:24-46.  `seed` feeds the library's permutation generator when shuffle=True (the reference draws
+    `randperm` from Julia's global RNG, coorddesc.jl:131-132)."""
 
     def __init__(self, T=np.float64, *, maxiter=100, verbose=False, tol=None, update_H=True, alpha=0.0, l1ratio=0.0,
-                 regularization="both", shuffle=False):
+                 regularization="both", shuffle=False, seed=0):
         T = np.dtype(T)
         self.T, self.maxiter, self.verbose = T, int(maxiter), bool(verbose)
         self.tol = T.type(np.cbrt(_eps(T)) if tol is None else tol)
         self.update_H = bool(update_H)
         self.alpha, self.l1ratio = T.type(alpha), T.type(l1ratio)
-        self.regularization, self.shuffle = regularization, bool(shuffle)
+        if regularization not in _CD_REG:
+            raise ArgumentError("regularization must be one of :both, :components, :transformation, :none")
+        self.regularization, self.shuffle, self.seed = regularization, bool(shuffle), int(seed)
 
 
 class SPA:
@@ -286,10 +293,15 @@ class Session:
             name = "multmse" if alg.obj == "mse" else "multdiv"
         elif isinstance(alg, GreedyCD):
             name = "greedycd"
-        elif isinstance(alg, (ProjectedALS, ALSPGrad, CoordinateDescent, SPA)):
+        elif isinstance(alg, ProjectedALS):
+            name = "projals"
+        elif isinstance(alg, CoordinateDescent):
+            name = "cd"
+        elif isinstance(alg, ALSPGrad):
+            name = "alspgrad"
+        elif isinstance(alg, SPA):
             raise NotImplementedError(
-                f"{type(alg).__name__} is not on the accelerated path (SURVEY.md section 8f); "
-                "this package has no CPU fallback")
+                "SPA is not on the accelerated path (SURVEY.md section 8f); this package has no CPU fallback")
         else:
             raise TypeError(f"unknown algorithm type {type(alg).__name__}")
         if self.shape is None:
@@ -305,15 +317,31 @@ class Session:
         Hf = H if H.flags.f_contiguous else np.asfortranarray(H)
         if alg.verbose and self._trace_cb is None:
             self.set_trace(_print_trace)
-        r = self.solve_raw(name, T, Wf.ctypes.data, p, Hf.ctypes.data, k, k, alg.maxiter, alg.tol, alg.lambda_w,
-                           alg.lambda_h, alg.update_H, alg.verbose, False)
+        if name == "cd":
+            res = _lib.NmfResult()
+            fn = getattr(self._lib, f"nmfb200_solve_cd_{_SFX[T]}")
+            self._check(fn(self._h, ctypes.c_void_p(Wf.ctypes.data), p, ctypes.c_void_p(Hf.ctypes.data), k, k, alg.maxiter,
+                           float(alg.tol), float(alg.alpha), float(alg.l1ratio), _CD_REG[alg.regularization], int(alg.shuffle),
+                           alg.seed & ((1 << 64) - 1), int(alg.update_H), int(alg.verbose), 0, ctypes.byref(res)))
+            r = res
+        elif name == "alspgrad":
+            res = _lib.NmfResult()
+            fn = getattr(self._lib, f"nmfb200_solve_alspgrad_{_SFX[T]}")
+            self._check(fn(self._h, ctypes.c_void_p(Wf.ctypes.data), p, ctypes.c_void_p(Hf.ctypes.data), k, k, alg.maxiter,
+                           alg.maxsubiter, float(alg.tol), float(alg.tolg), int(alg.update_H), int(alg.verbose), 0,
+                           ctypes.byref(res)))
+            r = res
+        else:
+            r = self.solve_raw(name, T, Wf.ctypes.data, p, Hf.ctypes.data, k, k, alg.maxiter, alg.tol, alg.lambda_w,
+                               alg.lambda_h, alg.update_H, alg.verbose, False)
         if Wf is not W:
             W[...] = Wf
         if Hf is not H:
             H[...] = Hf
         info = {"engine": "tc" if r.engine == 1 else "simt", "solve_ms": r.solve_ms, "upload_ms": r.upload_ms,
                 "last_dev": r.last_dev, "coordinate_updates": r.coordinate_updates, "kernel_launches": r.kernel_launches,
-                "hot_kernel_ms": r.hot_kernel_ms, "hot_kernel_launches": r.hot_kernel_launches}
+                "hot_kernel_ms": r.hot_kernel_ms, "hot_kernel_launches": r.hot_kernel_launches,
+                "sub_iterations": r.sub_iterations, "tolg_final": r.tolg_final}
         return Result(W, H, r.niters, bool(r.converged), r.objvalue, info)
 
 
@@ -369,7 +397,7 @@ def solve_replicates(alg, session: Session, W, H, *, replicates: int, initH: boo
 
 
 _NOT_ACCEL_INIT = ("nndsvd", "nndsvda", "nndsvdar", "spa")
-_NOT_ACCEL_ALG = ("projals", "alspgrad", "cd", "spa")
+_NOT_ACCEL_ALG = ("spa",)
 
 
 def nnmf(X: np.ndarray, k: int, *, init: str = "nndsvdar", initdata=None, alg: str = "greedycd", maxiter: int = 100,
@@ -422,6 +450,12 @@ def nnmf(X: np.ndarray, k: int, *, init: str = "nndsvdar", initdata=None, alg: s
         inst = MultUpdate(T, obj="div", maxiter=maxiter, tol=tol, verbose=verbose, update_H=update_H)
     elif alg == "greedycd":
         inst = GreedyCD(T, maxiter=maxiter, tol=tol, verbose=verbose, update_H=update_H)
+    elif alg == "projals":  # :60-61
+        inst = ProjectedALS(T, maxiter=maxiter, tol=tol, verbose=verbose, update_H=update_H)
+    elif alg == "alspgrad":  # :62-63
+        inst = ALSPGrad(T, maxiter=maxiter, tol=tol, verbose=verbose, update_H=update_H)
+    elif alg == "cd":  # :68-69
+        inst = CoordinateDescent(T, maxiter=maxiter, tol=tol, verbose=verbose, update_H=update_H)
     elif alg in _NOT_ACCEL_ALG:
         if alg == "spa" and init != "spa":
             raise ArgumentError("Invalid value for init, use :spa instead.")  # :74-76

@@ -80,18 +80,19 @@ void set_X_impl(nmfb200_handle* h, const T* X, int64_t p, int64_t n, int64_t ldx
 }
 
 template <typename T>
-void solve_impl(nmfb200_handle* h, int alg, T* W, int64_t ldw, T* H, int64_t ldh, int64_t k, int64_t maxiter, double tol,
-                double lambda_w, double lambda_h, int update_H, int verbose, int on_device, nmfb200_result* out) {
+void solve_args(nmfb200_handle* h, const SolveArgs& a, T* W, int64_t ldw, T* H, int64_t ldh, nmfb200_result* out) {
     NMF_REQUIRE(out != nullptr && W != nullptr && H != nullptr, NMFB200_EINVAL, "NULL argument");
     std::memset(out, 0, sizeof(*out));
     NMF_REQUIRE(h->x_elt != 0, NMFB200_ESTATE, "nmfb200_set_X must precede solve");
     NMF_REQUIRE(h->x_elt == (int)sizeof(T), NMFB200_ESTATE, "X was set with a different element type");
-    NMF_REQUIRE(maxiter > 1, NMFB200_EINVAL, "maxiter must be greater than 1.");   // multupd.jl:28, greedycd.jl:25
-    NMF_REQUIRE(tol > 0, NMFB200_EINVAL, "tol must be positive.");                 // multupd.jl:29, greedycd.jl:26
-    NMF_REQUIRE(lambda_w >= 0, NMFB200_EINVAL, "lambda_w must be non-negative.");  // multupd.jl:30, greedycd.jl:27
-    NMF_REQUIRE(lambda_h >= 0, NMFB200_EINVAL, "lambda_h must be non-negative.");  // multupd.jl:31, greedycd.jl:28
-    NMF_REQUIRE(k >= 1 && ldw >= h->p && ldh >= k, NMFB200_EDIM, "Dimensions of X, W, and H are inconsistent.");  // common.jl:12-14
-    SolveArgs a{alg, k, maxiter, tol, lambda_w, lambda_h, update_H, verbose, on_device};
+    if (a.alg <= 2) {  // the MultUpdate / GreedyCD constructors validate; the other three do not
+        NMF_REQUIRE(a.maxiter > 1, NMFB200_EINVAL, "maxiter must be greater than 1.");   // multupd.jl:28, greedycd.jl:25
+        NMF_REQUIRE(a.tol > 0, NMFB200_EINVAL, "tol must be positive.");                 // multupd.jl:29, greedycd.jl:26
+        NMF_REQUIRE(a.lambda_w >= 0, NMFB200_EINVAL, "lambda_w must be non-negative.");  // multupd.jl:30, greedycd.jl:27
+        NMF_REQUIRE(a.lambda_h >= 0, NMFB200_EINVAL, "lambda_h must be non-negative.");  // multupd.jl:31, greedycd.jl:28
+    }
+    NMF_REQUIRE(a.alg != 4 || (a.cd_regularization >= 0 && a.cd_regularization <= 3), NMFB200_EINVAL, "regularization must be 0..3");
+    NMF_REQUIRE(a.k >= 1 && ldw >= h->p && ldh >= a.k, NMFB200_EDIM, "Dimensions of X, W, and H are inconsistent.");  // common.jl:12-14
     bool use_tc = false;
     if (sizeof(T) == 4 && h->engine_opt != 1) {
         use_tc = tc_supported(h, a);
@@ -101,6 +102,13 @@ void solve_impl(nmfb200_handle* h, int alg, T* W, int64_t ldw, T* H, int64_t ldh
     }
     if (use_tc) tc_solve(h, a, (float*)W, ldw, (float*)H, ldh, out);
     else simt_solve<T>(h, a, W, ldw, H, ldh, out);
+}
+
+template <typename T>
+void solve_impl(nmfb200_handle* h, int alg, T* W, int64_t ldw, T* H, int64_t ldh, int64_t k, int64_t maxiter, double tol,
+                double lambda_w, double lambda_h, int update_H, int verbose, int on_device, nmfb200_result* out) {
+    SolveArgs a{alg, k, maxiter, tol, lambda_w, lambda_h, update_H, verbose, on_device};
+    solve_args<T>(h, a, W, ldw, H, ldh, out);
 }
 
 }  // namespace
@@ -227,6 +235,37 @@ NMFB200_DEFINE_SOLVE(nmfb200_solve_multdiv_f32, 1, float)
 NMFB200_DEFINE_SOLVE(nmfb200_solve_multdiv_f64, 1, double)
 NMFB200_DEFINE_SOLVE(nmfb200_solve_greedycd_f32, 2, float)
 NMFB200_DEFINE_SOLVE(nmfb200_solve_greedycd_f64, 2, double)
+NMFB200_DEFINE_SOLVE(nmfb200_solve_projals_f32, 3, float)
+NMFB200_DEFINE_SOLVE(nmfb200_solve_projals_f64, 3, double)
+
+#define NMFB200_DEFINE_SOLVE_CD(NAME, T)                                                                                     \
+    int NAME(nmfb200_handle* h, T* W, int64_t ldw, T* H, int64_t ldh, int64_t k, int64_t maxiter, T tol, T alpha, T l1ratio, \
+             int regularization, int shuffle, uint64_t seed, int update_H, int verbose, int on_device, nmfb200_result* out) { \
+        return guarded(h, [&] {                                                                                              \
+            SolveArgs a{4, k, maxiter, (double)tol, 0.0, 0.0, update_H, verbose, on_device};                                 \
+            a.cd_alpha = (double)alpha;                                                                                      \
+            a.cd_l1ratio = (double)l1ratio;                                                                                  \
+            a.cd_regularization = regularization;                                                                            \
+            a.cd_shuffle = shuffle;                                                                                          \
+            a.cd_seed = seed;                                                                                                \
+            solve_args<T>(h, a, W, ldw, H, ldh, out);                                                                        \
+        });                                                                                                                  \
+    }
+NMFB200_DEFINE_SOLVE_CD(nmfb200_solve_cd_f32, float)
+NMFB200_DEFINE_SOLVE_CD(nmfb200_solve_cd_f64, double)
+
+#define NMFB200_DEFINE_SOLVE_ALSPGRAD(NAME, T)                                                                               \
+    int NAME(nmfb200_handle* h, T* W, int64_t ldw, T* H, int64_t ldh, int64_t k, int64_t maxiter, int64_t maxsubiter, T tol, \
+             T tolg, int update_H, int verbose, int on_device, nmfb200_result* out) {                                        \
+        return guarded(h, [&] {                                                                                              \
+            SolveArgs a{5, k, maxiter, (double)tol, 0.0, 0.0, update_H, verbose, on_device};                                 \
+            a.maxsubiter = maxsubiter;                                                                                       \
+            a.tolg = (double)tolg;                                                                                           \
+            solve_args<T>(h, a, W, ldw, H, ldh, out);                                                                        \
+        });                                                                                                                  \
+    }
+NMFB200_DEFINE_SOLVE_ALSPGRAD(nmfb200_solve_alspgrad_f32, float)
+NMFB200_DEFINE_SOLVE_ALSPGRAD(nmfb200_solve_alspgrad_f64, double)
 
 int nmfb200_comm_unique_id(void* out_id_128) {
     if (!out_id_128) return NMFB200_EINVAL;

@@ -227,11 +227,19 @@ struct nmfb200_handle {
 namespace nmfb200 {
 
 struct SolveArgs {
-    int alg;  // 0 multmse, 1 multdiv, 2 greedycd
+    int alg;  // 0 multmse, 1 multdiv, 2 greedycd, 3 projals, 4 cd, 5 alspgrad
     int64_t k;
     int64_t maxiter;
     double tol, lambda_w, lambda_h;
     int update_H, verbose, on_device;
+    // CoordinateDescent (coorddesc.jl:24-46)
+    double cd_alpha = 0, cd_l1ratio = 0;
+    int cd_regularization = 0;  // 0 :both, 1 :components, 2 :transformation, 3 :none
+    int cd_shuffle = 0;
+    uint64_t cd_seed = 0;
+    // ALSPGrad (alspgrad.jl:352-373)
+    int64_t maxsubiter = 200;
+    double tolg = 0;
 };
 
 // engines (one translation unit each)

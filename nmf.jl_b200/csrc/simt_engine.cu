@@ -6,6 +6,8 @@
 //     mathematics without the p x n intermediate.
 //   * reductions run in parallel (pairwise order) instead of Julia's sequential order.
 // Layouts on device are the caller's: column-major X (p x n), W (p x k), H (k x n).
+#include <algorithm>
+
 #include "common.cuh"
 #include "gcd_kernels.cuh"
 
@@ -183,7 +185,7 @@ __global__ void stop_final_kernel(const double* __restrict__ acc, int64_t k, T t
 }
 
 // ---- objectives (StatsBase.sqL2dist / gkldiv semantics: differences in T, Float64 accumulator)
-template <typename T, int MODE>  // MODE 0: sum (x-y)^2, 1: gkldiv, 2: sum |y| (x ignored)
+template <typename T, int MODE>  // MODE 0: sum (x-y)^2, 1: gkldiv, 2: sum |y| (x ignored), 3: sum y^2 (x ignored)
 __global__ void objective_partials_kernel(const T* __restrict__ X, int64_t p, int64_t n, int64_t ldx, const T* __restrict__ Y,
                                           double* __restrict__ part) {
     __shared__ double red[256];
@@ -192,6 +194,8 @@ __global__ void objective_partials_kernel(const T* __restrict__ X, int64_t p, in
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
         if (MODE == 2) {
             s += (double)fabs(Y[i]);
+        } else if (MODE == 3) {
+            s += (double)mul_rn(Y[i], Y[i]);
         } else {
             int64_t r = i % p, c = i / p;
             T a = X[r + c * ldx], b = Y[i];
@@ -253,6 +257,150 @@ __global__ void copy2d_kernel(T* __restrict__ dst, int64_t ldd, const T* __restr
     }
 }
 
+
+// ---- ProjectedALS pieces (projals.jl:77-107, utils.jl:15-24, :34-41, :63-84) ------------------------
+template <typename T>
+__global__ void add_diag_kernel(T* __restrict__ A, int k, T a) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < k) A[(int64_t)i * k + i] = add_rn(A[(int64_t)i * k + i], a);
+}
+
+// projectnn! (utils.jl:34-41): NaN < 0 is false => NaN preserved
+template <typename T>
+__global__ void clamp_nn_kernel(T* __restrict__ A, int64_t len) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
+        if (A[i] < T(0)) A[i] = T(0);
+}
+
+// inv(A) for a symmetric positive definite k x k matrix (what potrf!/potrs! and potrf!/potri! deliver, utils.jl:63-84),
+// by in-place Gauss-Jordan elimination without pivoting (stable for SPD) in Float64, one CTA.  work: k*k doubles.
+// info[0] = j+1 if pivot j is not positive (Julia: PosDefException), else untouched.
+template <typename T>
+__global__ void __launch_bounds__(1024) spd_inverse_kernel(const T* __restrict__ A, int k, double* __restrict__ work, T* __restrict__ inv,
+                                                           int* __restrict__ info) {
+    extern __shared__ double sh[];  // [k] pivot column, [k] scaled pivot row
+    double* colj = sh;
+    double* rowj = sh + k;
+    __shared__ int bad;
+    const int n2 = k * k;
+    if (threadIdx.x == 0) bad = 0;
+    for (int e = threadIdx.x; e < n2; e += blockDim.x) work[e] = (double)A[e];
+    __syncthreads();
+    for (int j = 0; j < k; ++j) {
+        const double piv = work[(size_t)j * k + j];
+        if (!(piv > 0.0)) {  // uniform: every thread reads the same element
+            if (threadIdx.x == 0) info[0] = j + 1;
+            bad = 1;
+        }
+        const double ipiv = 1.0 / piv;
+        for (int e = threadIdx.x; e < k; e += blockDim.x) {
+            colj[e] = work[(size_t)j * k + e];          // column j: element (e, j)   (col-major: e + j*k)
+            rowj[e] = work[(size_t)e * k + j] * ipiv;   // row j / pivot: element (j, e)
+        }
+        __syncthreads();
+        if (bad) return;
+        for (int e = threadIdx.x; e < n2; e += blockDim.x) {
+            const int r = e % k, c = e / k;
+            double v;
+            if (r == j) v = (c == j) ? ipiv : rowj[c];
+            else if (c == j) v = -colj[r] * ipiv;
+            else v = work[e] - colj[r] * rowj[c];
+            work[e] = v;
+        }
+        __syncthreads();
+    }
+    for (int e = threadIdx.x; e < n2; e += blockDim.x) inv[e] = (T)work[e];
+}
+
+// ---- CoordinateDescent sweep (coorddesc.jl:138-157) ------------------------------------------------------
+// One thread per row i of the factor F(i, r) = Fp[i*sFr + r*sFc]; the row lives in shared memory (transposed:
+// conflict-free), components are visited in `perm` order, the gradient is accumulated sequentially from
+// -(XHt[i,t] - l1) exactly like the reference's scalar loop (un-fused multiply-add).  HHt (k x k col-major, l2
+// already on the diagonal) is read through the read-only cache (warp-uniform addresses => broadcast).
+// Z(i, t) = Zp[i*sZr + t*sZc] is X*O.  The violation sum (coorddesc.jl:150) is not formed: it is stored in the
+// reference's state and never read.
+template <typename T>
+__global__ void cd_sweep_kernel(T* __restrict__ Fp, int64_t sFr, int64_t sFc, const T* __restrict__ HHt, const T* __restrict__ Zp,
+                                int64_t sZr, int64_t sZc, int64_t rows, int k, const int* __restrict__ perm, T l1) {
+    extern __shared__ unsigned char cd_smem_raw[];
+    T* row = (T*)cd_smem_raw;  // [k][blockDim.x]
+    const int tx = threadIdx.x, nt = blockDim.x;
+    const int64_t i = (int64_t)blockIdx.x * nt + tx;
+    if (i >= rows) return;
+    for (int r = 0; r < k; ++r) row[r * nt + tx] = Fp[i * sFr + r * sFc];
+    for (int tt = 0; tt < k; ++tt) {
+        const int t = perm[tt];
+        T x = Zp[i * sZr + t * sZc];
+        if (l1 > T(0)) x = sub_rn(x, l1);                                   // coorddesc.jl:126-128
+        T grad = -x;                                                        // :141
+        const T* hrow = HHt + t;                                            // HHt[t, r] = HHt[t + r*k]
+        for (int r = 0; r < k; ++r) grad = add_rn(grad, mul_rn(__ldg(hrow + (int64_t)r * k), row[r * nt + tx]));  // :143-145
+        const T hess = __ldg(HHt + (int64_t)t * k + t);                     // :153
+        if (hess != T(0)) {
+            T v = sub_rn(row[t * nt + tx], div_rn(grad, hess));             // :155
+            row[t * nt + tx] = (v > T(0) || v != v) ? v : T(0);             // max(v, 0): NaN propagates
+        }
+    }
+    for (int r = 0; r < k; ++r) Fp[i * sFr + r * sFc] = row[r * nt + tx];
+}
+
+// ---- ALSPGrad pieces (alspgrad.jl:86-191, :242-347) ------------------------------------------------------
+template <typename T>
+__global__ void sub_inplace_kernel(T* __restrict__ G, const T* __restrict__ B, int64_t len) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
+        G[i] = sub_rn(G[i], B[i]);                                          // :118-120
+}
+// Fn = max(F - alpha*G, 0), D = Fn - F  (:134-138)
+template <typename T>
+__global__ void pg_step_kernel(const T* __restrict__ F, const T* __restrict__ G, T alpha, T* __restrict__ Fn, T* __restrict__ D, int64_t len) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        T f = F[i];
+        T v = sub_rn(f, mul_rn(alpha, G[i]));
+        v = (v > T(0) || v != v) ? v : T(0);
+        Fn[i] = v;
+        D[i] = sub_rn(v, f);
+    }
+}
+// MODE 0: sum g^2 over {g < 0 or x > 0} (projgradnorm, :9-19); 1: sum a*b (BLAS.dot); 2: sum (a-b)^2 (isapprox norm)
+template <typename T, int MODE>
+__global__ void pair_reduce_kernel(const T* __restrict__ a, const T* __restrict__ b, int64_t len, double* __restrict__ part) {
+    __shared__ double red[256];
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        T x = a[i], y = b[i];
+        if (MODE == 0) { if (x < T(0) || y > T(0)) s += (double)mul_rn(x, x); }
+        else if (MODE == 1) s += (double)x * (double)y;
+        else { T d = sub_rn(x, y); s += (double)mul_rn(d, d); }
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part[blockIdx.x] = red[0];
+}
+
+// `randperm` stand-in for CoordinateDescent(shuffle=true): splitmix64 + Fisher-Yates, identical to oracle ShufflePerm
+struct ShufflePerm {
+    uint64_t s;
+    uint64_t next() {
+        s += 0x9E3779B97F4A7C15ull;
+        uint64_t z = s;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    }
+    void perm(std::vector<int>& a, int k) {
+        a.resize(k);
+        for (int i = 0; i < k; ++i) a[i] = i;
+        for (int i = k - 1; i >= 1; --i) {
+            int j = (int)(next() % (uint64_t)(i + 1));
+            std::swap(a[i], a[j]);
+        }
+    }
+};
+
 inline int ew_blocks(int64_t len) { return (int)std::min<int64_t>(ceil_div(len, 256), 148 * 16); }
 
 template <typename T>
@@ -288,6 +436,7 @@ struct Simt {
         double* part = h->buf_t<double>("simt.obj_part", (size_t)nb + 1);
         if (mode == 0) objective_partials_kernel<T, 0><<<nb, 256, 0, st>>>(Xp, rows, cols, ld, Y, part);
         else if (mode == 1) objective_partials_kernel<T, 1><<<nb, 256, 0, st>>>(Xp, rows, cols, ld, Y, part);
+        else if (mode == 3) objective_partials_kernel<T, 3><<<nb, 256, 0, st>>>(Xp, rows, cols, ld, Y, part);
         else objective_partials_kernel<T, 2><<<nb, 256, 0, st>>>(Xp, rows, cols, ld, Y, part);
         sum_partials_kernel<<<1, 256, 0, st>>>(part, nb, part + nb);
         h->launches += 2;
@@ -306,6 +455,16 @@ struct Simt {
         gemm((int)p, (int)n, (int)k, W, 1, ldw, H, 1, ldh, WH, 1, p);
         if (alg == 1) return (double)(T)reduce_objective(1, X, p, n, ldx, WH);  // gkldiv, Result converts to T
         T r = mul_rn_host(T(0.5), (T)reduce_objective(0, X, p, n, ldx, WH));
+        if (alg == 3) {  // projals.jl:66-75: + (0.5*lambda) * abs2(norm(F)), norm in T
+            if (lambda_w > 0) {
+                T nw = (T)std::sqrt(reduce_objective(3, nullptr, p, k, p, W));
+                r = (T)(r + (T)(T(0.5) * (T)lambda_w) * (T)(nw * nw));
+            }
+            if (lambda_h > 0) {
+                T nh = (T)std::sqrt(reduce_objective(3, nullptr, k, n, k, H) / (h->comm ? h->nranks : 1));
+                r = (T)(r + (T)(T(0.5) * (T)lambda_h) * (T)(nh * nh));
+            }
+        }
         if (alg == 2) {  // greedycd.jl:85-90
             if (lambda_w > 0) {
                 double l1 = reduce_objective(2, nullptr, p, k, p, W);
@@ -422,6 +581,164 @@ struct Simt {
         NMF_CUDA(cudaGetLastError());
     }
 
+    // ---- ProjectedALS iteration (projals.jl:77-107).  The k x k systems are solved through the explicit inverse
+    // (Float64 Gauss-Jordan in one CTA) followed by a GEMM, for H (reference: potrs!) as well as W (reference: potri!).
+    void spd_inverse(const T* A, T* inv, int* info) {
+        double* work = h->buf_t<double>("simt.inv_work", (size_t)k * k);
+        spd_inverse_kernel<T><<<1, 1024, 2 * (size_t)k * sizeof(double), st>>>(A, (int)k, work, inv, info);
+        h->launches += 1;
+    }
+    void iter_projals(T* W, T* H, bool update_H, T lw, T lh, int* info) {
+        T* num_h = h->buf_t<T>("simt.num_h", (size_t)k * n + (size_t)k * k);  // [W'X | W'W] packed for one allreduce
+        T* gram = num_h + (size_t)k * n;
+        T* inv = h->buf_t<T>("simt.inv", (size_t)k * k);
+        if (update_H) {
+            gemm((int)k, (int)n, (int)p, W, p, 1, X, 1, ldx, num_h, 1, k);   // W'X        (projals.jl:92)
+            gemm((int)k, (int)k, (int)p, W, p, 1, W, 1, p, gram, 1, k);     // W'W        (:91)
+            h->allreduce_sum(num_h, (size_t)k * n + (size_t)k * k);
+            if (lh != T(0)) { add_diag_kernel<T><<<(unsigned)ceil_div(k, 256), 256, 0, st>>>(gram, (int)k, lh); h->launches += 1; }
+            spd_inverse(gram, inv, info);                                    // pdsolve!   (:93)
+            gemm((int)k, (int)n, (int)k, inv, 1, k, num_h, 1, k, H, 1, k);
+            clamp_nn_kernel<T><<<ew_blocks(k * n), 256, 0, st>>>(H, k * n);  // projectnn! (:94)
+            h->launches += 1;
+        }
+        T* gramh = h->buf_t<T>("simt.gramh", (size_t)k * k);
+        T* num_w = h->buf_t<T>("simt.num_w", (size_t)p * k);
+        gemm((int)k, (int)k, (int)n, H, 1, k, H, k, 1, gramh, 1, k);         // HH'        (:99)
+        if (lw != T(0)) { add_diag_kernel<T><<<(unsigned)ceil_div(k, 256), 256, 0, st>>>(gramh, (int)k, lw); h->launches += 1; }
+        gemm((int)p, (int)k, (int)n, X, 1, ldx, H, k, 1, num_w, 1, p);       // XH'        (:100)
+        spd_inverse(gramh, inv, info);                                       // pdrsolve!  (:101)
+        gemm((int)p, (int)k, (int)k, num_w, 1, p, inv, 1, k, W, 1, p);
+        clamp_nn_kernel<T><<<ew_blocks(p * k), 256, 0, st>>>(W, p * k);      // projectnn! (:102)
+        h->launches += 1;
+        NMF_CUDA(cudaGetLastError());
+    }
+
+    // ---- CoordinateDescent half-step (coorddesc.jl:108-160): factor F (rows x k) against O (cols x k)
+    void cd_half(T* F, int64_t sFr, int64_t sFc, const T* O, int64_t sOr, int64_t sOc, int64_t rows, int64_t cols, int64_t sXr,
+                 int64_t sXc, T l1, T l2, bool contraction_sharded, ShufflePerm* rng) {
+        // packed [Z = X*O (rows x k, row-major) | HHt = O'O (k x k)]
+        T* Z = h->buf_t<T>("simt.gcd_Z", (size_t)std::max(p, n) * k + (size_t)k * k);
+        T* HHt = Z + (size_t)rows * k;
+        gemm((int)k, (int)k, (int)cols, O, sOc, sOr, O, sOr, sOc, HHt, 1, k);        // :112
+        gemm((int)rows, (int)k, (int)cols, X, sXr, sXc, O, sOr, sOc, Z, k, 1);      // :118
+        if (contraction_sharded) h->allreduce_sum(Z, (size_t)rows * k + (size_t)k * k);
+        if (l2 > T(0)) { add_diag_kernel<T><<<(unsigned)ceil_div(k, 256), 256, 0, st>>>(HHt, (int)k, l2); h->launches += 1; }  // :123-125
+        std::vector<int> perm;
+        if (rng) rng->perm(perm, (int)k);                                            // :129-133
+        else { perm.resize(k); for (int i = 0; i < (int)k; ++i) perm[i] = i; }
+        int* dperm = (int*)h->buf("simt.cd_perm", (size_t)k * sizeof(int));
+        NMF_CUDA(cudaMemcpyAsync(dperm, perm.data(), (size_t)k * sizeof(int), cudaMemcpyHostToDevice, st));
+        NMF_CUDA(cudaStreamSynchronize(st));  // perm is a stack object; the copy must have left it
+        int nt = 128;
+        while (nt > 32 && (size_t)nt * k * sizeof(T) > 200 * 1024) nt >>= 1;
+        const size_t smem = (size_t)nt * k * sizeof(T);
+        NMF_REQUIRE(smem <= 200 * 1024, NMFB200_ENOTSUP, "CoordinateDescent: k too large for the row kernel");
+        NMF_CUDA(cudaFuncSetAttribute(cd_sweep_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cd_sweep_kernel<T><<<(unsigned)ceil_div(rows, nt), nt, smem, st>>>(F, sFr, sFc, HHt, Z, k, 1, rows, (int)k, dperm, l1);  // :138-157
+        h->launches += 1;
+        NMF_CUDA(cudaGetLastError());
+    }
+    void iter_cd(T* W, T* H, bool update_H, T l1W, T l2W, T l1H, T l2H, ShufflePerm* rng) {
+        cd_half(W, 1, p, H, k, 1, p, n, 1, ldx, l1W, l2W, false, rng);                        // coorddesc.jl:168
+        if (update_H) cd_half(H, k, 1, W, 1, p, n, p, ldx, 1, l1H, l2H, h->comm != nullptr, rng);  // :171-176
+    }
+
+    // ---- ALSPGrad (alspgrad.jl:400-425) ----------------------------------------------------------------
+    double pair_reduce(int mode, const T* a, const T* b, int64_t len) {
+        int nb = ew_blocks(len);
+        double* part = h->buf_t<double>("simt.pg_part", (size_t)nb + 1);
+        if (mode == 0) pair_reduce_kernel<T, 0><<<nb, 256, 0, st>>>(a, b, len, part);
+        else if (mode == 1) pair_reduce_kernel<T, 1><<<nb, 256, 0, st>>>(a, b, len, part);
+        else pair_reduce_kernel<T, 2><<<nb, 256, 0, st>>>(a, b, len, part);
+        sum_partials_kernel<<<1, 256, 0, st>>>(part, nb, part + nb);
+        h->launches += 2;
+        double v = 0;
+        NMF_CUDA(cudaMemcpyAsync(&v, part + nb, sizeof(double), cudaMemcpyDeviceToHost, st));
+        NMF_CUDA(cudaStreamSynchronize(st));
+        return v;
+    }
+    // _alspgrad_updateh! (left = true: G = gram*F - cross, F is k x n) / _alspgrad_updatew! (left = false:
+    // G = F*gram - cross, F is p x k).  Control flow on the host, exactly the reference's; returns the sub-iteration count.
+    int64_t pg_subsolve(T* F, const T* gram, const T* cross, bool left, int64_t maxsub, int traceiter, T tolg, T beta, T sigma) {
+        const int64_t rows = left ? k : p, cols = left ? n : k, len = rows * cols;
+        T* G = h->buf_t<T>("simt.pg_G", (size_t)std::max(k * n, p * k));
+        T* Fn = h->buf_t<T>("simt.pg_Fn", (size_t)std::max(k * n, p * k));
+        T* Fp = h->buf_t<T>("simt.pg_Fp", (size_t)std::max(k * n, p * k));
+        T* D = h->buf_t<T>("simt.pg_D", (size_t)std::max(k * n, p * k));
+        T* GD = h->buf_t<T>("simt.pg_GD", (size_t)std::max(k * n, p * k));
+        auto mul = [&](T* dst, const T* src) {
+            if (left) gemm((int)k, (int)n, (int)k, gram, 1, k, src, 1, k, dst, 1, k);
+            else gemm((int)p, (int)k, (int)k, src, 1, p, gram, 1, k, dst, 1, p);
+        };
+        const size_t bytes = (size_t)len * sizeof(T);
+        const T epsT = std::numeric_limits<T>::epsilon();
+        int64_t t = 0;
+        bool converged = false, decr_alpha = true;
+        T alpha = T(1);
+        while (!converged && t < maxsub) {
+            ++t;
+            mul(G, F);                                                               // :117
+            sub_inplace_kernel<T><<<ew_blocks(len), 256, 0, st>>>(G, cross, len);    // :118-120
+            h->launches += 1;
+            const T pgnrm = (T)std::sqrt((T)pair_reduce(0, G, F, len));              // :123
+            if (pgnrm < tolg) converged = true;
+            int it = 0;
+            if (!converged) {
+                while (it < traceiter) {
+                    ++it;
+                    NMF_REQUIRE(std::isfinite((double)alpha), NMFB200_EINVAL, "alpha is not finite");   // :132
+                    pg_step_kernel<T><<<ew_blocks(len), 256, 0, st>>>(F, G, alpha, Fn, D, len);  // :134-139
+                    h->launches += 1;
+                    const T dv1 = (T)pair_reduce(1, G, D, len);                      // :142
+                    mul(GD, D);                                                      // :143
+                    const T dv2 = (T)pair_reduce(1, GD, D, len);                     // :144
+                    const bool suff_decr = (T)((T)((T)(T(1) - sigma) * dv1) + (T)(T(0.5) * dv2)) < T(0);  // :147
+                    if (it == 1) {
+                        decr_alpha = !suff_decr;                                     // :150
+                        NMF_CUDA(cudaMemcpyAsync(Fp, F, bytes, cudaMemcpyDeviceToDevice, st));  // :151
+                    }
+                    if (decr_alpha) {
+                        if (suff_decr) {
+                            NMF_CUDA(cudaMemcpyAsync(F, Fn, bytes, cudaMemcpyDeviceToDevice, st));  // :156
+                            break;
+                        }
+                        alpha = (T)(alpha * beta);                                   // :159
+                    } else {
+                        // isapprox(Hp, Hn, atol=eps(T)): rtol = 0 when atol > 0  =>  norm(Hp - Hn) <= eps(T)
+                        const bool close = (T)std::sqrt((T)pair_reduce(2, Fp, Fn, len)) <= epsT;
+                        if (!suff_decr || close) {                                   // :162
+                            NMF_CUDA(cudaMemcpyAsync(F, Fp, bytes, cudaMemcpyDeviceToDevice, st));  // :163
+                            break;
+                        }
+                        alpha = (T)(alpha / beta);                                   // :166
+                        NMF_CUDA(cudaMemcpyAsync(Fp, Fn, bytes, cudaMemcpyDeviceToDevice, st));  // :167
+                    }
+                }
+            }
+        }
+        return t;
+    }
+    int64_t iter_alspgrad(T* W, T* H, bool update_H, int64_t maxsub, T* tolg) {
+        int64_t sub = 0;
+        T* gram = h->buf_t<T>("simt.gramh", (size_t)k * k);
+        if (update_H) {
+            T* wtx = h->buf_t<T>("simt.num_h", (size_t)k * n + (size_t)k * k);
+            gemm((int)k, (int)k, (int)p, W, p, 1, W, 1, p, gram, 1, k);              // set_w! (:55-59)
+            gemm((int)k, (int)n, (int)p, W, p, 1, X, 1, ldx, wtx, 1, k);
+            const int64_t itH = pg_subsolve(H, gram, wtx, true, maxsub, 20, *tolg, T(0.2), T(0.01));   // :405-407
+            sub += itH;
+            if (itH == 1) *tolg = (T)((double)*tolg * 0.1);                          // :409-411
+        }
+        T* xht = h->buf_t<T>("simt.num_w", (size_t)p * k);
+        gemm((int)k, (int)k, (int)n, H, 1, k, H, k, 1, gram, 1, k);                  // set_h! (:211-215)
+        gemm((int)p, (int)k, (int)n, X, 1, ldx, H, k, 1, xht, 1, p);
+        const int64_t itW = pg_subsolve(W, gram, xht, false, maxsub, 20, *tolg, T(0.2), T(0.01));      // :415-417
+        sub += itW;
+        if (itW == 1) *tolg = (T)((double)*tolg * 0.1);                              // :419-421
+        return sub;
+    }
+
     void iter_greedycd(T* W, T* H, bool update_H, T lw, T lh, unsigned long long* d_updates) {
         // W-step: F = W (p x k), O = H' (n x k): O(c, a) = H[a + c*k]; X(r, c) = X[r + c*ldx]
         gcd_half(W, 1, p, H, k, 1, p, n, 1, ldx, lw, /*rows_sharded=*/h->comm != nullptr, d_updates);
@@ -449,6 +766,23 @@ void simt_solve(nmfb200_handle* h, const SolveArgs& a, T* Wc, int64_t ldw, T* Hc
         lh = std::max(lh, delta);
     }
     const T tol = (T)a.tol;
+    NMF_REQUIRE(a.alg <= 2 || h->comm == nullptr || a.alg == 3 || a.alg == 4, NMFB200_ENOTSUP, "ALSPGrad is single-GPU in this build");
+    // CoordinateDescentUpd (coorddesc.jl:61-80): l1/l2 weights per factor
+    T l1W = T(0), l2W = T(0), l1H = T(0), l2H = T(0);
+    if (a.alg == 4) {
+        const T alpha = (T)a.cd_alpha, ratio = (T)a.cd_l1ratio;
+        const T aH = (a.cd_regularization == 0 || a.cd_regularization == 1) ? alpha : T(0);
+        const T aW = (a.cd_regularization == 0 || a.cd_regularization == 2) ? alpha : T(0);
+        l1W = (T)(aW * ratio);
+        l2W = (T)(aW * (T)(T(1) - ratio));
+        l1H = (T)(aH * ratio);
+        l2H = (T)(aH * (T)(T(1) - ratio));
+    }
+    ShufflePerm shuffle_rng{a.cd_seed};
+    T tolg = (T)a.tolg;
+    int64_t sub_iterations = 0;
+    int* d_info = (int*)h->buf("simt.info", 16);
+    NMF_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), h->stream));
 
     cudaEvent_t e0, e1, e2;
     NMF_CUDA(cudaEventCreate(&e0));
@@ -493,8 +827,17 @@ void simt_solve(nmfb200_handle* h, const SolveArgs& a, T* Wc, int64_t ldw, T* Hc
         NMF_CUDA(cudaMemcpyAsync(preH, H, (size_t)k * n * sizeof(T), cudaMemcpyDeviceToDevice, st));
         if (a.alg == 0) s.iter_multmse(W, H, a.update_H != 0, lw, lh, delta);
         else if (a.alg == 1) s.iter_multdiv(W, H, a.update_H != 0, lw, lh, delta, t == 1);
-        else s.iter_greedycd(W, H, a.update_H != 0, lw, lh, d_updates);
+        else if (a.alg == 2) s.iter_greedycd(W, H, a.update_H != 0, lw, lh, d_updates);
+        else if (a.alg == 3) s.iter_projals(W, H, a.update_H != 0, lw, lh, d_info);
+        else if (a.alg == 4) s.iter_cd(W, H, a.update_H != 0, l1W, l2W, l1H, l2H, a.cd_shuffle ? &shuffle_rng : nullptr);
+        else sub_iterations += s.iter_alspgrad(W, H, a.update_H != 0, a.maxsubiter, &tolg);
         converged = s.stop(W, preW, H, preH, tol, &dev);
+        if (a.alg == 3) {  // potrf! failure (utils.jl:68,78 -> PosDefException)
+            int info = 0;
+            NMF_CUDA(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+            NMF_CUDA(cudaStreamSynchronize(st));
+            NMF_REQUIRE(info == 0, NMFB200_EINVAL, "matrix is not positive definite; Cholesky factorization failed (pivot " + std::to_string(info) + ").");
+        }
         if (a.verbose) {
             double pre = objv;
             objv = s.objective(a.alg, W, H, lw, lh);
@@ -529,6 +872,8 @@ void simt_solve(nmfb200_handle* h, const SolveArgs& a, T* Wc, int64_t ldw, T* Hc
     out->upload_ms = ms_up;
     out->coordinate_updates = (int64_t)upd;
     out->kernel_launches = h->launches;
+    out->sub_iterations = sub_iterations;
+    out->tolg_final = (double)tolg;
 }
 
 double simt_objective_f32(nmfb200_handle* h, int alg, const float* W, int64_t ldw, const float* H, int64_t ldh, int64_t k,

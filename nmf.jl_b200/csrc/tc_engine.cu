@@ -2180,6 +2180,7 @@ void tc_solve_gcd_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t l
 }  // namespace
 
 bool tc_supported(const nmfb200_handle* h, const SolveArgs& a) {
+    if (a.alg > 2) return false;          // ProjectedALS / CoordinateDescent / ALSPGrad: exact engine
     if (a.alg == 1) {                     // MultUpdate(:div): quotient kernel + update kernel; k <= 128, single GPU
         if (h->comm != nullptr || a.k > 128 || h->p < 128 || h->n < 128) return false;
         if (h->engine_opt != 2 && h->p * h->n < ((int64_t)1 << 20)) return false;

@@ -1,8 +1,9 @@
 # NMFB200.jl -- thin Julia front-end of libnmfb200.so (include/nmfb200.h).
 #
 # Keeps the reference's API for the accelerated path: `nnmf`, `NMFB200.solve!`, `NMFB200.Result{T}`,
-# and the option types `MultUpdate{T}`, `GreedyCD{T}` (same keyword names, defaults and validation as
-# NMF.jl src/multupd.jl:9-43, src/greedycd.jl:10-31, src/interf.jl:3-101), so existing code can do
+# and the option types `MultUpdate{T}`, `GreedyCD{T}`, `ProjectedALS{T}`, `CoordinateDescent{T}`, `ALSPGrad{T}` (same
+# keyword names, defaults and validation as NMF.jl src/multupd.jl:9-43, src/greedycd.jl:10-31, src/projals.jl:18-35,
+# src/coorddesc.jl:24-46, src/alspgrad.jl:352-373, src/interf.jl:3-101), so existing code can do
 #     const NMF = NMFB200
 # All numerics live behind the C ABI; this file only validates, ccalls and maps status -> exception.
 # NOTE: Julia is not installed in the build image of this repository, so this file is written against
@@ -28,6 +29,8 @@ struct CResult            # nmfb200_result
     kernel_launches::Int64
     hot_kernel_ms::Float64
     hot_kernel_launches::Int64
+    sub_iterations::Int64
+    tolg_final::Float64
 end
 
 mutable struct Handle
@@ -115,6 +118,46 @@ mutable struct GreedyCD{T}              # src/greedycd.jl:10-31
     end
 end
 
+mutable struct ProjectedALS{T}          # src/projals.jl:18-35 (no validation in the reference)
+    maxiter::Int
+    verbose::Bool
+    tol::T
+    update_H::Bool
+    lambda_w::T
+    lambda_h::T
+    ProjectedALS{T}(; maxiter::Integer=100, verbose::Bool=false, tol::Real=cbrt(eps(T)), update_H::Bool=true,
+                    lambda_w::Real=cbrt(eps(T)), lambda_h::Real=cbrt(eps(T))) where T =
+        new{T}(maxiter, verbose, tol, update_H, lambda_w, lambda_h)
+end
+
+mutable struct CoordinateDescent{T}     # src/coorddesc.jl:24-46; `seed` replaces Julia's global RNG for shuffle=true
+    maxiter::Int
+    verbose::Bool
+    tol::T
+    update_H::Bool
+    α::T
+    l₁ratio::T
+    regularization::Symbol
+    shuffle::Bool
+    seed::UInt64
+    CoordinateDescent{T}(; maxiter::Integer=100, verbose::Bool=false, tol::Real=cbrt(eps(T)), update_H::Bool=true,
+                         α::Real=zero(T), regularization=:both, l₁ratio::Real=zero(T), shuffle::Bool=false,
+                         seed::Integer=rand(UInt64)) where T =
+        new{T}(maxiter, verbose, tol, update_H, α, l₁ratio, regularization, shuffle, seed)
+end
+
+mutable struct ALSPGrad{T}              # src/alspgrad.jl:352-373
+    maxiter::Int
+    maxsubiter::Int
+    tol::T
+    tolg::T
+    update_H::Bool
+    verbose::Bool
+    ALSPGrad{T}(; maxiter::Integer=100, maxsubiter::Integer=200, tol::Real=cbrt(eps(T)), tolg::Real=eps(T)^(1/4),
+                update_H::Bool=true, verbose::Bool=false) where T =
+        new{T}(maxiter, maxsubiter, tol, tolg, update_H, verbose)
+end
+
 # ---- set_X / solve! ---------------------------------------------------------------------------------------
 for (T, sfx) in ((Float32, "f32"), (Float64, "f64"))
     setx = Symbol("nmfb200_set_X_", sfx)
@@ -122,7 +165,27 @@ for (T, sfx) in ((Float32, "f32"), (Float64, "f64"))
         GC.@preserve X check(h, ccall(($(QuoteNode(setx)), libnmfb200), Cint,
             (Ptr{Cvoid}, Ptr{$T}, Int64, Int64, Int64, Cint), h.ptr, X, size(X, 1), size(X, 2), stride(X, 2), check_nonneg))
     end
-    for (alg, name) in ((:multmse, "multmse"), (:multdiv, "multdiv"), (:greedycd, "greedycd"))
+    cd = Symbol("nmfb200_solve_cd_", sfx)
+    @eval function _solve_cd(h::Handle, W::Matrix{$T}, H::Matrix{$T}, a::CoordinateDescent{$T})
+        res = Ref{CResult}()
+        reg = a.regularization == :both ? 0 : a.regularization == :components ? 1 : a.regularization == :transformation ? 2 : 3
+        GC.@preserve W H check(h, ccall(($(QuoteNode(cd)), libnmfb200), Cint,
+            (Ptr{Cvoid}, Ptr{$T}, Int64, Ptr{$T}, Int64, Int64, Int64, $T, $T, $T, Cint, Cint, UInt64, Cint, Cint, Cint, Ref{CResult}),
+            h.ptr, W, stride(W, 2), H, stride(H, 2), size(W, 2), a.maxiter, a.tol, a.α, a.l₁ratio, reg, a.shuffle, a.seed,
+            a.update_H, a.verbose, 0, res))
+        r = res[]
+        return Result{$T}(W, H, Int(r.niters), r.converged != 0, $T(r.objvalue))
+    end
+    pg = Symbol("nmfb200_solve_alspgrad_", sfx)
+    @eval function _solve_alspgrad(h::Handle, W::Matrix{$T}, H::Matrix{$T}, a::ALSPGrad{$T})
+        res = Ref{CResult}()
+        GC.@preserve W H check(h, ccall(($(QuoteNode(pg)), libnmfb200), Cint,
+            (Ptr{Cvoid}, Ptr{$T}, Int64, Ptr{$T}, Int64, Int64, Int64, Int64, $T, $T, Cint, Cint, Cint, Ref{CResult}),
+            h.ptr, W, stride(W, 2), H, stride(H, 2), size(W, 2), a.maxiter, a.maxsubiter, a.tol, a.tolg, a.update_H, a.verbose, 0, res))
+        r = res[]
+        return Result{$T}(W, H, Int(r.niters), r.converged != 0, $T(r.objvalue))
+    end
+    for (alg, name) in ((:multmse, "multmse"), (:multdiv, "multdiv"), (:greedycd, "greedycd"), (:projals, "projals"))
         cname = Symbol("nmfb200_solve_", name, "_", sfx)
         fname = Symbol("_solve_", name)
         @eval function $fname(h::Handle, W::Matrix{$T}, H::Matrix{$T}, maxiter, tol, lw, lh, update_H, verbose)
@@ -153,6 +216,22 @@ function solve!(alg::GreedyCD{T}, X::Matrix{T}, W::Matrix{T}, H::Matrix{T}; hand
     nmf_checksize(X, W, H)
     x_resident || set_X!(handle, X)
     _solve_greedycd(handle, W, H, alg.maxiter, alg.tol, alg.lambda_w, alg.lambda_h, alg.update_H, alg.verbose)
+end
+
+function solve!(alg::ProjectedALS{T}, X::Matrix{T}, W::Matrix{T}, H::Matrix{T}; handle::Handle=Handle(), x_resident::Bool=false) where T
+    nmf_checksize(X, W, H)                                    # src/projals.jl:37-39
+    x_resident || set_X!(handle, X)
+    _solve_projals(handle, W, H, alg.maxiter, alg.tol, alg.lambda_w, alg.lambda_h, alg.update_H, alg.verbose)
+end
+function solve!(alg::CoordinateDescent{T}, X::Matrix{T}, W::Matrix{T}, H::Matrix{T}; handle::Handle=Handle(), x_resident::Bool=false) where T
+    nmf_checksize(X, W, H)                                    # src/coorddesc.jl:49-51
+    x_resident || set_X!(handle, X)
+    _solve_cd(handle, W, H, alg)
+end
+function solve!(alg::ALSPGrad{T}, X::Matrix{T}, W::Matrix{T}, H::Matrix{T}; handle::Handle=Handle(), x_resident::Bool=false) where T
+    nmf_checksize(X, W, H)                                    # src/alspgrad.jl:381-383
+    x_resident || set_X!(handle, X)
+    _solve_alspgrad(handle, W, H, alg)
 end
 
 # ---- randinit (src/initialization.jl:4-17, src/utils.jl:26-32) and nnmf (src/interf.jl:3-101) -------------------
@@ -187,21 +266,25 @@ function nnmf(X::AbstractMatrix{T}, k::Integer; init::Symbol=:nndsvdar, initdata
     else
         W0 === nothing && H0 === nothing || @warn "Ignore W0 and H0 except for :custom initialization."
     end
-    W, H = init == :random ? randinit(p, n, k, T; normalize=true) :
+    initH = alg != :projals                                  # src/interf.jl:39
+    W, H = init == :random ? randinit(p, n, k, T; normalize=true, zeroh=!initH) :
            init == :custom ? (Matrix{T}(W0), Matrix{T}(H0)) :
            init in (:nndsvd, :nndsvda, :nndsvdar, :spa) ? error("init=:$init is not on the accelerated path yet; use :random or :custom") :
            throw(ArgumentError("Invalid value for init."))
     inst = alg == :multmse ? MultUpdate{T}(obj=:mse, maxiter=maxiter, tol=tol, verbose=verbose, update_H=update_H) :
            alg == :multdiv ? MultUpdate{T}(obj=:div, maxiter=maxiter, tol=tol, verbose=verbose, update_H=update_H) :
            alg == :greedycd ? GreedyCD{T}(maxiter=maxiter, tol=tol, verbose=verbose, update_H=update_H) :
-           alg in (:projals, :alspgrad, :cd, :spa) ? error("alg=:$alg is not on the accelerated path yet") :
+           alg == :projals ? ProjectedALS{T}(maxiter=maxiter, tol=tol, verbose=verbose, update_H=update_H) :
+           alg == :alspgrad ? ALSPGrad{T}(maxiter=maxiter, tol=tol, verbose=verbose, update_H=update_H) :
+           alg == :cd ? CoordinateDescent{T}(maxiter=maxiter, tol=tol, verbose=verbose, update_H=update_H) :
+           alg == :spa ? error("alg=:spa is not on the accelerated path") :
            throw(ArgumentError("Invalid algorithm."))
     h = Handle(device)
     Xm = Matrix{T}(X)
     set_X!(h, Xm)                                      # X stays resident on the GPU across replicates
     ret = solve!(inst, Xm, W, H; handle=h, x_resident=true)
     for _ in 2:replicates                              # src/interf.jl:91-98
-        Wr, Hr = randinit(p, n, k, T; normalize=true)
+        Wr, Hr = randinit(p, n, k, T; normalize=true, zeroh=!initH)
         tmp = solve!(inst, Xm, Wr, Hr; handle=h, x_resident=true)
         if ret.objvalue > tmp.objvalue
             ret = tmp

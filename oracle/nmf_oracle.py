@@ -20,6 +20,9 @@ Reference map (file:line under /root/reference/src):
   MultUpdate (ctor)  multupd.jl:9-43         solve_multupdate  multupd.jl:45-52
   MultUpdMSE         multupd.jl:56-116       MultUpdDiv        multupd.jl:121-193
   GreedyCD (ctor)    greedycd.jl:10-31       GreedyCDUpd       greedycd.jl:36-178
+  ProjectedALS       projals.jl:18-107       pdsolve/pdrsolve  utils.jl:63-84
+  CoordinateDescent  coorddesc.jl:24-181     ALSPGrad          alspgrad.jl:9-425
+  nndsvd             initialization.jl:26-137
   randinit           initialization.jl:4-17  normalize1_cols   utils.jl:26-32
   nnmf               interf.jl:3-83          solve_replicates  interf.jl:85-101
 """
@@ -71,6 +74,14 @@ def _clib():
             getattr(_lib, f"oracle_gkldiv_{sfx}").restype = dbl
             getattr(_lib, f"oracle_greedycd_rows_{sfx}").argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64]
             getattr(_lib, f"oracle_greedycd_rows_{sfx}").restype = i64
+            getattr(_lib, f"oracle_projectnn_{sfx}").argtypes = [vp, i64]
+            getattr(_lib, f"oracle_projectnn_{sfx}").restype = None
+            getattr(_lib, f"oracle_cd_sweep_{sfx}").argtypes = [vp, vp, vp, i64, i64, vp]
+            getattr(_lib, f"oracle_cd_sweep_{sfx}").restype = ct
+            getattr(_lib, f"oracle_projgradnorm_{sfx}").argtypes = [vp, vp, i64]
+            getattr(_lib, f"oracle_projgradnorm_{sfx}").restype = ct
+            getattr(_lib, f"oracle_pg_step_{sfx}").argtypes = [vp, vp, ct, vp, vp, i64]
+            getattr(_lib, f"oracle_pg_step_{sfx}").restype = None
     return _lib
 
 
@@ -392,12 +403,347 @@ def solve_greedycd(alg: GreedyCD, X, W, H, log=None) -> Result:
     return res
 
 
+# --------------------------------------------------------------------------------------------------
+# projals.jl
+# --------------------------------------------------------------------------------------------------
+def projectnn(A):
+    """utils.jl:34-41"""
+    assert A.flags.f_contiguous or A.flags.c_contiguous
+    _fn("oracle_projectnn", A.dtype)(_p(A), A.size)
+
+
+def adddiag(A, a):
+    """utils.jl:15-24"""
+    if a != 0.0:
+        A[np.diag_indices(A.shape[0])] += A.dtype.type(a)
+    return A
+
+
+def _lapack(name, T):
+    from scipy.linalg import lapack
+
+    return getattr(lapack, ("s" if np.dtype(T) == np.float32 else "d") + name)
+
+
+def pdsolve(A, x):
+    """utils.jl:63-70: potrf!('U', A); potrs!('U', A, x)  (LAPACK in T)."""
+    T = A.dtype
+    c, info = _lapack("potrf", T)(A, lower=0, overwrite_a=0)
+    if info != 0:
+        raise np.linalg.LinAlgError(f"potrf info={info}")   # Julia: PosDefException
+    sol, info = _lapack("potrs", T)(c, x, lower=0)
+    return _F(sol, dtype=T)
+
+
+def pdrsolve(A, B):
+    """utils.jl:72-84: x <- A * inv(B) with inv(B) by potrf!/potri!/copytri! (LAPACK in T)."""
+    T = B.dtype
+    c, info = _lapack("potrf", T)(B, lower=0, overwrite_a=0)
+    if info != 0:
+        raise np.linalg.LinAlgError(f"potrf info={info}")
+    inv, info = _lapack("potri", T)(c, lower=0)
+    inv = np.triu(inv) + np.triu(inv, 1).T          # copytri!(B, 'U')
+    return _mm(A, _F(inv, dtype=T))
+
+
+class ProjectedALS:
+    """projals.jl:18-35 (the reference constructor validates nothing)."""
+
+    def __init__(self, T=np.float64, maxiter=100, verbose=False, tol=None, update_H=True, lambda_w=None, lambda_h=None):
+        T = np.dtype(T)
+        c = np.cbrt(np.finfo(T).eps)
+        self.T = T
+        self.maxiter = int(maxiter)
+        self.verbose = bool(verbose)
+        self.tol = T.type(c if tol is None else tol)
+        self.update_H = bool(update_H)
+        self.lambda_w = T.type(c if lambda_w is None else lambda_w)
+        self.lambda_h = T.type(c if lambda_h is None else lambda_h)
+
+
+class ProjectedALSUpd:
+    """projals.jl:42-107"""
+
+    def __init__(self, T, update_H, lambda_w, lambda_h):
+        self.T, self.update_H, self.lambda_w, self.lambda_h = np.dtype(T), update_H, lambda_w, lambda_h
+
+    def prepare_state(self, X, W, H):  # :53-64
+        nmf_checksize(X, W, H)
+        return {"WH": _mm(W, H)}
+
+    def evaluate_objv(self, s, X, W, H):  # :66-75
+        T = self.T
+        r = T.type(0.5) * T.type(sqL2dist(X, s["WH"]))
+        if self.lambda_w > 0:
+            r = T.type(r + T.type(T.type(0.5) * self.lambda_w) * T.type(T.type(np.linalg.norm(W.ravel(order="K"))) ** 2))
+        if self.lambda_h > 0:
+            r = T.type(r + T.type(T.type(0.5) * self.lambda_h) * T.type(T.type(np.linalg.norm(H.ravel(order="K"))) ** 2))
+        return r
+
+    def update_wh(self, s, X, W, H):  # :77-107
+        if self.update_H:
+            WtW = adddiag(_mm(W.T, W), self.lambda_h)     # :91
+            H[...] = _mm(W.T, X)                          # :92
+            H[...] = pdsolve(WtW, H)                      # :93
+            projectnn(H)                                  # :94
+        HHt = adddiag(_mm(H, H.T), self.lambda_w)         # :99
+        XHt = _mm(X, H.T)                                 # :100
+        W[...] = pdrsolve(XHt, HHt)                       # :101
+        projectnn(W)                                      # :102
+        s["WH"] = _mm(W, H)                               # :105
+
+
+def solve_projals(alg: ProjectedALS, X, W, H, log=None) -> Result:
+    """projals.jl:37-39"""
+    upd = ProjectedALSUpd(alg.T, alg.update_H, alg.lambda_w, alg.lambda_h)
+    return nmf_skeleton(upd, X, W, H, alg.maxiter, alg.verbose, alg.tol, log=log)
+
+
+# --------------------------------------------------------------------------------------------------
+# coorddesc.jl
+# --------------------------------------------------------------------------------------------------
+_M64 = (1 << 64) - 1
+
+
+class ShufflePerm:
+    """Stand-in for `randperm(n_components)` (coorddesc.jl:131-132).  Julia's global RNG stream cannot be
+    reproduced outside Julia, so the project defines its own: splitmix64 seeded by the caller, Fisher-Yates from the
+    top.  The same generator is implemented in libnmfb200 (csrc/simt_engine.cu, `ShufflePerm`); one permutation is
+    drawn per call of _update_coord_descent! (W-step, then H-step), the state carries over within a solve."""
+
+    def __init__(self, seed: int):
+        self.s = int(seed) & _M64
+
+    def _next(self) -> int:
+        self.s = (self.s + 0x9E3779B97F4A7C15) & _M64
+        z = self.s
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+        return z ^ (z >> 31)
+
+    def perm(self, k: int) -> np.ndarray:
+        a = np.arange(k, dtype=np.int64)
+        for i in range(k - 1, 0, -1):
+            j = self._next() % (i + 1)
+            a[i], a[j] = a[j], a[i]
+        return a
+
+
+class CoordinateDescent:
+    """coorddesc.jl:24-46 (no validation in the reference constructor).  `seed` replaces Julia's global RNG for
+    shuffle=true."""
+
+    def __init__(self, T=np.float64, maxiter=100, verbose=False, tol=None, update_H=True, alpha=0.0, regularization="both",
+                 l1ratio=0.0, shuffle=False, seed=0):
+        T = np.dtype(T)
+        self.T = T
+        self.maxiter = int(maxiter)
+        self.verbose = bool(verbose)
+        self.tol = T.type(np.cbrt(np.finfo(T).eps) if tol is None else tol)
+        self.update_H = bool(update_H)
+        self.alpha = T.type(alpha)
+        self.l1ratio = T.type(l1ratio)
+        self.regularization = regularization
+        self.shuffle = bool(shuffle)
+        self.seed = int(seed)
+
+
+class CoordinateDescentUpd:
+    """coorddesc.jl:54-181"""
+
+    def __init__(self, T, alpha, l1ratio, regularization, shuffle, update_H, seed=0):
+        T = np.dtype(T)
+        aW = aH = T.type(0)
+        if regularization in ("both", "components"):        # :65-67
+            aH = T.type(alpha)
+        if regularization in ("both", "transformation"):    # :69-71
+            aW = T.type(alpha)
+        one = T.type(1)
+        self.T = T
+        self.l1W, self.l2W = T.type(aW * l1ratio), T.type(aW * T.type(one - l1ratio))   # :73-76
+        self.l1H, self.l2H = T.type(aH * l1ratio), T.type(aH * T.type(one - l1ratio))
+        self.shuffle, self.update_H = shuffle, update_H
+        self.rng = ShufflePerm(seed)
+        self.violation = T.type(0)
+
+    def prepare_state(self, X, W, H):  # :100
+        nmf_checksize(X, W, H)
+        return {}
+
+    def evaluate_objv(self, s, X, W, H):  # :102-105
+        return self.T.type(0.5) * self.T.type(sqL2dist(X, _mm(W, H)))
+
+    def _update(self, X, F, Ot, l1, l2):
+        """_update_coord_descent! :108-160 for F (rows x k) against Ot (cols x k); X is rows x cols."""
+        T = self.T
+        k = F.shape[1]
+        HHt = _mm(Ot.T, Ot)                      # :112
+        XHt = _mm(X, Ot)                         # :118
+        if l2 > 0.0:
+            HHt[np.diag_indices(k)] += T.type(l2)    # :123-125
+        if l1 > 0.0:
+            XHt -= T.type(l1)                        # :126-128
+        perm = self.rng.perm(k) if self.shuffle else np.arange(k, dtype=np.int64)   # :129-133
+        return _fn("oracle_cd_sweep", T)(_p(F), _p(_F(HHt)), _p(_F(XHt)), F.shape[0], k, _p(perm))
+
+    def update_wh(self, s, X, W, H):  # :163-181
+        Ht = _F(H.T)
+        v = self._update(X, W, Ht, self.l1W, self.l2W)                 # :168
+        if self.update_H:
+            v = self.T.type(v + self._update(X.T, Ht, W, self.l1H, self.l2H))   # :171-176
+            H[...] = Ht.T
+        self.violation = v
+
+
+def solve_cd(alg: CoordinateDescent, X, W, H, log=None) -> Result:
+    """coorddesc.jl:49-51"""
+    upd = CoordinateDescentUpd(alg.T, alg.alpha, alg.l1ratio, alg.regularization, alg.shuffle, alg.update_H, alg.seed)
+    return nmf_skeleton(upd, X, W, H, alg.maxiter, alg.verbose, alg.tol, log=log)
+
+
+# --------------------------------------------------------------------------------------------------
+# alspgrad.jl
+# --------------------------------------------------------------------------------------------------
+def projgradnorm(g, x):
+    """alspgrad.jl:9-19"""
+    g = np.ascontiguousarray(g.ravel(order="K"))
+    x = np.ascontiguousarray(x.ravel(order="K"))
+    return g.dtype.type(_fn("oracle_projgradnorm", g.dtype)(_p(g), _p(x), g.size))
+
+
+def _dot(a, b):
+    """BLAS.dot on the dense storage (alspgrad.jl:141,143)."""
+    return a.dtype.type(np.dot(a.ravel(order="K"), b.ravel(order="K")))
+
+
+def _alspgrad_sub(F, gram, cross, left: bool, maxiter, traceiter, tolg, beta, sigma):
+    """_alspgrad_updateh! (alspgrad.jl:86-191, left=True: G = gram*F - cross) and _alspgrad_updatew!
+    (alspgrad.jl:242-347, left=False: G = F*gram - cross).  F is updated in place; returns the number of
+    sub-iterations t.  Both routines are the same algorithm up to the side the k x k Gram multiplies from."""
+    T = F.dtype
+    assert _isF(F)
+    Fn = np.empty_like(F, order="F")
+    Fp = np.empty_like(F, order="F")
+    D = np.empty_like(F, order="F")
+    step = _fn("oracle_pg_step", T)
+    t = 0
+    converged = False
+    decr_alpha = True
+    alpha = T.type(1)                                   # :112
+    mul = (lambda M: _mm(gram, M)) if left else (lambda M: _mm(M, gram))
+    while not converged and t < maxiter:
+        t += 1
+        G = mul(F)                                      # :117
+        G -= cross                                      # :118-120
+        pgnrm = projgradnorm(G, F)                      # :123
+        if pgnrm < tolg:
+            converged = True
+        it = 0
+        if not converged:
+            while it < traceiter:
+                it += 1
+                if not np.isfinite(alpha):
+                    raise FloatingPointError("alpha is not finite")     # :132 `error("α is not finite")`
+                step(_p(F), _p(G), T.type(alpha), _p(Fn), _p(D), F.size)   # :134-139
+                dv1 = _dot(G, D)                        # :142
+                GD = mul(D)                             # :143
+                dv2 = _dot(GD, D)                       # :144
+                suff_decr = T.type(T.type(T.type(1 - sigma) * dv1) + T.type(T.type(0.5) * dv2)) < 0   # :147
+                if it == 1:
+                    decr_alpha = not suff_decr          # :150
+                    np.copyto(Fp, F)                    # :151
+                if decr_alpha:
+                    if suff_decr:
+                        np.copyto(F, Fn)                # :156
+                        break
+                    alpha = T.type(alpha * beta)        # :159
+                else:
+                    # isapprox(Hp, Hn, atol=eps(T)): rtol defaults to 0 when atol > 0  => norm(Hp - Hn) <= eps(T)
+                    close = T.type(np.linalg.norm((Fp - Fn).ravel(order="K"))) <= np.finfo(T).eps
+                    if (not suff_decr) or close:        # :162
+                        np.copyto(F, Fp)                # :163
+                        break
+                    alpha = T.type(alpha / beta)        # :166
+                    np.copyto(Fp, Fn)                   # :167
+    return t
+
+
+def alspgrad_updateh(X, W, H, maxiter=1000, traceiter=20, tolg=None, beta=0.2, sigma=0.01):
+    """alspgrad.jl:64-84"""
+    T = H.dtype
+    tolg = T.type(np.cbrt(np.finfo(T).eps) if tolg is None else tolg)
+    return _alspgrad_sub(H, _mm(W.T, W), _mm(W.T, X), True, maxiter, traceiter, tolg, T.type(beta), T.type(sigma))
+
+
+def alspgrad_updatew(X, W, H, maxiter=1000, traceiter=20, tolg=None, beta=0.2, sigma=0.01):
+    """alspgrad.jl:221-240"""
+    T = W.dtype
+    tolg = T.type(np.cbrt(np.finfo(T).eps) if tolg is None else tolg)
+    return _alspgrad_sub(W, _mm(H, H.T), _mm(X, H.T), False, maxiter, traceiter, tolg, T.type(beta), T.type(sigma))
+
+
+class ALSPGrad:
+    """alspgrad.jl:352-373"""
+
+    def __init__(self, T=np.float64, maxiter=100, maxsubiter=200, tol=None, tolg=None, update_H=True, verbose=False):
+        T = np.dtype(T)
+        eps = np.finfo(T).eps
+        self.T = T
+        self.maxiter, self.maxsubiter = int(maxiter), int(maxsubiter)
+        self.tol = T.type(np.cbrt(eps) if tol is None else tol)
+        self.tolg = T.type(eps ** 0.25 if tolg is None else tolg)
+        self.update_H, self.verbose = bool(update_H), bool(verbose)
+
+
+class ALSPGradUpd:
+    """alspgrad.jl:375-425 (mutable: tolg shrinks by 10x whenever a sub-solve stops after one iteration)."""
+
+    def __init__(self, T, update_H, maxsubiter, tolg):
+        self.T, self.update_H, self.maxsubiter, self.tolg = np.dtype(T), update_H, maxsubiter, np.dtype(T).type(tolg)
+        self.subiters = 0
+
+    def prepare_state(self, X, W, H):  # :385-396
+        nmf_checksize(X, W, H)
+        return {"WH": _mm(W, H)}
+
+    def evaluate_objv(self, s, X, W, H):  # :398
+        return self.T.type(0.5) * self.T.type(sqL2dist(X, s["WH"]))
+
+    def update_wh(self, s, X, W, H):  # :400-425
+        T = self.T
+        if self.update_H:
+            itH = _alspgrad_sub(H, _mm(W.T, W), _mm(W.T, X), True, self.maxsubiter, 20, self.tolg, T.type(0.2), T.type(0.01))
+            self.subiters += itH
+            if itH == 1:
+                self.tolg = T.type(self.tolg * 0.1)     # :409-411 (Float64 literal, stored back into ::T)
+        itW = _alspgrad_sub(W, _mm(H, H.T), _mm(X, H.T), False, self.maxsubiter, 20, self.tolg, T.type(0.2), T.type(0.01))
+        self.subiters += itW
+        if itW == 1:
+            self.tolg = T.type(self.tolg * 0.1)         # :419-421
+        s["WH"] = _mm(W, H)                             # :424
+
+
+def solve_alspgrad(alg: ALSPGrad, X, W, H, log=None) -> Result:
+    """alspgrad.jl:381-383"""
+    upd = ALSPGradUpd(alg.T, alg.update_H, alg.maxsubiter, alg.tolg)
+    res = nmf_skeleton(upd, X, W, H, alg.maxiter, alg.verbose, alg.tol, log=log)
+    res.subiters = upd.subiters
+    res.tolg_final = upd.tolg
+    return res
+
+
 def solve(alg, X, W, H, log=None) -> Result:
     """NMF.solve!(alg, X, W, H) dispatch for the algorithm types on the accelerated path."""
     if isinstance(alg, MultUpdate):
         return solve_multupdate(alg, X, W, H, log=log)
     if isinstance(alg, GreedyCD):
         return solve_greedycd(alg, X, W, H, log=log)
+    if isinstance(alg, ProjectedALS):
+        return solve_projals(alg, X, W, H, log=log)
+    if isinstance(alg, CoordinateDescent):
+        return solve_cd(alg, X, W, H, log=log)
+    if isinstance(alg, ALSPGrad):
+        return solve_alspgrad(alg, X, W, H, log=log)
     raise TypeError(f"oracle has no restatement for {type(alg).__name__}")
 
 
@@ -432,7 +778,8 @@ def solve_replicates(alg, X, W, H, replicates, initH, rng):
 def nnmf(X, k, init="nndsvdar", alg="greedycd", maxiter=100, tol=None, replicates=1, W0=None, H0=None,
          update_H=True, verbose=False, rng=None):
     """interf.jl:3-83 restricted to what the accelerated path covers: init in {:random, :custom},
-    alg in {:multmse, :multdiv, :greedycd}.  Validation order and messages follow the reference."""
+    alg in {:multmse, :multdiv, :greedycd, :projals, :alspgrad, :cd}.  Validation order and messages follow the
+    reference."""
     X = _F(X)
     T = X.dtype
     if tol is None:
@@ -475,8 +822,14 @@ def nnmf(X, k, init="nndsvdar", alg="greedycd", maxiter=100, tol=None, replicate
         inst = MultUpdate(T, obj="div", maxiter=maxiter, tol=tol, verbose=verbose, update_H=update_H)
     elif alg == "greedycd":
         inst = GreedyCD(T, maxiter=maxiter, tol=tol, verbose=verbose, update_H=update_H)
-    elif alg in ("projals", "alspgrad", "cd", "spa"):
-        raise NotImplementedError(f"alg=:{alg} is outside the restated hot path (SURVEY.md section 8f)")
+    elif alg == "projals":
+        inst = ProjectedALS(T, maxiter=maxiter, tol=tol, verbose=verbose, update_H=update_H)
+    elif alg == "alspgrad":
+        inst = ALSPGrad(T, maxiter=maxiter, tol=tol, verbose=verbose, update_H=update_H)
+    elif alg == "cd":
+        inst = CoordinateDescent(T, maxiter=maxiter, tol=tol, verbose=verbose, update_H=update_H)
+    elif alg == "spa":
+        raise NotImplementedError("alg=:spa is outside the restated hot path (SURVEY.md section 8f)")
     else:
         raise ArgumentError("Invalid algorithm.")
     return solve_replicates(inst, X, W, H, replicates, initH, rng)

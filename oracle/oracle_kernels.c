@@ -10,7 +10,8 @@
  * PARITY STATUS: Julia is not installable in the build image, so the oracle cannot be compared
  * bit-for-bit with a run of the reference ("parity unpinned" at bit level).  It is pinned against
  * every fixture the reference's own tests hold for this path (test/testproblems.jl laurberg6x3,
- * test/multupd.jl, test/greedycd.jl, test/interf.jl) -- see tests/test_oracle.py.
+ * test/multupd.jl, test/greedycd.jl, test/coorddesc.jl, test/alspgrad.jl, test/interf.jl) -- see
+ * tests/test_oracle.py.
  *
  * Conventions: all matrices column-major (Julia layout), 0-based indices here, 1-based in the
  * citations.  `ORACLE_T` is instantiated for float and double through the macro block at the end.
@@ -186,6 +187,58 @@ int64_t CAT(oracle_greedycd_rows, SFX)(T* F, T* G, const T* P, T* S, T* D, T* Fn
         F[i] = v;                                                                                      \
     }                                                                                                  \
     return updates;                                                                                    \
+}                                                                                                      \
+                                                                                                       \
+/* src/utils.jl:34-41 projectnn!: negatives to zero (NaN < 0 is false => NaN preserved) */             \
+void CAT(oracle_projectnn, SFX)(T* A, int64_t len) {                                                   \
+    for (int64_t i = 0; i < len; ++i)                                                                  \
+        if (A[i] < (T)0) A[i] = (T)0;                                                                  \
+}                                                                                                      \
+                                                                                                       \
+/* src/coorddesc.jl:138-157 -- the sweep of _update_coord_descent! after HHt (+l2 on the diagonal)     \
+ * and XHt (-l1) are formed.  F rows x k col-major ("W" in the reference, updated in place), HHt       \
+ * k x k, XHt rows x k, perm = the component order (0-based; 1:k or randperm, :131-135).  Components   \
+ * outer, rows inner, gradient accumulated sequentially starting from -XHt[i,t].  Returns the          \
+ * violation sum (:150; stored in the state, never used for stopping). */                              \
+T CAT(oracle_cd_sweep, SFX)(T* F, const T* HHt, const T* XHt, int64_t rows, int64_t k,                 \
+                            const int64_t* perm) {                                                     \
+    T violation = (T)0;                                                                                \
+    for (int64_t tt = 0; tt < k; ++tt) {                                                               \
+        int64_t t = perm[tt];                                                                          \
+        for (int64_t i = 0; i < rows; ++i) {                                                           \
+            T grad = -XHt[i + t * rows];                                                               \
+            for (int64_t r = 0; r < k; ++r) grad += HHt[t + r * k] * F[i + r * rows];                  \
+            T pg = (F[i + t * rows] == (T)0) ? (grad < (T)0 ? grad : (T)0) : grad;                     \
+            violation += (T)fabs((double)pg);                                                          \
+            T hess = HHt[t + t * k];                                                                   \
+            if (hess != (T)0) {                                                                        \
+                T v = F[i + t * rows] - grad / hess;                                                   \
+                F[i + t * rows] = CAT(jl_max, SFX)(v, (T)0);                                           \
+            }                                                                                          \
+        }                                                                                              \
+    }                                                                                                  \
+    return violation;                                                                                  \
+}                                                                                                      \
+                                                                                                       \
+/* src/alspgrad.jl:9-19 projgradnorm: sqrt of the sequential sum (in T) of g_i^2 over entries with     \
+ * g_i < 0 or x_i > 0 */                                                                               \
+T CAT(oracle_projgradnorm, SFX)(const T* g, const T* x, int64_t len) {                                 \
+    T v = (T)0;                                                                                        \
+    for (int64_t i = 0; i < len; ++i) {                                                                \
+        T gi = g[i];                                                                                   \
+        if (gi < (T)0 || x[i] > (T)0) v += gi * gi;                                                    \
+    }                                                                                                  \
+    return (T)sqrt((double)v);                                                                         \
+}                                                                                                      \
+                                                                                                       \
+/* src/alspgrad.jl:134-138 (and :290-294): Fn = max(F - alpha*G, 0), D = Fn - F */                     \
+void CAT(oracle_pg_step, SFX)(const T* F, const T* G, T alpha, T* Fn, T* D, int64_t len) {             \
+    for (int64_t i = 0; i < len; ++i) {                                                                \
+        T fi = F[i];                                                                                   \
+        T v = CAT(jl_max, SFX)((T)(fi - (T)(alpha * G[i])), (T)0);                                     \
+        Fn[i] = v;                                                                                     \
+        D[i] = v - fi;                                                                                 \
+    }                                                                                                  \
 }
 
 DEFINE_ORACLE(float, f32, FLT_EPSILON)

@@ -3,7 +3,7 @@
 The reference (Julia) cannot run in the build image and holds no golden vectors of its own, so these
 are produced by the oracle restatement (oracle/nmf_oracle.py) on seeded inputs.  Each file stores the
 inputs (X, W0, H0, options) and the oracle outputs (W, H, niters, converged, objvalue).
-Run from the repo root:  python tests/golden/make_golden.py
+Run from the repo root:  python tests/golden/make_golden.py [name-substring ...]
 """
 import os
 import sys
@@ -15,6 +15,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import nmf_oracle as O  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
+ONLY = sys.argv[1:]  # optional name filters: regenerate only the matching cases
 
 
 def planted(rng, p, n, k, T):
@@ -24,7 +25,28 @@ def planted(rng, p, n, k, T):
     return np.asfortranarray(Wg @ Hg, dtype=T)
 
 
+def case2(name, alg, T, p, n, k, data_seed, data="uniform", zeroh=False, **opts):
+    """ProjectedALS / CoordinateDescent / ALSPGrad: options stored as JSON."""
+    import json
+    if ONLY and not any(o in name for o in ONLY):
+        return
+    rng = np.random.default_rng(data_seed)
+    T = np.dtype(T)
+    X = np.asfortranarray(rng.random((p, n)), dtype=T) if data == "uniform" else planted(rng, p, n, k, T)
+    W0, H0 = O.randinit(p, n, k, T, rng, normalize=True, zeroh=zeroh)
+    W, H = W0.copy(order="F"), H0.copy(order="F")
+    cls = {"projals": O.ProjectedALS, "cd": O.CoordinateDescent, "alspgrad": O.ALSPGrad}[alg]
+    r = O.solve(cls(T, **opts), X, W, H)
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"), X=X, W0=W0, H0=H0, W=W, H=H, niters=r.niters, converged=r.converged,
+        objvalue=float(r.objvalue), alg=alg, k=k, opts=json.dumps(opts),
+    )
+    print(f"{name}: niters={r.niters} converged={r.converged} objvalue={float(r.objvalue):.9g}")
+
+
 def case(name, alg, T, p, n, k, maxiter, tol, seed, data="uniform", **kw):
+    if ONLY and not any(o in name for o in ONLY):
+        return
     rng = np.random.default_rng(seed)
     T = np.dtype(T)
     X = np.asfortranarray(rng.random((p, n)), dtype=T) if data == "uniform" else planted(rng, p, n, k, T)
@@ -55,3 +77,12 @@ if __name__ == "__main__":
     case("multdiv_f32_planted", "multdiv", np.float32, 64, 48, 4, 30, 1e-9, 5, data="planted")
     case("greedycd_f64_uniform", "greedycd", np.float64, 60, 50, 4, 12, 1e-12, 6)
     case("greedycd_f32_planted_reg", "greedycd", np.float32, 48, 40, 4, 12, 1e-9, 7, data="planted", lambda_w=1e-4, lambda_h=1e-4)
+    # SURVEY.md section 8f rows 1-2
+    case2("projals_f64_uniform", "projals", np.float64, 60, 48, 4, 8, zeroh=True, maxiter=20, tol=1e-12)
+    case2("projals_f32_planted", "projals", np.float32, 64, 56, 5, 9, data="planted", zeroh=True, maxiter=15, tol=1e-9, lambda_w=1e-2, lambda_h=2e-2)
+    case2("projals_f64_noH", "projals", np.float64, 40, 36, 3, 10, maxiter=10, tol=1e-12, update_H=False)
+    case2("cd_f64_uniform", "cd", np.float64, 56, 44, 4, 11, maxiter=15, tol=1e-12)
+    case2("cd_f32_planted_reg_shuffle", "cd", np.float32, 48, 60, 5, 12, data="planted", maxiter=15, tol=1e-9, alpha=1e-3, l1ratio=0.5, shuffle=True, seed=42)
+    case2("cd_f64_components_only", "cd", np.float64, 36, 40, 3, 13, maxiter=12, tol=1e-12, alpha=1e-2, l1ratio=0.25, regularization="components")
+    case2("alspgrad_f64_uniform", "alspgrad", np.float64, 48, 40, 4, 14, maxiter=8, tol=1e-12, maxsubiter=50)
+    case2("alspgrad_f32_planted", "alspgrad", np.float32, 40, 48, 3, 15, data="planted", maxiter=8, tol=1e-9, maxsubiter=50)

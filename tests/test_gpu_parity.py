@@ -16,11 +16,8 @@ def _relerr(a, b):
 
 
 def _inst(mod, g):
-    T = g["X"].dtype
-    alg = str(g["alg"])
-    kw = dict(maxiter=int(g["maxiter"]), tol=float(g["tol"]), lambda_w=float(g["lambda_w"]), lambda_h=float(g["lambda_h"]),
-              update_H=bool(g["update_H"]))
-    return mod.MultUpdate(T, obj=alg[4:], **kw) if alg.startswith("mult") else mod.GreedyCD(T, **kw)
+    from test_oracle import golden_instance
+    return golden_instance(mod, g)
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(g)[:-4] for g in GOLDEN])
@@ -37,10 +34,15 @@ def test_simt_engine_vs_golden(NMF, path):
     tol = 1e-9 if T == np.float64 else 2e-4
     if alg == "greedycd":  # argmax decisions can flip on last-bit differences of the GEMMs
         tol = 1e-6 if T == np.float64 else 2e-3
+    if alg == "projals":   # k x k solves amplify summation-order noise by cond(Gram + lambda I); GPU inverts in Float64
+        tol = 1e-7 if T == np.float64 else 5e-3
+    if alg == "alspgrad":  # Armijo decisions are discrete; dot products are accumulated in Float64 on the GPU
+        tol = 1e-7 if T == np.float64 else 5e-3
     assert abs(float(r.objvalue) - float(g["objvalue"])) <= tol * abs(float(g["objvalue"]))
     if alg != "greedycd":
         assert _relerr(W, g["W"]) <= tol and _relerr(H, g["H"]) <= tol
-    if not bool(g["update_H"]):
+    upd_H = bool(g["update_H"]) if "update_H" in g else bool(__import__("json").loads(str(g["opts"])).get("update_H", True))
+    if not upd_H:
         assert (H == g["H0"]).all()  # test/interf.jl:35 -- bit-identical
 
 
@@ -174,7 +176,7 @@ def test_abi_errors(NMF):
         with pytest.raises(TypeError):
             s.solve(NMF.MultUpdate(np.float32), W, H)
         with pytest.raises(NotImplementedError):
-            s.solve(NMF.ProjectedALS(np.float64), W, H)
+            s.solve(NMF.SPA(np.float64), W, H)
         import ctypes
         res = NMF._lib.NmfResult()
         st = s._lib.nmfb200_solve_multmse_f64(s._h, W.ctypes.data_as(ctypes.c_void_p), 10, H.ctypes.data_as(ctypes.c_void_p), 2, 2,

@@ -15,7 +15,7 @@ def test_header_symbols_exported_and_bound(NMF):
     hdr = open(os.path.join(ROOT, "include", "nmfb200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     declared = set(re.findall(r"\b(nmfb200_[A-Za-z0-9_]+)\s*\(", hdr)) - {"nmfb200_trace_fn"}
-    assert len(declared) >= 21
+    assert len(declared) >= 27
     NMF.build.build_library()
     lib = NMF._lib.load()  # resolves every bound symbol or raises
     assert declared == set(NMF._lib.SIGNATURES), (declared ^ set(NMF._lib.SIGNATURES))
@@ -29,8 +29,8 @@ def test_header_symbols_exported_and_bound(NMF):
 
 def test_result_struct_matches_header(NMF):
     import ctypes
-    # int64, int32, int32, 4 doubles, 2 int64, double, int64 -> 80 bytes, no padding surprises
-    assert ctypes.sizeof(NMF._lib.NmfResult) == 8 + 4 + 4 + 8 * 4 + 8 * 2 + 8 + 8
+    # int64, int32, int32, 4 doubles, 2 int64, double, int64, int64, double -> 96 bytes, no padding surprises
+    assert ctypes.sizeof(NMF._lib.NmfResult) == 8 + 4 + 4 + 8 * 4 + 8 * 2 + 8 + 8 + 8 + 8
 
 
 def test_library_built_for_sm100a_only(NMF):
@@ -111,8 +111,8 @@ def test_nnmf_validation_before_gpu(NMF):
         NMF.nnmf(X, 2, alg="spa", init="random")
     with pytest.raises(NMF.ArgumentError, match="maxiter must be greater than 1"):
         NMF.nnmf(X, 2, alg="multmse", init="random", maxiter=1)
-    with pytest.raises(NotImplementedError):
-        NMF.nnmf(X, 2, alg="projals", init="random")
+    with pytest.raises(NMF.ArgumentError, match="regularization"):
+        NMF.CoordinateDescent(np.float64, regularization="bogus")
     with pytest.raises(NotImplementedError):
         NMF.nnmf(X, 2)  # default init=:nndsvdar is a "next" row
     with warnings.catch_warnings(record=True) as w:
