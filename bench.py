@@ -230,9 +230,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     device_solve(max(args.warmup, 3), timed=False)
     barrier()
     with ClockSampler(local_rank) as clk:
-        res = device_solve(args.steps, timed=True)
+        res = device_solve(args.steps, timed=args.timeline)   # the headline loop: no per-kernel events in the stream
         barrier()
     assert res.niters == max(args.steps, 2) and res.engine == 1, "tensor-core engine did not run the requested iterations"
+    # second pass with CUDA events around every mu_update_kernel launch (roofline of the dominant kernel); the events
+    # serialise the launches (no programmatic-dependent-launch overlap), so this pass is not the throughput number
+    res_k = res if args.timeline else device_solve(args.steps, timed=True)
+    barrier()
     loop_ms = torch.tensor([res.solve_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(loop_ms, op=dist.ReduceOp.MAX)
@@ -242,37 +246,40 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     value = p_total * n * it_per_s
 
     # ---- end-to-end through the host API (host buffers in pinned memory)
-    e2e_iters = iters
-    Wh, Hh = W0.copy(order="F"), H0.copy(order="F")
-    sess2 = NMF.Session(device=local_rank, engine="tc")
-    if world > 1:
-        uid = [NMF.Session.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        sess2.comm_init(rank, world, uid[0])
-    sess2.set_option("check_every", max(e2e_iters, 1))
-    alg = NMF.MultUpdate(np.float32, obj="mse", maxiter=max(e2e_iters, 2), tol=1e-30)
-    for rep in range(2):  # first pass warms allocations, second is timed
-        Wh[...] = W0
-        Hh[...] = H0
-        barrier()
-        t0 = time.perf_counter()
-        sess2.set_X(X)
-        r2 = sess2.solve(alg, Wh, Hh)
-        torch.cuda.synchronize()
-        t_e2e = time.perf_counter() - t0
-    t_e2e_t = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t_e2e_t, op=dist.ReduceOp.MAX)
-    t_e2e = float(t_e2e_t.item())
-    e2e_value = p_total * n * r2.niters / t_e2e
-    h2d = (X.nbytes + W0.nbytes + H0.nbytes) / r2.niters
-    d2h = (W0.nbytes + H0.nbytes + 8) / r2.niters
-    objv = float(r2.objvalue)
-    sess2.close()
+    e2e_value = t_e2e = h2d = d2h = objv = float('nan')
+    r2 = None
+    if not args.no_e2e:
+        e2e_iters = iters
+        Wh, Hh = W0.copy(order="F"), H0.copy(order="F")
+        sess2 = NMF.Session(device=local_rank, engine="tc")
+        if world > 1:
+            uid = [NMF.Session.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            sess2.comm_init(rank, world, uid[0])
+        sess2.set_option("check_every", max(e2e_iters, 1))
+        alg = NMF.MultUpdate(np.float32, obj="mse", maxiter=max(e2e_iters, 2), tol=1e-30)
+        for rep in range(2):  # first pass warms allocations, second is timed
+            Wh[...] = W0
+            Hh[...] = H0
+            barrier()
+            t0 = time.perf_counter()
+            sess2.set_X(X)
+            r2 = sess2.solve(alg, Wh, Hh)
+            torch.cuda.synchronize()
+            t_e2e = time.perf_counter() - t0
+        t_e2e_t = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t_e2e_t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t_e2e_t.item())
+        e2e_value = p_total * n * r2.niters / t_e2e
+        h2d = (X.nbytes + W0.nbytes + H0.nbytes) / r2.niters
+        d2h = (W0.nbytes + H0.nbytes + 8) / r2.niters
+        objv = float(r2.objvalue)
+        sess2.close()
 
     # ---- roofline of the dominant kernel (mu_update_kernel: one launch per half-step)
-    launches = max(int(res.hot_kernel_launches), 1)
-    kern_ms = res.hot_kernel_ms / launches if res.hot_kernel_launches else float("nan")
+    launches = max(int(res_k.hot_kernel_launches), 1)
+    kern_ms = res_k.hot_kernel_ms / launches if res_k.hot_kernel_launches else float("nan")
     # algorithmic bytes per launch: the bf16 X panel once + the factor read & written in fp32
     alg_bytes = rows * n * 2 + 2 * ((rows + n) / 2) * k * 4
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
@@ -296,12 +303,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                        "l2": "inputs larger than L2: two 512 MiB bf16 X panels per iteration vs 126 MB L2, no flush needed",
                        "engine": "tc", "objvalue_e2e": objv},
             "clocks": clk.summary(),
-            "e2e": {"value": e2e_value, "unit": UNIT, "iters_per_sec": r2.niters / t_e2e, "seconds": t_e2e, "iters": r2.niters,
+            "e2e": {"value": e2e_value, "unit": UNIT, "iters_per_sec": (r2.niters / t_e2e) if r2 else None, "seconds": t_e2e, "iters": r2.niters if r2 else 0,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(res.kernel_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": traffic, "traffic_source": "profiles/r1f_update_kernel_ncu_full.md (ncu --set full, same workload)",
                          "kernel": "mu_update_kernel<128,0>", "kernel_ms": kern_ms, "launches_timed": launches,
+                         "loop_ms_per_step_with_kernel_events": res_k.solve_ms / max(res_k.niters, 1),
                          "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                          "tensor_tflops_whole_iteration": tflops, "tensor_frac_of_sustained_bf16": tflops / tf_peak},
         }
@@ -370,6 +378,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="experiments only: skip the end-to-end (host buffers) leg")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4"], help="cfg2 = headline (default); cfg3/cfg4 = secondary")
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc"])
     ap.add_argument("--timeline", action="store_true", help="print the per-phase event timeline of the iteration (stderr)")

@@ -187,8 +187,8 @@ int nmfb200_set_option(nmfb200_handle* h, const char* key, const char* value) {
             h->check_every = c;
         } else if (k == "tc_tile_rows") {
             h->tc_tile_rows = atoi(value);
-        } else if (k == "tc_prefetch") {
-            h->tc_prefetch = atoi(value);
+        } else if (k == "tc_pdl") {
+            h->tc_pdl = atoi(value);
         } else if (k == "tc_xchg") {
             if (v == "p2p") h->tc_xchg = 1;
             else if (v == "nccl") h->tc_xchg = 0;

@@ -112,10 +112,10 @@ struct nmfb200_handle {
     int check_every = 8;
     int time_kernels = 0;
     int tc_tile_rows = 0;  // 0 = auto
-    int tc_debug = 0;      // diagnostics (see UpdateParams::debug)
+    int tc_debug = 0;      // diagnostics: bit 3 (8) = record and print the phase clocks of the update kernel
     int tc_xchg = 1;       // multi-GPU exchange: 1 = fused peer-memory reduce-scatter/all-gather, 0 = ncclAllReduce
     nmfb200::Xchg xchg;
-    int tc_prefetch = 0;   // L2 prefetch distance of the X panel in k-blocks (0 = off)
+    int tc_pdl = 1;        // 1 = launch the update kernels as programmatic dependents of the reduce kernel before them
     std::vector<cudaEvent_t> ev_pool;  // events for time_kernels
     size_t ev_used = 0;
     nmfb200_trace_fn trace = nullptr;

@@ -19,6 +19,9 @@
 // the host polls that flag every `check_every` iterations.
 #include <cuda_bf16.h>
 
+#include <algorithm>
+#include <climits>
+
 #include "common.cuh"
 #include "gcd_kernels.cuh"
 #include "tc_ptx.cuh"
@@ -71,10 +74,8 @@ struct UpdateParams {
     const TcState* state;
     int64_t ldT;
     int R, Kdim;
-    int rotate;         // 1: CTA c walks the k-blocks starting at a hashed offset (wrap-around)
-    int prefetch;       // > 0: issue an L2 prefetch of the X tile `prefetch` k-blocks ahead of the ring
     int tile_rows;      // rows of F owned by one CTA (<= 128, multiple of 8); the TMA boxes of A / Fhi / Flo have this many rows
-    int debug;          // diagnostics only: bit 0 = load the B operand for the first k-block only (WRONG results)
+    long long* timing;  // diagnostics (tc_debug bit 3): CTA 0 records clock64() at its phase boundaries, see TSTAMP
     float lambda, delta;
 };
 
@@ -119,7 +120,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2(bf16 lo, bf16 hi) {
 template <int KP, int MODE>
 __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const __grid_constant__ UpdateParams prm) {
     using C = UpdCfg<KP>;
-    if (prm.state->converged) return;  // uniform: the loop has already met stop_condition
+    // The loop has already met stop_condition: nothing to do.  Under PDL (see launch_update) the predecessor may be
+    // deciding right now; a CTA that still reads 0 here streams its panel and skips the epilogue after pdl_wait().
+    if (__ldcg(&prm.state->converged)) return;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -138,16 +141,18 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
     static_assert(!STAGED || (KP / 32 + 2 * (KP / 64)) * 16384 + 2 * KP * 128 <= C::RING_BYTES, "staging does not fit in the ring");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#define TSTAMP(i) do { if (prm.timing != nullptr && blockIdx.x == 0) prm.timing[i] = clock64(); } while (0)
+    if (threadIdx.x == 0) TSTAMP(0);
+    if (prm.timing != nullptr && threadIdx.x == 0) {  // every CTA: global timer at entry (and exit, below)
+        long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        prm.timing[16 + 2 * blockIdx.x] = gt;
+    }
     const int tile_rows = prm.tile_rows;
     const int r0 = blockIdx.x * tile_rows;
     const uint32_t a_bytes = (uint32_t)tile_rows * 128u;
     const int nkb = (MODE == 2) ? 0 : (prm.Kdim + 63) / 64;
     constexpr int NPRE = (MODE == 1 || MODE == 4) ? 0 : 3 * C::NSLAB;
-    const int total = NPRE + nkb;
-    // De-correlate the CTAs: they all stream panels whose bases differ by exact multiples of the tile size
-    // (4 MiB at config 2) in lockstep.  CTA c starts its k-loop at a hashed block and wraps around (the sum
-    // over k is order independent; the order is fixed per CTA, so results stay deterministic).
-    const int kb_start = (prm.rotate && nkb > 0) ? (int)(((uint32_t)blockIdx.x * 0x9E3779B1u >> 8) % (uint32_t)nkb) : 0;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&prm.tmA);
@@ -171,36 +176,40 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Block order: the nkb numerator blocks FIRST (they depend on nothing the preceding kernel writes), then the NPRE
+    // denominator blocks (the Gram hi/lo they read is produced by the immediately preceding reduce kernel).
+    // The two single-thread loops below are the latency-critical part of the kernel: no per-block branches, no
+    // div/mod, everything loop-invariant is hoisted (an extra compare per block is measurable at 256 blocks).
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            int s = 0, kb = kb_start;
+            int s = 0;
             uint32_t ph = 0;
             uint8_t* dst = smem;
-            const int arow0 = blockIdx.x * nkb * tile_rows;
-            const bool dbg_noB = (prm.debug & 1) != 0;
-            for (int b = 0; b < total; ++b) {
+            int arow = blockIdx.x * nkb * tile_rows;   // tile-contiguous X: k-block kb of this tile starts at panel row arow0 + kb*tile_rows
+            const uint32_t num_tx = a_bytes + (uint32_t)C::B_BYTES;
+            for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(&empty_bar[s], ph ^ 1u);
-                if (b < NPRE) {  // Den = Fhi*Phi + Fhi*Plo + Flo*Phi
-                    mbar_arrive_expect_tx(&full_bar[s], a_bytes + C::B_BYTES);
-                    const int t = b / C::NSLAB, sl = b % C::NSLAB;
-                    tma_load_2d(dst, t == 2 ? &prm.tmFlo : &prm.tmFhi, &full_bar[s], 64 * sl, r0);
-                    tma_load_2d(dst + C::A_BYTES, t == 1 ? &prm.tmPlo : &prm.tmPhi, &full_bar[s], 64 * sl, 0);
-                } else {
-                    const bool skipB = dbg_noB && b >= NPRE + C::STAGES;  // diagnostic: stale B after the first ring fill
-                    mbar_arrive_expect_tx(&full_bar[s], a_bytes + (skipB ? 0u : (uint32_t)C::B_BYTES));
-                    tma_load_2d(dst, &prm.tmA, &full_bar[s], 0, arow0 + kb * tile_rows);  // tile-contiguous X
-                    if (!skipB) tma_load_2d(dst + C::A_BYTES, &prm.tmB, &full_bar[s], 64 * kb, 0);
-                    if (prm.prefetch > 0 && (b - NPRE) + prm.prefetch < nkb) {
-                        int kp = kb + prm.prefetch;
-                        if (kp >= nkb) kp -= nkb;
-                        tma_prefetch_2d(&prm.tmA, 0, arow0 + kp * tile_rows);
-                    }
-                    if (++kb == nkb) kb = 0;
-                }
+                mbar_arrive_expect_tx(&full_bar[s], num_tx);
+                tma_load_2d(dst, &prm.tmA, &full_bar[s], 0, arow);
+                tma_load_2d(dst + C::A_BYTES, &prm.tmB, &full_bar[s], 64 * kb, 0);
+                arow += tile_rows;
                 dst += C::STAGE_BYTES;
                 if (++s == C::STAGES) { s = 0; ph ^= 1u; dst = smem; }
+            }
+            if (NPRE > 0) {
+                pdl_wait();  // the Gram of the other factor comes from the preceding (reduce) kernel
+#pragma unroll
+                for (int bd = 0; bd < NPRE; ++bd) {  // Den = Fhi*Phi + Fhi*Plo + Flo*Phi
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    mbar_arrive_expect_tx(&full_bar[s], num_tx);
+                    const int t = bd / C::NSLAB, sl = bd % C::NSLAB;   // compile-time after unrolling
+                    tma_load_2d(dst, t == 2 ? &prm.tmFlo : &prm.tmFhi, &full_bar[s], 64 * sl, r0);
+                    tma_load_2d(dst + C::A_BYTES, t == 1 ? &prm.tmPlo : &prm.tmPhi, &full_bar[s], 64 * sl, 0);
+                    dst += C::STAGE_BYTES;
+                    if (++s == C::STAGES) { s = 0; ph ^= 1u; dst = smem; }
+                }
             }
         }
         __syncwarp();
@@ -213,21 +222,29 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
             const uint64_t adesc0 = make_kmajor_sw128_desc(smem_u32(smem));
             const uint64_t bdesc0 = make_kmajor_sw128_desc(smem_u32(smem + C::A_BYTES));
             uint64_t adesc = adesc0, bdesc = bdesc0;
-            for (int b = 0; b < total; ++b) {
+            // one k-block: wait for its operands, 4 x (K = 16 bf16 = 32 B per 128-B swizzle row), free the stage
+            auto block = [&](uint32_t d, uint32_t acc0) {
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
-                const bool pre = b < NPRE;
-                const uint32_t d = pre ? tmem_base + KP : tmem_base;
-                const bool first = pre ? (b == 0) : (b == NPRE);
+                umma_bf16(d, adesc, bdesc, idesc, acc0);
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)  // 4 x (K = 16 bf16 = 32 B) per 128-B swizzle row
-                    umma_bf16(d, adesc + 2 * kk, bdesc + 2 * kk, idesc, (!first || kk > 0) ? 1u : 0u);
+                for (int kk = 1; kk < 4; ++kk) umma_bf16(d, adesc + 2 * kk, bdesc + 2 * kk, idesc, 1u);
                 umma_commit(&empty_bar[s]);  // frees the stage when these MMAs have read it
                 adesc += C::STAGE_BYTES >> 4;  // descriptor start address is in 16-byte units
                 bdesc += C::STAGE_BYTES >> 4;
                 if (++s == C::STAGES) { s = 0; ph ^= 1u; adesc = adesc0; bdesc = bdesc0; }
+            };
+            int kb = 0;
+            if (nkb > 0) { block(tmem_base, 0u); kb = 1; TSTAMP(1); }   // first operands have landed
+            for (; kb < nkb; ++kb) block(tmem_base, 1u);
+            TSTAMP(2);                                                   // numerator blocks issued
+            if (NPRE > 0) {
+                block(tmem_base + KP, 0u);
+#pragma unroll 1
+                for (int bd = 1; bd < NPRE; ++bd) block(tmem_base + KP, 1u);
             }
             umma_commit(tmem_full);
+            TSTAMP(3);                                                   // all MMAs issued
         }
         __syncwarp();
     } else if (warp >= 2) {
@@ -237,8 +254,14 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
         const int row = r0 + 32 * q + lane;
         const bool valid = (32 * q + lane) < tile_rows && row < prm.R;
         const uint32_t t_lane = tmem_base + ((uint32_t)(32 * q) << 16);
+        pdl_wait();  // from here on we read / overwrite what the preceding kernel wrote / read
+        const bool stop = __ldcg(&prm.state->converged) != 0;  // uniform: the preceding kernel is complete
+        if (threadIdx.x == 64) TSTAMP(4);    // preceding kernel complete
         mbar_wait(tmem_full, 0);
         tc_fence_after();
+        if (threadIdx.x == 64) TSTAMP(5);    // accumulators complete
+        do {
+        if (stop) break;  // converged while this kernel was streaming (PDL): leave F untouched
         float* convw = conv_s + q * 2 * KP;
         const float lambda = prm.lambda, delta = prm.delta;
         float gcd_rowmax = -1.0f;
@@ -396,10 +419,12 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                 fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA / tensor-core (async) proxy
                 tc_fence_before();     // our TMEM reads are complete (the Gram below reuses the Num columns)
             }
+            if (threadIdx.x == 64) TSTAMP(6);  // this warp's ratio / staging done
             // combine the four lane quarters: named barrier over the 256 epilogue threads
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if constexpr (STAGED) {
                 if (threadIdx.x == 64) {
+                    TSTAMP(7);                 // all epilogue warps done
 #pragma unroll
                     for (int b = 0; b < KP / 32; ++b) tma_store_2d(&prm.tmF32, SF + b * 16384, 32 * b, r0);
 #pragma unroll
@@ -432,6 +457,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                 if (prm.gram_part != nullptr) {
                     mbar_wait(gram_bar, 0);
                     tc_fence_after();
+                    if (threadIdx.x == 64) TSTAMP(8);  // tile Gram MMAs complete
                     const int a = 32 * q + lane;
                     float* gp = prm.gram_part + ((size_t)blockIdx.x * KP + a) * KP;
 #pragma unroll 1
@@ -447,12 +473,25 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                         }
                     }
                 }
-                if (threadIdx.x == 64) tma_store_wait_all<0>();  // smem must stay valid until the bulk stores have drained
+                // smem must stay valid until the bulk stores have READ it; their global writes complete with the kernel
+                if (threadIdx.x == 64) {
+                    TSTAMP(9);                 // tile Gram written
+                    tma_store_wait_read<0>();
+                    TSTAMP(10);                // bulk stores have read their staging buffers
+                }
             }
         }
+        } while (0);
         tc_fence_before();
     }
     __syncthreads();
+    if (threadIdx.x == 0) TSTAMP(11);
+    if (prm.timing != nullptr && threadIdx.x == 0) {
+        long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        prm.timing[16 + 2 * blockIdx.x + 1] = gt;
+    }
+#undef TSTAMP
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -579,6 +618,7 @@ __global__ void __launch_bounds__(192, 1) gram_kernel(const __grid_constant__ Gr
 __global__ void __launch_bounds__(256) gram_reduce_kernel(const float* __restrict__ part, int nparts, int nelem, float* __restrict__ P,
                                                           bf16* __restrict__ Phi, bf16* __restrict__ Plo, int do_split,
                                                           const TcState* st) {
+    pdl_launch_dependents();  // the next update kernel may start streaming X now; it waits for us before it reads P
     if (st->converged) return;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int sub = t & 3;
@@ -797,6 +837,7 @@ __global__ void __launch_bounds__(256) gram_conv_reduce_kernel(const float* __re
                                                                const float* __restrict__ partW, int tilesW, const float* __restrict__ partH,
                                                                int tilesH, int KP, int k, int update_H, double* __restrict__ acc, float tol,
                                                                TcState* st, int do_decide, float* __restrict__ wsums_f32) {
+    pdl_launch_dependents();  // the next H-step may start streaming X now; it waits for us before it reads P / `converged`
     if (st->converged) return;
     if ((int)blockIdx.x < gram_blocks) {
         gram_reduce_body(gpart, nparts, nelem, P, Phi, Plo, do_split, blockIdx.x);
@@ -1015,16 +1056,14 @@ struct TcSolver {
     // gram_dst = where the fp32 Gram goes (default F.P).  KP <= 128: the update kernel's staged epilogue produces the
     // per-tile contributions itself (only a reduce launch follows); KP = 256: separate gram_kernel pass.
     void launch_update(int mode, const Factor& F, const Factor& O, const bf16* Xs, int Kdim, float lambda, float delta,
-                       float* num_io, float* conv_override = nullptr, int gram = -1, float* gram_dst = nullptr) {
+                       float* num_io, float* conv_override = nullptr, int gram = -1, float* gram_dst = nullptr, bool pdl = false) {
         UpdateParams prm;
         const bool fused_gram = gram >= 0 && KP <= 128 && (mode == 0 || mode == 2);
         prm.gram_part = fused_gram ? h->buf_t<float>("tc.gram_part", (size_t)std::max(F.tiles, 1) * KP * KP) : nullptr;
         prm.tmF32 = make_tmap_f32(F.m, KP, (uint64_t)F.R, KP, (uint32_t)F.tile_rows);
         prm.tmT = make_tmap_bf16(F.bT, (uint64_t)F.R, (uint64_t)F.rowsT, (uint64_t)F.ldT, KP);
         prm.tile_rows = F.tile_rows;
-        prm.debug = h->tc_debug;
-        prm.rotate = (h->tc_debug & 4) ? 1 : 0;
-        prm.prefetch = h->tc_prefetch;  // measured: lockstep CTAs share each B tile in L2; rotation costs ~4%
+        prm.timing = (h->tc_debug & 8) ? (long long*)h->buf("tc.timing", (16 + 2 * 4096) * sizeof(long long)) : nullptr;
         const uint64_t nkb = (uint64_t)ceil_div(Kdim, 64);
         prm.tmA = make_tmap_bf16(Xs, 64, (uint64_t)F.tiles * nkb * F.tile_rows, 64, (uint32_t)F.tile_rows);
         prm.tmB = make_tmap_bf16(O.bT, (uint64_t)Kdim, KP, (uint64_t)O.ldT, KP);
@@ -1042,11 +1081,25 @@ struct TcSolver {
         const int smem = UpdCfg<KP>::SMEM_BYTES;
         const bool timed = h->time_kernels == 1 && mode != 2;
         if (timed) NMF_CUDA(cudaEventRecord(h->next_event(), st));
-        if (mode == 0) mu_update_kernel<KP, 0><<<F.tiles, UpdCfg<KP>::THREADS, smem, st>>>(prm);
-        else if (mode == 1) mu_update_kernel<KP, 1><<<F.tiles, UpdCfg<KP>::THREADS, smem, st>>>(prm);
-        else if (mode == 2) mu_update_kernel<KP, 2><<<F.tiles, UpdCfg<KP>::THREADS, smem, st>>>(prm);
-        else if (mode == 3) mu_update_kernel<KP, 3><<<F.tiles, UpdCfg<KP>::THREADS, smem, st>>>(prm);
-        else mu_update_kernel<KP, 4><<<F.tiles, UpdCfg<KP>::THREADS, smem, st>>>(prm);
+        void (*kern)(const UpdateParams) = mode == 0   ? mu_update_kernel<KP, 0>
+                                           : mode == 1 ? mu_update_kernel<KP, 1>
+                                           : mode == 2 ? mu_update_kernel<KP, 2>
+                                           : mode == 3 ? mu_update_kernel<KP, 3>
+                                                       : mu_update_kernel<KP, 4>;
+        cudaLaunchConfig_t cfg;
+        std::memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)F.tiles);
+        cfg.blockDim = dim3(UpdCfg<KP>::THREADS);
+        cfg.dynamicSmemBytes = (size_t)smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        if (pdl) {  // programmatic dependent launch: start streaming X while the preceding reduce kernel is still running
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+        }
+        NMF_CUDA(cudaLaunchKernelEx(&cfg, kern, prm));
         if (timed) NMF_CUDA(cudaEventRecord(h->next_event(), st));
         h->launches += 1;
         last_fused_gram = fused_gram;
@@ -1564,6 +1617,10 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
     float devmax = 0.f;
     TcState hs;
     const int post_blocks = 1 + (KP * KP + 255) / 256;
+    // Single GPU: both update kernels are launched as programmatic dependents of the small reduce kernel in front of
+    // them, so their X streaming overlaps that kernel and the launch gap (the reduce results are only needed by the
+    // denominator blocks and the epilogue, which wait for it).
+    const bool pdl = !multi && h->tc_pdl != 0;
     // verbose (common.jl:54-59, 76-82): objective before the loop and after every iteration, through the trace callback
     double v_objv = std::numeric_limits<double>::quiet_NaN(), v_t0 = 0;
     auto wall = []() {
@@ -1588,7 +1645,7 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
             h->mark("start");
             if (a.update_H) {
                 if (!multi) {
-                    s.launch_update(0, H, W, Xr, (int)p, lh, delta, nullptr, nullptr, 1);  // H-step (+ tile Grams of the new H)
+                    s.launch_update(0, H, W, Xr, (int)p, lh, delta, nullptr, nullptr, 1, nullptr, pdl);  // H-step (+ tile Grams of the new H)
                     h->mark("updH");
                 } else {
                     s.launch_update(1, H, W, Xr, (int)p, lh, delta, packed);  // partial numerators of this shard
@@ -1623,7 +1680,7 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
             // W-step (local rows) + W'W for the next H-step (partial per rank when sharded; not needed if H is fixed)
             const int gramW = (a.update_H || !multi) ? (multi ? 0 : 1) : -1;
             s.defer_gram_reduce = true;
-            s.launch_update(0, W, H, Xc, (int)n, lw, delta, nullptr, nullptr, gramW, packed_P);
+            s.launch_update(0, W, H, Xc, (int)n, lw, delta, nullptr, nullptr, gramW, packed_P, pdl);
             s.defer_gram_reduce = false;
             h->mark("updW");
             const int gram_blocks = (s.last_fused_gram && gramW >= 0) ? (4 * KP * KP + 255) / 256 : 0;
@@ -1688,6 +1745,24 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
     out->kernel_launches = h->launches;
     out->hot_kernel_ms = h->drain_event_pairs(&out->hot_kernel_launches);
     h->report_marks(iters);
+    if (h->tc_debug & 8) {  // phase clocks of CTA 0 in the last update launch (SM cycles since kernel entry)
+        std::vector<long long> tv(16 + 2 * 4096);
+        NMF_CUDA(cudaMemcpy(tv.data(), h->buf("tc.timing", tv.size() * sizeof(long long)), tv.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        const long long* t = tv.data();
+        const int nct = std::min(W.tiles, 4096);
+        long long s_min = LLONG_MAX, s_max = 0, e_min = LLONG_MAX, e_max = 0;
+        for (int c = 0; c < nct; ++c) {
+            s_min = std::min(s_min, t[16 + 2 * c]); s_max = std::max(s_max, t[16 + 2 * c]);
+            e_min = std::min(e_min, t[17 + 2 * c]); e_max = std::max(e_max, t[17 + 2 * c]);
+        }
+        fprintf(stderr, "[nmfb200] last update launch, %d CTAs (globaltimer ns): first entry 0, last entry %lld, first exit %lld, last exit %lld\n",
+                nct, s_max - s_min, e_min - s_min, e_max - s_min);
+        static const char* names[12] = {"entry", "first_operands", "first_den_block", "mma_issued", "pred_complete", "accum_complete",
+                                        "ratio_done", "all_warps_done", "gram_mma_done", "gram_written", "stores_read", "exit"};
+        fprintf(stderr, "[nmfb200] mu_update_kernel CTA 0 phase clocks (cycles since entry):");
+        for (int i = 1; i < 12; ++i) fprintf(stderr, " %s=%lld", names[i], t[i] - t[0]);
+        fprintf(stderr, "\n");
+    }
 }
 
 // ---- MultUpdate(:div) on the tensor-core engine (multupd.jl:150-193) ----------------------------------------------

@@ -46,6 +46,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor
+// in the stream is still running; it must not touch anything the predecessor writes (or overwrite anything it
+// reads) before pdl_wait(), which returns once the predecessor has completed and its writes are visible.
+// Both are no-ops in a kernel that was launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // ---- TMA ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)m) : "memory");
