@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <utility>
 
 #include "common.cuh"
 #include "gcd_kernels.cuh"
@@ -120,9 +121,6 @@ __device__ __forceinline__ uint32_t pack_bf16x2(bf16 lo, bf16 hi) {
 template <int KP, int MODE>
 __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const __grid_constant__ UpdateParams prm) {
     using C = UpdCfg<KP>;
-    // The loop has already met stop_condition: nothing to do.  Under PDL (see launch_update) the predecessor may be
-    // deciding right now; a CTA that still reads 0 here streams its panel and skips the epilogue after pdl_wait().
-    if (__ldcg(&prm.state->converged)) return;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -131,6 +129,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
     uint64_t* tmem_full = empty_bar + C::STAGES;
     uint64_t* gram_bar = tmem_full + 1;
     uint32_t* tmem_slot = (uint32_t*)(gram_bar + 1);
+    uint32_t* stop_slot = tmem_slot + 1;
     float* conv_s = (float*)(smem + C::RING_BYTES + 1024);  // [4 warps][2][KP]
     // Staged epilogue (KP <= 128, modes that write the factor): the ring is idle once the accumulators are complete
     constexpr bool STAGED = (KP <= 128) && (MODE == 0 || MODE == 2 || MODE == 4);
@@ -155,6 +154,10 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
     constexpr int NPRE = (MODE == 1 || MODE == 4) ? 0 : 3 * C::NSLAB;
 
     if (warp == 0 && lane == 0) {
+        // Has the loop already met stop_condition?  ONE thread samples the flag for the whole CTA: under PDL (see
+        // launch_update) the preceding kernel may be writing it right now, and the early exit below must be uniform.
+        // A CTA that still sees 0 here streams its panel and skips the epilogue after pdl_wait().
+        *stop_slot = (uint32_t)__ldcg(&prm.state->converged);
         prefetch_tmap(&prm.tmA);
         prefetch_tmap(&prm.tmB);
         if (MODE != 1 && MODE != 4) {
@@ -176,6 +179,10 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (*stop_slot != 0u) {  // uniform early exit
+        if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+        return;
+    }
     // Block order: the nkb numerator blocks FIRST (they depend on nothing the preceding kernel writes), then the NPRE
     // denominator blocks (the Gram hi/lo they read is produced by the immediately preceding reduce kernel).
     // The two single-thread loops below are the latency-critical part of the kernel: no per-block branches, no
@@ -183,7 +190,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
 
     if (warp == 0) {
         // ===== TMA producer =====
-        if (lane == 0) {
+        if (elect_one()) {
             int s = 0;
             uint32_t ph = 0;
             uint8_t* dst = smem;
@@ -215,7 +222,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
         __syncwarp();
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = make_idesc(FMT_BF16, 128, KP);
             int s = 0;
             uint32_t ph = 0;
@@ -257,7 +264,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
         pdl_wait();  // from here on we read / overwrite what the preceding kernel wrote / read
         const bool stop = __ldcg(&prm.state->converged) != 0;  // uniform: the preceding kernel is complete
         if (threadIdx.x == 64) TSTAMP(4);    // preceding kernel complete
-        mbar_wait(tmem_full, 0);
+        mbar_wait(tmem_full, 0);   // (parking the epilogue warps in a named barrier instead of this poll was measured: no difference)
         tc_fence_after();
         if (threadIdx.x == 64) TSTAMP(5);    // accumulators complete
         do {
@@ -473,10 +480,11 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                         }
                     }
                 }
-                // smem must stay valid until the bulk stores have READ it; their global writes complete with the kernel
+                // the staging buffers must stay valid until the bulk stores have drained (waiting only for the smem reads,
+                // .read, measured the same)
                 if (threadIdx.x == 64) {
                     TSTAMP(9);                 // tile Gram written
-                    tma_store_wait_read<0>();
+                    tma_store_wait_all<0>();
                     TSTAMP(10);                // bulk stores have read their staging buffers
                 }
             }
@@ -618,7 +626,10 @@ __global__ void __launch_bounds__(192, 1) gram_kernel(const __grid_constant__ Gr
 __global__ void __launch_bounds__(256) gram_reduce_kernel(const float* __restrict__ part, int nparts, int nelem, float* __restrict__ P,
                                                           bf16* __restrict__ Phi, bf16* __restrict__ Plo, int do_split,
                                                           const TcState* st) {
-    pdl_launch_dependents();  // the next update kernel may start streaming X now; it waits for us before it reads P
+    // The update kernel behind us may start streaming X as soon as every block has passed this point; it waits for our
+    // completion before it reads P.  (Pre-launching THIS kernel behind the running update kernel was measured too:
+    // its resident blocks polling in griddepcontrol.wait slow the single-thread TMA / MMA loops, 4770 -> 4400 it/s.)
+    pdl_launch_dependents();
     if (st->converged) return;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int sub = t & 3;
@@ -1043,6 +1054,25 @@ struct Factor {  // one factor in row-factor layout
     int tile_rows = 128;
 };
 
+// Launch with or without the programmatic-stream-serialization attribute (PDL).
+template <typename... KArgs, typename... Args>
+void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    if (pdl) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    NMF_CUDA(cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...));
+}
+
 template <int KP>
 struct TcSolver {
     nmfb200_handle* h;
@@ -1086,27 +1116,15 @@ struct TcSolver {
                                            : mode == 2 ? mu_update_kernel<KP, 2>
                                            : mode == 3 ? mu_update_kernel<KP, 3>
                                                        : mu_update_kernel<KP, 4>;
-        cudaLaunchConfig_t cfg;
-        std::memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3((unsigned)F.tiles);
-        cfg.blockDim = dim3(UpdCfg<KP>::THREADS);
-        cfg.dynamicSmemBytes = (size_t)smem;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        if (pdl) {  // programmatic dependent launch: start streaming X while the preceding reduce kernel is still running
-            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            attr[0].val.programmaticStreamSerializationAllowed = 1;
-            cfg.attrs = attr;
-            cfg.numAttrs = 1;
-        }
-        NMF_CUDA(cudaLaunchKernelEx(&cfg, kern, prm));
+        // pdl: programmatic dependent launch -- start streaming X while the preceding reduce kernel is still running
+        launch_k(kern, dim3((unsigned)F.tiles), dim3(UpdCfg<KP>::THREADS), (size_t)smem, st, pdl, prm);
         if (timed) NMF_CUDA(cudaEventRecord(h->next_event(), st));
         h->launches += 1;
         last_fused_gram = fused_gram;
         last_gram_part = prm.gram_part;
         if (fused_gram && !defer_gram_reduce) {
-            gram_reduce_kernel<<<(4 * KP * KP + 255) / 256, 256, 0, st>>>(prm.gram_part, F.tiles, KP * KP, gram_dst ? gram_dst : F.P, F.Phi,
-                                                                           F.Plo, gram, state);
+            launch_k(gram_reduce_kernel, dim3((4 * KP * KP + 255) / 256), dim3(256), 0, st, false, (const float*)prm.gram_part, F.tiles, KP * KP,
+                     gram_dst ? gram_dst : F.P, F.Phi, F.Plo, gram, (const TcState*)state);
             h->launches += 1;
         } else if (gram >= 0 && !fused_gram) {
             launch_gram(F, gram != 0, gram_dst);
@@ -1394,10 +1412,7 @@ __global__ void __launch_bounds__(ObjCfg<KP>::THREADS, 1) objective_tc_kernel(co
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&tempty[b]);
-                mbar_arrive(&emptyX[sx]);
-            }
+            if (lane == 0) mbar_arrive(&tempty[b]);   // TMEM buffer b may be overwritten
             float part = 0.f;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
@@ -1414,6 +1429,12 @@ __global__ void __launch_bounds__(ObjCfg<KP>::THREADS, 1) objective_tc_kernel(co
                 }
             }
             acc += (double)part;   // 32 fp32 terms per step, then Float64 (StatsBase accumulates in Float64)
+            // Release the X stage only now that its values have been CONSUMED: the shared-memory loads above are
+            // asynchronous, and an arrive issued right behind them let the producer's TMA overwrite the stage while
+            // they were still in flight (seen as a run-to-run wobble of ~1e-5 in the objective with KP = 64).
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&emptyX[sx]);
             if (++sx == C::SX) { sx = 0; phx ^= 1u; }
         }
 #pragma unroll
@@ -1685,9 +1706,9 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
             h->mark("updW");
             const int gram_blocks = (s.last_fused_gram && gramW >= 0) ? (4 * KP * KP + 255) / 256 : 0;
             // one launch: Gram reduce (if produced by the staged epilogue) + stop_condition reduce / decision
-            gram_conv_reduce_kernel<<<gram_blocks + 4 * (KP / 32), 256, 0, st>>>(
-                s.last_gram_part, W.tiles, KP * KP, packed_P ? packed_P : W.P, W.Phi, W.Plo, gramW > 0 ? 1 : 0, gram_blocks, W.conv, W.tiles,
-                H.conv, H.tiles, KP, (int)k, a.update_H, acc, tol, state, multi ? 0 : 1, packed_ws);
+            launch_k(gram_conv_reduce_kernel, dim3(gram_blocks + 4 * (KP / 32)), dim3(256), 0, st, false, (const float*)s.last_gram_part, W.tiles,
+                     KP * KP, packed_P ? packed_P : W.P, W.Phi, W.Plo, gramW > 0 ? 1 : 0, gram_blocks, (const float*)W.conv, W.tiles,
+                     (const float*)H.conv, H.tiles, KP, (int)k, (int)a.update_H, acc, tol, state, multi ? 0 : 1, packed_ws);
             h->launches += 1;
             h->mark("conv");
         }
@@ -1723,6 +1744,15 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
     // objective 0.5*||X - WH||^2 (multupd.jl:81): exact fp32 GEMM + fp64 reduction from the SIMT engine
     double objv = v_objv;
     if (!a.verbose && !tc_objective<KP>(h, 0, W, H, 0.0, 0.0, &objv)) objv = simt_objective_f32(h, 0, Wd, ldwd, Hd, ldhd, k, 0.0, 0.0);
+    if (h->tc_debug & 16) {  // diagnostics: is the objective kernel repeatable on fixed inputs?
+        fprintf(stderr, "[nmfb200] objective x8:");
+        for (int i = 0; i < 8; ++i) {
+            double v = 0;
+            tc_objective<KP>(h, 0, W, H, 0.0, 0.0, &v);
+            fprintf(stderr, " %.9g", v);
+        }
+        fprintf(stderr, "\n");
+    }
     if (!a.on_device) {
         NMF_CUDA(cudaMemcpy2DAsync(Wc, ldw * sizeof(float), Wd, p * sizeof(float), p * sizeof(float), k, cudaMemcpyDeviceToHost, st));
         NMF_CUDA(cudaMemcpy2DAsync(Hc, ldh * sizeof(float), Hd, k * sizeof(float), k * sizeof(float), n, cudaMemcpyDeviceToHost, st));
@@ -1906,10 +1936,7 @@ __global__ void __launch_bounds__(QuotCfg<KP>::THREADS, 1) div_quot_kernel(const
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&tempty[b]);             // TMEM buffer b may be overwritten
-                mbar_arrive(&emptyX[sx]);            // X stage may be refilled
-            }
+            if (lane == 0) mbar_arrive(&tempty[b]);  // TMEM buffer b may be overwritten
             uint4 qv[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -1923,6 +1950,10 @@ __global__ void __launch_bounds__(QuotCfg<KP>::THREADS, 1) div_quot_kernel(const
                 }
                 qv[c] = make_uint4(qo[0], qo[1], qo[2], qo[3]);
             }
+            // the X stage may be refilled only now that its values have been consumed (asynchronous shared-memory loads)
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&emptyX[sx]);
             // output staging buffer ob: its previous TMA store (two k-blocks ago) must have finished reading smem
             if (threadIdx.x == 64) tma_store_wait_read<1>();
             asm volatile("bar.sync 1, 256;" ::: "memory");

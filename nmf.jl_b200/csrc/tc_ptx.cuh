@@ -46,6 +46,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// One elected lane of a fully converged warp (elect.sync): the compiler then knows the region is single-threaded
+// and emits the uniform-datapath instructions (UTMALDG / UTCHMMA / UTCBAR) without a per-lane election loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- programmatic dependent launch (PDL) ----------------------------------------------------------
 // A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor
 // in the stream is still running; it must not touch anything the predecessor writes (or overwrite anything it

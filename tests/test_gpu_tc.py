@@ -83,6 +83,28 @@ def test_tc_convergence_matches_oracle_iteration(NMF, oracle):
     assert abs(float(r.objvalue) - float(ro.objvalue)) <= 1e-4 * float(ro.objvalue)
 
 
+def test_tc_convergence_is_repeatable_under_overlapped_launches(NMF):
+    """The update kernels start as programmatic dependents of the kernel that decides convergence (they stream X while it
+    runs and look at the flag afterwards).  Tolerance-bound solves must stop at the same iteration with bit-identical
+    factors every time, whatever the launch overlap did; small tiles make the overlap window relatively large."""
+    for (p, n, k, tol, every) in [(384, 256, 8, 3e-3, 5), (200, 1000, 40, 2e-3, 8), (1500, 300, 128, 4e-3, 3)]:
+        X, W0, H0 = _problem(NMF, p, n, k, seed=21 + k)
+        ref = None
+        with NMF.Session(engine="tc") as s:
+            s.set_option("check_every", every)
+            s.set_X(X)
+            for rep in range(12):
+                Wg, Hg = W0.copy(order="F"), H0.copy(order="F")
+                r = s.solve(NMF.MultUpdate(np.float32, maxiter=3000, tol=tol), Wg, Hg)
+                assert r.converged
+                cur = (r.niters, Wg.copy(), Hg.copy(), float(r.objvalue))
+                if ref is None:
+                    ref = cur
+                else:
+                    assert cur[0] == ref[0], (rep, cur[0], ref[0])
+                    assert (cur[1] == ref[1]).all() and (cur[2] == ref[2]).all() and cur[3] == ref[3]
+
+
 def test_tc_session_reuse_and_auto_engine(NMF, oracle):
     """X stays resident (bf16 caches built once); auto picks tc for Float32 multmse."""
     X, W0, H0 = _problem(NMF, 256, 320, 24, seed=13)
