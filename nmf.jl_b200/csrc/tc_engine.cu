@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(192, 1) gram_kernel(const __grid_constant__ Gr
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             for (int b = 0; b < nkb; ++b) {
                 const int s = b % C::STAGES;
                 const uint32_t ph = (uint32_t)(b / C::STAGES) & 1u;
@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(192, 1) gram_kernel(const __grid_constant__ Gr
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = make_idesc(FMT_BF16, 128, KP);
             for (int b = 0; b < nkb; ++b) {
                 const int s = b % C::STAGES;
@@ -1334,7 +1334,7 @@ __global__ void __launch_bounds__(ObjCfg<KP>::THREADS, 1) objective_tc_kernel(co
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_arrive_expect_tx(rf_full, C::RF_BYTES);
             for (int t = 0; t < C::NT; ++t)
                 for (int sl = 0; sl < C::NSLAB; ++sl)
@@ -1358,7 +1358,7 @@ __global__ void __launch_bounds__(ObjCfg<KP>::THREADS, 1) objective_tc_kernel(co
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = make_idesc(FMT_BF16, 128, 64);
             mbar_wait(rf_full, 0);
             int sc = 0;
@@ -1869,7 +1869,7 @@ __global__ void __launch_bounds__(QuotCfg<KP>::THREADS, 1) div_quot_kernel(const
 
     if (warp == 0) {
         // ===== TMA producer: resident row-factor tile, then per k-block the X tile and the column-factor rows =====
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_arrive_expect_tx(rf_full, C::RF_BYTES);
             for (int sl = 0; sl < C::NSLAB; ++sl) tma_load_2d(smem + sl * 128 * 128, &prm.tmR, rf_full, 64 * sl, row0);
             int sc = 0, sx = 0;
@@ -1889,7 +1889,7 @@ __global__ void __launch_bounds__(QuotCfg<KP>::THREADS, 1) div_quot_kernel(const
         __syncwarp();
     } else if (warp == 1) {
         // ===== MMA issuer: D = Rf * Cf' for every k-block, alternating TMEM buffers =====
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = make_idesc(FMT_BF16, 128, 64);
             mbar_wait(rf_full, 0);
             int sc = 0;
