@@ -162,6 +162,16 @@ int nmfb200_solve_alspgrad_f64(nmfb200_handle* h, double* W, int64_t ldw, double
                                int64_t maxiter, int64_t maxsubiter, double tol, double tolg, int update_H,
                                int verbose, int on_device, nmfb200_result* out);
 
+/* ---- initialisation support: the two X-sized products of the randomised range finder ------------
+ * NMF.nndsvd (initialization.jl:70-101) obtains its singular triplets from RandomizedLinAlg.rsvd(X, k) =
+ * `Q = qr(X * randn(n, k)).Q; svd(Q' * X)` (initialization.jl:78).  Everything in it is O((p+n) k^2) except the
+ * two products with X; these run here on the X that is already resident for the solve:
+ *   transpose_X == 0:  C (p x c, ldc) = X  * B (n x c, ldb)
+ *   transpose_X != 0:  C (n x c, ldc) = X' * B (p x c, ldb)
+ * B and C are column-major HOST arrays in the element type of X (EDIM / ESTATE as for solve). */
+int nmfb200_mul_X_f32(nmfb200_handle* h, int transpose_X, const float* B, int64_t ldb, int64_t c, float* C, int64_t ldc);
+int nmfb200_mul_X_f64(nmfb200_handle* h, int transpose_X, const double* B, int64_t ldb, int64_t c, double* C, int64_t ldc);
+
 /* ---- multi-GPU: rows of X / W sharded over ranks, H replicated -----------
  * No counterpart in the reference (single process).  One handle per rank/GPU.  The unique id is an
  * opaque 128-byte blob (an ncclUniqueId) created on rank 0 and distributed by the host program

@@ -16,8 +16,10 @@ from .api import (  # noqa: F401
     Result,
     Session,
     SPA,
+    nndsvd,
     nnmf,
     randinit,
+    rsvd,
     solve,
     solve_replicates,
 )

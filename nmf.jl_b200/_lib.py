@@ -75,6 +75,8 @@ SIGNATURES = {
     "nmfb200_solve_cd_f64": _solve_cd_sig(_d),
     "nmfb200_solve_alspgrad_f32": _solve_alspgrad_sig(_f),
     "nmfb200_solve_alspgrad_f64": _solve_alspgrad_sig(_d),
+    "nmfb200_mul_X_f32": (_i, [_vp, _i, _vp, _i64, _i64, _vp, _i64]),
+    "nmfb200_mul_X_f64": (_i, [_vp, _i, _vp, _i64, _i64, _vp, _i64]),
     "nmfb200_comm_unique_id": (_i, [_vp]),
     "nmfb200_comm_init": (_i, [_vp, _i, _i, _vp]),
     "nmfb200_comm_destroy": (_i, [_vp]),

@@ -278,6 +278,22 @@ class Session:
         self._check(self._lib.nmfb200_comm_init(self._h, rank, nranks, buf))
 
     # -- solve
+    def mul_X(self, B: np.ndarray, transpose: bool = False) -> np.ndarray:
+        """X * B (transpose=False) or X' * B on the resident X (nmfb200_mul_X_*): the two X-sized products of the
+        randomised range finder behind nndsvd (initialization.jl:78)."""
+        if self.dtype is None:
+            raise NmfB200Error("set_X must precede mul_X")
+        p, n = self.shape
+        B = _col_major(np.asarray(B), self.dtype)
+        rows_b, rows_c = (p, n) if transpose else (n, p)
+        if B.ndim != 2 or B.shape[0] != rows_b:
+            raise DimensionMismatch("Dimensions of X and B are inconsistent.")
+        c = B.shape[1]
+        C = np.empty((rows_c, c), dtype=self.dtype, order="F")
+        fn = getattr(self._lib, "nmfb200_mul_X_" + _SFX[self.dtype])
+        self._check(fn(self._h, 1 if transpose else 0, B.ctypes.data, rows_b, c, C.ctypes.data, rows_c))
+        return C
+
     def solve_raw(self, alg_name: str, T, W_ptr: int, ldw: int, H_ptr: int, ldh: int, k: int, maxiter: int, tol,
                   lambda_w, lambda_h, update_H: bool, verbose: bool, on_device: bool) -> _lib.NmfResult:
         T = np.dtype(T)
@@ -382,6 +398,80 @@ def randinit(p: int, n: int, k: int, T, *, normalize: bool = False, zeroh: bool 
     return W, H
 
 
+def rsvd(session: Session, k: int, rng=None):
+    """RandomizedLinAlg.rsvd(X, k) as called at initialization.jl:78 (`Q = qr(X * randn(n, k)).Q`, `svd(Q' * X)`,
+    `U = Q * U_B`; no oversampling, no power iterations).  The two products with X run on the GPU on the resident X
+    (Session.mul_X); the thin QR of the p x k sample and the SVD of the k x n projection are LAPACK calls on the host,
+    as in the reference.  The Gaussian test matrix comes from `rng` (Julia's global RNG cannot be reproduced).
+    Returns (U, s, V) with V n x k."""
+    rng = rng if rng is not None else np.random.default_rng()
+    p, n = session.shape
+    T = session.dtype
+    Omega = rng.standard_normal((n, k)).astype(T)
+    Q, _ = np.linalg.qr(session.mul_X(Omega))                     # Y = X * Omega on the GPU
+    Bt = session.mul_X(np.asfortranarray(Q), transpose=True)      # B' = X' * Q on the GPU (n x k)
+    Ub, s, Vt = np.linalg.svd(Bt.T, full_matrices=False)
+    return (Q @ Ub)[:, :k], s[:k], Vt[:k, :].T
+
+
+def _posnegnorm(x):
+    """initialization.jl:103-115 (zeros are counted with the negative part, contributing 0)."""
+    T = x.dtype.type
+    pos = x > 0
+    return np.sqrt(T(np.sum(x[pos] * x[pos], dtype=x.dtype))), np.sqrt(T(np.sum(x[~pos] * x[~pos], dtype=x.dtype)))
+
+
+def nndsvd(X: np.ndarray, k: int, *, zeroh: bool = False, variant: str = "std", initdata=None, rng=None,
+           session: Optional[Session] = None):
+    """NMF.nndsvd (initialization.jl:70-101) with `_nndsvd!` (:26-68).  `initdata` = (U, S, V) of an SVD of X (the
+    reference takes an `SVD` object); without it the triplets come from `rsvd`, whose X-sized products run on the
+    GPU (`session` with X resident; one is opened on device 0 if none is given).  variant: "std" | "a" | "ar"."""
+    X = np.asarray(X)
+    T = X.dtype
+    p, n = X.shape
+    if variant not in ("std", "a", "ar"):
+        raise ArgumentError("Invalid value for variant")
+    rng = rng if rng is not None else np.random.default_rng()
+    if initdata is None:
+        if session is None:
+            with Session() as s:
+                s.set_X(X)
+                U, sv, V = rsvd(s, k, rng)
+        else:
+            U, sv, V = rsvd(session, k, rng)
+    else:
+        U, sv, V = initdata[0][:, :k], initdata[1][:k], initdata[2][:, :k]
+    U, sv, V = np.asarray(U, dtype=T), np.asarray(sv, dtype=T), np.asarray(V, dtype=T)   # :31-33
+    if variant == "std":
+        v0 = T.type(0)
+    elif variant == "a":
+        v0 = T.type(X.mean(dtype=np.float64))            # convert(T, mean(X)), :37
+    else:
+        v0 = T.type(X.mean(dtype=np.float64) * 0.01)     # :37
+    W = np.empty((p, k), dtype=T, order="F")
+    Ht = np.empty((n, k), dtype=T, order="F")
+    for j in range(k):
+        x, y = U[:, j], V[:, j]
+        xp, xn = _posnegnorm(x)
+        yp, yn = _posnegnorm(y)
+        mp, mn = T.type(xp * yp), T.type(xn * yn)
+        vj = v0
+        if variant == "ar":
+            vj = T.type(vj * T.type(rng.random()))       # :49-51
+        if mp >= mn:                                     # :54-58 / :65-67
+            ss = np.sqrt(T.type(sv[j] * mp))
+            W[:, j] = np.where(x > 0, x * T.type(ss / xp), vj)
+            if not zeroh:
+                Ht[:, j] = np.where(y > 0, y * T.type(ss / yp), vj)
+        else:                                            # :59-63 / :68-70
+            ss = np.sqrt(T.type(sv[j] * mn))
+            W[:, j] = np.where(x < 0, -(x * T.type(ss / xn)), vj)
+            if not zeroh:
+                Ht[:, j] = np.where(y < 0, -(y * T.type(ss / yn)), vj)
+    H = np.zeros((k, n), dtype=T, order="F") if zeroh else np.asfortranarray(Ht.T)       # :88-98
+    return W, H
+
+
 def solve_replicates(alg, session: Session, W, H, *, replicates: int, initH: bool, rng=None) -> Result:
     """interf.jl:85-101; X stays resident on the GPU across replicates."""
     ret = session.solve(alg, W, H)
@@ -396,7 +486,8 @@ def solve_replicates(alg, session: Session, W, H, *, replicates: int, initH: boo
     return ret
 
 
-_NOT_ACCEL_INIT = ("nndsvd", "nndsvda", "nndsvdar", "spa")
+_NNDSVD_VARIANT = {"nndsvd": "std", "nndsvda": "a", "nndsvdar": "ar"}
+_NOT_ACCEL_INIT = ("spa",)
 _NOT_ACCEL_ALG = ("spa",)
 
 
@@ -439,9 +530,11 @@ def nnmf(X: np.ndarray, k: int, *, init: str = "nndsvdar", initdata=None, alg: s
         W, H = W0, H0
         if W.dtype != T or H.dtype != T:
             raise TypeError("W0 and H0 must have the element type of X")  # `W::Matrix{T}` assert, :57-58
+    elif init in _NNDSVD_VARIANT:  # :44-49 -- needs X on the GPU for the range finder: done below, once the session holds X
+        W = H = None
     elif init in _NOT_ACCEL_INIT:
         raise NotImplementedError(f"init=:{init} is not on the accelerated path yet (SURVEY.md section 8f); "
-                                  "pass init='random' or init='custom'")
+                                  "pass init='random', 'nndsvd', 'nndsvda', 'nndsvdar' or 'custom'")
     else:
         raise ArgumentError("Invalid value for init.")  # :55
     if alg == "multmse":  # :64-66
@@ -464,4 +557,7 @@ def nnmf(X: np.ndarray, k: int, *, init: str = "nndsvdar", initdata=None, alg: s
         raise ArgumentError("Invalid algorithm.")  # :79
     with Session(device=device, engine=engine) as s:
         s.set_X(X)
+        if W is None:
+            rng = rng if rng is not None else np.random.default_rng()
+            W, H = nndsvd(X, k, zeroh=not initH, variant=_NNDSVD_VARIANT[init], initdata=initdata, rng=rng, session=s)
         return solve_replicates(inst, s, W, H, replicates=replicates, initH=initH, rng=rng)

@@ -267,6 +267,19 @@ NMFB200_DEFINE_SOLVE_CD(nmfb200_solve_cd_f64, double)
 NMFB200_DEFINE_SOLVE_ALSPGRAD(nmfb200_solve_alspgrad_f32, float)
 NMFB200_DEFINE_SOLVE_ALSPGRAD(nmfb200_solve_alspgrad_f64, double)
 
+int nmfb200_mul_X_f32(nmfb200_handle* h, int transpose_X, const float* B, int64_t ldb, int64_t c, float* C, int64_t ldc) {
+    return guarded(h, [&] {
+        NMF_REQUIRE(h->x_elt == 4, NMFB200_ESTATE, h->x_elt ? "X was set with a different element type" : "nmfb200_set_X must precede mul_X");
+        simt_mul_X<float>(h, transpose_X, B, ldb, c, C, ldc);
+    });
+}
+int nmfb200_mul_X_f64(nmfb200_handle* h, int transpose_X, const double* B, int64_t ldb, int64_t c, double* C, int64_t ldc) {
+    return guarded(h, [&] {
+        NMF_REQUIRE(h->x_elt == 8, NMFB200_ESTATE, h->x_elt ? "X was set with a different element type" : "nmfb200_set_X must precede mul_X");
+        simt_mul_X<double>(h, transpose_X, B, ldb, c, C, ldc);
+    });
+}
+
 int nmfb200_comm_unique_id(void* out_id_128) {
     if (!out_id_128) return NMFB200_EINVAL;
     try {

@@ -247,6 +247,8 @@ template <typename T>
 void simt_solve(nmfb200_handle* h, const SolveArgs& a, T* W, int64_t ldw, T* H, int64_t ldh, nmfb200_result* out);
 double simt_objective_f32(nmfb200_handle* h, int alg, const float* W, int64_t ldw, const float* H, int64_t ldh, int64_t k,
                           double lambda_w, double lambda_h);
+template <typename T>
+void simt_mul_X(nmfb200_handle* h, int transpose_X, const T* B, int64_t ldb, int64_t c, T* C, int64_t ldc);
 bool tc_supported(const nmfb200_handle* h, const SolveArgs& a);
 void tc_solve(nmfb200_handle* h, const SolveArgs& a, float* W, int64_t ldw, float* H, int64_t ldh, nmfb200_result* out);
 void tc_release(nmfb200_handle* h);

@@ -883,6 +883,27 @@ double simt_objective_f32(nmfb200_handle* h, int alg, const float* W, int64_t ld
     return s.objective(alg, W, H, lambda_w, lambda_h, ldw, ldh);
 }
 
+// C = X * B or X' * B with host B, C (nmfb200_mul_X_*): the X-sized products of the randomised range finder behind
+// NMF.nndsvd (initialization.jl:78), on the resident X.
+template <typename T>
+void simt_mul_X(nmfb200_handle* h, int transpose_X, const T* B, int64_t ldb, int64_t c, T* C, int64_t ldc) {
+    const int64_t rowsB = transpose_X ? h->p : h->n, rowsC = transpose_X ? h->n : h->p;
+    NMF_REQUIRE(B != nullptr && C != nullptr, NMFB200_EINVAL, "NULL argument");
+    NMF_REQUIRE(c >= 1 && ldb >= rowsB && ldc >= rowsC, NMFB200_EDIM, "Dimensions of X, B and C are inconsistent.");
+    NMF_REQUIRE(rowsB <= INT32_MAX && rowsC <= INT32_MAX && c <= INT32_MAX, NMFB200_EDIM, "dimension exceeds 2^31-1");
+    cudaStream_t st = h->stream;
+    T* dB = h->buf_t<T>("mulx.B", (size_t)rowsB * c);
+    T* dC = h->buf_t<T>("mulx.C", (size_t)rowsC * c);
+    NMF_CUDA(cudaMemcpy2DAsync(dB, rowsB * sizeof(T), B, ldb * sizeof(T), rowsB * sizeof(T), c, cudaMemcpyHostToDevice, st));
+    Simt<T> s{h, st, h->p, h->n, c, (const T*)h->dX, h->ldx};
+    if (transpose_X) s.gemm((int)h->n, (int)c, (int)h->p, s.X, h->ldx, 1, dB, 1, rowsB, dC, 1, rowsC);
+    else s.gemm((int)h->p, (int)c, (int)h->n, s.X, 1, h->ldx, dB, 1, rowsB, dC, 1, rowsC);
+    NMF_CUDA(cudaMemcpy2DAsync(C, ldc * sizeof(T), dC, rowsC * sizeof(T), rowsC * sizeof(T), c, cudaMemcpyDeviceToHost, st));
+    NMF_CUDA(cudaStreamSynchronize(st));
+}
+template void simt_mul_X<float>(nmfb200_handle*, int, const float*, int64_t, int64_t, float*, int64_t);
+template void simt_mul_X<double>(nmfb200_handle*, int, const double*, int64_t, int64_t, double*, int64_t);
+
 template void simt_solve<float>(nmfb200_handle*, const SolveArgs&, float*, int64_t, float*, int64_t, nmfb200_result*);
 template void simt_solve<double>(nmfb200_handle*, const SolveArgs&, double*, int64_t, double*, int64_t, nmfb200_result*);
 

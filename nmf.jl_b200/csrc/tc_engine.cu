@@ -904,6 +904,7 @@ __global__ void __launch_bounds__(256) gram_conv_reduce_kernel(const float* __re
 __global__ void __launch_bounds__(256) post_allreduce_kernel(double* __restrict__ acc, const float* __restrict__ wsums_f32, int has_prev,
                                                              int KP, int k, float tol, TcState* st, const float* __restrict__ P,
                                                              bf16* __restrict__ Phi, bf16* __restrict__ Plo, XchgDev x, unsigned int epoch) {
+    pdl_launch_dependents();  // the MODE 2 ratio kernel may set itself up now; it waits for our completion before it reads anything
     if (x.G > 0) xchg_wait_all(x, 1, epoch);  // peer-memory exchange: every rank's reduced segment has landed here
     if (st->converged) return;
     __shared__ float devs[256];
@@ -1641,7 +1642,7 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
     // Single GPU: both update kernels are launched as programmatic dependents of the small reduce kernel in front of
     // them, so their X streaming overlaps that kernel and the launch gap (the reduce results are only needed by the
     // denominator blocks and the epilogue, which wait for it).
-    const bool pdl = !multi && h->tc_pdl != 0;
+    const bool pdl = h->tc_pdl != 0;  // multi-GPU: the MODE 1 numerator kernel and the W-step follow gram_conv_reduce / gram_reduce too
     // verbose (common.jl:54-59, 76-82): objective before the loop and after every iteration, through the trace callback
     double v_objv = std::numeric_limits<double>::quiet_NaN(), v_t0 = 0;
     auto wall = []() {
@@ -1669,7 +1670,7 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
                     s.launch_update(0, H, W, Xr, (int)p, lh, delta, nullptr, nullptr, 1, nullptr, pdl);  // H-step (+ tile Grams of the new H)
                     h->mark("updH");
                 } else {
-                    s.launch_update(1, H, W, Xr, (int)p, lh, delta, packed);  // partial numerators of this shard
+                    s.launch_update(1, H, W, Xr, (int)p, lh, delta, packed, nullptr, -1, nullptr, pdl);  // partial numerators of this shard
                     h->mark("mode1");
                     // THE exchange step: [numerators | W'W | W-side stop sums of the previous iteration]
                     unsigned int ep = 0;
@@ -1687,7 +1688,7 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
                     h->launches += 1;
                     pending = false;
                     h->mark("post");
-                    s.launch_update(2, H, W, Xr, (int)p, lh, delta, packed, nullptr, 1);   // ratio with the reduced numerators
+                    s.launch_update(2, H, W, Xr, (int)p, lh, delta, packed, nullptr, 1, nullptr, pdl);   // ratio with the reduced numerators
                     h->mark("mode2");
                 }
                 h->mark("gramH");

@@ -10,6 +10,8 @@
 # the header but has not been executed there; the tested binding is nmf.jl_b200/_lib.py (same calls).
 module NMFB200
 
+using LinearAlgebra: qr!, svd!
+
 export nnmf
 
 const libnmfb200 = get(ENV, "NMFB200_LIB", joinpath(@__DIR__, "..", "libnmfb200.so"))
@@ -246,6 +248,65 @@ function randinit(p::Integer, n::Integer, k::Integer, T::DataType; normalize::Bo
     return W, H
 end
 
+# ---- NNDSVD (src/initialization.jl:26-137).  rsvd: RandomizedLinAlg.rsvd(X, k) as called at :78, with its two
+# X-sized products on the GPU (nmfb200_mul_X_*, X resident); thin QR and the k x n SVD stay LAPACK calls.
+for (T, sfx) in ((Float32, "f32"), (Float64, "f64"))
+    fname = "nmfb200_mul_X_" * sfx
+    @eval function mul_X(h::Handle, B::Matrix{$T}, rowsC::Integer; transpose::Bool=false)   # rowsC = transpose ? n : p
+        C = Matrix{$T}(undef, rowsC, size(B, 2))
+        GC.@preserve B C check(h, ccall(($fname, libnmfb200), Cint,
+            (Ptr{Cvoid}, Cint, Ptr{$T}, Int64, Int64, Ptr{$T}, Int64),
+            h.ptr, transpose ? 1 : 0, B, stride(B, 2), size(B, 2), C, stride(C, 2)))
+        return C
+    end
+end
+
+function rsvd(h::Handle, ::Type{T}, p::Integer, n::Integer, k::Integer) where T
+    Q = Matrix(qr!(mul_X(h, randn(T, n, k), p)).Q)          # Y = X * Omega on the GPU
+    Bt = mul_X(h, Q, n; transpose=true)                     # B' = X' * Q on the GPU
+    F = svd!(Matrix(Bt'))
+    return (Q * F.U)[:, 1:k], F.S[1:k], Matrix(F.Vt[1:k, :]')
+end
+
+function posnegnorm(x::AbstractArray{T}) where T             # src/initialization.jl:103-115
+    pn = zero(T); nn = zero(T)
+    for xi in x
+        xi > zero(T) ? (pn += abs2(xi)) : (nn += abs2(xi))
+    end
+    return sqrt(pn), sqrt(nn)
+end
+
+function nndsvd(X::AbstractMatrix{T}, k::Integer; zeroh::Bool=false, variant::Symbol=:std, initdata=nothing,
+                handle::Union{Handle,Nothing}=nothing) where T
+    p, n = size(X)
+    ivar = variant == :std ? 0 : variant == :a ? 1 : variant == :ar ? 2 : throw(ArgumentError("Invalid value for variant"))
+    U, s, V = if initdata === nothing
+        h = handle === nothing ? (h0 = Handle(); set_X!(h0, Matrix{T}(X)); h0) : handle
+        rsvd(h, T, p, n, k)
+    else
+        (initdata.U[:, 1:k], initdata.S[1:k], initdata.V[:, 1:k])
+    end
+    U = T.(U); s = T.(s); V = T.(V)
+    v0 = ivar == 0 ? zero(T) : ivar == 1 ? convert(T, sum(X) / length(X)) : convert(T, sum(X) / length(X) * 0.01)
+    W = Matrix{T}(undef, p, k); Ht = Matrix{T}(undef, n, k)
+    for j in 1:k                                             # src/initialization.jl:40-67
+        x = view(U, :, j); y = view(V, :, j)
+        xp, xn = posnegnorm(x); yp, yn = posnegnorm(y)
+        mp = xp * yp; mn = xn * yn
+        vj = ivar == 2 ? v0 * rand(T) : v0
+        if mp >= mn
+            ss = sqrt(s[j] * mp)
+            W[:, j] .= ifelse.(x .> 0, x .* (ss / xp), vj)
+            zeroh || (Ht[:, j] .= ifelse.(y .> 0, y .* (ss / yp), vj))
+        else
+            ss = sqrt(s[j] * mn)
+            W[:, j] .= ifelse.(x .< 0, .-(x .* (ss / xn)), vj)
+            zeroh || (Ht[:, j] .= ifelse.(y .< 0, .-(y .* (ss / yn)), vj))
+        end
+    end
+    return W, (zeroh ? zeros(T, k, n) : Matrix(Ht'))
+end
+
 function nnmf(X::AbstractMatrix{T}, k::Integer; init::Symbol=:nndsvdar, initdata=nothing, alg::Symbol=:greedycd,
               maxiter::Integer=100, tol::Real=cbrt(eps(T) / 100), replicates::Integer=1,
               W0::Union{AbstractMatrix{T},Nothing}=nothing, H0::Union{AbstractMatrix{T},Nothing}=nothing,
@@ -267,10 +328,8 @@ function nnmf(X::AbstractMatrix{T}, k::Integer; init::Symbol=:nndsvdar, initdata
         W0 === nothing && H0 === nothing || @warn "Ignore W0 and H0 except for :custom initialization."
     end
     initH = alg != :projals                                  # src/interf.jl:39
-    W, H = init == :random ? randinit(p, n, k, T; normalize=true, zeroh=!initH) :
-           init == :custom ? (Matrix{T}(W0), Matrix{T}(H0)) :
-           init in (:nndsvd, :nndsvda, :nndsvdar, :spa) ? error("init=:$init is not on the accelerated path yet; use :random or :custom") :
-           throw(ArgumentError("Invalid value for init."))
+    init in (:random, :custom, :nndsvd, :nndsvda, :nndsvdar) || (init == :spa ? error("init=:spa is not on the accelerated path") :
+                                                                 throw(ArgumentError("Invalid value for init.")))
     inst = alg == :multmse ? MultUpdate{T}(obj=:mse, maxiter=maxiter, tol=tol, verbose=verbose, update_H=update_H) :
            alg == :multdiv ? MultUpdate{T}(obj=:div, maxiter=maxiter, tol=tol, verbose=verbose, update_H=update_H) :
            alg == :greedycd ? GreedyCD{T}(maxiter=maxiter, tol=tol, verbose=verbose, update_H=update_H) :
@@ -281,7 +340,10 @@ function nnmf(X::AbstractMatrix{T}, k::Integer; init::Symbol=:nndsvdar, initdata
            throw(ArgumentError("Invalid algorithm."))
     h = Handle(device)
     Xm = Matrix{T}(X)
-    set_X!(h, Xm)                                      # X stays resident on the GPU across replicates
+    set_X!(h, Xm)                                      # X stays resident on the GPU across init, solve and replicates
+    W, H = init == :random ? randinit(p, n, k, T; normalize=true, zeroh=!initH) :
+           init == :custom ? (Matrix{T}(W0), Matrix{T}(H0)) :
+           nndsvd(Xm, k; zeroh=!initH, variant=(init == :nndsvd ? :std : init == :nndsvda ? :a : :ar), initdata=initdata, handle=h)
     ret = solve!(inst, Xm, W, H; handle=h, x_resident=true)
     for _ in 2:replicates                              # src/interf.jl:91-98
         Wr, Hr = randinit(p, n, k, T; normalize=true, zeroh=!initH)

@@ -762,6 +762,76 @@ def randinit(p, n, k, T, rng, normalize=False, zeroh=False):
     return W, H
 
 
+def rsvd(X, k, rng):
+    """RandomizedLinAlg.rsvd(A, n) as NMF.jl calls it (initialization.jl:78; dependency un-vendored, compat "0.1",
+    restated from its published source: `Q = rrange(A, n)` = thin Q of `A * randn(size(A, 2), n)` (no oversampling, no
+    power iterations), then `svd_restricted`: `B = Q'A`, `svd(B)`, `U = Q * U_B`).  The Gaussian test matrix comes
+    from the caller's NumPy Generator (Julia's global RNG stream cannot be reproduced).  Returns (U, s, V)."""
+    X = np.asarray(X)
+    Omega = rng.standard_normal((X.shape[1], k)).astype(X.dtype)
+    Q, _ = np.linalg.qr(X @ Omega)
+    Ub, s, Vt = np.linalg.svd(Q.T @ X, full_matrices=False)
+    return (Q @ Ub)[:, :k], s[:k], Vt[:k, :].T
+
+
+def _posnegnorm(x):
+    """initialization.jl:103-115: zeros are counted with the negative part (contributing 0)."""
+    T = x.dtype.type
+    pn, nn = T(0), T(0)
+    for xi in x:
+        if xi > 0:
+            pn = T(pn + xi * xi)
+        else:
+            nn = T(nn + xi * xi)
+    return np.sqrt(pn), np.sqrt(nn)
+
+
+def nndsvd(X, k, zeroh=False, variant="std", initdata=None, rng=None):
+    """initialization.jl:26-101.  `initdata` = (U, S, V) of an SVD of X (the reference takes an `SVD` object and uses
+    `.U[:,1:k], .S[1:k], .V[:,1:k]`); without it the factors come from `rsvd` above.  variant in {"std","a","ar"}.
+    Element type follows X; sums are sequential in T like posnegnorm / mean."""
+    X = _F(X)
+    T = X.dtype
+    p, n = X.shape
+    if variant not in ("std", "a", "ar"):
+        raise ArgumentError("Invalid value for variant")
+    rng = rng if rng is not None else np.random.default_rng()
+    if initdata is None:
+        U, s, V = rsvd(X, k, rng)
+    else:
+        U, s, V = initdata[0][:, :k], initdata[1][:k], initdata[2][:, :k]
+    U, s, V = U.astype(T), s.astype(T), V.astype(T)          # :31-33
+    one = T.type(1)
+    if variant == "std":
+        v0 = T.type(0)
+    elif variant == "a":
+        v0 = T.type(X.mean(dtype=np.float64))                # convert(T, mean(X)), :37
+    else:
+        v0 = T.type(X.mean(dtype=np.float64) * 0.01)         # convert(T, mean(X) * 0.01), :37
+    W = np.empty((p, k), dtype=T, order="F")
+    Ht = np.empty((n, k), dtype=T, order="F")
+    for j in range(k):
+        x, y = U[:, j], V[:, j]
+        xp, xn = _posnegnorm(x)
+        yp, yn = _posnegnorm(y)
+        mp, mn = T.type(xp * yp), T.type(xn * yn)
+        vj = v0
+        if variant == "ar":
+            vj = T.type(vj * T.type(rng.random()))           # vj *= rand(T), :49-51
+        if mp >= mn:                                         # :54-58
+            ss = np.sqrt(T.type(s[j] * mp))
+            W[:, j] = np.where(x > 0, x * T.type(ss / xp), vj)          # scalepos!, :117-126
+            if not zeroh:
+                Ht[:, j] = np.where(y > 0, y * T.type(ss / yp), vj)
+        else:                                                # :59-63
+            ss = np.sqrt(T.type(s[j] * mn))
+            W[:, j] = np.where(x < 0, -(x * T.type(ss / xn)), vj)       # scaleneg!, :128-137
+            if not zeroh:
+                Ht[:, j] = np.where(y < 0, -(y * T.type(ss / yn)), vj)
+    H = np.zeros((k, n), dtype=T, order="F") if zeroh else _F(Ht.T)      # :88-98
+    return W, H
+
+
 def solve_replicates(alg, X, W, H, replicates, initH, rng):
     """interf.jl:85-101"""
     ret = solve(alg, X, W, H)
@@ -776,8 +846,8 @@ def solve_replicates(alg, X, W, H, replicates, initH, rng):
 
 
 def nnmf(X, k, init="nndsvdar", alg="greedycd", maxiter=100, tol=None, replicates=1, W0=None, H0=None,
-         update_H=True, verbose=False, rng=None):
-    """interf.jl:3-83 restricted to what the accelerated path covers: init in {:random, :custom},
+         update_H=True, verbose=False, rng=None, initdata=None):
+    """interf.jl:3-83 restricted to what the accelerated path covers: init in {:random, :custom, :nndsvd, :nndsvda, :nndsvdar},
     alg in {:multmse, :multdiv, :greedycd, :projals, :alspgrad, :cd}.  Validation order and messages follow the
     reference."""
     X = _F(X)
@@ -812,8 +882,10 @@ def nnmf(X, k, init="nndsvdar", alg="greedycd", maxiter=100, tol=None, replicate
         W, H = randinit(p, n, k, T, rng, normalize=True, zeroh=not initH)
     elif init == "custom":
         W, H = _F(W0, dtype=T), _F(H0, dtype=T)
-    elif init in ("nndsvd", "nndsvda", "nndsvdar", "spa"):
-        raise NotImplementedError(f"init=:{init} is outside the restated hot path (SURVEY.md section 8f)")
+    elif init in ("nndsvd", "nndsvda", "nndsvdar"):          # interf.jl:44-49
+        W, H = nndsvd(X, k, zeroh=not initH, variant={"nndsvd": "std", "nndsvda": "a", "nndsvdar": "ar"}[init], initdata=initdata, rng=rng)
+    elif init == "spa":
+        raise NotImplementedError("init=:spa is outside the restated hot path (SURVEY.md section 8f)")
     else:
         raise ArgumentError("Invalid value for init.")
     if alg == "multmse":

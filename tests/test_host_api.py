@@ -114,7 +114,7 @@ def test_nnmf_validation_before_gpu(NMF):
     with pytest.raises(NMF.ArgumentError, match="regularization"):
         NMF.CoordinateDescent(np.float64, regularization="bogus")
     with pytest.raises(NotImplementedError):
-        NMF.nnmf(X, 2)  # default init=:nndsvdar is a "next" row
+        NMF.nnmf(X, 2, init="spa")  # SPA initialisation is out of scope
     with warnings.catch_warnings(record=True) as w:
         warnings.simplefilter("always")
         with pytest.raises(NMF.ArgumentError):
@@ -129,6 +129,34 @@ def test_randinit(NMF):  # test/initialization.jl:4-27
     np.testing.assert_allclose(W.sum(axis=0), 1.0, rtol=1e-6)
     W, H = NMF.randinit(10, 7, 3, np.float64, zeroh=True)
     assert (H == 0).all() and H.shape == (3, 7)
+
+
+def test_nndsvd_with_initdata_matches_oracle_and_reference_properties(NMF, oracle):
+    """test/initialization.jl:29-53 on the host mirror (initdata given => no device work) and equality with the oracle."""
+    rng = np.random.default_rng(5678)
+    X = rng.random((8, 12))
+    U, s, Vt = np.linalg.svd(X, full_matrices=False)
+    F = (U, s, Vt.T)
+    for T in (np.float64, np.float32):
+        Xt = X.astype(T)
+        for variant in ("std", "a", "ar"):
+            W, H = NMF.nndsvd(Xt, 5, variant=variant, initdata=F, rng=np.random.default_rng(3))
+            Wo, Ho = oracle.nndsvd(Xt, 5, variant=variant, initdata=F, rng=np.random.default_rng(3))
+            assert W.shape == (8, 5) and H.shape == (5, 12) and W.dtype == T and W.flags.f_contiguous and H.flags.f_contiguous
+            assert (W >= 0).all() and (H >= 0).all()
+            np.testing.assert_allclose(W, Wo, rtol=1e-6 if T == np.float32 else 1e-13, atol=0)
+            np.testing.assert_allclose(H, Ho, rtol=1e-6 if T == np.float32 else 1e-13, atol=0)
+        W2, H2 = NMF.nndsvd(Xt, 5, zeroh=True, initdata=F)
+        W1, H1 = NMF.nndsvd(Xt, 5, initdata=F)
+        assert (W2 == W1).all() and (H2 == 0).all()                      # test/initialization.jl:39-44
+        U2, s2, Vt2 = np.linalg.svd(2 * X, full_matrices=False)
+        Wb, Hb = NMF.nndsvd(2 * Xt, 5, initdata=(U2, s2, Vt2.T))
+        np.testing.assert_allclose(Wb, np.sqrt(T(2)) * W1, rtol=1e-5)    # :46-49
+        np.testing.assert_allclose(Hb, np.sqrt(T(2)) * H1, rtol=1e-5)
+        War, _ = NMF.nndsvd(Xt, 5, variant="ar", initdata=F)
+        assert (War > 0).all()                                           # :51-52
+    with pytest.raises(NMF.ArgumentError, match="variant"):
+        NMF.nndsvd(X, 5, variant="bogus", initdata=F)
 
 
 def test_no_gpu_fails_loudly(NMF):

@@ -79,6 +79,32 @@ class _nullcontext:
         return False
 
 
+# test/initialization.jl:29-53
+def test_nndsvd_reference_properties(oracle):
+    rng = np.random.default_rng(5678)
+    for T in (np.float64, np.float32):
+        X = rng.random((8, 12)).astype(T)
+        W, H = oracle.nndsvd(X, 5, rng=np.random.default_rng(1))
+        assert W.shape == (8, 5) and H.shape == (5, 12) and (W >= 0).all() and (H >= 0).all() and W.dtype == T
+        W2, H2 = oracle.nndsvd(X, 5, zeroh=True, rng=np.random.default_rng(1))   # same "seed" as above
+        assert (W2 == W).all() and (H2 == 0).all()
+        U, s, Vt = np.linalg.svd(X.astype(np.float64), full_matrices=False)
+        W1, H1 = oracle.nndsvd(X, 5, initdata=(U, s, Vt.T))
+        U, s, Vt = np.linalg.svd(2 * X.astype(np.float64), full_matrices=False)
+        Wb, Hb = oracle.nndsvd(2 * X, 5, initdata=(U, s, Vt.T))
+        np.testing.assert_allclose(Wb, np.sqrt(T(2)) * W1, rtol=1e-5)
+        np.testing.assert_allclose(Hb, np.sqrt(T(2)) * H1, rtol=1e-5)
+        War, _ = oracle.nndsvd(X, 5, variant="ar", rng=np.random.default_rng(2))
+        assert (War > 0).all()
+    # the randomised range finder captures an exactly rank-k matrix exactly, so its triplets reproduce X
+    Xl = np.maximum(rng.random((30, 4)) - 0.3, 0) @ np.maximum(rng.random((4, 20)) - 0.3, 0)
+    U, s, V = oracle.rsvd(Xl, 4, np.random.default_rng(0))
+    np.testing.assert_allclose((U * s) @ V.T, Xl, atol=1e-10)
+    # nnmf with the reference's default arguments (init=:nndsvdar, alg=:greedycd) runs and fits a planted problem
+    r = oracle.nnmf(Xl, 4, rng=np.random.default_rng(3), maxiter=500)
+    assert np.linalg.norm(Xl - r.W @ r.H) <= 1e-2 * np.linalg.norm(Xl)
+
+
 # test/initialization.jl:22-27
 def test_randinit_normalize(oracle):
     rng = np.random.default_rng(3)
