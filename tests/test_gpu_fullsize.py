@@ -1,0 +1,131 @@
+"""BASELINE.json's full-size configurations through the C ABI, checked by what does not need a CPU run of the same
+size: (1) two iterations of config 2 against the oracle itself (the as-written update costs ~0.3 s per iteration on
+the host), (2) size-independent properties -- non-negativity, the monotone decrease of the objective that the
+multiplicative updates guarantee (Lee & Seung; multupd.jl:83-116, :150-193) and that GreedyCD's exact coordinate steps
+imply (greedycd.jl:94-166), agreement of the returned objvalue with an independent evaluation of the objective from the
+returned factors, equivariance under a permutation of the rows of X, bit-repeatability.
+Data are generated on the device (torch is only the allocator / random generator here)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _device_problem(p, n, k, seed, planted_rank=None):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    if planted_rank:
+        A = torch.clamp(torch.rand((n, planted_rank), device="cuda", generator=g) - 0.3, min=0)
+        B = torch.clamp(torch.rand((planted_rank, p), device="cuda", generator=g) - 0.3, min=0)
+        dX = (A @ B).contiguous()                                    # C-order (n, p) == column-major p x n
+        dX += 0.01 * torch.rand((n, p), device="cuda", generator=g)
+    else:
+        dX = torch.rand((n, p), device="cuda", generator=g)
+    dW = torch.rand((k, p), device="cuda", generator=g)              # column-major p x k
+    dW /= dW.sum(dim=1, keepdim=True)                                # normalize1_cols! (utils.jl:26-32)
+    dH = torch.rand((n, k), device="cuda", generator=g)              # column-major k x n
+    return dX, dW, dH
+
+
+def _objective_mse(dX, dW, dH, chunk=2048):
+    """0.5 * ||X - W H||^2 from the factors, fp32 GEMM per column chunk, fp64 accumulation (independent of the library)."""
+    tot = 0.0
+    for j0 in range(0, dX.shape[0], chunk):
+        R = dX[j0:j0 + chunk] - dH[j0:j0 + chunk] @ dW               # (chunk, p): rows j of X' minus (W H)'
+        tot += float((R.double() ** 2).sum())
+    return 0.5 * tot
+
+
+def _solve(NMF, sess, alg, dW, dH, p, k, iters, tol=1e-30, lw=0.0, lh=0.0, verbose=False):
+    return sess.solve_raw(alg, np.float32, dW.data_ptr(), p, dH.data_ptr(), k, k, iters, tol, lw, lh, True, verbose, True)
+
+
+def test_config2_multmse_16384_k128_vs_oracle_and_properties(NMF, oracle):
+    p = n = 16384
+    k = 128
+    dX, dW0, dH0 = _device_problem(p, n, k, seed=2)
+    with NMF.Session(engine="tc") as s:
+        s.set_X_device(dX.data_ptr(), p, n, p, np.float32, keepalive=dX)
+        # (1) two iterations against the oracle (same X, W0, H0)
+        dW, dH = dW0.clone(), dH0.clone()
+        r = _solve(NMF, s, "multmse", dW, dH, p, k, 2)
+        assert r.engine == 1 and r.niters == 2
+        X = np.asfortranarray(dX.cpu().numpy().T)
+        Wo = np.asfortranarray(dW0.cpu().numpy().T)
+        Ho = np.asfortranarray(dH0.cpu().numpy().T)
+        ro = oracle.solve(oracle.MultUpdate(np.float32, obj="mse", maxiter=2, tol=1e-30), X, Wo, Ho)
+        W = dW.cpu().numpy().T
+        H = dH.cpu().numpy().T
+        assert np.linalg.norm(W - Wo) <= 5e-3 * np.linalg.norm(Wo)
+        assert np.linalg.norm(H - Ho) <= 5e-3 * np.linalg.norm(Ho)
+        assert abs(r.objvalue - float(ro.objvalue)) <= 1e-4 * float(ro.objvalue)       # north-star bar
+        del X, Wo, Ho
+        # (2) objective: returned value == independent evaluation; monotone over iterations; factors non-negative
+        prev = None
+        for iters in (2, 6, 12):
+            dW, dH = dW0.clone(), dH0.clone()
+            r = _solve(NMF, s, "multmse", dW, dH, p, k, iters)
+            assert bool((dW >= 0).all()) and bool((dH >= 0).all()) and bool(torch.isfinite(dW).all()) and bool(torch.isfinite(dH).all())
+            obj = _objective_mse(dX, dW, dH)
+            assert abs(r.objvalue - obj) <= 2e-5 * obj, (iters, r.objvalue, obj)
+            assert prev is None or r.objvalue <= prev * (1 + 1e-6)
+            prev = r.objvalue
+        # (3) bit-repeatable
+        dW2, dH2 = dW0.clone(), dH0.clone()
+        r2 = _solve(NMF, s, "multmse", dW2, dH2, p, k, 12)
+        assert bool((dW2 == dW).all()) and bool((dH2 == dH).all()) and r2.objvalue == r.objvalue
+    # (4) permuting the rows of X and W0 permutes the rows of W and leaves H alone (up to summation order)
+    perm = torch.randperm(p, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+    dXp = dX[:, perm].contiguous()
+    dWp, dHp = dW0[:, perm].contiguous(), dH0.clone()
+    with NMF.Session(engine="tc") as s:
+        s.set_X_device(dXp.data_ptr(), p, n, p, np.float32, keepalive=dXp)
+        rp = _solve(NMF, s, "multmse", dWp, dHp, p, k, 12)
+    assert abs(rp.objvalue - r.objvalue) <= 1e-5 * r.objvalue
+    assert float(torch.linalg.norm(dWp - dW[:, perm]) / torch.linalg.norm(dW)) <= 2e-3
+    assert float(torch.linalg.norm(dHp - dH) / torch.linalg.norm(dH)) <= 2e-3
+
+
+def test_config3_multdiv_8192x65536_k64_properties(NMF):
+    p, n, k = 8192, 65536, 64
+    dX, dW0, dH0 = _device_problem(p, n, k, seed=3)
+    objs = []
+    with NMF.Session(engine="tc") as s:
+        s.set_X_device(dX.data_ptr(), p, n, p, np.float32, keepalive=dX)
+        for iters in (2, 5, 9):
+            dW, dH = dW0.clone(), dH0.clone()
+            r = _solve(NMF, s, "multdiv", dW, dH, p, k, iters)
+            assert r.engine == 1 and r.niters == iters
+            assert bool((dW >= 0).all()) and bool((dH >= 0).all()) and bool(torch.isfinite(dW).all()) and bool(torch.isfinite(dH).all())
+            objs.append(r.objvalue)
+        # generalised KL divergence of the returned factors, evaluated independently on a slab of columns, scaled up
+        # (X ~ U[0,1) i.i.d.: the slab is a fair sample); the library value must agree with the extrapolation to 2 %
+        J = 4096
+        Y = dH[:J] @ dW
+        Xs = dX[:J]
+        kl = float((torch.where(Xs > 0, Xs * torch.log(Xs / Y), torch.zeros_like(Xs)) - Xs + Y).double().sum()) * (n / J)
+        assert abs(objs[-1] - kl) <= 2e-2 * kl, (objs[-1], kl)
+    assert objs[0] >= objs[1] >= objs[2] > 0           # the KL updates never increase the divergence
+
+
+def test_config4_greedycd_32768_k256_properties(NMF):
+    p = n = 32768
+    k = 256
+    dX, dW0, dH0 = _device_problem(p, n, k, seed=4, planted_rank=64)
+    objs, updates = [], []
+    with NMF.Session(engine="tc") as s:
+        s.set_X_device(dX.data_ptr(), p, n, p, np.float32, keepalive=dX)
+        for iters in (2, 4):
+            dW, dH = dW0.clone(), dH0.clone()
+            r = _solve(NMF, s, "greedycd", dW, dH, p, k, iters)
+            assert r.engine == 1 and r.niters == iters
+            assert bool((dW >= 0).all()) and bool((dH >= 0).all()) and bool(torch.isfinite(dW).all()) and bool(torch.isfinite(dH).all())
+            objs.append(r.objvalue)
+            updates.append(int(r.coordinate_updates))
+        obj = _objective_mse(dX, dW, dH)
+        # KP = 256: the objective kernel forms W*H from the bf16 hi parts only (no room for the hi/lo split): 1e-3
+        assert abs(objs[-1] - obj) <= 1e-3 * obj, (objs[-1], obj)
+    obj0 = _objective_mse(dX, dW0, dH0)
+    assert obj0 > objs[0] > objs[1] > 0 and updates[1] > updates[0] > 0
