@@ -349,6 +349,9 @@ def run_secondary(args):
     sess = NMF.Session(device=0, engine=args.engine)
     sess.set_X_device(dX.data_ptr(), p, n, p, np.float32, keepalive=dX)
     sess.set_option("check_every", max(args.steps, 1))
+    for kv in args.opt:
+        key, val = kv.split("=")
+        sess.set_option(key, val)
     out = {}
     for iters, tag in ((max(args.warmup, 2), "warm"), (max(args.steps, 2), "timed")):
         dW.copy_(W0)

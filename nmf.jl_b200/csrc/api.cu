@@ -189,6 +189,8 @@ int nmfb200_set_option(nmfb200_handle* h, const char* key, const char* value) {
             h->tc_tile_rows = atoi(value);
         } else if (k == "tc_pdl") {
             h->tc_pdl = atoi(value);
+        } else if (k == "tc_div_fused") {
+            h->tc_div_fused = atoi(value);
         } else if (k == "tc_xchg") {
             if (v == "p2p") h->tc_xchg = 1;
             else if (v == "nccl") h->tc_xchg = 0;

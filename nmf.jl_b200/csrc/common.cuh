@@ -116,6 +116,7 @@ struct nmfb200_handle {
     int tc_xchg = 1;       // multi-GPU exchange: 1 = fused peer-memory reduce-scatter/all-gather, 0 = ncclAllReduce
     nmfb200::Xchg xchg;
     int tc_pdl = 1;        // 1 = launch the update kernels as programmatic dependents of the reduce kernel before them
+    int tc_div_fused = 1;  // MultUpdate(:div): 1 = quotient tile stays on chip (div_fused_kernel), 0 = bf16 Q panel through HBM
     std::vector<cudaEvent_t> ev_pool;  // events for time_kernels
     size_t ev_used = 0;
     nmfb200_trace_fn trace = nullptr;

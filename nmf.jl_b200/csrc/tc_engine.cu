@@ -68,7 +68,9 @@ struct UpdateParams {
     bf16* Fhi;          // [R][KP]
     bf16* Flo;          // [R][KP]
     bf16* FbT;          // [KP][ldT] transposed bf16 copy
-    float* num_io;      // MODE 1: raw numerators out, MODE 2: reduced numerators in ([R][KP])
+    float* num_io;      // MODE 1: raw numerators out, MODE 2: reduced numerators in ([R][KP]); MODE 5: num_splits k-split partials in
+    int num_splits;     // MODE 5: numerators = sum over s < num_splits of num_io[s * num_split_stride + ...] (in order)
+    int64_t num_split_stride;
     float* conv_part;   // [tiles][2][KP]   (MODE 3: [tiles] per-CTA max of D, greedycd.jl:132-137)
     const float* Pfull; // MODE 3: fp32 Gram of the other factor ([KP][KP]); its diagonal enters S and D
     const float* colsum; // MODE 4: column sums of the other factor (sW / sH of multupd.jl:176,188), [KP]
@@ -118,6 +120,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(bf16 lo, bf16 hi) {
 // all-reduce).  MODE 2: no main loop, numerators read from num_io (after the all-reduce).
 // MODE 4: MultUpdate(:div): Xs is the quotient panel Q, no denominator MMAs; F <- F * Num / (colsum + lambda) (multupd.jl:177-179,189-191).
 // MODE 3: GreedyCD gradient: G = F*P - Xs*O (+lambda) -> num_io, per-CTA max_r D[i,r] -> conv_part (greedycd.jl:117-137).
+// MODE 5: MultUpdate(:div) after div_fused_kernel: no main loop, numerators = sum of the k-split partials in num_io, then as MODE 4.
 template <int KP, int MODE>
 __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const __grid_constant__ UpdateParams prm) {
     using C = UpdCfg<KP>;
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
     uint32_t* stop_slot = tmem_slot + 1;
     float* conv_s = (float*)(smem + C::RING_BYTES + 1024);  // [4 warps][2][KP]
     // Staged epilogue (KP <= 128, modes that write the factor): the ring is idle once the accumulators are complete
-    constexpr bool STAGED = (KP <= 128) && (MODE == 0 || MODE == 2 || MODE == 4);
+    constexpr bool STAGED = (KP <= 128) && (MODE == 0 || MODE == 2 || MODE == 4 || MODE == 5);
     uint8_t* const SF = smem;                              // fp32 tile:  KP/32 boxes of 128 rows x 128 B
     uint8_t* const SH = SF + (KP / 32) * 16384;            // bf16 hi:    KP/64 boxes
     uint8_t* const SL = SH + (KP / 64) * 16384;            // bf16 lo
@@ -150,8 +153,8 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
     const int tile_rows = prm.tile_rows;
     const int r0 = blockIdx.x * tile_rows;
     const uint32_t a_bytes = (uint32_t)tile_rows * 128u;
-    const int nkb = (MODE == 2) ? 0 : (prm.Kdim + 63) / 64;
-    constexpr int NPRE = (MODE == 1 || MODE == 4) ? 0 : 3 * C::NSLAB;
+    const int nkb = (MODE == 2 || MODE == 5) ? 0 : (prm.Kdim + 63) / 64;
+    constexpr int NPRE = (MODE == 1 || MODE == 4 || MODE == 5) ? 0 : 3 * C::NSLAB;
 
     if (warp == 0 && lane == 0) {
         // Has the loop already met stop_condition?  ONE thread samples the flag for the whole CTA: under PDL (see
@@ -160,7 +163,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
         *stop_slot = (uint32_t)__ldcg(&prm.state->converged);
         prefetch_tmap(&prm.tmA);
         prefetch_tmap(&prm.tmB);
-        if (MODE != 1 && MODE != 4) {
+        if (MODE != 1 && MODE != 4 && MODE != 5) {
             prefetch_tmap(&prm.tmFhi);
             prefetch_tmap(&prm.tmFlo);
             prefetch_tmap(&prm.tmPhi);
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
 #pragma unroll 1
                 for (int bd = 1; bd < NPRE; ++bd) block(tmem_base + KP, 1u);
             }
-            umma_commit(tmem_full);
+            if (MODE != 5) umma_commit(tmem_full);
             TSTAMP(3);                                                   // all MMAs issued
         }
         __syncwarp();
@@ -264,7 +267,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
         pdl_wait();  // from here on we read / overwrite what the preceding kernel wrote / read
         const bool stop = __ldcg(&prm.state->converged) != 0;  // uniform: the preceding kernel is complete
         if (threadIdx.x == 64) TSTAMP(4);    // preceding kernel complete
-        mbar_wait(tmem_full, 0);   // (parking the epilogue warps in a named barrier instead of this poll was measured: no difference)
+        if (MODE != 5) mbar_wait(tmem_full, 0);   // (parking the epilogue warps in a named barrier instead of this poll was measured: no difference)
         tc_fence_after();
         if (threadIdx.x == 64) TSTAMP(5);    // accumulators complete
         do {
@@ -280,8 +283,8 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
         for (int c0 = chalf * (KP / 2); c0 < (chalf + 1) * (KP / 2); c0 += 32) {
             uint32_t num_u[32], den_u[32];
             float f[32];
-            if (MODE != 2) tmem_ld32(t_lane + c0, num_u);
-            if (MODE != 1 && MODE != 4) tmem_ld32(t_lane + KP + c0, den_u);
+            if (MODE != 2 && MODE != 5) tmem_ld32(t_lane + c0, num_u);
+            if (MODE != 1 && MODE != 4 && MODE != 5) tmem_ld32(t_lane + KP + c0, den_u);
             if (MODE == 1) {
                 tmem_ld_wait();
                 if (valid) {
@@ -309,9 +312,28 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                         num_u[4 * j + 2] = __float_as_uint(v.z); num_u[4 * j + 3] = __float_as_uint(v.w);
                     }
                 }
+                if (MODE == 5) {  // k-split partial numerators of div_fused_kernel, summed in split order (deterministic)
+                    const float* nbase = prm.num_io + (size_t)row * KP + c0;
+                    float acc[32];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 v = __ldcg((const float4*)nbase + j);
+                        acc[4 * j] = v.x; acc[4 * j + 1] = v.y; acc[4 * j + 2] = v.z; acc[4 * j + 3] = v.w;
+                    }
+                    for (int sp = 1; sp < prm.num_splits; ++sp) {
+                        const float4* ns = (const float4*)(nbase + (size_t)sp * prm.num_split_stride);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float4 v = __ldcg(ns + j);
+                            acc[4 * j] += v.x; acc[4 * j + 1] += v.y; acc[4 * j + 2] += v.z; acc[4 * j + 3] += v.w;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) num_u[j] = __float_as_uint(acc[j]);
+                }
             } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) { f[j] = 0.f; if (MODE == 2) num_u[j] = 0u; }
+                for (int j = 0; j < 32; ++j) { f[j] = 0.f; if (MODE == 2 || MODE == 5) num_u[j] = 0u; }
             }
             tmem_ld_wait();
             if (MODE == 3) {
@@ -343,7 +365,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     float v;
-                    if (MODE == 4) {
+                    if (MODE == 4 || MODE == 5) {
                         v = f[j + e] * __fdividef(__uint_as_float(num_u[j + e]), prm.colsum[c0 + j + e] + lambda);  // multupd.jl:178 / :190
                     } else {
                         float num = __uint_as_float(num_u[j + e]) - lambda;
@@ -1082,6 +1104,8 @@ struct TcSolver {
     bool defer_gram_reduce = false;  // the caller will run gram_conv_reduce_kernel itself
     bool last_fused_gram = false;
     float* last_gram_part = nullptr;
+    int num_splits = 1;              // MODE 5: k-split partial numerators behind num_io
+    int64_t num_split_stride = 0;
 
     // gram: -1 = no Gram of the updated factor wanted; 0 / 1 = wanted, without / with the bf16 hi-lo split;
     // gram_dst = where the fp32 Gram goes (default F.P).  KP <= 128: the update kernel's staged epilogue produces the
@@ -1104,6 +1128,8 @@ struct TcSolver {
         prm.tmPlo = make_tmap_bf16(O.Plo, KP, KP, KP, KP);
         prm.F = F.m; prm.Fhi = F.hi; prm.Flo = F.lo; prm.FbT = F.bT; prm.ldT = F.ldT;
         prm.num_io = num_io;
+        prm.num_splits = num_splits;
+        prm.num_split_stride = num_split_stride;
         prm.conv_part = conv_override ? conv_override : F.conv;
         prm.Pfull = O.P;
         prm.colsum = O.colsum;
@@ -1116,7 +1142,8 @@ struct TcSolver {
                                            : mode == 1 ? mu_update_kernel<KP, 1>
                                            : mode == 2 ? mu_update_kernel<KP, 2>
                                            : mode == 3 ? mu_update_kernel<KP, 3>
-                                                       : mu_update_kernel<KP, 4>;
+                                           : mode == 4 ? mu_update_kernel<KP, 4>
+                                                       : mu_update_kernel<KP, 5>;
         // pdl: programmatic dependent launch -- start streaming X while the preceding reduce kernel is still running
         launch_k(kern, dim3((unsigned)F.tiles), dim3(UpdCfg<KP>::THREADS), (size_t)smem, st, pdl, prm);
         if (timed) NMF_CUDA(cudaEventRecord(h->next_event(), st));
@@ -1154,6 +1181,7 @@ struct TcSolver {
         NMF_CUDA(cudaFuncSetAttribute(mu_update_kernel<KP, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, UpdCfg<KP>::SMEM_BYTES));
         NMF_CUDA(cudaFuncSetAttribute(mu_update_kernel<KP, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, UpdCfg<KP>::SMEM_BYTES));
         NMF_CUDA(cudaFuncSetAttribute(mu_update_kernel<KP, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, UpdCfg<KP>::SMEM_BYTES));
+        NMF_CUDA(cudaFuncSetAttribute(mu_update_kernel<KP, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, UpdCfg<KP>::SMEM_BYTES));
         NMF_CUDA(cudaFuncSetAttribute(gram_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, GramCfg<KP>::SMEM_BYTES));
         done = true;
     }
@@ -1979,6 +2007,233 @@ __global__ void __launch_bounds__(QuotCfg<KP>::THREADS, 1) div_quot_kernel(const
     }
 }
 
+// ---- fused quotient + numerator (MultUpdate :div) --------------------------------------------------------------
+// One half-step without the Q panel round trip through HBM: per 128 x 64 tile of X
+//   MMA 1:  D[128 x 64]  = Rf_tile * Cf_blk'        (K = KP)      -> TMEM buffer b           (as div_quot_kernel)
+//   warps:  Q = X_tile / (D + delta) -> bf16 Q tile in shared memory, in the swizzled K-major image an A operand needs
+//   MMA 2:  Num[128 x KP] += Q_tile * (Cf_blk)      (K = 64)      -> TMEM accumulator        (as mu_update_kernel MODE 4)
+// so X is read once (2 B per cell and half-step instead of 6).  The numerators go to num_part[blockIdx.y][R][KP]
+// (k-split partials, summed in order by mu_update_kernel<KP,5>, which also applies F .* Num ./ (colsum + lambda)).
+struct DivFusedParams {
+    CUtensorMap tmX;   // X panel  bf16 tile-contiguous [tiles*nkb*128][64], box 64 x 128
+    CUtensorMap tmR;   // row factor hi  bf16 [R][KP],   box 64 x 128
+    CUtensorMap tmC;   // col factor hi  bf16 [C][KP],   box 64 x 64     (B operand of MMA 1)
+    CUtensorMap tmT;   // col factor hi transposed bf16 [KP][ldC], box 64 x KP (B operand of MMA 2)
+    const TcState* state;
+    float* num_part;   // [gridDim.y][R][KP]
+    int R;
+    int nkb, kchunk;
+    float delta;
+};
+
+template <int KP>
+struct DivFusedCfg {
+    static constexpr int NSLAB = KP / 64;
+    static constexpr int RF_BYTES = NSLAB * 128 * 128;   // resident row-factor tile
+    static constexpr int C_BYTES = NSLAB * 64 * 128;     // 64 rows x KP   (MMA 1 B operand)
+    static constexpr int T_BYTES = KP * 128;             // KP rows x 64   (MMA 2 B operand)
+    static constexpr int X_BYTES = 128 * 128;
+    static constexpr int SC = KP == 64 ? 4 : 2, ST = KP == 64 ? 4 : 3, SX = KP == 64 ? 4 : 3, SQ = 2;
+    static constexpr int OFF_C = RF_BYTES;
+    static constexpr int OFF_T = OFF_C + SC * C_BYTES;
+    static constexpr int OFF_X = OFF_T + ST * T_BYTES;
+    static constexpr int OFF_Q = OFF_X + SX * X_BYTES;
+    static constexpr int OFF_BAR = OFF_Q + SQ * X_BYTES;
+    static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
+    static constexpr int THREADS = 320;                  // w0 producer, w1 MMA, w2..w9 quotient / epilogue
+    static constexpr int TMEM_COLS = 256;                // D: 2 x 64 columns at [0,128); Num: KP columns at [128, 128+KP)
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+template <int KP>
+__global__ void __launch_bounds__(DivFusedCfg<KP>::THREADS, 1) div_fused_kernel(const __grid_constant__ DivFusedParams prm) {
+    using C = DivFusedCfg<KP>;
+    if (prm.state->converged) return;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* fullC = (uint64_t*)(smem + C::OFF_BAR);
+    uint64_t* emptyC = fullC + C::SC;
+    uint64_t* fullT = emptyC + C::SC;
+    uint64_t* emptyT = fullT + C::ST;
+    uint64_t* fullX = emptyT + C::ST;
+    uint64_t* emptyX = fullX + C::SX;
+    uint64_t* tfull = emptyX + C::SX;    // [2]  D buffer complete (MMA 1 -> warps)
+    uint64_t* tempty = tfull + 2;        // [2]  D buffer drained  (warps -> MMA 1)
+    uint64_t* qfull = tempty + 2;        // [SQ] Q tile written    (warps -> MMA 2)
+    uint64_t* qempty = qfull + C::SQ;    // [SQ] Q tile consumed   (MMA 2 -> warps)
+    uint64_t* rf_full = qempty + C::SQ;
+    uint64_t* num_full = rf_full + 1;
+    uint32_t* tmem_slot = (uint32_t*)(num_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kb0 = blockIdx.y * prm.kchunk;
+    const int nkb = min(prm.nkb, kb0 + prm.kchunk) - kb0;         // k-blocks of this CTA (>= 1 by construction of the grid)
+    const int row0 = blockIdx.x * 128;
+    const int prow0 = (blockIdx.x * prm.nkb + kb0) * 128;         // first panel row of this CTA's first tile
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&prm.tmX);
+        prefetch_tmap(&prm.tmR);
+        prefetch_tmap(&prm.tmC);
+        prefetch_tmap(&prm.tmT);
+        for (int i = 0; i < C::SC; ++i) { mbar_init(&fullC[i], 1); mbar_init(&emptyC[i], 1); }
+        for (int i = 0; i < C::ST; ++i) { mbar_init(&fullT[i], 1); mbar_init(&emptyT[i], 1); }
+        for (int i = 0; i < C::SX; ++i) { mbar_init(&fullX[i], 1); mbar_init(&emptyX[i], 8); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+        for (int i = 0; i < C::SQ; ++i) { mbar_init(&qfull[i], 8); mbar_init(&qempty[i], 1); }
+        mbar_init(rf_full, 1);
+        mbar_init(num_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_num = tmem_base + 128;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (elect_one()) {
+            mbar_arrive_expect_tx(rf_full, C::RF_BYTES);
+            for (int sl = 0; sl < C::NSLAB; ++sl) tma_load_2d(smem + sl * 128 * 128, &prm.tmR, rf_full, 64 * sl, row0);
+            int sc = 0, st = 0, sx = 0;
+            uint32_t phc = 0, pht = 0, phx = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(&emptyX[sx], phx ^ 1u);
+                mbar_arrive_expect_tx(&fullX[sx], C::X_BYTES);
+                tma_load_2d(smem + C::OFF_X + sx * C::X_BYTES, &prm.tmX, &fullX[sx], 0, prow0 + kb * 128);
+                mbar_wait(&emptyC[sc], phc ^ 1u);
+                mbar_arrive_expect_tx(&fullC[sc], C::C_BYTES);
+                for (int sl = 0; sl < C::NSLAB; ++sl)
+                    tma_load_2d(smem + C::OFF_C + sc * C::C_BYTES + sl * 64 * 128, &prm.tmC, &fullC[sc], 64 * sl, 64 * (kb0 + kb));
+                mbar_wait(&emptyT[st], pht ^ 1u);
+                mbar_arrive_expect_tx(&fullT[st], C::T_BYTES);
+                tma_load_2d(smem + C::OFF_T + st * C::T_BYTES, &prm.tmT, &fullT[st], 64 * (kb0 + kb), 0);
+                if (++sx == C::SX) { sx = 0; phx ^= 1u; }
+                if (++sc == C::SC) { sc = 0; phc ^= 1u; }
+                if (++st == C::ST) { st = 0; pht ^= 1u; }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer: MMA 1 of block kb, then MMA 2 of block kb - 1 (its Q tile is being produced meanwhile) =====
+        if (elect_one()) {
+            constexpr uint32_t idesc1 = make_idesc(FMT_BF16, 128, 64);
+            constexpr uint32_t idesc2 = make_idesc(FMT_BF16, 128, KP);
+            mbar_wait(rf_full, 0);
+            int sc = 0, st = 0;
+            uint32_t phc = 0, pht = 0;
+            auto mma2 = [&](int j) {
+                const int o = j % C::SQ;
+                mbar_wait(&qfull[o], ((uint32_t)(j / C::SQ)) & 1u);
+                mbar_wait(&fullT[st], pht);
+                tc_fence_after();
+                const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(smem + C::OFF_Q + o * C::X_BYTES));
+                const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(smem + C::OFF_T + st * C::T_BYTES));
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) umma_bf16(tmem_num, adesc + 2 * kk, bdesc + 2 * kk, idesc2, (j > 0 || kk > 0) ? 1u : 0u);
+                umma_commit(&qempty[o]);
+                umma_commit(&emptyT[st]);
+                if (++st == C::ST) { st = 0; pht ^= 1u; }
+            };
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int b = kb & 1;
+                mbar_wait(&tempty[b], (((uint32_t)kb >> 1) & 1u) ^ 1u);  // the warps have drained this D buffer
+                mbar_wait(&fullC[sc], phc);
+                tc_fence_after();
+                const uint32_t cbase = smem_u32(smem + C::OFF_C + sc * C::C_BYTES);
+#pragma unroll
+                for (int sl = 0; sl < C::NSLAB; ++sl) {
+                    const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(smem + sl * 128 * 128));
+                    const uint64_t bdesc = make_kmajor_sw128_desc(cbase + sl * 64 * 128);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_bf16(tmem_base + b * 64, adesc + 2 * kk, bdesc + 2 * kk, idesc1, (sl > 0 || kk > 0) ? 1u : 0u);
+                }
+                umma_commit(&emptyC[sc]);
+                umma_commit(&tfull[b]);
+                if (++sc == C::SC) { sc = 0; phc ^= 1u; }
+                if (kb > 0) mma2(kb - 1);
+            }
+            mma2(nkb - 1);
+            umma_commit(num_full);
+        }
+        __syncwarp();
+    } else {
+        // ===== quotient warps: warp e handles TMEM lane quarter (warp % 4) and column half e / 4 =====
+        const int e = warp - 2;
+        const int q = warp & 3, hf = e >> 2;
+        const int r = 32 * q + lane;                 // row inside the tile
+        const float delta = prm.delta;
+        int sx = 0;
+        uint32_t phx = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int b = kb & 1, o = kb % C::SQ;
+            mbar_wait(&tfull[b], ((uint32_t)kb >> 1) & 1u);
+            tc_fence_after();
+            uint32_t d[32];
+            tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + b * 64 + 32 * hf, d);
+            mbar_wait(&fullX[sx], phx);
+            const uint8_t* xt = smem + C::OFF_X + sx * C::X_BYTES + r * 128;
+            uint4 xv[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) xv[c] = *(const uint4*)(xt + (((4 * hf + c) ^ (r & 7)) << 4));
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[b]);  // TMEM buffer b may be overwritten
+            uint4 qv[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint32_t xin[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w};
+                uint32_t qo[4];
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const float x0 = __uint_as_float(xin[w] << 16), x1 = __uint_as_float(xin[w] & 0xffff0000u);
+                    const float d0 = __uint_as_float(d[8 * c + 2 * w]) + delta, d1 = __uint_as_float(d[8 * c + 2 * w + 1]) + delta;
+                    qo[w] = pack_bf16x2(__float2bfloat16_rn(__fdividef(x0, d0)), __float2bfloat16_rn(__fdividef(x1, d1)));
+                }
+                qv[c] = make_uint4(qo[0], qo[1], qo[2], qo[3]);
+            }
+            // Q stage o: MMA 2 of block kb - SQ must have read it
+            mbar_wait(&qempty[o], (((uint32_t)(kb / C::SQ)) & 1u) ^ 1u);
+            uint8_t* ot = smem + C::OFF_Q + o * C::X_BYTES + r * 128;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) *(uint4*)(ot + (((4 * hf + c) ^ (r & 7)) << 4)) = qv[c];
+            fence_proxy_async();     // generic-proxy stores (Q) and consumed loads (X) before the async proxy touches either stage
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&emptyX[sx]);            // X stage may be refilled (its values have been consumed)
+                mbar_arrive(&qfull[o]);              // this warp's part of the Q tile is in place
+            }
+            if (++sx == C::SX) { sx = 0; phx ^= 1u; }
+        }
+        // numerators of this (tile, k-chunk): TMEM -> num_part[blockIdx.y][row][.]
+        mbar_wait(num_full, 0);
+        tc_fence_after();
+        const int row = row0 + r;
+        float* dst_row = prm.num_part + ((size_t)blockIdx.y * prm.R + row) * KP;
+#pragma unroll 1
+        for (int c0 = hf * (KP / 2); c0 < (hf + 1) * (KP / 2); c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_num + ((uint32_t)(32 * q) << 16) + c0, v);
+            tmem_ld_wait();
+            if (row < prm.R) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    ((float4*)(dst_row + c0))[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                                __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
 // column sums of a row-factor [R][KP] (sW = sum(W,1), sH = sum(H,2): multupd.jl:176,188): per 128-row tile, then reduced
 __global__ void __launch_bounds__(256) colsum_tiles_kernel(const float* __restrict__ Fm, int R, int KP, float* __restrict__ part,
                                                            const TcState* st) {
@@ -2041,7 +2296,7 @@ void tc_solve_div_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t l
     double* acc = h->buf_t<double>("tc.acc", 4 * KP);
     const int nkbH = (int)ceil_div(p, 64), nkbW = (int)ceil_div(n, 64);
     const size_t q_elems = std::max((size_t)H.tiles * nkbH, (size_t)W.tiles * nkbW) * 128 * 64;
-    bf16* Q = h->buf_t<bf16>("tc.Q", q_elems);
+    bf16* Q = h->tc_div_fused != 0 ? nullptr : h->buf_t<bf16>("tc.Q", q_elems);
     float* cs_part = h->buf_t<float>("tc.colsum_part", (size_t)std::max(W.tiles, H.tiles) * KP);
     NMF_CUDA(cudaMemsetAsync(state, 0, sizeof(TcState), st));
     NMF_CUDA(cudaMemsetAsync(W.bT, 0, (size_t)W.rowsT * W.ldT * sizeof(bf16), st));
@@ -2063,10 +2318,58 @@ void tc_solve_div_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t l
     TcSolver<KP> s{h, st, state};
     NMF_CUDA(cudaEventRecord(e1, st));
 
-    // one half-step: Q = X ./ (Rf Cf' + delta) over Rf's panel, column sums of Cf, then Rf <- Rf .* (Q Cf) ./ (colsum + lambda)
+    // one half-step: Q = X ./ (Rf Cf' + delta) over Rf's panel, column sums of Cf, then Rf <- Rf .* (Q Cf) ./ (colsum + lambda).
+    // Fused form (default): div_fused_kernel keeps Q on chip (quotient tile -> shared memory -> second MMA) and writes k-split
+    // partial numerators; mu_update_kernel<KP,5> sums them and applies the ratio.  Unfused form (option tc_div_fused=0):
+    // div_quot_kernel writes a bf16 Q panel that mu_update_kernel<KP,4> streams like X.
+    const bool fused = h->tc_div_fused != 0;
+    if (fused) {
+        static bool fattr = false;
+        if (!fattr) {
+            NMF_CUDA(cudaFuncSetAttribute(div_fused_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, DivFusedCfg<KP>::SMEM_BYTES));
+            fattr = true;
+        }
+    }
+    auto pick_ksplit = [](int tiles, int nkb) {  // fewest k-chunks (>= 16 k-blocks each) that fill whole waves of 148 CTAs to >= 93 %
+        int best = 1;
+        double best_eff = 0;
+        for (int ks = 1; ks <= std::max(1, nkb / 16) && ks <= 16; ++ks) {
+            const int ctas = tiles * ks;
+            const double eff = (double)ctas / (double)(ceil_div(ctas, 148) * 148);
+            if (eff > best_eff + 1e-9) { best_eff = eff; best = ks; }
+            if (eff >= 0.93) { best = ks; break; }
+        }
+        return best;
+    };
     auto half_step = [&](Factor& Rf, Factor& Cf, const bf16* Xs, int nkb, int Kdim, float lambda) {
-        QuotParams qp;
         const uint64_t prow = (uint64_t)Rf.tiles * nkb * 128;
+        colsum_tiles_kernel<<<Cf.tiles, 256, 0, st>>>(Cf.m, Cf.R, KP, cs_part, state);
+        colsum_reduce_kernel<<<KP / 32, 256, 0, st>>>(cs_part, Cf.tiles, KP, Cf.colsum, state);
+        h->launches += 2;
+        if (fused) {
+            DivFusedParams fp;
+            fp.tmX = make_tmap_bf16(Xs, 64, prow, 64, 128);
+            fp.tmR = make_tmap_bf16(Rf.hi, KP, (uint64_t)Rf.R, KP, 128);
+            fp.tmC = make_tmap_bf16(Cf.hi, KP, (uint64_t)Cf.R, KP, 64);
+            fp.tmT = make_tmap_bf16(Cf.bT, (uint64_t)Kdim, KP, (uint64_t)Cf.ldT, KP);
+            fp.state = state;
+            fp.R = Rf.R;
+            fp.nkb = nkb;
+            int ksplit = pick_ksplit(Rf.tiles, nkb);
+            fp.kchunk = (int)ceil_div(nkb, ksplit);
+            ksplit = (int)ceil_div(nkb, fp.kchunk);
+            fp.num_part = h->buf_t<float>("tc.div_num_part", (size_t)ksplit * Rf.R * KP);
+            fp.delta = delta;
+            div_fused_kernel<KP><<<dim3(Rf.tiles, ksplit), DivFusedCfg<KP>::THREADS, DivFusedCfg<KP>::SMEM_BYTES, st>>>(fp);
+            h->launches += 1;
+            s.num_splits = ksplit;
+            s.num_split_stride = (int64_t)Rf.R * KP;
+            s.launch_update(5, Rf, Cf, Xs, Kdim, lambda, delta, fp.num_part);
+            s.num_splits = 1;
+            s.num_split_stride = 0;
+            return;
+        }
+        QuotParams qp;
         qp.tmX = make_tmap_bf16(Xs, 64, prow, 64, 128);
         qp.tmQ = make_tmap_bf16(Q, 64, prow, 64, 128);
         qp.tmR = make_tmap_bf16(Rf.hi, KP, (uint64_t)Rf.R, KP, 128);
@@ -2079,9 +2382,7 @@ void tc_solve_div_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t l
         ksplit = (int)ceil_div(nkb, qp.kchunk);
         qp.delta = delta;
         div_quot_kernel<KP><<<dim3(Rf.tiles, ksplit), QuotCfg<KP>::THREADS, QuotCfg<KP>::SMEM_BYTES, st>>>(qp);
-        colsum_tiles_kernel<<<Cf.tiles, 256, 0, st>>>(Cf.m, Cf.R, KP, cs_part, state);
-        colsum_reduce_kernel<<<KP / 32, 256, 0, st>>>(cs_part, Cf.tiles, KP, Cf.colsum, state);
-        h->launches += 3;
+        h->launches += 1;
         s.launch_update(4, Rf, Cf, Q, Kdim, lambda, delta, nullptr);
     };
 
