@@ -2040,8 +2040,11 @@ struct DivFusedCfg {
     static constexpr int OFF_Q = OFF_X + SX * X_BYTES;
     static constexpr int OFF_BAR = OFF_Q + SQ * X_BYTES;
     static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
-    static constexpr int THREADS = 320;                  // w0 producer, w1 MMA, w2..w9 quotient / epilogue
+    static constexpr int NW = 16;                        // quotient warps: 4 per TMEM lane quarter, CPW columns of the 64-wide tile each
+    static constexpr int CPW = 256 / NW;                 // 16 (NW = 16) or 32 (NW = 8)
+    static constexpr int THREADS = 64 + 32 * NW;         // w0 producer, w1 MMA, w2.. quotient / epilogue
     static constexpr int TMEM_COLS = 256;                // D: 2 x 64 columns at [0,128); Num: KP columns at [128, 128+KP)
+    static_assert(NW == 8 || NW == 16, "quotient warps");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
@@ -2077,9 +2080,9 @@ __global__ void __launch_bounds__(DivFusedCfg<KP>::THREADS, 1) div_fused_kernel(
         prefetch_tmap(&prm.tmT);
         for (int i = 0; i < C::SC; ++i) { mbar_init(&fullC[i], 1); mbar_init(&emptyC[i], 1); }
         for (int i = 0; i < C::ST; ++i) { mbar_init(&fullT[i], 1); mbar_init(&emptyT[i], 1); }
-        for (int i = 0; i < C::SX; ++i) { mbar_init(&fullX[i], 1); mbar_init(&emptyX[i], 8); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
-        for (int i = 0; i < C::SQ; ++i) { mbar_init(&qfull[i], 8); mbar_init(&qempty[i], 1); }
+        for (int i = 0; i < C::SX; ++i) { mbar_init(&fullX[i], 1); mbar_init(&emptyX[i], C::NW); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], C::NW); }
+        for (int i = 0; i < C::SQ; ++i) { mbar_init(&qfull[i], C::NW); mbar_init(&qempty[i], 1); }
         mbar_init(rf_full, 1);
         mbar_init(num_full, 1);
         fence_barrier_init();
@@ -2160,31 +2163,34 @@ __global__ void __launch_bounds__(DivFusedCfg<KP>::THREADS, 1) div_fused_kernel(
         }
         __syncwarp();
     } else {
-        // ===== quotient warps: warp e handles TMEM lane quarter (warp % 4) and column half e / 4 =====
+        // ===== quotient warps: warp e handles TMEM lane quarter (warp % 4) and columns [CPW*cp, CPW*cp + CPW) of the tile =====
         const int e = warp - 2;
-        const int q = warp & 3, hf = e >> 2;
+        const int q = warp & 3, cp = e >> 2;
         const int r = 32 * q + lane;                 // row inside the tile
         const float delta = prm.delta;
+        constexpr int CPW = C::CPW;                  // columns per warp
+        constexpr int NCH = CPW / 8;                 // 16-byte chunks (8 bf16) per row and warp
         int sx = 0;
         uint32_t phx = 0;
         for (int kb = 0; kb < nkb; ++kb) {
             const int b = kb & 1, o = kb % C::SQ;
             mbar_wait(&tfull[b], ((uint32_t)kb >> 1) & 1u);
             tc_fence_after();
-            uint32_t d[32];
-            tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + b * 64 + 32 * hf, d);
+            uint32_t d[CPW];
+            if constexpr (CPW == 32) tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + b * 64 + CPW * cp, *(uint32_t(*)[32])d);
+            else tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + b * 64 + CPW * cp, *(uint32_t(*)[16])d);
             mbar_wait(&fullX[sx], phx);
             const uint8_t* xt = smem + C::OFF_X + sx * C::X_BYTES + r * 128;
-            uint4 xv[4];
+            uint4 xv[NCH];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) xv[c] = *(const uint4*)(xt + (((4 * hf + c) ^ (r & 7)) << 4));
+            for (int c = 0; c < NCH; ++c) xv[c] = *(const uint4*)(xt + (((NCH * cp + c) ^ (r & 7)) << 4));
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[b]);  // TMEM buffer b may be overwritten
-            uint4 qv[4];
+            uint4 qv[NCH];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < NCH; ++c) {
                 const uint32_t xin[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w};
                 uint32_t qo[4];
 #pragma unroll
@@ -2199,7 +2205,7 @@ __global__ void __launch_bounds__(DivFusedCfg<KP>::THREADS, 1) div_fused_kernel(
             mbar_wait(&qempty[o], (((uint32_t)(kb / C::SQ)) & 1u) ^ 1u);
             uint8_t* ot = smem + C::OFF_Q + o * C::X_BYTES + r * 128;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) *(uint4*)(ot + (((4 * hf + c) ^ (r & 7)) << 4)) = qv[c];
+            for (int c = 0; c < NCH; ++c) *(uint4*)(ot + (((NCH * cp + c) ^ (r & 7)) << 4)) = qv[c];
             fence_proxy_async();     // generic-proxy stores (Q) and consumed loads (X) before the async proxy touches either stage
             __syncwarp();
             if (lane == 0) {
@@ -2208,19 +2214,22 @@ __global__ void __launch_bounds__(DivFusedCfg<KP>::THREADS, 1) div_fused_kernel(
             }
             if (++sx == C::SX) { sx = 0; phx ^= 1u; }
         }
-        // numerators of this (tile, k-chunk): TMEM -> num_part[blockIdx.y][row][.]
+        // numerators of this (tile, k-chunk): TMEM -> num_part[blockIdx.y][row][.]; warp (q, cp) takes KP / (NW/4) columns
         mbar_wait(num_full, 0);
         tc_fence_after();
         const int row = row0 + r;
         float* dst_row = prm.num_part + ((size_t)blockIdx.y * prm.R + row) * KP;
+        constexpr int NCOL = KP / (C::NW / 4);       // 16 or 32 (KP = 64), 32 or 64 (KP = 128)
+        constexpr int STEP = NCOL >= 32 ? 32 : 16;
 #pragma unroll 1
-        for (int c0 = hf * (KP / 2); c0 < (hf + 1) * (KP / 2); c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem_num + ((uint32_t)(32 * q) << 16) + c0, v);
+        for (int c0 = cp * NCOL; c0 < (cp + 1) * NCOL; c0 += STEP) {
+            uint32_t v[STEP];
+            if constexpr (STEP == 32) tmem_ld32(tmem_num + ((uint32_t)(32 * q) << 16) + c0, *(uint32_t(*)[32])v);
+            else tmem_ld16(tmem_num + ((uint32_t)(32 * q) << 16) + c0, *(uint32_t(*)[16])v);
             tmem_ld_wait();
             if (row < prm.R) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
+                for (int j = 0; j < STEP / 4; ++j)
                     ((float4*)(dst_row + c0))[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
             }
