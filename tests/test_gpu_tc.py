@@ -164,6 +164,28 @@ def test_tc_multdiv_vs_oracle(NMF, oracle, p, n, k, iters):
     assert eo <= 1e-4
 
 
+def test_tc_multdiv_fused_matches_unfused_and_is_repeatable(NMF):
+    """The default :div half-step keeps the quotient tile on chip (div_fused_kernel + k-split partial numerators);
+    option tc_div_fused=0 selects the older form that writes a bf16 Q panel.  Same rounding points (bf16 X, bf16 Q,
+    fp32 accumulation), different summation order and reciprocal form: factors agree to 1e-3, objective to 1e-5; the
+    fused form is bit-repeatable (fixed k-split order)."""
+    for (p, n, k, iters) in [(640, 900, 48, 8), (2048, 1300, 128, 5)]:
+        X, W0, H0 = _problem(NMF, p, n, k, seed=31 + k)
+        outs = {}
+        for fused in (1, 0, 1):
+            with NMF.Session(engine="tc") as s:
+                s.set_option("tc_div_fused", fused)
+                s.set_X(X)
+                Wg, Hg = W0.copy(order="F"), H0.copy(order="F")
+                r = s.solve(NMF.MultUpdate(np.float32, obj="div", maxiter=iters, tol=1e-9), Wg, Hg)
+                assert r.info["engine"] == "tc" and r.niters == iters
+                if fused in outs:   # second fused run: bitwise equal to the first
+                    assert (outs[fused][0] == Wg).all() and (outs[fused][1] == Hg).all() and outs[fused][2] == float(r.objvalue)
+                outs[fused] = (Wg, Hg, float(r.objvalue))
+        assert _relerr(outs[1][0], outs[0][0]) <= 1e-3 and _relerr(outs[1][1], outs[0][1]) <= 1e-3
+        assert abs(outs[1][2] - outs[0][2]) <= 1e-5 * outs[0][2]
+
+
 def test_tc_multdiv_update_H_false(NMF):
     X, W0, H0 = _problem(NMF, 256, 384, 16, seed=17)
     Wg, Hg = W0.copy(order="F"), H0.copy(order="F")
