@@ -87,7 +87,14 @@ int nmfb200_set_stream(nmfb200_handle* h, void* stream);
  *                                               update kernel (multiple of 8 in [8,128]; 0 = auto).
  *   "tc_xchg"      = "p2p" | "nccl"          -- multi-GPU exchange of the tensor-core engine: fused peer-memory
  *                                               reduce-scatter/all-gather over NVLink (default) or ncclAllReduce.
- *   "tc_debug"     = "<int>"                 -- diagnostics for profiling experiments, 0 in production.
+ *   "tc_pdl"       = "0" | "1"               -- 1 (default): the tensor-core update kernels are launched as programmatic
+ *                                               dependents of the small reduce kernel in front of them (their X streaming
+ *                                               overlaps it); 0: plain stream order.  Results are identical.
+ *   "tc_div_fused" = "0" | "1"               -- MultUpdate(:div) on the tensor-core engine: 1 (default) keeps the quotient
+ *                                               tile X./(WH+delta) on chip between two tensor-core products; 0 writes it
+ *                                               as a bf16 panel through HBM (older form, kept for comparison).
+ *   "tc_debug"     = "<int>"                 -- diagnostics for profiling experiments (bit 3: phase clocks of the update
+ *                                               kernel on stderr), 0 in production.
  *   "time_kernels" = "0" | "1"               -- bracket every launch of the dominant kernel with
  *                                               CUDA events and report the sum in nmfb200_result. */
 int nmfb200_set_option(nmfb200_handle* h, const char* key, const char* value);
