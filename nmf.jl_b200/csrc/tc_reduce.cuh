@@ -1,0 +1,195 @@
+// tc_reduce.cuh -- stop_condition finish (common.jl:92-111), merged Gram + stop reduce, post-exchange decision kernel
+// Part of the tensor-core engine; included only by tc_engine.cu, inside namespace nmfb200 and its
+// anonymous namespace.
+#pragma once
+
+// ---- stop_condition finish (common.jl:92-111) ---------------------------------------------------------
+// acc (double [4][KP]) = {dev_w, sum_w, dev_h, sum_h}.  conv_reduce_kernel: grid = 4 * KP/32 blocks of 8 warps;
+// block (q, cb) sums quantity q of components [32cb, 32cb+32) over all tiles (warp w takes tiles w, w+8, ...;
+// 8 loads in flight; fixed combination order => deterministic).  With do_decide the last block to finish
+// (atomic ticket) applies the reference's test; multi-GPU runs the decision as a separate launch after the
+// packed all-reduce (post_allreduce_kernel).
+__device__ void conv_decide(const double* acc, int KP, int k, float tol, TcState* st, float* devs, int* fail) {
+    const int a = threadIdx.x;
+    if (a == 0) *fail = 0;
+    __syncthreads();
+    float dev = 0.f;
+    if (a < k) {
+        float dw = (float)__ldcg(acc + a), sw = (float)__ldcg(acc + KP + a), dh = (float)__ldcg(acc + 2 * KP + a),
+              sh = (float)__ldcg(acc + 3 * KP + a);
+        float rw = dw / sw, rh = dh / sh;
+        float m = (rw != rw) ? rw : ((rh != rh) ? rh : fmaxf(rw, rh));  // Julia max(): NaN propagates (common.jl:105)
+        dev = sqrtf(m);
+        if (sqrtf(dw) > tol * sqrtf(sw) || sqrtf(dh) > tol * sqrtf(sh)) atomicExch(fail, 1);  // common.jl:106
+    }
+    if (a < 256) devs[a] = dev;
+    __syncthreads();
+    if (a == 0) {
+        float dm = 0.f;
+        for (int i = 0; i < k; ++i) dm = (dm != dm) ? dm : ((devs[i] != devs[i]) ? devs[i] : fmaxf(dm, devs[i]));
+        st->devmax = dm;
+        st->iters += 1;
+        if (!*fail) st->converged = 1;
+    }
+}
+
+__global__ void __launch_bounds__(256) conv_reduce_kernel(const float* __restrict__ partW, int tilesW, const float* __restrict__ partH,
+                                                          int tilesH, int KP, int k, int update_H, double* __restrict__ acc, float tol,
+                                                          TcState* st, int do_decide, float* __restrict__ wsums_f32) {
+    if (st->converged) return;
+    __shared__ double red[8][32];
+    __shared__ float devs[256];
+    __shared__ int fail, is_last;
+    const int cbs = KP / 32;
+    const int q = blockIdx.x / cbs, cb = blockIdx.x % cbs;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = cb * 32 + lane;
+    const float* part = (q < 2 ? partW : partH) + (size_t)(q & 1) * KP + c;
+    const int tiles = q < 2 ? tilesW : (update_H ? tilesH : 0);
+    double s = 0.0;
+    int t = w;
+    for (; t + 56 < tiles; t += 64) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcg(part + (size_t)(t + 8 * u) * 2 * KP);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += (double)v[u];
+    }
+    for (; t < tiles; t += 8) s += (double)__ldcg(part + (size_t)t * 2 * KP);
+    red[w][lane] = s;
+    __syncthreads();
+    if (w == 0) {
+        double tot = red[0][lane];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) tot += red[i][lane];
+        if (q >= 2 && !update_H) tot = (q == 2) ? 0.0 : 1.0;  // H untouched: dev_h = 0 (sum_h only scales a ratio of 0)
+        acc[(size_t)q * KP + c] = tot;
+        if (wsums_f32 && q < 2) wsums_f32[(size_t)q * KP + c] = (float)tot;  // multi-GPU: rides in the packed all-reduce
+    }
+    if (!do_decide) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int prev = atomicAdd(&st->ticket, 1u);
+        is_last = (prev == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) st->ticket = 0u;
+    conv_decide(acc, KP, k, tol, st, devs, &fail);
+}
+
+// One launch for the two small reductions that follow the W-step: blocks [0, gram_blocks) reduce the per-tile Gram
+// contributions (gram_reduce_kernel's work), the remaining 4*KP/32 blocks reduce the stop_condition partial sums and the
+// last of them decides (conv_reduce_kernel's work).
+__device__ __forceinline__ void gram_reduce_body(const float* __restrict__ part, int nparts, int nelem, float* __restrict__ P,
+                                                 bf16* __restrict__ Phi, bf16* __restrict__ Plo, int do_split, int block) {
+    const int t = block * blockDim.x + threadIdx.x;
+    const int sub = t & 3;
+    const int i = t >> 2;
+    float acc = 0.f;
+    if (i < nelem) {
+        int g = sub;
+        for (; g + 28 < nparts; g += 32) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(part + (size_t)(g + 4 * u) * nelem + i);
+            acc += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+        }
+        for (; g < nparts; g += 4) acc += __ldcg(part + (size_t)g * nelem + i);
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (i < nelem && sub == 0) {
+        P[i] = acc;
+        if (do_split) {
+            bf16 hi = __float2bfloat16_rn(acc);
+            Phi[i] = hi;
+            Plo[i] = __float2bfloat16_rn(acc - __bfloat162float(hi));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) gram_conv_reduce_kernel(const float* __restrict__ gpart, int nparts, int nelem, float* __restrict__ P,
+                                                               bf16* __restrict__ Phi, bf16* __restrict__ Plo, int do_split, int gram_blocks,
+                                                               const float* __restrict__ partW, int tilesW, const float* __restrict__ partH,
+                                                               int tilesH, int KP, int k, int update_H, double* __restrict__ acc, float tol,
+                                                               TcState* st, int do_decide, float* __restrict__ wsums_f32) {
+    pdl_launch_dependents();  // the next H-step may start streaming X now; it waits for us before it reads P / `converged`
+    if (st->converged) return;
+    if ((int)blockIdx.x < gram_blocks) {
+        gram_reduce_body(gpart, nparts, nelem, P, Phi, Plo, do_split, blockIdx.x);
+        return;
+    }
+    __shared__ double red[8][32];
+    __shared__ float devs[256];
+    __shared__ int fail, is_last;
+    const int cblock = blockIdx.x - gram_blocks, nconv = gridDim.x - gram_blocks;
+    const int cbs = KP / 32;
+    const int q = cblock / cbs, cb = cblock % cbs;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = cb * 32 + lane;
+    const float* part = (q < 2 ? partW : partH) + (size_t)(q & 1) * KP + c;
+    const int tiles = q < 2 ? tilesW : (update_H ? tilesH : 0);
+    double s = 0.0;
+    int t = w;
+    for (; t + 56 < tiles; t += 64) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcg(part + (size_t)(t + 8 * u) * 2 * KP);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += (double)v[u];
+    }
+    for (; t < tiles; t += 8) s += (double)__ldcg(part + (size_t)t * 2 * KP);
+    red[w][lane] = s;
+    __syncthreads();
+    if (w == 0) {
+        double tot = red[0][lane];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) tot += red[i][lane];
+        if (q >= 2 && !update_H) tot = (q == 2) ? 0.0 : 1.0;
+        acc[(size_t)q * KP + c] = tot;
+        if (wsums_f32 && q < 2) wsums_f32[(size_t)q * KP + c] = (float)tot;
+    }
+    if (!do_decide) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int prev = atomicAdd(&st->ticket, 1u);
+        is_last = (prev == (unsigned)nconv - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) st->ticket = 0u;
+    conv_decide(acc, KP, k, tol, st, devs, &fail);
+}
+
+// multi-GPU, after the packed all-reduce: block 0 finishes stop_condition of the PREVIOUS iteration (its W-side
+// sums travelled in the tail of the packed buffer; nothing of the current iteration has touched W or H yet),
+// the other blocks split the reduced Gram W'W into bf16 hi/lo.
+__global__ void __launch_bounds__(256) post_allreduce_kernel(double* __restrict__ acc, const float* __restrict__ wsums_f32, int has_prev,
+                                                             int KP, int k, float tol, TcState* st, const float* __restrict__ P,
+                                                             bf16* __restrict__ Phi, bf16* __restrict__ Plo, XchgDev x, unsigned int epoch) {
+    pdl_launch_dependents();  // the MODE 2 ratio kernel may set itself up now; it waits for our completion before it reads anything
+    if (x.G > 0) xchg_wait_all(x, 1, epoch);  // peer-memory exchange: every rank's reduced segment has landed here
+    if (st->converged) return;
+    __shared__ float devs[256];
+    __shared__ int fail;
+    if (blockIdx.x == 0) {
+        if (!has_prev) return;
+        for (int i = threadIdx.x; i < 2 * KP; i += blockDim.x) acc[i] = (double)__ldcg(wsums_f32 + i);
+        __syncthreads();
+        conv_decide(acc, KP, k, tol, st, devs, &fail);
+        return;
+    }
+    if (P == nullptr) return;
+    const int i = (blockIdx.x - 1) * blockDim.x + threadIdx.x;
+    if (i < KP * KP) {
+        float v = P[i];
+        bf16 hi = __float2bfloat16_rn(v);
+        Phi[i] = hi;
+        Plo[i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+}

@@ -1,0 +1,650 @@
+// tc_update.cuh -- device state, the update kernel (mu_update_kernel, all modes), the stand-alone Gram kernel and the Gram reduce
+// Part of the tensor-core engine; included only by tc_engine.cu, inside namespace nmfb200 and its
+// anonymous namespace.
+#pragma once
+
+struct TcState {
+    int converged;
+    int iters;
+    float devmax;
+    unsigned int ticket;
+};
+
+// ---- peer-memory exchange (multi-GPU) ---------------------------------------------------------------
+// The packed vector [numerators n x KP | W'W KP x KP | W-side stop sums 2 x KP] is treated as Rtot = n+KP+2
+// rows of KP floats, cut into G contiguous segments of RS rows; rank j owns (reduces) segment j.
+// Arena of every rank (IPC-mapped into all peers): flags | packed [G*RS][KP].  A rank's kernels write their
+// partial sums into its own `packed`; the exchange kernel PULLS its segment from every peer over NVLink, sums
+// in rank order and PUSHES the reduced segment into every peer's `packed` (reduce-scatter + all-gather fused).
+struct XchgDev {
+    float* packed[XCHG_MAX_RANKS];        // packed[j] = rank j's packed vector (mapped peer memory)
+    unsigned int* flags[XCHG_MAX_RANKS];  // flags[j][phase * XCHG_MAX_RANKS + src]: "src reached epoch in phase"
+    unsigned int* ticket;                 // local counter for the last-block pattern
+    int G, rank, RS;
+};
+
+// ---- kernel parameter block (tensor maps must live in __grid_constant__ param space) ---------------
+struct UpdateParams {
+    CUtensorMap tmA;    // Xs   bf16 tile-contiguous [tiles*nkb*tile_rows][64], box 64 x tile_rows
+    CUtensorMap tmB;    // O^T  bf16 [KP][Kdim]    box 64 x KP
+    CUtensorMap tmFhi;  // F hi bf16 [R][KP]       box 64 x 128
+    CUtensorMap tmFlo;  // F lo
+    CUtensorMap tmPhi;  // P hi bf16 [KP][KP]      box 64 x KP
+    CUtensorMap tmPlo;  // P lo
+    CUtensorMap tmF32;  // F fp32 [R][KP]          box 32 x tile_rows (staged epilogue store)
+    CUtensorMap tmT;    // F^T bf16 [KP][R]        box 64 x KP        (staged epilogue store of the transposed copy)
+    float* gram_part;   // staged epilogue: [tiles][KP][KP] fp32 Gram contribution of each tile (nullptr = skip)
+    float* F;           // [R][KP] fp32 master, updated in place
+    bf16* Fhi;          // [R][KP]
+    bf16* Flo;          // [R][KP]
+    bf16* FbT;          // [KP][ldT] transposed bf16 copy
+    float* num_io;      // MODE 1: raw numerators out, MODE 2: reduced numerators in ([R][KP]); MODE 5: num_splits k-split partials in
+    int num_splits;     // MODE 5: numerators = sum over s < num_splits of num_io[s * num_split_stride + ...] (in order)
+    int64_t num_split_stride;
+    float* conv_part;   // [tiles][2][KP]   (MODE 3: [tiles] per-CTA max of D, greedycd.jl:132-137)
+    const float* Pfull; // MODE 3: fp32 Gram of the other factor ([KP][KP]); its diagonal enters S and D
+    const float* colsum; // MODE 4: column sums of the other factor (sW / sH of multupd.jl:176,188), [KP]
+    const TcState* state;
+    int64_t ldT;
+    int R, Kdim;
+    int tile_rows;      // rows of F owned by one CTA (<= 128, multiple of 8); the TMA boxes of A / Fhi / Flo have this many rows
+    long long* timing;  // diagnostics (tc_debug bit 3): CTA 0 records clock64() at its phase boundaries, see TSTAMP
+    float lambda, delta;
+};
+
+template <int KP>
+struct UpdCfg {
+    static constexpr int A_BYTES = 128 * 128;   // A part of a stage: up to 128 rows x 64 bf16
+    static constexpr int B_BYTES = KP * 128;    // B part: KP rows x 64 bf16
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    // One ring, A and B of a k-block travel together (one wait + one commit per block on the MMA thread).
+    // Deeper / split rings were measured and bought nothing (profiles/r1b_pipeline_experiments.md).
+    static constexpr int STAGES = KP == 256 ? 4 : (KP == 128 ? 6 : 8);
+    static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+    static constexpr int CONV_BYTES = 4 * 2 * KP * 4;
+    static constexpr int SMEM_BYTES = RING_BYTES + CONV_BYTES + 1024 + 1024;  // ring | barriers (1 KB) | conv scratch | align slack
+    static constexpr int TMEM_COLS = 2 * KP;
+    static constexpr int NSLAB = KP / 64;
+    static constexpr int THREADS = 320;  // w0 TMA producer, w1 MMA issuer, w2-9 epilogue (lane quarter = warp % 4, column half = (warp-2)/4)
+};
+
+// sum v[j] over the 32 lanes of the warp; afterwards v[0] on lane l holds the total of column l
+__device__ __forceinline__ void warp_transpose_reduce(float (&v)[32], int lane) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < o; ++i) {
+            float send = up ? v[i] : v[i + o];
+            float keep = up ? v[i + o] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(bf16 lo, bf16 hi) {
+    return (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
+}
+
+// MODE 0: fused (single GPU).  MODE 1: numerators only -> num_io (row-sharded H-step, before the
+// all-reduce).  MODE 2: no main loop, numerators read from num_io (after the all-reduce).
+// MODE 4: MultUpdate(:div): Xs is the quotient panel Q, no denominator MMAs; F <- F * Num / (colsum + lambda) (multupd.jl:177-179,189-191).
+// MODE 3: GreedyCD gradient: G = F*P - Xs*O (+lambda) -> num_io, per-CTA max_r D[i,r] -> conv_part (greedycd.jl:117-137).
+// MODE 5: MultUpdate(:div) after div_fused_kernel: no main loop, numerators = sum of the k-split partials in num_io, then as MODE 4.
+template <int KP, int MODE>
+__global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const __grid_constant__ UpdateParams prm) {
+    using C = UpdCfg<KP>;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = (uint64_t*)(smem + C::RING_BYTES);
+    uint64_t* empty_bar = full_bar + C::STAGES;
+    uint64_t* tmem_full = empty_bar + C::STAGES;
+    uint64_t* gram_bar = tmem_full + 1;
+    uint32_t* tmem_slot = (uint32_t*)(gram_bar + 1);
+    uint32_t* stop_slot = tmem_slot + 1;
+    float* conv_s = (float*)(smem + C::RING_BYTES + 1024);  // [4 warps][2][KP]
+    // Staged epilogue (KP <= 128, modes that write the factor): the ring is idle once the accumulators are complete
+    constexpr bool STAGED = (KP <= 128) && (MODE == 0 || MODE == 2 || MODE == 4 || MODE == 5);
+    uint8_t* const SF = smem;                              // fp32 tile:  KP/32 boxes of 128 rows x 128 B
+    uint8_t* const SH = SF + (KP / 32) * 16384;            // bf16 hi:    KP/64 boxes
+    uint8_t* const SL = SH + (KP / 64) * 16384;            // bf16 lo
+    uint8_t* const ST = SL + (KP / 64) * 16384;            // transposed: 2 boxes of KP rows x 128 B (64 tile rows each)
+    static_assert(!STAGED || (KP / 32 + 2 * (KP / 64)) * 16384 + 2 * KP * 128 <= C::RING_BYTES, "staging does not fit in the ring");
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#define TSTAMP(i) do { if (prm.timing != nullptr && blockIdx.x == 0) prm.timing[i] = clock64(); } while (0)
+    if (threadIdx.x == 0) TSTAMP(0);
+    if (prm.timing != nullptr && threadIdx.x == 0) {  // every CTA: global timer at entry (and exit, below)
+        long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        prm.timing[16 + 2 * blockIdx.x] = gt;
+    }
+    const int tile_rows = prm.tile_rows;
+    const int r0 = blockIdx.x * tile_rows;
+    const uint32_t a_bytes = (uint32_t)tile_rows * 128u;
+    const int nkb = (MODE == 2 || MODE == 5) ? 0 : (prm.Kdim + 63) / 64;
+    constexpr int NPRE = (MODE == 1 || MODE == 4 || MODE == 5) ? 0 : 3 * C::NSLAB;
+
+    if (warp == 0 && lane == 0) {
+        // Has the loop already met stop_condition?  ONE thread samples the flag for the whole CTA: under PDL (see
+        // launch_update) the preceding kernel may be writing it right now, and the early exit below must be uniform.
+        // A CTA that still sees 0 here streams its panel and skips the epilogue after pdl_wait().
+        *stop_slot = (uint32_t)__ldcg(&prm.state->converged);
+        prefetch_tmap(&prm.tmA);
+        prefetch_tmap(&prm.tmB);
+        if (MODE != 1 && MODE != 4 && MODE != 5) {
+            prefetch_tmap(&prm.tmFhi);
+            prefetch_tmap(&prm.tmFlo);
+            prefetch_tmap(&prm.tmPhi);
+            prefetch_tmap(&prm.tmPlo);
+        }
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full, 1);
+        mbar_init(gram_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (*stop_slot != 0u) {  // uniform early exit
+        if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+        return;
+    }
+    // Block order: the nkb numerator blocks FIRST (they depend on nothing the preceding kernel writes), then the NPRE
+    // denominator blocks (the Gram hi/lo they read is produced by the immediately preceding reduce kernel).
+    // The two single-thread loops below are the latency-critical part of the kernel: no per-block branches, no
+    // div/mod, everything loop-invariant is hoisted (an extra compare per block is measurable at 256 blocks).
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (elect_one()) {
+            int s = 0;
+            uint32_t ph = 0;
+            uint8_t* dst = smem;
+            int arow = blockIdx.x * nkb * tile_rows;   // tile-contiguous X: k-block kb of this tile starts at panel row arow0 + kb*tile_rows
+            const uint32_t num_tx = a_bytes + (uint32_t)C::B_BYTES;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                mbar_arrive_expect_tx(&full_bar[s], num_tx);
+                tma_load_2d(dst, &prm.tmA, &full_bar[s], 0, arow);
+                tma_load_2d(dst + C::A_BYTES, &prm.tmB, &full_bar[s], 64 * kb, 0);
+                arow += tile_rows;
+                dst += C::STAGE_BYTES;
+                if (++s == C::STAGES) { s = 0; ph ^= 1u; dst = smem; }
+            }
+            if (NPRE > 0) {
+                pdl_wait();  // the Gram of the other factor comes from the preceding (reduce) kernel
+#pragma unroll
+                for (int bd = 0; bd < NPRE; ++bd) {  // Den = Fhi*Phi + Fhi*Plo + Flo*Phi
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    mbar_arrive_expect_tx(&full_bar[s], num_tx);
+                    const int t = bd / C::NSLAB, sl = bd % C::NSLAB;   // compile-time after unrolling
+                    tma_load_2d(dst, t == 2 ? &prm.tmFlo : &prm.tmFhi, &full_bar[s], 64 * sl, r0);
+                    tma_load_2d(dst + C::A_BYTES, t == 1 ? &prm.tmPlo : &prm.tmPhi, &full_bar[s], 64 * sl, 0);
+                    dst += C::STAGE_BYTES;
+                    if (++s == C::STAGES) { s = 0; ph ^= 1u; dst = smem; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc(FMT_BF16, 128, KP);
+            int s = 0;
+            uint32_t ph = 0;
+            const uint64_t adesc0 = make_kmajor_sw128_desc(smem_u32(smem));
+            const uint64_t bdesc0 = make_kmajor_sw128_desc(smem_u32(smem + C::A_BYTES));
+            uint64_t adesc = adesc0, bdesc = bdesc0;
+            // one k-block: wait for its operands, 4 x (K = 16 bf16 = 32 B per 128-B swizzle row), free the stage
+            auto block = [&](uint32_t d, uint32_t acc0) {
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                umma_bf16(d, adesc, bdesc, idesc, acc0);
+#pragma unroll
+                for (int kk = 1; kk < 4; ++kk) umma_bf16(d, adesc + 2 * kk, bdesc + 2 * kk, idesc, 1u);
+                umma_commit(&empty_bar[s]);  // frees the stage when these MMAs have read it
+                adesc += C::STAGE_BYTES >> 4;  // descriptor start address is in 16-byte units
+                bdesc += C::STAGE_BYTES >> 4;
+                if (++s == C::STAGES) { s = 0; ph ^= 1u; adesc = adesc0; bdesc = bdesc0; }
+            };
+            int kb = 0;
+            if (nkb > 0) { block(tmem_base, 0u); kb = 1; TSTAMP(1); }   // first operands have landed
+            for (; kb < nkb; ++kb) block(tmem_base, 1u);
+            TSTAMP(2);                                                   // numerator blocks issued
+            if (NPRE > 0) {
+                block(tmem_base + KP, 0u);
+#pragma unroll 1
+                for (int bd = 1; bd < NPRE; ++bd) block(tmem_base + KP, 1u);
+            }
+            if (MODE != 5) umma_commit(tmem_full);
+            TSTAMP(3);                                                   // all MMAs issued
+        }
+        __syncwarp();
+    } else if (warp >= 2) {
+        // ===== epilogue: warps 2..9, TMEM lane quarter = warp % 4, columns [chalf*KP/2, (chalf+1)*KP/2) =====
+        const int q = warp & 3;
+        const int chalf = (warp - 2) >> 2;
+        const int row = r0 + 32 * q + lane;
+        const bool valid = (32 * q + lane) < tile_rows && row < prm.R;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(32 * q) << 16);
+        pdl_wait();  // from here on we read / overwrite what the preceding kernel wrote / read
+        const bool stop = __ldcg(&prm.state->converged) != 0;  // uniform: the preceding kernel is complete
+        if (threadIdx.x == 64) TSTAMP(4);    // preceding kernel complete
+        if (MODE != 5) mbar_wait(tmem_full, 0);   // (parking the epilogue warps in a named barrier instead of this poll was measured: no difference)
+        tc_fence_after();
+        if (threadIdx.x == 64) TSTAMP(5);    // accumulators complete
+        do {
+        if (stop) break;  // converged while this kernel was streaming (PDL): leave F untouched
+        float* convw = conv_s + q * 2 * KP;
+        const float lambda = prm.lambda, delta = prm.delta;
+        float gcd_rowmax = -1.0f;
+        if (MODE == 3) {  // diagonal of P into shared memory (conv scratch is free in this mode)
+            for (int i = threadIdx.x - 64; i < KP; i += 256) conv_s[i] = prm.Pfull[(size_t)i * KP + i];
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+#pragma unroll 1
+        for (int c0 = chalf * (KP / 2); c0 < (chalf + 1) * (KP / 2); c0 += 32) {
+            uint32_t num_u[32], den_u[32];
+            float f[32];
+            if (MODE != 2 && MODE != 5) tmem_ld32(t_lane + c0, num_u);
+            if (MODE != 1 && MODE != 4 && MODE != 5) tmem_ld32(t_lane + KP + c0, den_u);
+            if (MODE == 1) {
+                tmem_ld_wait();
+                if (valid) {
+                    float4* dst = (float4*)(prm.num_io + (size_t)row * KP + c0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        dst[j] = make_float4(__uint_as_float(num_u[4 * j]), __uint_as_float(num_u[4 * j + 1]),
+                                             __uint_as_float(num_u[4 * j + 2]), __uint_as_float(num_u[4 * j + 3]));
+                }
+                continue;
+            }
+            if (valid) {
+                const float4* src = (const float4*)(prm.F + (size_t)row * KP + c0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 v = src[j];
+                    f[4 * j] = v.x; f[4 * j + 1] = v.y; f[4 * j + 2] = v.z; f[4 * j + 3] = v.w;
+                }
+                if (MODE == 2) {
+                    const float4* ns = (const float4*)(prm.num_io + (size_t)row * KP + c0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 v = ns[j];
+                        num_u[4 * j] = __float_as_uint(v.x); num_u[4 * j + 1] = __float_as_uint(v.y);
+                        num_u[4 * j + 2] = __float_as_uint(v.z); num_u[4 * j + 3] = __float_as_uint(v.w);
+                    }
+                }
+                if (MODE == 5) {  // k-split partial numerators of div_fused_kernel, summed in split order (deterministic)
+                    const float* nbase = prm.num_io + (size_t)row * KP + c0;
+                    float acc[32];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 v = __ldcg((const float4*)nbase + j);
+                        acc[4 * j] = v.x; acc[4 * j + 1] = v.y; acc[4 * j + 2] = v.z; acc[4 * j + 3] = v.w;
+                    }
+                    for (int sp = 1; sp < prm.num_splits; ++sp) {
+                        const float4* ns = (const float4*)(nbase + (size_t)sp * prm.num_split_stride);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float4 v = __ldcg(ns + j);
+                            acc[4 * j] += v.x; acc[4 * j + 1] += v.y; acc[4 * j + 2] += v.z; acc[4 * j + 3] += v.w;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) num_u[j] = __float_as_uint(acc[j]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { f[j] = 0.f; if (MODE == 2 || MODE == 5) num_u[j] = 0u; }
+            }
+            tmem_ld_wait();
+            if (MODE == 3) {
+                float g[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float gv = __uint_as_float(den_u[j]) - __uint_as_float(num_u[j]);       // G = F P - Z   (greedycd.jl:119-120)
+                    if (lambda > 0.f) gv += lambda;                                           // :121-123
+                    g[j] = gv;
+                    const float prr = conv_s[c0 + j];
+                    const float w = f[j];
+                    const float t = w - gv / (1.1920928955078125e-07f + prr);                 // :127
+                    const float sv = fmaxf(t, 0.f) - w;
+                    const float dv = -gv * sv - 0.5f * prr * sv * sv;                         // :128
+                    if (valid) gcd_rowmax = fmaxf(gcd_rowmax, dv);
+                }
+                if (valid) {
+                    float4* dst = (float4*)(prm.num_io + (size_t)row * KP + c0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dst[j] = make_float4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
+                }
+                continue;
+            }
+            float d2[32], s2[32];
+            uint32_t hi_p[16], lo_p[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                float fn[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    float v;
+                    if (MODE == 4 || MODE == 5) {
+                        v = f[j + e] * __fdividef(__uint_as_float(num_u[j + e]), prm.colsum[c0 + j + e] + lambda);  // multupd.jl:178 / :190
+                    } else {
+                        float num = __uint_as_float(num_u[j + e]) - lambda;
+                        num = (num > 0.f || num != num) ? num : 0.f;         // Julia max(0, x): NaN propagates
+                        float den = __uint_as_float(den_u[j + e]) + delta;
+                        v = f[j + e] * __fdividef(num, den);                 // multupd.jl:102 / :113 (2-ulp divide; operands are bf16-derived)
+                    }
+                    fn[e] = valid ? v : 0.f;
+                    float dd = fn[e] - f[j + e], ss = fn[e] + f[j + e];      // common.jl:98-99 / :103-104
+                    d2[j + e] = dd * dd;
+                    s2[j + e] = ss * ss;
+                    f[j + e] = fn[e];
+                }
+                bf16 h0 = __float2bfloat16_rn(fn[0]), h1 = __float2bfloat16_rn(fn[1]);
+                bf16 l0 = __float2bfloat16_rn(fn[0] - __bfloat162float(h0));
+                bf16 l1 = __float2bfloat16_rn(fn[1] - __bfloat162float(h1));
+                hi_p[j / 2] = pack_bf16x2(h0, h1);
+                lo_p[j / 2] = pack_bf16x2(l0, l1);
+            }
+            if constexpr (STAGED) {
+                // stage the four forms of the new tile in the (idle) ring, in the swizzled images the TMA stores expect
+                const int rr = 32 * q + lane;
+                uint8_t* sf = SF + (c0 >> 5) * 16384 + rr * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *(float4*)(sf + ((j ^ (rr & 7)) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                uint8_t* sh = SH + (c0 >> 6) * 16384 + rr * 128;
+                uint8_t* sl = SL + (c0 >> 6) * 16384 + rr * 128;
+                const int cb = (c0 & 63) >> 3;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    *(uint4*)(sh + (((cb + j) ^ (rr & 7)) << 4)) = make_uint4(hi_p[4 * j], hi_p[4 * j + 1], hi_p[4 * j + 2], hi_p[4 * j + 3]);
+                    *(uint4*)(sl + (((cb + j) ^ (rr & 7)) << 4)) = make_uint4(lo_p[4 * j], lo_p[4 * j + 1], lo_p[4 * j + 2], lo_p[4 * j + 3]);
+                }
+                uint8_t* st = ST + (rr >> 6) * (KP * 128) + ((rr & 7) << 1);
+                const int rch = (rr & 63) >> 3;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int a = c0 + j;
+                    const uint32_t pk = hi_p[j / 2];
+                    *(unsigned short*)(st + a * 128 + ((rch ^ (a & 7)) << 4)) = (unsigned short)((j & 1) ? (pk >> 16) : (pk & 0xffffu));
+                }
+            } else if (valid) {
+                float4* dst = (float4*)(prm.F + (size_t)row * KP + c0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                uint4* dh = (uint4*)(prm.Fhi + (size_t)row * KP + c0);
+                uint4* dl = (uint4*)(prm.Flo + (size_t)row * KP + c0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    dh[j] = make_uint4(hi_p[4 * j], hi_p[4 * j + 1], hi_p[4 * j + 2], hi_p[4 * j + 3]);
+                    dl[j] = make_uint4(lo_p[4 * j], lo_p[4 * j + 1], lo_p[4 * j + 2], lo_p[4 * j + 3]);
+                }
+                // transposed bf16 copy: FbT[a][row]; a warp writes 32 consecutive rows (64 B) per component
+                unsigned short* tb = (unsigned short*)prm.FbT + (size_t)c0 * prm.ldT + row;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    uint32_t pk = hi_p[j / 2];
+                    tb[(size_t)j * prm.ldT] = (unsigned short)((j & 1) ? (pk >> 16) : (pk & 0xffffu));
+                }
+            }
+            warp_transpose_reduce(d2, lane);
+            warp_transpose_reduce(s2, lane);
+            convw[c0 + lane] = d2[0];
+            convw[KP + c0 + lane] = s2[0];
+        }
+        if (MODE == 3) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) gcd_rowmax = fmaxf(gcd_rowmax, __shfl_xor_sync(0xffffffffu, gcd_rowmax, o));
+            asm volatile("bar.sync 1, 256;" ::: "memory");   // everybody is done reading the diagonal
+            if (lane == 0) conv_s[warp - 2] = gcd_rowmax;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (threadIdx.x == 64) {
+                float m = conv_s[0];
+                for (int i = 1; i < 8; ++i) m = fmaxf(m, conv_s[i]);
+                prm.conv_part[blockIdx.x] = m;
+            }
+        } else if (MODE != 1) {
+            if constexpr (STAGED) {
+                fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA / tensor-core (async) proxy
+                tc_fence_before();     // our TMEM reads are complete (the Gram below reuses the Num columns)
+            }
+            if (threadIdx.x == 64) TSTAMP(6);  // this warp's ratio / staging done
+            // combine the four lane quarters: named barrier over the 256 epilogue threads
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if constexpr (STAGED) {
+                if (threadIdx.x == 64) {
+                    TSTAMP(7);                 // all epilogue warps done
+#pragma unroll
+                    for (int b = 0; b < KP / 32; ++b) tma_store_2d(&prm.tmF32, SF + b * 16384, 32 * b, r0);
+#pragma unroll
+                    for (int b = 0; b < KP / 64; ++b) {
+                        tma_store_2d(&prm.tmFhi, SH + b * 16384, 64 * b, r0);
+                        tma_store_2d(&prm.tmFlo, SL + b * 16384, 64 * b, r0);
+                    }
+                    tma_store_2d(&prm.tmT, ST, r0, 0);
+                    if (tile_rows > 64) tma_store_2d(&prm.tmT, ST + KP * 128, r0 + 64, 0);
+                    tma_store_commit();
+                    if (prm.gram_part != nullptr) {  // Gram contribution of this tile: T T' (K = 128 rows), into the Num columns
+                        tc_fence_after();
+                        constexpr uint32_t gdesc_i = make_idesc(FMT_BF16, 128, KP);
+#pragma unroll
+                        for (int hb = 0; hb < 2; ++hb) {
+                            const uint64_t td = make_kmajor_sw128_desc(smem_u32(ST + hb * KP * 128));
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) umma_bf16(tmem_base, td + 2 * kk, td + 2 * kk, gdesc_i, (hb > 0 || kk > 0) ? 1u : 0u);
+                        }
+                        umma_commit(gram_bar);
+                    }
+                }
+            }
+            const int t = threadIdx.x - 64;  // 0..255
+            for (int i = t; i < 2 * KP; i += 256) {
+                float s = conv_s[i] + conv_s[2 * KP + i] + conv_s[4 * KP + i] + conv_s[6 * KP + i];
+                prm.conv_part[(size_t)blockIdx.x * 2 * KP + i] = s;
+            }
+            if constexpr (STAGED) {
+                if (prm.gram_part != nullptr) {
+                    mbar_wait(gram_bar, 0);
+                    tc_fence_after();
+                    if (threadIdx.x == 64) TSTAMP(8);  // tile Gram MMAs complete
+                    const int a = 32 * q + lane;
+                    float* gp = prm.gram_part + ((size_t)blockIdx.x * KP + a) * KP;
+#pragma unroll 1
+                    for (int c0 = chalf * (KP / 2); c0 < (chalf + 1) * (KP / 2); c0 += 32) {
+                        uint32_t v[32];
+                        tmem_ld32(t_lane + c0, v);
+                        tmem_ld_wait();
+                        if (a < KP) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                ((float4*)(gp + c0))[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                        }
+                    }
+                }
+                // the staging buffers must stay valid until the bulk stores have drained (waiting only for the smem reads,
+                // .read, measured the same)
+                if (threadIdx.x == 64) {
+                    TSTAMP(9);                 // tile Gram written
+                    tma_store_wait_all<0>();
+                    TSTAMP(10);                // bulk stores have read their staging buffers
+                }
+            }
+        }
+        } while (0);
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) TSTAMP(11);
+    if (prm.timing != nullptr && threadIdx.x == 0) {
+        long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        prm.timing[16 + 2 * blockIdx.x + 1] = gt;
+    }
+#undef TSTAMP
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// ---- Gram: P += T T'  for T = FbT ([KP][R] bf16, rows of length R contiguous) ------------------------
+struct GramParams {
+    CUtensorMap tmT;  // bf16 [KP][R], box 64 x 128
+    float* part;      // [gridDim.x][KP][KP] fp32 partial Grams (plain stores, reduced by gram_reduce_kernel)
+    const TcState* state;
+    int R, chunk;     // rows (K extent) per CTA, multiple of 64
+};
+
+template <int KP>
+struct GramCfg {
+    static constexpr int MT = (KP + 127) / 128;         // 128-row M tiles
+    static constexpr int STAGE_BYTES = MT * 128 * 128;  // the tile is both A and B operand
+    static constexpr int STAGES = 4;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
+    static constexpr int TMEM_COLS = (MT * KP) < 32 ? 32 : (MT * KP);  // 64, 128, 512
+};
+
+template <int KP>
+__global__ void __launch_bounds__(192, 1) gram_kernel(const __grid_constant__ GramParams prm) {
+    using C = GramCfg<KP>;
+    if (prm.state->converged) return;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = (uint64_t*)(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + C::STAGES;
+    uint64_t* tmem_full = empty_bar + C::STAGES;
+    uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k_begin = blockIdx.x * prm.chunk;
+    const int k_end = min(prm.R, k_begin + prm.chunk);
+    const int nkb = (k_end - k_begin + 63) / 64;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&prm.tmT);
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            for (int b = 0; b < nkb; ++b) {
+                const int s = b % C::STAGES;
+                const uint32_t ph = (uint32_t)(b / C::STAGES) & 1u;
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
+                // NOTE: columns >= k_end inside the last 64-block belong to the next CTA's chunk only if
+                // chunk % 64 != 0; chunk is a multiple of 64, and columns >= R are zero-filled by TMA.
+                for (int m = 0; m < C::MT; ++m)
+                    tma_load_2d(smem + s * C::STAGE_BYTES + m * 128 * 128, &prm.tmT, &full_bar[s], k_begin + 64 * b, 128 * m);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc(FMT_BF16, 128, KP);
+            for (int b = 0; b < nkb; ++b) {
+                const int s = b % C::STAGES;
+                const uint32_t ph = (uint32_t)(b / C::STAGES) & 1u;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t base = smem_u32(smem + s * C::STAGE_BYTES);
+                const uint64_t bdesc = make_kmajor_sw128_desc(base);  // B = first KP rows of the tile
+#pragma unroll
+                for (int m = 0; m < C::MT; ++m) {
+                    const uint64_t adesc = make_kmajor_sw128_desc(base + m * 128 * 128);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_bf16(tmem_base + m * KP, adesc + 2 * kk, bdesc + 2 * kk, idesc, (b > 0 || kk > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(tmem_full);
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        float* part = prm.part + (size_t)blockIdx.x * KP * KP;
+#pragma unroll 1
+        for (int m = 0; m < C::MT; ++m) {
+            const int a = 128 * m + 32 * q + lane;
+#pragma unroll 1
+            for (int c0 = 0; c0 < KP; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + m * KP + c0, v);
+                tmem_ld_wait();
+                if (a < KP) {
+                    float4* dst = (float4*)(part + (size_t)a * KP + c0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                             __uint_as_float(v[4 * j + 3]));
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// P[e] = sum_g part[g][e]; writes the fp32 Gram and (do_split) its bf16 hi/lo split.  Four lanes per element
+// (each sums every 4th partial with 8 loads in flight), combined with two shuffles: fixed order => deterministic.
+__global__ void __launch_bounds__(256) gram_reduce_kernel(const float* __restrict__ part, int nparts, int nelem, float* __restrict__ P,
+                                                          bf16* __restrict__ Phi, bf16* __restrict__ Plo, int do_split,
+                                                          const TcState* st) {
+    // The update kernel behind us may start streaming X as soon as every block has passed this point; it waits for our
+    // completion before it reads P.  (Pre-launching THIS kernel behind the running update kernel was measured too:
+    // its resident blocks polling in griddepcontrol.wait slow the single-thread TMA / MMA loops, 4770 -> 4400 it/s.)
+    pdl_launch_dependents();
+    if (st->converged) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int sub = t & 3;
+    const int i = t >> 2;
+    float acc = 0.f;
+    if (i < nelem) {
+        int g = sub;
+        for (; g + 28 < nparts; g += 32) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(part + (size_t)(g + 4 * u) * nelem + i);
+            acc += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+        }
+        for (; g < nparts; g += 4) acc += __ldcg(part + (size_t)g * nelem + i);
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (i < nelem && sub == 0) {
+        P[i] = acc;
+        if (do_split) {
+            bf16 hi = __float2bfloat16_rn(acc);
+            Phi[i] = hi;
+            Plo[i] = __float2bfloat16_rn(acc - __bfloat162float(hi));
+        }
+    }
+}
