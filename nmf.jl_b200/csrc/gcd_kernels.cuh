@@ -174,13 +174,14 @@ __global__ void __launch_bounds__(256) gcd_rows_tc_kernel(float* __restrict__ F,
             const float d = -g[e] * s - 0.5f * prr[e] * s * s;
             if (d > bv) { bv = d; bi = lane + 32 * e; bs = s; }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            const float os = __shfl_xor_sync(0xffffffffu, bs, o);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; bs = os; }
-        }
+        // first arg-max over the warp with two REDUX instructions instead of 15 shuffles: the maximum of an order-preserving
+        // integer image of D, then the smallest index among the lanes that hold it (findmax's tie rule, greedycd.jl:158)
+        const unsigned ub = __float_as_uint(bv + 0.0f);   // -0 -> +0: the two zeros must tie, as they do for findmax
+        const unsigned key = (ub & 0x80000000u) ? ~ub : (ub | 0x80000000u);
+        const unsigned kmax = __reduce_max_sync(0xffffffffu, key);
+        bi = (int)__reduce_min_sync(0xffffffffu, key == kmax ? (unsigned)bi : 0x7fffffffu);
+        bs = __shfl_sync(0xffffffffu, bs, bi & 31);    // component bi lives on lane bi % 32
+        bv = __uint_as_float((kmax & 0x80000000u) ? (kmax & 0x7fffffffu) : ~kmax);
         if (bv < thresh) break;                        // :145-147
         const float* prow = P + (size_t)bi * KP;       // symmetric P: row q contiguous
 #pragma unroll
