@@ -421,6 +421,9 @@ __global__ void __launch_bounds__(DivFusedCfg<KP>::THREADS, 1) div_fused_kernel(
         tc_fence_before();
     }
     __syncthreads();
+    // Launched as a programmatic dependent of colsum_reduce_kernel (whose output only the NEXT kernel reads): do not
+    // complete before it has, so that plain stream order behind us still implies "column sums are final".
+    pdl_wait();
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -430,6 +433,7 @@ __global__ void __launch_bounds__(DivFusedCfg<KP>::THREADS, 1) div_fused_kernel(
 // column sums of a row-factor [R][KP] (sW = sum(W,1), sH = sum(H,2): multupd.jl:176,188): per 128-row tile, then reduced
 __global__ void __launch_bounds__(256) colsum_tiles_kernel(const float* __restrict__ Fm, int R, int KP, float* __restrict__ part,
                                                            const TcState* st) {
+    pdl_launch_dependents();  // PDL chain colsum_tiles -> colsum_reduce -> div_fused: the big kernel does not wait for these two
     if (st->converged) return;
     __shared__ float red[256];
     const int groups = 256 / KP > 0 ? 256 / KP : 1;
@@ -447,6 +451,8 @@ __global__ void __launch_bounds__(256) colsum_tiles_kernel(const float* __restri
 }
 __global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restrict__ part, int tiles, int KP, float* __restrict__ out,
                                                             const TcState* st) {
+    pdl_launch_dependents();  // div_fused_kernel (which never reads the column sums) may start now
+    pdl_wait();               // ... while we wait for colsum_tiles_kernel's partial sums
     if (st->converged) return;
     __shared__ double red[8][32];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;

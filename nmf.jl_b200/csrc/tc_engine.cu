@@ -114,8 +114,10 @@ struct TcSolver {
         h->launches += 2;
     }
 
-    static void set_attrs() {
-        static bool done = false;
+    // cudaFuncSetAttribute is per device: remember it per device ordinal (a process may hold handles on several GPUs)
+    static void set_attrs(int device) {
+        static bool done_on[64] = {};
+        bool& done = done_on[device & 63];
         if (done) return;
         NMF_CUDA(cudaFuncSetAttribute(mu_update_kernel<KP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, UpdCfg<KP>::SMEM_BYTES));
         NMF_CUDA(cudaFuncSetAttribute(mu_update_kernel<KP, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, UpdCfg<KP>::SMEM_BYTES));
@@ -132,7 +134,7 @@ struct TcSolver {
 
 template <int KP>
 void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, float* Hc, int64_t ldh, nmfb200_result* out) {
-    TcSolver<KP>::set_attrs();
+    TcSolver<KP>::set_attrs(h->device);
     cudaStream_t st = h->stream;
     const int64_t p = h->p, n = h->n, k = a.k;
     const float delta = std::sqrt(std::numeric_limits<float>::epsilon());
@@ -360,8 +362,9 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
 
 template <int KP>
 void tc_solve_div_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, float* Hc, int64_t ldh, nmfb200_result* out) {
-    TcSolver<KP>::set_attrs();
-    static bool quot_attr = false;
+    TcSolver<KP>::set_attrs(h->device);
+    static bool quot_attr_on[64] = {};
+    bool& quot_attr = quot_attr_on[h->device & 63];
     if (!quot_attr) {
         NMF_CUDA(cudaFuncSetAttribute(div_quot_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, QuotCfg<KP>::SMEM_BYTES));
         quot_attr = true;
@@ -413,7 +416,8 @@ void tc_solve_div_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t l
     // div_quot_kernel writes a bf16 Q panel that mu_update_kernel<KP,4> streams like X.
     const bool fused = h->tc_div_fused != 0;
     if (fused) {
-        static bool fattr = false;
+        static bool fattr_on[64] = {};
+        bool& fattr = fattr_on[h->device & 63];
         if (!fattr) {
             NMF_CUDA(cudaFuncSetAttribute(div_fused_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, DivFusedCfg<KP>::SMEM_BYTES));
             fattr = true;
@@ -432,8 +436,9 @@ void tc_solve_div_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t l
     };
     auto half_step = [&](Factor& Rf, Factor& Cf, const bf16* Xs, int nkb, int Kdim, float lambda) {
         const uint64_t prow = (uint64_t)Rf.tiles * nkb * 128;
+        const bool pdl = fused && h->tc_pdl != 0;
         colsum_tiles_kernel<<<Cf.tiles, 256, 0, st>>>(Cf.m, Cf.R, KP, cs_part, state);
-        colsum_reduce_kernel<<<KP / 32, 256, 0, st>>>(cs_part, Cf.tiles, KP, Cf.colsum, state);
+        launch_k(colsum_reduce_kernel, dim3(KP / 32), dim3(256), 0, st, pdl, (const float*)cs_part, Cf.tiles, KP, Cf.colsum, (const TcState*)state);
         h->launches += 2;
         if (fused) {
             DivFusedParams fp;
@@ -449,7 +454,7 @@ void tc_solve_div_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t l
             ksplit = (int)ceil_div(nkb, fp.kchunk);
             fp.num_part = h->buf_t<float>("tc.div_num_part", (size_t)ksplit * Rf.R * KP);
             fp.delta = delta;
-            div_fused_kernel<KP><<<dim3(Rf.tiles, ksplit), DivFusedCfg<KP>::THREADS, DivFusedCfg<KP>::SMEM_BYTES, st>>>(fp);
+            launch_k(div_fused_kernel<KP>, dim3(Rf.tiles, ksplit), dim3(DivFusedCfg<KP>::THREADS), (size_t)DivFusedCfg<KP>::SMEM_BYTES, st, pdl, fp);
             h->launches += 1;
             s.num_splits = ksplit;
             s.num_split_stride = (int64_t)Rf.R * KP;
@@ -569,7 +574,7 @@ __global__ void __launch_bounds__(256) gcd_repack_kernel(const float* __restrict
 
 template <int KP>
 void tc_solve_gcd_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, float* Hc, int64_t ldh, nmfb200_result* out) {
-    TcSolver<KP>::set_attrs();
+    TcSolver<KP>::set_attrs(h->device);
     cudaStream_t st = h->stream;
     const int64_t p = h->p, n = h->n, k = a.k;
     const float lw = (float)a.lambda_w, lh = (float)a.lambda_h, tol = (float)a.tol;

@@ -222,7 +222,8 @@ bool tc_objective(nmfb200_handle* h, int alg, const Factor& W, const Factor& H, 
     const int64_t p = h->p, n = h->n;
     if (n < 128 || p < 64 || (h->ldx % 4) != 0 || (((uintptr_t)h->dX) & 15) != 0) return false;
     cudaStream_t st = h->stream;
-    static bool attr = false;
+    static bool attr_on[64] = {};   // per device ordinal (cudaFuncSetAttribute is per device)
+    bool& attr = attr_on[h->device & 63];
     if (!attr) {
         NMF_CUDA(cudaFuncSetAttribute(objective_tc_kernel<KP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ObjCfg<KP>::SMEM_BYTES));
         NMF_CUDA(cudaFuncSetAttribute(objective_tc_kernel<KP, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ObjCfg<KP>::SMEM_BYTES));
