@@ -66,7 +66,27 @@ def case(name, alg, T, p, n, k, maxiter, tol, seed, data="uniform", **kw):
     print(f"{name}: niters={r.niters} converged={r.converged} objvalue={float(r.objvalue):.9g}")
 
 
+def case_nndsvd(name, T, p, n, k, seed, variant, zeroh=False, data="uniform"):
+    """NNDSVD initialisation (initialization.jl:26-101) from a caller-supplied SVD (`initdata`), so that the fixture
+    does not depend on a random range finder.  Stored under golden/init/ (the solver fixtures are globbed by name)."""
+    if ONLY and not any(o in name for o in ONLY):
+        return
+    rng = np.random.default_rng(seed)
+    T = np.dtype(T)
+    X = np.asfortranarray(rng.random((p, n)), dtype=T) if data == "uniform" else planted(rng, p, n, k, T)
+    U, S, Vt = np.linalg.svd(X.astype(np.float64), full_matrices=False)
+    W, H = O.nndsvd(X, k, zeroh=zeroh, variant=variant, initdata=(U, S, Vt.T), rng=np.random.default_rng(seed + 1000))
+    os.makedirs(os.path.join(OUT, "init"), exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, "init", name + ".npz"), X=X, U=U[:, :k], S=S[:k], V=Vt[:k, :].T, W=W, H=H, k=k,
+                        variant=variant, zeroh=zeroh, rng_seed=seed + 1000)
+    print(f"{name}: variant={variant} zeroh={zeroh} |W|={np.linalg.norm(W):.9g} |H|={np.linalg.norm(H):.9g}")
+
+
 if __name__ == "__main__":
+    case_nndsvd("nndsvd_f64_std", np.float64, 40, 56, 5, 21, "std")
+    case_nndsvd("nndsvd_f32_a_planted", np.float32, 48, 36, 4, 22, "a", data="planted")
+    case_nndsvd("nndsvd_f64_ar_zeroh", np.float64, 32, 44, 6, 23, "ar", zeroh=True)
+    case_nndsvd("nndsvd_f32_ar", np.float32, 36, 28, 3, 24, "ar")
     # BASELINE config 1: nnmf(rand(200,150), 5; alg=:multmse, init=:random, maxiter=50), Float64,
     # tol = cbrt(eps/100) as nnmf passes it (interf.jl:8)
     case("cfg1_multmse_f64", "multmse", np.float64, 200, 150, 5, 50, np.cbrt(np.finfo(np.float64).eps / 100), 0)

@@ -159,6 +159,23 @@ def test_nndsvd_with_initdata_matches_oracle_and_reference_properties(NMF, oracl
         NMF.nndsvd(X, 5, variant="bogus", initdata=F)
 
 
+def test_nndsvd_matches_golden_fixtures(NMF, oracle):
+    """tests/golden/init/*.npz (oracle outputs for a stored SVD, generator: tests/golden/make_golden.py)."""
+    import glob
+    import os
+    files = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "init", "*.npz")))
+    assert len(files) >= 4
+    for f in files:
+        g = np.load(f)
+        X, k = g["X"], int(g["k"])
+        tol = 1e-6 if X.dtype == np.float32 else 1e-13
+        for mod in (NMF, oracle):
+            W, H = mod.nndsvd(X, k, zeroh=bool(g["zeroh"]), variant=str(g["variant"]), initdata=(g["U"], g["S"], g["V"]),
+                              rng=np.random.default_rng(int(g["rng_seed"])))
+            np.testing.assert_allclose(W, g["W"], rtol=tol, atol=0)
+            np.testing.assert_allclose(H, g["H"], rtol=tol, atol=0)
+
+
 def test_no_gpu_fails_loudly(NMF):
     """Without a CUDA device the product must raise, never fall back to a CPU path."""
     import torch
