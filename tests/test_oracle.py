@@ -71,6 +71,29 @@ def test_reference_kat_update_H_false(oracle, T, alg):
     assert (ret.W != W).any()
 
 
+# test/interf.jl:6-27: every (alg, init) pair of nnmf runs; external SVD as initdata; replicates, then :custom restart
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+def test_reference_interf_all_alg_init_pairs(oracle, T):
+    import warnings as _w
+    rng = np.random.default_rng(17)
+    p, n, k = 5, 8, 3
+    X = np.asfortranarray(np.maximum(rng.random((p, k)) - 0.3, 0) @ np.maximum(rng.random((k, n)) - 0.3, 0), dtype=T)
+    with _w.catch_warnings():
+        _w.simplefilter("ignore")
+        for alg in ("multmse", "multdiv", "projals", "alspgrad", "cd", "greedycd"):
+            for init in ("random", "nndsvd", "nndsvda", "nndsvdar"):     # :spa is out of scope
+                ret = oracle.nnmf(X, k, alg=alg, init=init, rng=np.random.default_rng(1))
+                assert ret.W.shape == (p, k) and ret.H.shape == (k, n) and ret.W.dtype == T
+                assert np.isfinite(ret.W).all() and np.isfinite(ret.H).all() and (ret.W >= 0).all() and (ret.H >= 0).all()
+        U, s, Vt = np.linalg.svd(X.astype(np.float64), full_matrices=False)
+        for alg in ("multmse", "multdiv", "projals", "alspgrad", "cd", "greedycd"):
+            ret = oracle.nnmf(X, k, alg=alg, init="nndsvd", initdata=(U, s, Vt.T))
+            assert np.isfinite(float(ret.objvalue))
+        rep = oracle.nnmf(X, k, replicates=10, maxiter=10, alg="multmse", init="random", rng=np.random.default_rng(2))
+        ret = oracle.nnmf(X, k, W0=rep.W, H0=rep.H, init="custom")
+        assert float(ret.objvalue) <= float(rep.objvalue) * (1 + 1e-6) + 1e-12
+
+
 class _nullcontext:
     def __enter__(self):
         return None
