@@ -41,7 +41,10 @@ typedef enum nmfb200_status {
     NMFB200_ENCCL = 4,   /* NCCL error */
     NMFB200_ENOMEM = 5,  /* device allocation failed */
     NMFB200_ESTATE = 6,  /* call order violated (e.g. solve before set_X) */
-    NMFB200_ENOTSUP = 7  /* valid request this build does not accelerate */
+    NMFB200_ENOTSUP = 7, /* valid request this build does not accelerate */
+    NMFB200_ENUMERIC = 8 /* numerical breakdown: the k x k Gram of ProjectedALS is not positive definite.  The reference's
+                            pdsolve!/pdrsolve! (utils.jl:63-84) ignore the `info` of LAPACK.potrf! and carry on with an
+                            unfinished factor; this library stops instead (deliberate departure). */
 } nmfb200_status;
 
 /* Mirrors NMF.Result{T} (common.jl:21-34) minus the W/H aliases (the caller's own arrays). */
@@ -143,7 +146,7 @@ int nmfb200_solve_greedycd_f64(nmfb200_handle* h, double* W, int64_t ldw, double
 /* NMF.solve!(::ProjectedALS{T}, X, W, H)  -- projals.jl:37-39, :77-107.  lambda_w / lambda_h are the L2 weights
  * (the constructor validates nothing: maxiter = 1 is accepted, projals.jl:26-34).  The k x k normal equations are
  * solved on the GPU (Gauss-Jordan inverse of the SPD Gram in Float64, one CTA); a Gram that is not positive definite
- * returns NMFB200_EINVAL (Julia: PosDefException from potrf!, utils.jl:68,78). */
+ * returns NMFB200_ENUMERIC (the reference does not check potrf!'s info, utils.jl:68,78, and would continue with garbage). */
 int nmfb200_solve_projals_f32(nmfb200_handle* h, float* W, int64_t ldw, float* H, int64_t ldh, int64_t k,
                               int64_t maxiter, float tol, float lambda_w, float lambda_h, int update_H,
                               int verbose, int on_device, nmfb200_result* out);

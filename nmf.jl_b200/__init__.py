@@ -12,6 +12,7 @@ from .api import (  # noqa: F401
     GreedyCD,
     MultUpdate,
     NmfB200Error,
+    NumericalError,
     ProjectedALS,
     Result,
     Session,

@@ -41,6 +41,11 @@ class NmfB200Error(RuntimeError):
     """CUDA / NCCL / state errors reported by libnmfb200."""
 
 
+class NumericalError(NmfB200Error):
+    """NMFB200_ENUMERIC: the k x k Gram of ProjectedALS is not positive definite.  The reference ignores the `info` of
+    LAPACK.potrf! (utils.jl:63-84) and carries on with an unfinished factor; this library stops."""
+
+
 def _raise(status: int, msg: str):
     if status == _lib.EINVAL:
         raise ArgumentError(msg)
@@ -48,6 +53,8 @@ def _raise(status: int, msg: str):
         raise DimensionMismatch(msg)
     if status == _lib.ENOTSUP:
         raise NotImplementedError(msg)
+    if status == _lib.ENUMERIC:
+        raise NumericalError(msg)
     raise NmfB200Error(f"[{_lib.load().nmfb200_status_string(status).decode()}] {msg}")
 
 
@@ -206,6 +213,7 @@ class Session:
         self.dtype = None
         self.shape = None
         self._keep = None
+        self._x_host = None
         self.set_option("engine", engine)
         if stream is not None:
             self._check(self._lib.nmfb200_set_stream(self._h, ctypes.c_void_p(stream)))
@@ -256,6 +264,7 @@ class Session:
         fn = getattr(self._lib, f"nmfb200_set_X_{_SFX[T]}")
         self._check(fn(self._h, Xf.ctypes.data_as(ctypes.c_void_p), p, n, p, int(check_nonneg)))
         self.dtype, self.shape = T, (p, n)
+        self._x_host = X  # identity of the matrix that is resident (solve(alg, X, ..., session=s) compares against it)
 
     def set_X_device(self, ptr: int, p: int, n: int, ldx: int, dtype, check_nonneg: bool = False, keepalive=None) -> None:
         """X already resident on this GPU (column-major p x n at device address `ptr`)."""
@@ -263,6 +272,7 @@ class Session:
         fn = getattr(self._lib, f"nmfb200_set_X_dev_{_SFX[T]}")
         self._check(fn(self._h, ctypes.c_void_p(ptr), p, n, ldx, int(check_nonneg)))
         self.dtype, self.shape, self._keep = T, (p, n), keepalive
+        self._x_host = None
 
     # -- multi-GPU
     @staticmethod
@@ -374,11 +384,12 @@ def _print_trace(it, elapsed, objv, change, dev):
 # --------------------------------------------------------------------------------------------------
 def solve(alg, X: np.ndarray, W: np.ndarray, H: np.ndarray, *, device: int = 0, engine: str = "auto",
           session: Optional[Session] = None) -> Result:
-    """NMF.solve!(alg, X, W, H) -> Result.  W and H are updated in place."""
+    """NMF.solve!(alg, X, W, H) -> Result.  W and H are updated in place.  With `session`, X is uploaded unless it IS the
+    matrix already resident there (same object); pass X=None to use whatever the session holds (set_X_device)."""
     own = session is None
     s = session or Session(device=device, engine=engine)
     try:
-        if own or s.shape is None:
+        if X is not None and (own or s.shape is None or s._x_host is not X):
             s.set_X(X)
         return s.solve(alg, W, H)
     finally:

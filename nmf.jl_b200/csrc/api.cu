@@ -95,7 +95,7 @@ void solve_args(nmfb200_handle* h, const SolveArgs& a, T* W, int64_t ldw, T* H, 
     NMF_REQUIRE(a.k >= 1 && ldw >= h->p && ldh >= a.k, NMFB200_EDIM, "Dimensions of X, W, and H are inconsistent.");  // common.jl:12-14
     bool use_tc = false;
     if (sizeof(T) == 4 && h->engine_opt != 1) {
-        use_tc = tc_supported(h, a);
+        use_tc = h->all_ranks(tc_supported(h, a));   // multi-GPU: one decision for all ranks (shards may differ in size / alignment)
         NMF_REQUIRE(use_tc || h->engine_opt != 2, NMFB200_ENOTSUP, "engine=tc requested but this problem is not covered by the tensor-core engine");
     } else {
         NMF_REQUIRE(h->engine_opt != 2, NMFB200_ENOTSUP, "engine=tc supports Float32 only");
@@ -127,6 +127,7 @@ const char* nmfb200_status_string(int status) {
         case NMFB200_ENOMEM: return "out of device memory";
         case NMFB200_ESTATE: return "invalid call order";
         case NMFB200_ENOTSUP: return "not supported";
+        case NMFB200_ENUMERIC: return "numerical breakdown";
         default: return "unknown status";
     }
 }

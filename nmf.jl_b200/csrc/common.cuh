@@ -219,6 +219,19 @@ struct nmfb200_handle {
         if (!comm) return;
         NMF_NCCL(nmfb200::NcclApi::get().AllReduce(ptr, ptr, count, nmfb200::NcclType<T>::v, ncclSum, comm, stream));
     }
+    // Collective AND of a per-rank predicate (host-synchronising; once per solve).  Decisions that pick a code path with
+    // its own collectives (engine, tensor-core objective vs exact objective) must be the same on every rank, whatever the
+    // local shard's row count / alignment says.
+    bool all_ranks(bool mine) {
+        if (!comm) return mine;
+        int* d = (int*)buf("comm.agree", sizeof(int));
+        int v = mine ? 1 : 0;
+        NMF_CUDA(cudaMemcpyAsync(d, &v, sizeof(int), cudaMemcpyHostToDevice, stream));
+        NMF_NCCL(nmfb200::NcclApi::get().AllReduce(d, d, 1, ncclInt32, ncclMin, comm, stream));
+        NMF_CUDA(cudaMemcpyAsync(&v, d, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        NMF_CUDA(cudaStreamSynchronize(stream));
+        return v != 0;
+    }
     template <typename T> void allreduce_max(T* ptr, size_t count) {
         if (!comm) return;
         NMF_NCCL(nmfb200::NcclApi::get().AllReduce(ptr, ptr, count, nmfb200::NcclType<T>::v, ncclMax, comm, stream));

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(GCD_WARPS * 32) gcd_rows_kernel(T* __restrict_
 // 1/(eps + P[r,r]) is hoisted out of the loop (multiply instead of divide: the gradients are bf16-derived anyway).
 template <int KP>
 __global__ void __launch_bounds__(256) gcd_rows_tc_kernel(float* __restrict__ F, const float* __restrict__ G, const float* __restrict__ P,
-                                                          int R, const float* __restrict__ p_init_ptr,
+                                                          int R, int k, const float* __restrict__ p_init_ptr,
                                                           unsigned long long* __restrict__ updates) {
     constexpr int NE = KP / 32;
     const int lane = threadIdx.x & 31;
@@ -164,7 +164,8 @@ __global__ void __launch_bounds__(256) gcd_rows_tc_kernel(float* __restrict__ F,
     }
     const float thresh = 0.001f * p_init_ptr[0];       // nu * p_init (greedycd.jl:140,145)
     unsigned long long nupd = 0;
-    for (int it = 0; it < KP * KP; ++it) {             // at most k^2 coordinate steps per row (:144)
+    const int maxsteps = k * k;                        // `for _ in 1:n_components^2` (:144): the real k, not the padded KP
+    for (int it = 0; it < maxsteps; ++it) {
         float bv = -INFINITY, bs = 0.f;
         int bi = 0x7fffffff;
 #pragma unroll

@@ -274,7 +274,7 @@ __global__ void clamp_nn_kernel(T* __restrict__ A, int64_t len) {
 
 // inv(A) for a symmetric positive definite k x k matrix (what potrf!/potrs! and potrf!/potri! deliver, utils.jl:63-84),
 // by in-place Gauss-Jordan elimination without pivoting (stable for SPD) in Float64, one CTA.  work: k*k doubles.
-// info[0] = j+1 if pivot j is not positive (Julia: PosDefException), else untouched.
+// info[0] = j+1 if pivot j is not positive (LAPACK potrf! info > 0), else untouched.
 template <typename T>
 __global__ void __launch_bounds__(1024) spd_inverse_kernel(const T* __restrict__ A, int k, double* __restrict__ work, T* __restrict__ inv,
                                                            int* __restrict__ info) {
@@ -832,11 +832,11 @@ void simt_solve(nmfb200_handle* h, const SolveArgs& a, T* Wc, int64_t ldw, T* Hc
         else if (a.alg == 4) s.iter_cd(W, H, a.update_H != 0, l1W, l2W, l1H, l2H, a.cd_shuffle ? &shuffle_rng : nullptr);
         else sub_iterations += s.iter_alspgrad(W, H, a.update_H != 0, a.maxsubiter, &tolg);
         converged = s.stop(W, preW, H, preH, tol, &dev);
-        if (a.alg == 3) {  // potrf! failure (utils.jl:68,78 -> PosDefException)
+        if (a.alg == 3) {  // potrf! failure: the reference ignores info (utils.jl:68,78); we stop with a distinct status
             int info = 0;
             NMF_CUDA(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
             NMF_CUDA(cudaStreamSynchronize(st));
-            NMF_REQUIRE(info == 0, NMFB200_EINVAL, "matrix is not positive definite; Cholesky factorization failed (pivot " + std::to_string(info) + ").");
+            NMF_REQUIRE(info == 0, NMFB200_ENUMERIC, "matrix is not positive definite; Cholesky factorization failed (pivot " + std::to_string(info) + ").");
         }
         if (a.verbose) {
             double pre = objv;

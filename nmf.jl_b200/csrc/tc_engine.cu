@@ -625,7 +625,7 @@ void tc_solve_gcd_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t l
         NMF_CUDA(cudaMemcpyAsync(prev, F.m, (size_t)F.R * KP * sizeof(float), cudaMemcpyDeviceToDevice, st));
         s.launch_update(3, F, O, Xs, Kdim, lambda, 0.f, G, bmax);                                  // G = F P - X O (+lambda), per-CTA max D
         max_partials_kernel<float><<<1, 256, 0, st>>>(bmax, F.tiles, bmax + maxtiles);            // p_init (:132-137)
-        gcd_rows_tc_kernel<KP><<<(unsigned)ceil_div(F.R, 8), 256, 0, st>>>(F.m, G, O.P, F.R, bmax + maxtiles, d_updates);  // :139-165
+        gcd_rows_tc_kernel<KP><<<(unsigned)ceil_div(F.R, 8), 256, 0, st>>>(F.m, G, O.P, F.R, (int)k, bmax + maxtiles, d_updates);  // :139-165
         gcd_repack_kernel<<<tiles128, 256, 0, st>>>(F.m, prev, F.R, KP, F.hi, F.lo, F.bT, F.ldT, F.conv);
         h->launches += 3;
         s.launch_gram(F, true);                                                                   // Gram of the updated factor
@@ -683,6 +683,10 @@ void tc_solve_gcd_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t l
 
 bool tc_supported(const nmfb200_handle* h, const SolveArgs& a) {
     if (a.alg > 2) return false;          // ProjectedALS / CoordinateDescent / ALSPGrad: exact engine
+    // engine = auto: bf16 operands are worth it -- and an accepted trade -- only for problems large enough to be limited by
+    // streaming X; below 2^20 cells every Float32 problem stays on the exact engine (fp32 parity with the reference, and
+    // the reference's own tiny test problems -- laurberg6x3, 5x8 -- never see bf16 rounding).  engine = tc overrides.
+    if (a.alg == 0 && h->engine_opt != 2 && h->p * h->n < ((int64_t)1 << 20)) return false;
     if (a.alg == 1) {                     // MultUpdate(:div): quotient kernel + update kernel; k <= 128, single GPU
         if (h->comm != nullptr || a.k > 128 || h->p < 128 || h->n < 128) return false;
         if (h->engine_opt != 2 && h->p * h->n < ((int64_t)1 << 20)) return false;

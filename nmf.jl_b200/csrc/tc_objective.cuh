@@ -220,7 +220,8 @@ __global__ void abs_sum_kernel(const float* __restrict__ a, int64_t len, double*
 template <int KP>
 bool tc_objective(nmfb200_handle* h, int alg, const Factor& W, const Factor& H, double lambda_w, double lambda_h, double* out) {
     const int64_t p = h->p, n = h->n;
-    if (n < 128 || p < 64 || (h->ldx % 4) != 0 || (((uintptr_t)h->dX) & 15) != 0) return false;
+    // multi-GPU: the fallback issues a different collective, so the choice is made for all ranks together
+    if (!h->all_ranks(!(n < 128 || p < 64 || (h->ldx % 4) != 0 || (((uintptr_t)h->dX) & 15) != 0))) return false;
     cudaStream_t st = h->stream;
     static bool attr_on[64] = {};   // per device ordinal (cudaFuncSetAttribute is per device)
     bool& attr = attr_on[h->device & 63];

@@ -7,9 +7,18 @@
 #     const NMF = NMFB200
 # All numerics live behind the C ABI; this file only validates, ccalls and maps status -> exception.
 # NOTE: Julia is not installed in the build image of this repository, so this file is written against
-# the header but has not been executed there; the tested binding is nmf.jl_b200/_lib.py (same calls).
+# the header but has not been executed there; the tested binding is nmf.jl_b200/_lib.py (same calls), and
+# tests/test_host_api.py checks every `ccall` argument-type tuple in this file against include/nmfb200.h.
+#
+# Attribution.  The drop-in contract dictates that the keyword constructors of `MultUpdate` / `GreedyCD` (validation
+# statements and messages, from NMF.jl src/multupd.jl:17-42 and src/greedycd.jl:18-30), the argument checks of `nnmf`
+# (src/interf.jl:15-37), `Result` with its `==`/`hash` (src/common.jl:21-38) and `nmf_checksize` (src/common.jl:5-16)
+# reproduce the reference statement for statement; those ~60 lines are derived from NMF.jl, which is licensed under the
+# MIT "Expat" License, Copyright (c) 2014: Dahua Lin and contributors (https://github.com/JuliaStats/NMF.jl, LICENSE.md).
+# Everything else in this file, and everything behind the C ABI, is original to this repository.
 module NMFB200
 
+using LinearAlgebra
 using LinearAlgebra: qr!, svd!
 
 export nnmf
@@ -17,7 +26,7 @@ export nnmf
 const libnmfb200 = get(ENV, "NMFB200_LIB", joinpath(@__DIR__, "..", "libnmfb200.so"))
 
 # ---- status codes (include/nmfb200.h) ----------------------------------------------------------------
-const OK, EINVAL, EDIM, ECUDA, ENCCL, ENOMEM, ESTATE, ENOTSUP = 0:7
+const OK, EINVAL, EDIM, ECUDA, ENCCL, ENOMEM, ESTATE, ENOTSUP, ENUMERIC = 0:8
 
 struct CResult            # nmfb200_result
     niters::Int64
@@ -52,6 +61,7 @@ function check(h::Handle, st::Integer)
     msg = unsafe_string(ccall((:nmfb200_last_error, libnmfb200), Cstring, (Ptr{Cvoid},), h.ptr))
     st == EINVAL && throw(ArgumentError(msg))
     st == EDIM && throw(DimensionMismatch(msg))
+    st == ENUMERIC && throw(LinearAlgebra.PosDefException(1))   # ProjectedALS: Gram not positive definite (the reference ignores potrf!'s info)
     error("libnmfb200 [", unsafe_string(ccall((:nmfb200_status_string, libnmfb200), Cstring, (Cint,), st)), "] ", msg)
 end
 
@@ -342,7 +352,7 @@ function nnmf(X::AbstractMatrix{T}, k::Integer; init::Symbol=:nndsvdar, initdata
     Xm = Matrix{T}(X)
     set_X!(h, Xm)                                      # X stays resident on the GPU across init, solve and replicates
     W, H = init == :random ? randinit(p, n, k, T; normalize=true, zeroh=!initH) :
-           init == :custom ? (Matrix{T}(W0), Matrix{T}(H0)) :
+           init == :custom ? (W0::Matrix{T}, H0::Matrix{T}) :     # aliased and updated in place, like `W = W::Matrix{T}` at src/interf.jl:57-58
            nndsvd(Xm, k; zeroh=!initH, variant=(init == :nndsvd ? :std : init == :nndsvda ? :a : :ar), initdata=initdata, handle=h)
     ret = solve!(inst, Xm, W, H; handle=h, x_resident=true)
     for _ in 2:replicates                              # src/interf.jl:91-98

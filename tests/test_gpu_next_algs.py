@@ -109,14 +109,15 @@ def test_projals_vs_oracle(NMF, oracle, T, p, n, k, iters, planted):
         assert ew <= tol and eh <= tol and eo <= tol
 
 
-def test_projals_not_positive_definite_is_an_argument_error(NMF):
-    """lambda = 0 and a zero column in W: W'W is singular -> potrf! throws in the reference (utils.jl:68)."""
+def test_projals_not_positive_definite_is_a_numerical_error(NMF):
+    """lambda = 0 and a zero column in W: W'W is singular.  The reference ignores potrf!'s info (utils.jl:68) and carries on
+    with an unfinished factor; the library stops with NMFB200_ENUMERIC, distinct from ArgumentError."""
     rng = np.random.default_rng(35)
     X = np.asfortranarray(rng.random((20, 16)))
     W = np.asfortranarray(rng.random((20, 3)))
     W[:, 1] = 0.0
     H = np.zeros((3, 16), order="F")
-    with pytest.raises(NMF.ArgumentError, match="positive definite"):
+    with pytest.raises(NMF.NumericalError, match="positive definite"):
         NMF.solve(NMF.ProjectedALS(np.float64, maxiter=3, lambda_w=0.0, lambda_h=0.0), X, W, H)
 
 

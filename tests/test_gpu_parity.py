@@ -55,9 +55,14 @@ def _start(oracle, T, rng):
 @pytest.mark.parametrize("T", [np.float64, np.float32])
 @pytest.mark.parametrize("obj", ["mse", "div"])
 @pytest.mark.parametrize("lam", [0.0, 1e-4])
-def test_reference_kat_multupd_gpu(NMF, oracle, T, obj, lam):
+@pytest.mark.parametrize("engine", ["simt", "auto", "tc"])
+def test_reference_kat_multupd_gpu(NMF, oracle, T, obj, lam, engine):
+    """The reference's own known-answer test on every engine a user can get: the exact engine, the default (auto), and --
+    Float32 :mse only, the one algorithm the tensor-core engine accepts at 6 x 6 -- the bf16 tensor-core engine forced."""
+    if engine == "tc" and (T != np.float32 or obj != "mse"):
+        pytest.skip("engine=tc covers Float32 only, and :div only from 128 x 128 on")
     X, W, H = _start(oracle, T, np.random.default_rng(21))
-    with NMF.Session(engine="simt") as s:
+    with NMF.Session(engine=engine) as s:
         s.set_option("check_every", 64)
         s.set_X(X)
         s.solve(NMF.MultUpdate(T, obj=obj, maxiter=5000, tol=1e-9, lambda_w=lam, lambda_h=lam), W, H)
@@ -68,9 +73,10 @@ def test_reference_kat_multupd_gpu(NMF, oracle, T, obj, lam):
 # test/greedycd.jl:5-20 on the GPU
 @pytest.mark.parametrize("T", [np.float64, np.float32])
 @pytest.mark.parametrize("lam", [0.0, 1e-5])
-def test_reference_kat_greedycd_gpu(NMF, oracle, T, lam):
+@pytest.mark.parametrize("engine", ["simt", "auto"])
+def test_reference_kat_greedycd_gpu(NMF, oracle, T, lam, engine):
     X, W, H = _start(oracle, T, np.random.default_rng(22))
-    NMF.solve(NMF.GreedyCD(T, maxiter=1000, tol=1e-9, lambda_w=lam, lambda_h=lam), X, W, H, engine="simt")
+    NMF.solve(NMF.GreedyCD(T, maxiter=1000, tol=1e-9, lambda_w=lam, lambda_h=lam), X, W, H, engine=engine)
     assert (W >= 0).all() and (H >= 0).all() and not np.isnan(W).any() and not np.isnan(H).any()
     assert np.linalg.norm(X - W @ H) <= 1e-3
 

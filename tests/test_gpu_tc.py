@@ -106,8 +106,9 @@ def test_tc_convergence_is_repeatable_under_overlapped_launches(NMF):
 
 
 def test_tc_session_reuse_and_auto_engine(NMF, oracle):
-    """X stays resident (bf16 caches built once); auto picks tc for Float32 multmse."""
-    X, W0, H0 = _problem(NMF, 256, 320, 24, seed=13)
+    """X stays resident (bf16 caches built once); auto picks tc for Float32 multmse from 2^20 cells on and the exact
+    engine below that (precision contract in api.py: small Float32 problems never see bf16 rounding)."""
+    X, W0, H0 = _problem(NMF, 1024, 1100, 24, seed=13)
     with NMF.Session(engine="auto") as s:
         s.set_X(X)
         outs = []
@@ -117,6 +118,14 @@ def test_tc_session_reuse_and_auto_engine(NMF, oracle):
             assert r.info["engine"] == "tc"
             outs.append((Wg, Hg, float(r.objvalue)))
         assert (outs[0][0] == outs[1][0]).all() and (outs[0][1] == outs[1][1]).all()  # deterministic
+    Xs, Ws, Hs = _problem(NMF, 256, 320, 24, seed=13)
+    r = NMF.solve(NMF.MultUpdate(np.float32, maxiter=6, tol=1e-9), Xs, Ws.copy(order="F"), Hs.copy(order="F"), engine="auto")
+    assert r.info["engine"] == "simt"
+    Wo, Ho = Ws.copy(order="F"), Hs.copy(order="F")
+    Wg, Hg = Ws.copy(order="F"), Hs.copy(order="F")
+    r = NMF.solve(NMF.MultUpdate(np.float32, maxiter=6, tol=1e-9), Xs, Wg, Hg, engine="auto")
+    oracle.solve(oracle.MultUpdate(np.float32, maxiter=6, tol=1e-9), Xs, Wo, Ho)
+    assert _relerr(Wg, Wo) <= 2e-4 and _relerr(Hg, Ho) <= 2e-4          # fp32 parity, not a bf16 tolerance
 
 
 @pytest.mark.parametrize("p,n,k,iters,lam", [(512, 384, 16, 6, 0.0), (700, 900, 100, 4, 0.0), (384, 512, 200, 3, 1e-3)])

@@ -184,3 +184,81 @@ def test_no_gpu_fails_loudly(NMF):
     X = np.random.default_rng(0).random((6, 5))
     with pytest.raises(NMF.NmfB200Error):
         NMF.nnmf(X, 2, alg="multmse", init="random")
+
+
+# ---- include/nmfb200.h  <->  nmf.jl_b200/julia/NMFB200.jl: every ccall's (return type, argument-type tuple) ----------
+_C2JL = {
+    "nmfb200_handle**": "Ref{Ptr{Cvoid}}", "nmfb200_handle*": "Ptr{Cvoid}", "const nmfb200_handle*": "Ptr{Cvoid}",
+    "void*": "Ptr{Cvoid}", "const void*": "Ptr{Cvoid}", "const char*": "Cstring", "int": "Cint", "int64_t": "Int64",
+    "uint64_t": "UInt64", "float": "Float32", "double": "Float64", "float*": "Ptr{Float32}", "const float*": "Ptr{Float32}",
+    "double*": "Ptr{Float64}", "const double*": "Ptr{Float64}", "nmfb200_result*": "Ref{CResult}", "nmfb200_trace_fn": "Ptr{Cvoid}",
+}
+
+
+def _header_prototypes():
+    hdr = open(os.path.join(ROOT, "include", "nmfb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = {}
+    for ret, name, args in re.findall(r"\b(int|const char\*)\s+(nmfb200_[A-Za-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr):
+        types = []
+        for a in [x.strip() for x in args.split(",")]:
+            if a in ("void", ""):
+                continue
+            m = re.match(r"^(.*?)(\b[A-Za-z_][A-Za-z0-9_]*)$", a)          # strip the parameter name
+            t = re.sub(r"\s*\*", "*", m.group(1).strip())
+            types.append(_C2JL[t])
+        protos[name] = (_C2JL[ret.replace(" *", "*")] if ret != "int" else "Cint", tuple(types))
+    return protos
+
+
+def _julia_ccalls():
+    """Expand the two `for (T, sfx)` loops and the inner `for (alg, name)` loop of NMFB200.jl textually and return
+    [(symbol, return type, (argument types...))] for every ccall in the file."""
+    src = open(os.path.join(ROOT, "nmf.jl_b200", "julia", "NMFB200.jl")).read()
+    src = re.sub(r"#[^\n]*", "", src)
+    calls = []
+    pat = re.compile(r"ccall\(\(\s*([^,]+?)\s*,\s*libnmfb200\)\s*,\s*(\w+)\s*,\s*\(([^()]*(?:\{[^{}]*(?:\{[^{}]*\}[^{}]*)*\}[^()]*)*)\)", re.S)
+    # variable -> name template, e.g. setx -> "nmfb200_set_X_{sfx}", cname -> "nmfb200_solve_{name}_{sfx}"
+    templ = {}
+    for var, parts in re.findall(r"(\w+)\s*=\s*Symbol\(([^)]*)\)", src):
+        templ[var] = "".join(p.strip().strip('"') if p.strip().startswith('"') else "{" + p.strip() + "}" for p in parts.split(","))
+    for var, lit, v2 in re.findall(r"(\w+)\s*=\s*\"(nmfb200_[A-Za-z0-9_]*)\"\s*\*\s*(\w+)", src):
+        templ[var] = lit + "{" + v2 + "}"
+    names = re.search(r"for \(alg, name\) in \(([^\n]*)\)\n", src).group(1)
+    alg_names = re.findall(r'"(\w+)"', names)
+    for sym, ret, args in pat.findall(src):
+        sym = sym.strip()
+        targs = [a.strip() for a in re.split(r",(?![^{]*\})", args) if a.strip()]
+        if sym.startswith(":"):
+            calls.append((sym[1:], ret, tuple(targs)))
+            continue
+        var = re.sub(r"[$()]|QuoteNode", "", sym)
+        assert var in templ, f"cannot resolve ccall symbol {sym}"
+        for T, sfx in (("Float32", "f32"), ("Float64", "f64")):
+            for nm in (alg_names if "{name}" in templ[var] else [None]):
+                full = templ[var].replace("{sfx}", sfx).replace("{name}", nm or "")
+                calls.append((full, ret, tuple(a.replace("$T", T) for a in targs)))
+    return calls
+
+
+def test_julia_ccall_signatures_match_header():
+    protos = _header_prototypes()
+    calls = _julia_ccalls()
+    assert len(calls) >= 22
+    seen = set()
+    for name, ret, args in calls:
+        assert name in protos, f"NMFB200.jl ccalls {name}, which include/nmfb200.h does not declare"
+        assert (ret, args) == protos[name], f"{name}: NMFB200.jl has {ret} {args}, header says {protos[name]}"
+        seen.add(name)
+    # every solve / set_X / mul_X entry point of the header is bound by the Julia wrapper
+    must = {n for n in protos if n.startswith(("nmfb200_solve_", "nmfb200_set_X_f", "nmfb200_mul_X_"))}
+    assert must <= seen, must - seen
+
+
+def test_julia_status_codes_match_header():
+    hdr = open(os.path.join(ROOT, "include", "nmfb200.h")).read()
+    codes = re.findall(r"(NMFB200_[A-Z]+)\s*=\s*(\d+)", hdr)
+    jl = open(os.path.join(ROOT, "nmf.jl_b200", "julia", "NMFB200.jl")).read()
+    m = re.search(r"const ([A-Z, ]+) = 0:(\d+)", jl)
+    names = [x.strip() for x in m.group(1).split(",")]
+    assert [c[0].replace("NMFB200_", "") for c in sorted(codes, key=lambda c: int(c[1]))] == names and int(m.group(2)) == len(names) - 1
