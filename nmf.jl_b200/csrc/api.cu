@@ -47,8 +47,7 @@ template <typename T>
 void set_X_impl(nmfb200_handle* h, const T* X, int64_t p, int64_t n, int64_t ldx, int check_nonneg, bool on_device) {
     NMF_REQUIRE(X != nullptr, NMFB200_EINVAL, "X is NULL");
     NMF_REQUIRE(p > 0 && n > 0 && ldx >= p, NMFB200_EDIM, "invalid dimensions for X");
-    if (h->x_owned) h->drop("X");
-    h->x_owned = false;
+    h->x_owned = false;   // an owned buffer ("X") is kept and reused by buf() when the next matrix fits
     h->dX = nullptr;
     h->x_elt = 0;
     const T* dX = X;
@@ -196,6 +195,14 @@ int nmfb200_set_option(nmfb200_handle* h, const char* key, const char* value) {
             if (v == "p2p") h->tc_xchg = 1;
             else if (v == "nccl") h->tc_xchg = 0;
             else throw Error{NMFB200_EINVAL, "tc_xchg must be p2p|nccl"};
+        } else if (k == "emulate_shards") {
+            int g = atoi(value);
+            NMF_REQUIRE(g >= 0 && g <= XCHG_MAX_RANKS, NMFB200_EINVAL, "emulate_shards must be 0..8");
+            h->emulate_shards = g;
+        } else if (k == "precision") {
+            if (v == "bf16") h->tc_precision = 0;
+            else if (v == "bf16x3") h->tc_precision = 1;
+            else throw Error{NMFB200_EINVAL, "precision must be bf16|bf16x3"};
         } else if (k == "tc_debug") {
             h->tc_debug = atoi(value);
         } else if (k == "time_kernels") {

@@ -87,15 +87,15 @@ template <> struct NcclType<double> { static constexpr ncclDataType_t v = ncclFl
 
 namespace nmfb200 {
 constexpr int XCHG_MAX_RANKS = 8;
-// Peer-memory exchange arena (one per rank, mapped into every peer through CUDA IPC): the fused
-// reduce-scatter / all-gather of the row-sharded H-step writes straight into the peers' HBM over NVLink.
+// Peer-memory arenas of a row-sharded solve (one per rank; a real rank maps every peer's arena through CUDA IPC, logical
+// ranks of an emulated solve simply allocate theirs on the same GPU).  Layout and protocol: csrc/tc_shard.cuh.
 struct Xchg {
     bool ready = false;
+    bool ipc = false;                         // arenas of the other ranks are IPC mappings (real multi-GPU)
     int G = 0, rank = 0;
-    size_t rows_per_seg = 0, row_floats = 0;  // segment geometry the arena was built for
-    void* arena_local = nullptr;
-    size_t arena_bytes = 0;
-    void* arena_peer[XCHG_MAX_RANKS] = {};    // [rank] -> mapped base (own entry = arena_local)
+    size_t arena_bytes = 0;                   // geometry the arenas were built for
+    void* arena_local = nullptr;              // real multi-GPU: this rank's arena (cudaMalloc)
+    void* arena[XCHG_MAX_RANKS] = {};         // [rank] -> base (own / logical ranks: local allocation; peers: IPC mapping)
     unsigned int epoch = 0;
 };
 }  // namespace nmfb200
@@ -113,7 +113,9 @@ struct nmfb200_handle {
     int time_kernels = 0;
     int tc_tile_rows = 0;  // 0 = auto
     int tc_debug = 0;      // diagnostics: bit 3 (8) = record and print the phase clocks of the update kernel
-    int tc_xchg = 1;       // multi-GPU exchange: 1 = fused peer-memory reduce-scatter/all-gather, 0 = ncclAllReduce
+    int tc_xchg = 1;       // multi-GPU on the tensor-core engine needs peer memory; 0 = keep multi-GPU solves on the exact engine (NCCL)
+    int emulate_shards = 0;  // > 1: run the row-sharded tensor-core algorithm with this many LOGICAL ranks on this one GPU
+    int tc_precision = 0;  // 0 = bf16 operands; 1 = bf16x3 (hi/lo split of X and of the streamed factor: fp32-class products)
     nmfb200::Xchg xchg;
     int tc_pdl = 1;        // 1 = launch the update kernels as programmatic dependents of the reduce kernel before them
     int tc_div_fused = 1;  // MultUpdate(:div): 1 = quotient tile stays on chip (div_fused_kernel), 0 = bf16 Q panel through HBM
@@ -128,8 +130,14 @@ struct nmfb200_handle {
     const void* dX = nullptr;
     bool x_owned = false;
     uint64_t x_epoch = 0;     // bumped on every set_X; engines key their derived caches on it
-    uint64_t tc_x_epoch = 0;  // epoch the bf16 caches were built for
-    int tc_x_trH = 0, tc_x_trW = 0;  // ... and their tile heights
+    struct XCacheKey {        // what a pair of bf16 X caches was built for (per buffer-name prefix: whole X, or a row shard)
+        uint64_t epoch = 0;
+        const void* X = nullptr;
+        int64_t p = 0;
+        int trH = 0, trW = 0;
+        bool operator==(const XCacheKey& o) const { return epoch == o.epoch && X == o.X && p == o.p && trH == o.trH && trW == o.trW; }
+    };
+    std::map<std::string, XCacheKey> tc_x_cache;
 
     // multi-GPU
     ncclComm_t comm = nullptr;

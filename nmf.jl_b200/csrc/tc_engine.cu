@@ -33,18 +33,32 @@ namespace {
 using bf16 = __nv_bfloat16;
 using namespace ptx;
 #include "tc_update.cuh"
-#include "tc_xchg.cuh"
 #include "tc_reduce.cuh"
 #include "tc_layout.cuh"
+
+// Extra launch arguments of mu_update_kernel in a row-sharded solve (tc_shard.cuh); nullptr for a single-GPU launch.
+struct ShardLaunch {
+    int tile0 = 0, wait_first = 0, num_row0 = 0;
+    int G = 0, tiles_per_owner = 1, tiles_total = 0;
+    unsigned int epoch = 0;
+    float* num_peer[XCHG_MAX_RANKS] = {};
+    unsigned int* num_flag[XCHG_MAX_RANKS] = {};
+    unsigned int* own_cnt = nullptr;
+    int n_peer = 0;
+    bf16* peer_bT[XCHG_MAX_RANKS - 1] = {};   // MODE 2: the peers' copies of F^T ([rowsT][ldT], same geometry as F.bT)
+};
 
 template <int KP>
 struct TcSolver {
     nmfb200_handle* h;
     cudaStream_t st;
     TcState* state;
+    std::string pfx = "tc";          // prefix of the handle's named buffers (one set per logical rank)
+    const ShardLaunch* sl = nullptr; // row-sharded launch extras for the NEXT launch_update (reset by the caller)
     bool defer_gram_reduce = false;  // the caller will run gram_conv_reduce_kernel itself
     bool last_fused_gram = false;
     float* last_gram_part = nullptr;
+    int last_gram_parts = 0;
     int num_splits = 1;              // MODE 5: k-split partial numerators behind num_io
     int64_t num_split_stride = 0;
 
@@ -55,13 +69,24 @@ struct TcSolver {
                        float* num_io, float* conv_override = nullptr, int gram = -1, float* gram_dst = nullptr, bool pdl = false) {
         UpdateParams prm;
         const bool fused_gram = gram >= 0 && KP <= 128 && (mode == 0 || mode == 2);
-        prm.gram_part = fused_gram ? h->buf_t<float>("tc.gram_part", (size_t)std::max(F.tiles, 1) * KP * KP) : nullptr;
+        std::memset(&prm, 0, sizeof(prm));
+        prm.gram_part = fused_gram ? h->buf_t<float>(pfx + ".gram_part", (size_t)std::max(F.tiles, 1) * KP * KP) : nullptr;
         prm.tmF32 = make_tmap_f32(F.m, KP, (uint64_t)F.R, KP, (uint32_t)F.tile_rows);
         prm.tmT = make_tmap_bf16(F.bT, (uint64_t)F.R, (uint64_t)F.rowsT, (uint64_t)F.ldT, KP);
         prm.tile_rows = F.tile_rows;
         prm.timing = (h->tc_debug & 8) ? (long long*)h->buf("tc.timing", (16 + 2 * 4096) * sizeof(long long)) : nullptr;
         const uint64_t nkb = (uint64_t)ceil_div(Kdim, 64);
-        prm.tmA = make_tmap_bf16(Xs, 64, (uint64_t)F.tiles * nkb * F.tile_rows, 64, (uint32_t)F.tile_rows);
+        const int tile0 = sl ? sl->tile0 : 0;
+        prm.tmA = make_tmap_bf16(Xs, 64, (uint64_t)(tile0 + F.tiles) * nkb * F.tile_rows, 64, (uint32_t)F.tile_rows);
+        if (sl) {
+            prm.tile0 = sl->tile0; prm.wait_first = sl->wait_first; prm.num_row0 = sl->num_row0;
+            prm.G = sl->G; prm.tiles_per_owner = sl->tiles_per_owner; prm.tiles_total = sl->tiles_total; prm.epoch = sl->epoch;
+            for (int j = 0; j < XCHG_MAX_RANKS; ++j) { prm.num_peer[j] = sl->num_peer[j]; prm.num_flag[j] = sl->num_flag[j]; }
+            prm.own_cnt = sl->own_cnt;
+            prm.n_peer = sl->n_peer;
+            for (int j = 0; j < sl->n_peer; ++j)
+                prm.tmT_peer[j] = make_tmap_bf16(sl->peer_bT[j], (uint64_t)F.R, (uint64_t)F.rowsT, (uint64_t)F.ldT, KP);
+        }
         prm.tmB = make_tmap_bf16(O.bT, (uint64_t)Kdim, KP, (uint64_t)O.ldT, KP);
         prm.tmFhi = make_tmap_bf16(F.hi, KP, (uint64_t)F.R, KP, (uint32_t)F.tile_rows);
         prm.tmFlo = make_tmap_bf16(F.lo, KP, (uint64_t)F.R, KP, (uint32_t)F.tile_rows);
@@ -91,6 +116,7 @@ struct TcSolver {
         h->launches += 1;
         last_fused_gram = fused_gram;
         last_gram_part = prm.gram_part;
+        last_gram_parts = F.tiles;
         if (fused_gram && !defer_gram_reduce) {
             launch_k(gram_reduce_kernel, dim3((4 * KP * KP + 255) / 256), dim3(256), 0, st, false, (const float*)prm.gram_part, F.tiles, KP * KP,
                      gram_dst ? gram_dst : F.P, F.Phi, F.Plo, gram, (const TcState*)state);
@@ -100,18 +126,29 @@ struct TcSolver {
         }
     }
 
-    void launch_gram(const Factor& F, bool split, float* P_dst = nullptr) {
+    // partial Grams of rows [k0, k1) of F (k1 < 0: all rows) -> last_gram_part / last_gram_parts; no reduce
+    void launch_gram_parts(const Factor& F, int k0 = 0, int k1 = -1) {
         GramParams g;
+        if (k1 < 0) k1 = F.R;
         g.tmT = make_tmap_bf16(F.bT, (uint64_t)F.R, (uint64_t)F.rowsT, (uint64_t)F.ldT, 128);
         // ~128 CTAs at most, each a multiple of 64 rows and at least 256
-        g.chunk = (int)std::max<int64_t>(256, round_up(ceil_div(F.R, 128), 64));
-        const int grid = (int)ceil_div(F.R, g.chunk);
-        g.part = h->buf_t<float>("tc.gram_part", (size_t)grid * KP * KP);
+        g.chunk = (int)std::max<int64_t>(256, round_up(ceil_div(std::max(k1 - k0, 1), 128), 64));
+        const int grid = (int)std::max<int64_t>(1, ceil_div(k1 - k0, g.chunk));
+        g.part = h->buf_t<float>(pfx + ".gram_part", (size_t)grid * KP * KP);
         g.state = state;
         g.R = F.R;
+        g.k0 = k0;
+        g.k1 = k1;
         gram_kernel<KP><<<grid, 192, GramCfg<KP>::SMEM_BYTES, st>>>(g);
-        gram_reduce_kernel<<<(4 * KP * KP + 255) / 256, 256, 0, st>>>(g.part, grid, KP * KP, P_dst ? P_dst : F.P, F.Phi, F.Plo, split ? 1 : 0, state);
-        h->launches += 2;
+        h->launches += 1;
+        last_gram_part = g.part;
+        last_gram_parts = grid;
+    }
+    void launch_gram(const Factor& F, bool split, float* P_dst = nullptr) {
+        launch_gram_parts(F);
+        gram_reduce_kernel<<<(4 * KP * KP + 255) / 256, 256, 0, st>>>(last_gram_part, last_gram_parts, KP * KP, P_dst ? P_dst : F.P, F.Phi, F.Plo,
+                                                                       split ? 1 : 0, state);
+        h->launches += 1;
     }
 
     // cudaFuncSetAttribute is per device: remember it per device ordinal (a process may hold handles on several GPUs)
@@ -131,6 +168,7 @@ struct TcSolver {
 };
 
 #include "tc_objective.cuh"
+#include "tc_shard.cuh"
 
 template <int KP>
 void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, float* Hc, int64_t ldh, nmfb200_result* out) {
@@ -173,24 +211,7 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
     NMF_CUDA(cudaGetLastError());
 
     TcSolver<KP> s{h, st, state};
-    const bool multi = h->comm != nullptr;
-    // multi-GPU (rows of X, W sharded; H replicated): packed all-reduce buffer [ (W_g' X_g)' : n x KP | W_g' W_g : KP x KP ]
-    // multi-GPU exchange of the packed vector [numerators n x KP | W'W | W-side stop sums]:
-    //   p2p  : MODE 1 stores its rows into the owner rank's HBM, reduce + all-gather kernel, flag barriers (NVLink)
-    //   nccl : ncclAllReduce on a local packed buffer
-    XchgDev xd;
-    std::memset(&xd, 0, sizeof(xd));
-    const bool p2p = multi && xchg_setup(h, n, KP, &xd);
-    if (!p2p) std::memset(&xd, 0, sizeof(xd));  // G = 0: consumers do not wait on peer flags
-    const size_t packed_len = (size_t)n * KP + (size_t)KP * KP + 2 * KP;
-    float* packed = !multi ? nullptr : (p2p ? xd.packed[xd.rank] : h->buf_t<float>("tc.packed", packed_len));
-    float* packed_P = multi ? packed + (size_t)n * KP : nullptr;   // gram_reduce writes the local Gram partial here
-    float* packed_ws = multi ? packed_P + (size_t)KP * KP : nullptr;  // conv_reduce writes the local W-side stop sums here
-    float* ws_small = multi ? h->buf_t<float>("tc.ws_small", 2 * KP) : nullptr;  // stand-alone decision (end of batch)
-    if (multi) NMF_CUDA(cudaMemsetAsync(packed_ws, 0, 2 * KP * sizeof(float), st));
-    XchgDev xnone;
-    std::memset(&xnone, 0, sizeof(xnone));
-    s.launch_gram(W, !multi, packed_P);       // P_W = W'W for the first H-step (partial per rank when sharded)
+    s.launch_gram(W, true);                   // P_W = W'W for the first H-step
     if (!a.update_H) s.launch_gram(H, true);  // H never changes: P_H once
     NMF_CUDA(cudaEventRecord(e1, st));
 
@@ -200,11 +221,10 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
     int64_t iters = 0;
     float devmax = 0.f;
     TcState hs;
-    const int post_blocks = 1 + (KP * KP + 255) / 256;
-    // Single GPU: both update kernels are launched as programmatic dependents of the small reduce kernel in front of
-    // them, so their X streaming overlaps that kernel and the launch gap (the reduce results are only needed by the
-    // denominator blocks and the epilogue, which wait for it).
-    const bool pdl = h->tc_pdl != 0;  // multi-GPU: the MODE 1 numerator kernel and the W-step follow gram_conv_reduce / gram_reduce too
+    // Both update kernels are launched as programmatic dependents of the small reduce kernel in front of them, so their X
+    // streaming overlaps that kernel and the launch gap (the reduce results are only needed by the denominator blocks and
+    // the epilogue, which wait for it).
+    const bool pdl = h->tc_pdl != 0;
     // verbose (common.jl:54-59, 76-82): objective before the loop and after every iteration, through the trace callback
     double v_objv = std::numeric_limits<double>::quiet_NaN(), v_t0 = 0;
     auto wall = []() {
@@ -225,61 +245,25 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
     while (enq < a.maxiter) {
         int64_t batch = a.verbose ? 1 : std::min<int64_t>(h->check_every, a.maxiter - enq);
         for (int64_t i = 0; i < batch; ++i) {
-            bool pending = multi && i > 0;  // the previous iteration of this batch still awaits its decision
             h->mark("start");
             if (a.update_H) {
-                if (!multi) {
-                    s.launch_update(0, H, W, Xr, (int)p, lh, delta, nullptr, nullptr, 1, nullptr, pdl);  // H-step (+ tile Grams of the new H)
-                    h->mark("updH");
-                } else {
-                    s.launch_update(1, H, W, Xr, (int)p, lh, delta, packed, nullptr, -1, nullptr, pdl);  // partial numerators of this shard
-                    h->mark("mode1");
-                    // THE exchange step: [numerators | W'W | W-side stop sums of the previous iteration]
-                    unsigned int ep = 0;
-                    if (p2p) {
-                        ep = ++h->xchg.epoch;
-                        xchg_reduce_gather_kernel<<<148, 256, 0, st>>>(xd, KP, ep);  // NVLink peer memory, one launch
-                        h->launches += 1;
-                        h->mark("xchg");
-                    } else {
-                        h->allreduce_sum(packed, packed_len);
-                        h->mark("nccl");
-                    }
-                    post_allreduce_kernel<<<post_blocks, 256, 0, st>>>(acc, packed_ws, pending ? 1 : 0, KP, (int)k, tol, state, packed_P,
-                                                                       W.Phi, W.Plo, xd, ep);
-                    h->launches += 1;
-                    pending = false;
-                    h->mark("post");
-                    s.launch_update(2, H, W, Xr, (int)p, lh, delta, packed, nullptr, 1, nullptr, pdl);   // ratio with the reduced numerators
-                    h->mark("mode2");
-                }
-                h->mark("gramH");
+                s.launch_update(0, H, W, Xr, (int)p, lh, delta, nullptr, nullptr, 1, nullptr, pdl);  // H-step (+ tile Grams of the new H)
+                h->mark("updH");
             }
-            if (pending) {  // update_H = false: no packed exchange to ride on
-                NMF_CUDA(cudaMemcpyAsync(ws_small, packed_ws, 2 * KP * sizeof(float), cudaMemcpyDeviceToDevice, st));
-                h->allreduce_sum(ws_small, (size_t)2 * KP);
-                post_allreduce_kernel<<<1, 256, 0, st>>>(acc, ws_small, 1, KP, (int)k, tol, state, nullptr, nullptr, nullptr, xnone, 0u);
-                h->launches += 1;
-            }
-            // W-step (local rows) + W'W for the next H-step (partial per rank when sharded; not needed if H is fixed)
-            const int gramW = (a.update_H || !multi) ? (multi ? 0 : 1) : -1;
+            // W-step + W'W for the next H-step (not needed if H is fixed)
+            const int gramW = a.update_H ? 1 : -1;
             s.defer_gram_reduce = true;
-            s.launch_update(0, W, H, Xc, (int)n, lw, delta, nullptr, nullptr, gramW, packed_P, pdl);
+            s.launch_update(0, W, H, Xc, (int)n, lw, delta, nullptr, nullptr, gramW, nullptr, pdl);
             s.defer_gram_reduce = false;
             h->mark("updW");
             const int gram_blocks = (s.last_fused_gram && gramW >= 0) ? (4 * KP * KP + 255) / 256 : 0;
-            // one launch: Gram reduce (if produced by the staged epilogue) + stop_condition reduce / decision
-            launch_k(gram_conv_reduce_kernel, dim3(gram_blocks + 4 * (KP / 32)), dim3(256), 0, st, false, (const float*)s.last_gram_part, W.tiles,
-                     KP * KP, packed_P ? packed_P : W.P, W.Phi, W.Plo, gramW > 0 ? 1 : 0, gram_blocks, (const float*)W.conv, W.tiles,
-                     (const float*)H.conv, H.tiles, KP, (int)k, (int)a.update_H, acc, tol, state, multi ? 0 : 1, packed_ws);
+            // one launch: Gram reduce (if the staged epilogue produced tile Grams; KP = 256 ran gram_kernel + reduce inside
+            // launch_update) + stop_condition reduce / decision
+            launch_k(gram_conv_reduce_kernel, dim3(gram_blocks + 4 * (KP / 32)), dim3(256), 0, st, false, (const float*)s.last_gram_part,
+                     W.tiles, KP * KP, W.P, W.Phi, W.Plo, 1, gram_blocks, (const float*)W.conv, W.tiles, (const float*)H.conv, H.tiles,
+                     KP, (int)k, (int)a.update_H, acc, tol, state, 1, (float*)nullptr);
             h->launches += 1;
             h->mark("conv");
-        }
-        if (multi) {  // decision of the last iteration of the batch
-            NMF_CUDA(cudaMemcpyAsync(ws_small, packed_ws, 2 * KP * sizeof(float), cudaMemcpyDeviceToDevice, st));
-            h->allreduce_sum(ws_small, (size_t)2 * KP);
-            post_allreduce_kernel<<<1, 256, 0, st>>>(acc, ws_small, 1, KP, (int)k, tol, state, nullptr, nullptr, nullptr, xnone, 0u);
-            h->launches += 1;
         }
         enq += batch;
         NMF_CUDA(cudaGetLastError());
@@ -688,11 +672,14 @@ bool tc_supported(const nmfb200_handle* h, const SolveArgs& a) {
     // the reference's own tiny test problems -- laurberg6x3, 5x8 -- never see bf16 rounding).  engine = tc overrides.
     if (a.alg == 0 && h->engine_opt != 2 && h->p * h->n < ((int64_t)1 << 20)) return false;
     if (a.alg == 1) {                     // MultUpdate(:div): quotient kernel + update kernel; k <= 128, single GPU
-        if (h->comm != nullptr || a.k > 128 || h->p < 128 || h->n < 128) return false;
+        if (h->comm != nullptr || h->emulate_shards > 1 || a.k > 128 || h->p < 128 || h->n < 128) return false;
         if (h->engine_opt != 2 && h->p * h->n < ((int64_t)1 << 20)) return false;
     }
+    const bool sharded = h->comm != nullptr || h->emulate_shards > 1;
+    if (a.alg == 0 && h->comm != nullptr && !h->tc_xchg) return false;   // option tc_xchg=nccl: multi-GPU solves stay on the exact engine
+    if (a.alg == 0 && sharded && (h->comm ? h->nranks : h->emulate_shards) > XCHG_MAX_RANKS) return false;
     if (a.alg == 2) {                     // GreedyCD: bf16 gradients; single GPU; auto-selected for large problems only
-        if (h->comm != nullptr) return false;
+        if (sharded) return false;
         if (h->engine_opt != 2 && h->p * h->n < ((int64_t)1 << 24)) return false;
     }
     if (a.verbose && (a.alg != 0 || h->n < 128 || h->p < 64 || (h->ldx % 4) != 0)) return false;  // per-iteration objective: MU-MSE only
@@ -714,6 +701,14 @@ void tc_solve(nmfb200_handle* h, const SolveArgs& a, float* W, int64_t ldw, floa
             case 64: tc_solve_gcd_kp<64>(h, a, W, ldw, H, ldh, out); return;
             case 128: tc_solve_gcd_kp<128>(h, a, W, ldw, H, ldh, out); return;
             case 256: tc_solve_gcd_kp<256>(h, a, W, ldw, H, ldh, out); return;
+            default: throw Error{NMFB200_ENOTSUP, "k > 256 is not covered by the tensor-core engine"};
+        }
+    }
+    if (h->comm != nullptr || h->emulate_shards > 1) {   // rows of X / W sharded over ranks (real or logical): tc_shard.cuh
+        switch (pick_kp(a.k)) {
+            case 64: tc_solve_sharded_kp<64>(h, a, W, ldw, H, ldh, out); return;
+            case 128: tc_solve_sharded_kp<128>(h, a, W, ldw, H, ldh, out); return;
+            case 256: tc_solve_sharded_kp<256>(h, a, W, ldw, H, ldh, out); return;
             default: throw Error{NMFB200_ENOTSUP, "k > 256 is not covered by the tensor-core engine"};
         }
     }

@@ -159,7 +159,7 @@ int pick_tile_rows(int R, int forced) {
     return R >= 128 ? 128 : (int)round_up(std::max(R, 8), 8);
 }
 
-Factor alloc_factor(nmfb200_handle* h, const char* tag, int R, int KP) {
+Factor alloc_factor(nmfb200_handle* h, const std::string& tag, int R, int KP) {
     Factor f;
     std::string t(tag);
     f.R = R;
@@ -179,29 +179,32 @@ Factor alloc_factor(nmfb200_handle* h, const char* tag, int R, int KP) {
     return f;
 }
 
-// bf16 tile-contiguous caches of X in both orientations (built once per set_X / tile shape)
-void build_x_caches(nmfb200_handle* h, bf16** Xr_out, bf16** Xc_out) {
+// bf16 tile-contiguous caches of X in both orientations (built once per set_X / tile shape / shard geometry).
+// X, p, ldx describe the rows this (logical) rank works on: the whole matrix, or a row shard of it (pfx names the buffers).
+void build_x_caches(nmfb200_handle* h, const std::string& pfx, const float* X, int64_t p, int64_t n, int64_t ldx, bf16** Xr_out,
+                    bf16** Xc_out) {
     cudaStream_t st = h->stream;
-    const int64_t p = h->p, n = h->n;
     const int trH = pick_tile_rows((int)n, h->tc_tile_rows), trW = pick_tile_rows((int)p, h->tc_tile_rows);
     const int64_t tilesH = ceil_div(n, trH), tilesW = ceil_div(p, trW);
     const int nkbH = (int)ceil_div(p, 64), nkbW = (int)ceil_div(n, 64);
-    bf16* Xr_ = h->buf_t<bf16>("tc.Xr", (size_t)tilesH * nkbH * trH * 64);  // rows = columns of X, contraction over p
-    bf16* Xc_ = h->buf_t<bf16>("tc.Xc", (size_t)tilesW * nkbW * trW * 64);  // rows = rows of X, contraction over n
-    if (h->tc_x_epoch != h->x_epoch || h->tc_x_trH != trH || h->tc_x_trW != trW) {
-        const float* X = (const float*)h->dX;
+    bf16* Xr_ = h->buf_t<bf16>(pfx + ".Xr", (size_t)tilesH * nkbH * trH * 64);  // rows = columns of X, contraction over p
+    bf16* Xc_ = h->buf_t<bf16>(pfx + ".Xc", (size_t)tilesW * nkbW * trW * 64);  // rows = rows of X, contraction over n
+    nmfb200_handle::XCacheKey key{h->x_epoch, (const void*)X, p, trH, trW};
+    nmfb200_handle::XCacheKey& have = h->tc_x_cache[pfx];
+    if (!(have == key)) {
         cvt_tiled_direct_kernel<<<dim3((unsigned)(tilesH * trH), (unsigned)std::min<int64_t>(ceil_div((int64_t)nkbH * 64, 256), 64)), 256, 0, st>>>(
-            X, h->ldx, (int)n, (int)p, trH, nkbH, Xr_);
+            X, ldx, (int)n, (int)p, trH, nkbH, Xr_);
         NMF_REQUIRE(trW % 8 == 0, NMFB200_EINVAL, "tile rows must be a multiple of 8");
         // the transpose kernel walks 64 logical rows per block; cover the padded row range of the last tile too
         cvt_tiled_transpose_kernel<<<dim3((unsigned)nkbW, (unsigned)ceil_div(tilesW * trW, 64)), dim3(32, 8), 0, st>>>(
-            X, h->ldx, (int)p, (int)n, trW, nkbW, (int)tilesW, Xc_);
+            X, ldx, (int)p, (int)n, trW, nkbW, (int)tilesW, Xc_);
         h->launches += 2;
         NMF_CUDA(cudaGetLastError());
-        h->tc_x_epoch = h->x_epoch;
-        h->tc_x_trH = trH;
-        h->tc_x_trW = trW;
+        have = key;
     }
     *Xr_out = Xr_;
     *Xc_out = Xc_;
+}
+void build_x_caches(nmfb200_handle* h, bf16** Xr_out, bf16** Xc_out) {
+    build_x_caches(h, "tc", (const float*)h->dX, h->p, h->n, h->ldx, Xr_out, Xc_out);
 }

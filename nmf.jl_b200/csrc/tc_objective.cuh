@@ -215,13 +215,19 @@ __global__ void abs_sum_kernel(const float* __restrict__ a, int64_t len, double*
     if (threadIdx.x == 0) part[blockIdx.x] = red[0];
 }
 
-// Objective of the current factors (row-factor layout with fresh hi/lo copies) on tensor cores.  Returns false if
-// the shape is not covered (caller falls back to the exact fp32 GEMM + reduction of the SIMT engine).
+// Objective of the current factors (row-factor layout with fresh hi/lo copies) on tensor cores, in three steps so that a
+// row-sharded solve can combine the partial sums of its ranks:
+//   tc_objective_covers(...)  -- can the tensor-core kernel take this (shard of) X?  (alignment / minimum size)
+//   tc_objective_enqueue(...) -- launches; returns a device pointer res[3] = {data term, |W|_1, |H|_1} (Float64 partial sums
+//                                over the rows of X / W given; H is replicated)
+//   tc_objective_value(...)   -- the reference's rounding of the combined sums (multupd.jl:81,148; greedycd.jl:82-92)
+inline bool tc_objective_covers(const float* X, int64_t p, int64_t n, int64_t ldx) {
+    return !(n < 128 || p < 64 || (ldx % 4) != 0 || (((uintptr_t)X) & 15) != 0);
+}
+
 template <int KP>
-bool tc_objective(nmfb200_handle* h, int alg, const Factor& W, const Factor& H, double lambda_w, double lambda_h, double* out) {
-    const int64_t p = h->p, n = h->n;
-    // multi-GPU: the fallback issues a different collective, so the choice is made for all ranks together
-    if (!h->all_ranks(!(n < 128 || p < 64 || (h->ldx % 4) != 0 || (((uintptr_t)h->dX) & 15) != 0))) return false;
+double* tc_objective_enqueue(nmfb200_handle* h, const std::string& pfx, int alg, const float* X, int64_t p, int64_t n, int64_t ldx,
+                             const Factor& W, const Factor& H, double lambda_w, double lambda_h) {
     cudaStream_t st = h->stream;
     static bool attr_on[64] = {};   // per device ordinal (cudaFuncSetAttribute is per device)
     bool& attr = attr_on[h->device & 63];
@@ -231,7 +237,7 @@ bool tc_objective(nmfb200_handle* h, int alg, const Factor& W, const Factor& H, 
         attr = true;
     }
     ObjParams op;
-    op.tmX = make_tmap_f32(h->dX, (uint64_t)p, (uint64_t)n, (uint64_t)h->ldx, 128);
+    op.tmX = make_tmap_f32(X, (uint64_t)p, (uint64_t)n, (uint64_t)ldx, 128);
     op.tmRhi = make_tmap_bf16(H.hi, KP, (uint64_t)n, KP, 128);
     op.tmRlo = make_tmap_bf16(H.lo, KP, (uint64_t)n, KP, 128);
     op.tmChi = make_tmap_bf16(W.hi, KP, (uint64_t)p, KP, 64);
@@ -242,11 +248,12 @@ bool tc_objective(nmfb200_handle* h, int alg, const Factor& W, const Factor& H, 
     op.kchunk = (int)ceil_div(op.nkb, ksplit);
     ksplit = (int)ceil_div(op.nkb, op.kchunk);
     const int nparts = tiles * ksplit;
-    double* part = h->buf_t<double>("tc.obj_part", (size_t)nparts + 2048 + 4);
+    double* part = h->buf_t<double>(pfx + ".obj_part", (size_t)nparts + 2048 + 4);
     op.part = part;
     if (alg == 1) objective_tc_kernel<KP, 1><<<dim3(tiles, ksplit), ObjCfg<KP>::THREADS, ObjCfg<KP>::SMEM_BYTES, st>>>(op);
     else objective_tc_kernel<KP, 0><<<dim3(tiles, ksplit), ObjCfg<KP>::THREADS, ObjCfg<KP>::SMEM_BYTES, st>>>(op);
     double* res = part + nparts;  // [0] data term, [1] |W|_1, [2] |H|_1
+    NMF_CUDA(cudaMemsetAsync(res, 0, 4 * sizeof(double), st));
     sum_double_kernel<<<1, 256, 0, st>>>(part, nparts, res);
     h->launches += 2;
     const bool l1w = alg == 2 && lambda_w > 0, l1h = alg == 2 && lambda_h > 0;
@@ -262,19 +269,26 @@ bool tc_objective(nmfb200_handle* h, int alg, const Factor& W, const Factor& H, 
         h->launches += 2;
     }
     NMF_CUDA(cudaGetLastError());
-    if (h->comm) {  // rows of X / W are sharded: the data term and |W|_1 are partial sums; H is replicated
-        h->allreduce_sum(res, 2);
-    }
+    return res;
+}
+
+inline double tc_objective_value(int alg, const double hres[3], double lambda_w, double lambda_h) {
+    if (alg == 1) return (double)(float)hres[0];              // gkldiv returns Float64; Result{T} converts (common.jl:32)
+    float r = 0.5f * (float)hres[0];                          // convert(T, 0.5) * sqL2dist (multupd.jl:81)
+    if (alg == 2 && lambda_w > 0) r = r + (float)lambda_w * (float)hres[1];   // greedycd.jl:85-90
+    if (alg == 2 && lambda_h > 0) r = r + (float)lambda_h * (float)hres[2];
+    return (double)r;
+}
+
+// Single-GPU form.  Returns false if the shape is not covered (caller falls back to the exact fp32 GEMM + reduction of
+// the SIMT engine).
+template <int KP>
+bool tc_objective(nmfb200_handle* h, int alg, const Factor& W, const Factor& H, double lambda_w, double lambda_h, double* out) {
+    if (!tc_objective_covers((const float*)h->dX, h->p, h->n, h->ldx)) return false;
+    double* res = tc_objective_enqueue<KP>(h, "tc", alg, (const float*)h->dX, h->p, h->n, h->ldx, W, H, lambda_w, lambda_h);
     double hres[3] = {0, 0, 0};
-    NMF_CUDA(cudaMemcpyAsync(hres, res, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    NMF_CUDA(cudaStreamSynchronize(st));
-    if (alg == 1) {
-        *out = (double)(float)hres[0];                       // gkldiv returns Float64; Result{T} converts (common.jl:32)
-    } else {
-        float r = 0.5f * (float)hres[0];                     // convert(T, 0.5) * sqL2dist (multupd.jl:81)
-        if (l1w) r = r + (float)lambda_w * (float)hres[1];   // greedycd.jl:85-90
-        if (l1h) r = r + (float)lambda_h * (float)hres[2];
-        *out = (double)r;
-    }
+    NMF_CUDA(cudaMemcpyAsync(hres, res, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    NMF_CUDA(cudaStreamSynchronize(h->stream));
+    *out = tc_objective_value(alg, hres, lambda_w, lambda_h);
     return true;
 }

@@ -1,4 +1,4 @@
-// tc_reduce.cuh -- stop_condition finish (common.jl:92-111), merged Gram + stop reduce, post-exchange decision kernel
+// tc_reduce.cuh -- stop_condition finish (common.jl:92-111), merged Gram + stop reduce (the sharded counterparts are in tc_shard.cuh)
 // Part of the tensor-core engine; included only by tc_engine.cu, inside namespace nmfb200 and its
 // anonymous namespace.
 #pragma once
@@ -7,8 +7,7 @@
 // acc (double [4][KP]) = {dev_w, sum_w, dev_h, sum_h}.  conv_reduce_kernel: grid = 4 * KP/32 blocks of 8 warps;
 // block (q, cb) sums quantity q of components [32cb, 32cb+32) over all tiles (warp w takes tiles w, w+8, ...;
 // 8 loads in flight; fixed combination order => deterministic).  With do_decide the last block to finish
-// (atomic ticket) applies the reference's test; multi-GPU runs the decision as a separate launch after the
-// packed all-reduce (post_allreduce_kernel).
+// (atomic ticket) applies the reference's test; row-sharded solves decide in shard_post_kernel (tc_shard.cuh).
 __device__ void conv_decide(const double* acc, int KP, int k, float tol, TcState* st, float* devs, int* fail) {
     const int a = threadIdx.x;
     if (a == 0) *fail = 0;
@@ -164,32 +163,4 @@ __global__ void __launch_bounds__(256) gram_conv_reduce_kernel(const float* __re
     __threadfence();
     if (threadIdx.x == 0) st->ticket = 0u;
     conv_decide(acc, KP, k, tol, st, devs, &fail);
-}
-
-// multi-GPU, after the packed all-reduce: block 0 finishes stop_condition of the PREVIOUS iteration (its W-side
-// sums travelled in the tail of the packed buffer; nothing of the current iteration has touched W or H yet),
-// the other blocks split the reduced Gram W'W into bf16 hi/lo.
-__global__ void __launch_bounds__(256) post_allreduce_kernel(double* __restrict__ acc, const float* __restrict__ wsums_f32, int has_prev,
-                                                             int KP, int k, float tol, TcState* st, const float* __restrict__ P,
-                                                             bf16* __restrict__ Phi, bf16* __restrict__ Plo, XchgDev x, unsigned int epoch) {
-    pdl_launch_dependents();  // the MODE 2 ratio kernel may set itself up now; it waits for our completion before it reads anything
-    if (x.G > 0) xchg_wait_all(x, 1, epoch);  // peer-memory exchange: every rank's reduced segment has landed here
-    if (st->converged) return;
-    __shared__ float devs[256];
-    __shared__ int fail;
-    if (blockIdx.x == 0) {
-        if (!has_prev) return;
-        for (int i = threadIdx.x; i < 2 * KP; i += blockDim.x) acc[i] = (double)__ldcg(wsums_f32 + i);
-        __syncthreads();
-        conv_decide(acc, KP, k, tol, st, devs, &fail);
-        return;
-    }
-    if (P == nullptr) return;
-    const int i = (blockIdx.x - 1) * blockDim.x + threadIdx.x;
-    if (i < KP * KP) {
-        float v = P[i];
-        bf16 hi = __float2bfloat16_rn(v);
-        Phi[i] = hi;
-        Plo[i] = __float2bfloat16_rn(v - __bfloat162float(hi));
-    }
 }

@@ -10,18 +10,14 @@ struct TcState {
     unsigned int ticket;
 };
 
-// ---- peer-memory exchange (multi-GPU) ---------------------------------------------------------------
-// The packed vector [numerators n x KP | W'W KP x KP | W-side stop sums 2 x KP] is treated as Rtot = n+KP+2
-// rows of KP floats, cut into G contiguous segments of RS rows; rank j owns (reduces) segment j.
-// Arena of every rank (IPC-mapped into all peers): flags | packed [G*RS][KP].  A rank's kernels write their
-// partial sums into its own `packed`; the exchange kernel PULLS its segment from every peer over NVLink, sums
-// in rank order and PUSHES the reduced segment into every peer's `packed` (reduce-scatter + all-gather fused).
-struct XchgDev {
-    float* packed[XCHG_MAX_RANKS];        // packed[j] = rank j's packed vector (mapped peer memory)
-    unsigned int* flags[XCHG_MAX_RANKS];  // flags[j][phase * XCHG_MAX_RANKS + src]: "src reached epoch in phase"
-    unsigned int* ticket;                 // local counter for the last-block pattern
-    int G, rank, RS;
-};
+// ---- row-sharded solves (multi-GPU, or G logical shards on one GPU): see tc_shard.cuh -----------------------
+// Flag phases of the per-rank arena (flags[phase * XCHG_MAX_RANKS + src] = last epoch `src` has published):
+constexpr int PH_NUM = 0;     // src's partial numerators for MY H rows are in my slot[src]
+constexpr int PH_H = 1;       // src's updated H rows (bf16 transposed slab), its partial Gram H'H and H-side stop sums are here
+constexpr int PH_PW = 2;      // src's partial Gram W'W and W-side stop sums are here
+constexpr int PH_BAR = 3;     // plain barrier (rank alignment before a timed region)
+constexpr int PH_GATHER = 4;  // src's fp32 H rows are here (end of solve / verbose)
+constexpr int N_PHASES = 5;
 
 // ---- kernel parameter block (tensor maps must live in __grid_constant__ param space) ---------------
 struct UpdateParams {
@@ -50,7 +46,29 @@ struct UpdateParams {
     int tile_rows;      // rows of F owned by one CTA (<= 128, multiple of 8); the TMA boxes of A / Fhi / Flo have this many rows
     long long* timing;  // diagnostics (tc_debug bit 3): CTA 0 records clock64() at its phase boundaries, see TSTAMP
     float lambda, delta;
+    // ---- row-sharded solves (tc_shard.cuh); all zero for a single-GPU launch
+    int tile0;          // first tile of this launch (MODE 2: the rank's own H rows only)
+    int wait_first;     // producer: griddepcontrol.wait before the first operand load (W-step under PDL: H arrives from peers)
+    int num_row0;       // MODE 2: numerator slots are indexed by (row - num_row0)
+    int G;              // number of ranks (0 = not sharded)
+    int tiles_per_owner;                       // MODE 1: tile t belongs to rank t / tiles_per_owner
+    int tiles_total;
+    unsigned int epoch;
+    float* num_peer[XCHG_MAX_RANKS];           // MODE 1: [owner] -> slot[my rank] in the owner's arena (peer memory)
+    unsigned int* num_flag[XCHG_MAX_RANKS];    // MODE 1: [owner] -> flags[PH_NUM][my rank] in the owner's arena
+    unsigned int* own_cnt;                     // MODE 1: [G] local counters "tiles of owner o finished"
+    int n_peer;                                // MODE 2: transposed tile is also stored into n_peer peer copies of F^T
+    CUtensorMap tmT_peer[XCHG_MAX_RANKS - 1];
 };
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 template <int KP>
 struct UpdCfg {
@@ -121,7 +139,8 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
         prm.timing[16 + 2 * blockIdx.x] = gt;
     }
     const int tile_rows = prm.tile_rows;
-    const int r0 = blockIdx.x * tile_rows;
+    const int tile = (int)blockIdx.x + prm.tile0;
+    const int r0 = tile * tile_rows;
     const uint32_t a_bytes = (uint32_t)tile_rows * 128u;
     const int nkb = (MODE == 2 || MODE == 5) ? 0 : (prm.Kdim + 63) / 64;
     constexpr int NPRE = (MODE == 1 || MODE == 4 || MODE == 5) ? 0 : 3 * C::NSLAB;
@@ -167,8 +186,9 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
             int s = 0;
             uint32_t ph = 0;
             uint8_t* dst = smem;
-            int arow = blockIdx.x * nkb * tile_rows;   // tile-contiguous X: k-block kb of this tile starts at panel row arow0 + kb*tile_rows
+            int arow = tile * nkb * tile_rows;   // tile-contiguous X: k-block kb of this tile starts at panel row arow0 + kb*tile_rows
             const uint32_t num_tx = a_bytes + (uint32_t)C::B_BYTES;
+            if (prm.wait_first) pdl_wait();   // sharded W-step: the other factor's rows arrive from peers, confirmed by the kernel in front
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(&empty_bar[s], ph ^ 1u);
                 mbar_arrive_expect_tx(&full_bar[s], num_tx);
@@ -258,7 +278,11 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
             if (MODE == 1) {
                 tmem_ld_wait();
                 if (valid) {
-                    float4* dst = (float4*)(prm.num_io + (size_t)row * KP + c0);
+                    // sharded: straight into the slot the OWNER of this tile keeps for this rank (peer memory over NVLink)
+                    float* base = prm.G > 0 ? prm.num_peer[tile / prm.tiles_per_owner] +
+                                                  ((size_t)(tile % prm.tiles_per_owner) * tile_rows + (32 * q + lane)) * KP
+                                            : prm.num_io + (size_t)row * KP;
+                    float4* dst = (float4*)(base + c0);
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         dst[j] = make_float4(__uint_as_float(num_u[4 * j]), __uint_as_float(num_u[4 * j + 1]),
@@ -273,17 +297,10 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                     float4 v = src[j];
                     f[4 * j] = v.x; f[4 * j + 1] = v.y; f[4 * j + 2] = v.z; f[4 * j + 3] = v.w;
                 }
-                if (MODE == 2) {
-                    const float4* ns = (const float4*)(prm.num_io + (size_t)row * KP + c0);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float4 v = ns[j];
-                        num_u[4 * j] = __float_as_uint(v.x); num_u[4 * j + 1] = __float_as_uint(v.y);
-                        num_u[4 * j + 2] = __float_as_uint(v.z); num_u[4 * j + 3] = __float_as_uint(v.w);
-                    }
-                }
-                if (MODE == 5) {  // k-split partial numerators of div_fused_kernel, summed in split order (deterministic)
-                    const float* nbase = prm.num_io + (size_t)row * KP + c0;
+                if (MODE == 5 || MODE == 2) {
+                    // MODE 5: k-split partial numerators of div_fused_kernel; MODE 2: the per-rank partial numerators of a
+                    // row-sharded H-step (slot s = rank s).  Summed in slot order => deterministic, same on every rank.
+                    const float* nbase = prm.num_io + (size_t)(row - prm.num_row0) * KP + c0;
                     float acc[32];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -402,6 +419,21 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
             convw[c0 + lane] = d2[0];
             convw[KP + c0 + lane] = s2[0];
         }
+        if (MODE == 1 && prm.G > 0) {
+            // this tile's partial numerators are in the owner's slot: count it, and the last tile for an owner raises the flag
+            __threadfence_system();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (threadIdx.x == 64) {
+                const int owner = tile / prm.tiles_per_owner;
+                const int owned = min(prm.tiles_per_owner, prm.tiles_total - owner * prm.tiles_per_owner);
+                const unsigned prev = atomicAdd(prm.own_cnt + owner, 1u);
+                if (prev == (unsigned)owned - 1u) {
+                    prm.own_cnt[owner] = 0u;
+                    __threadfence_system();
+                    st_release_sys(prm.num_flag[owner], prm.epoch);
+                }
+            }
+        }
         if (MODE == 3) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) gcd_rowmax = fmaxf(gcd_rowmax, __shfl_xor_sync(0xffffffffu, gcd_rowmax, o));
@@ -433,6 +465,12 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                     }
                     tma_store_2d(&prm.tmT, ST, r0, 0);
                     if (tile_rows > 64) tma_store_2d(&prm.tmT, ST + KP * 128, r0 + 64, 0);
+                    if (MODE == 2) {   // row-sharded H-step: the all-gather of the new rows is these stores into the peers' copies
+                        for (int j = 0; j < prm.n_peer; ++j) {
+                            tma_store_2d(&prm.tmT_peer[j], ST, r0, 0);
+                            if (tile_rows > 64) tma_store_2d(&prm.tmT_peer[j], ST + KP * 128, r0 + 64, 0);
+                        }
+                    }
                     tma_store_commit();
                     if (prm.gram_part != nullptr) {  // Gram contribution of this tile: T T' (K = 128 rows), into the Num columns
                         tc_fence_after();
@@ -477,6 +515,10 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                 if (threadIdx.x == 64) {
                     TSTAMP(9);                 // tile Gram written
                     tma_store_wait_all<0>();
+                    if (MODE == 2 && prm.n_peer > 0) {   // peer copies written through the async proxy: order them before the flag
+                        asm volatile("fence.proxy.async;" ::: "memory");   // that the following kernel publishes at system scope
+                        __threadfence_system();
+                    }
                     TSTAMP(10);                // bulk stores have read their staging buffers
                 }
             }
@@ -504,6 +546,7 @@ struct GramParams {
     float* part;      // [gridDim.x][KP][KP] fp32 partial Grams (plain stores, reduced by gram_reduce_kernel)
     const TcState* state;
     int R, chunk;     // rows (K extent) per CTA, multiple of 64
+    int k0, k1;       // the Gram covers rows [k0, k1) of the factor (k1 = R: all; a row-sharded solve sums its own H rows only)
 };
 
 template <int KP>
@@ -527,8 +570,8 @@ __global__ void __launch_bounds__(192, 1) gram_kernel(const __grid_constant__ Gr
     uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int k_begin = blockIdx.x * prm.chunk;
-    const int k_end = min(prm.R, k_begin + prm.chunk);
+    const int k_begin = prm.k0 + blockIdx.x * prm.chunk;
+    const int k_end = min(prm.k1, k_begin + prm.chunk);
     const int nkb = (k_end - k_begin + 63) / 64;
 
     if (warp == 0 && lane == 0) {
@@ -554,7 +597,7 @@ __global__ void __launch_bounds__(192, 1) gram_kernel(const __grid_constant__ Gr
                 mbar_wait(&empty_bar[s], ph ^ 1u);
                 mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
                 // NOTE: columns >= k_end inside the last 64-block belong to the next CTA's chunk only if
-                // chunk % 64 != 0; chunk is a multiple of 64, and columns >= R are zero-filled by TMA.
+                // chunk % 64 != 0; chunk, k0 and k1 (unless k1 = R) are multiples of 64, and columns >= R are zero-filled by TMA.
                 for (int m = 0; m < C::MT; ++m)
                     tma_load_2d(smem + s * C::STAGE_BYTES + m * 128 * 128, &prm.tmT, &full_bar[s], k_begin + 64 * b, 128 * m);
             }

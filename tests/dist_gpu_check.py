@@ -26,7 +26,9 @@ def main():
     ok = True
     cases = [("multmse", "tc", 1000, 768, 96, 12, np.float32), ("multmse", "simt", 301, 200, 7, 10, np.float64),
              ("multdiv", "simt", 257, 190, 6, 8, np.float64), ("greedycd", "simt", 120, 90, 5, 4, np.float64),
-             ("multmse", "tc", 515, 640, 32, 400, np.float32)]
+             ("multmse", "tc", 515, 640, 32, 400, np.float32),
+             ("multmse", "tc", 1001, 896, 64, 9, np.float32),      # 1001 rows: shards of 501 / 500 (world 2) differ in p_local % 4
+             ("multmse", "tc", 2048, 1024, 200, 6, np.float32)]    # KP = 256
     for (algname, engine, p, n, k, iters, T) in cases:
         rng = np.random.default_rng(42)
         X = np.asfortranarray(rng.random((p, n)), dtype=T)
