@@ -114,6 +114,10 @@ struct nmfb200_handle {
     int tc_tile_rows = 0;  // 0 = auto
     int tc_debug = 0;      // diagnostics: bit 3 (8) = record and print the phase clocks of the update kernel
     int tc_xchg = 1;       // multi-GPU on the tensor-core engine needs peer memory; 0 = keep multi-GPU solves on the exact engine (NCCL)
+    int tc_fused_hstep = 1;  // row-sharded solves, k <= 128: one launch for the H-step (own tiles finish the update in the numerator kernel)
+    int tc_side_stream = 1;  // row-sharded solves: run the H-Gram exchange (K4/K5) on a side stream, concurrently with the W-step
+    cudaStream_t side_stream = nullptr;
+    std::vector<cudaStream_t> vstreams;  // logical ranks (emulate_shards): one stream each for launches that wait on each other
     int emulate_shards = 0;  // > 1: run the row-sharded tensor-core algorithm with this many LOGICAL ranks on this one GPU
     int tc_precision = 0;  // 0 = bf16 operands; 1 = bf16x3 (hi/lo split of X and of the streamed factor: fp32-class products)
     nmfb200::Xchg xchg;

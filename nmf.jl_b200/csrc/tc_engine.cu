@@ -46,6 +46,13 @@ struct ShardLaunch {
     unsigned int* own_cnt = nullptr;
     int n_peer = 0;
     bf16* peer_bT[XCHG_MAX_RANKS - 1] = {};   // MODE 2: the peers' copies of F^T ([rowsT][ldT], same geometry as F.bT)
+    int64_t slot_rows = 0;                    // MODE 1: rows of one numerator slot (num_peer[o] is fp32 [slot_rows][KP])
+    const unsigned int* num_wait = nullptr;   // MODE 2: this rank's PH_NUM flag row
+    const unsigned int* den_flag = nullptr;   // MODE 0: local "Gram of the other factor is in place" flag (side stream)
+    int rank = 0;
+    unsigned int* hbt_cnt = nullptr;          // MODE 2 / 6: counter of finished own tiles
+    unsigned int* hbt_flag[XCHG_MAX_RANKS] = {};
+    const unsigned int* hbt_wait = nullptr;   // MODE 0: this rank's PH_HBT flag row
 };
 
 template <int KP>
@@ -54,6 +61,7 @@ struct TcSolver {
     cudaStream_t st;
     TcState* state;
     std::string pfx = "tc";          // prefix of the handle's named buffers (one set per logical rank)
+    std::string gram_tag = "gram_part";  // name of the tile-Gram buffer the next launch fills
     const ShardLaunch* sl = nullptr; // row-sharded launch extras for the NEXT launch_update (reset by the caller)
     bool defer_gram_reduce = false;  // the caller will run gram_conv_reduce_kernel itself
     bool last_fused_gram = false;
@@ -68,9 +76,9 @@ struct TcSolver {
     void launch_update(int mode, const Factor& F, const Factor& O, const bf16* Xs, int Kdim, float lambda, float delta,
                        float* num_io, float* conv_override = nullptr, int gram = -1, float* gram_dst = nullptr, bool pdl = false) {
         UpdateParams prm;
-        const bool fused_gram = gram >= 0 && KP <= 128 && (mode == 0 || mode == 2);
+        const bool fused_gram = gram >= 0 && KP <= 128 && (mode == 0 || mode == 2 || mode == 6);
         std::memset(&prm, 0, sizeof(prm));
-        prm.gram_part = fused_gram ? h->buf_t<float>(pfx + ".gram_part", (size_t)std::max(F.tiles, 1) * KP * KP) : nullptr;
+        prm.gram_part = fused_gram ? h->buf_t<float>(pfx + "." + gram_tag, (size_t)std::max(F.tiles, 1) * KP * KP) : nullptr;
         prm.tmF32 = make_tmap_f32(F.m, KP, (uint64_t)F.R, KP, (uint32_t)F.tile_rows);
         prm.tmT = make_tmap_bf16(F.bT, (uint64_t)F.R, (uint64_t)F.rowsT, (uint64_t)F.ldT, KP);
         prm.tile_rows = F.tile_rows;
@@ -86,6 +94,15 @@ struct TcSolver {
             prm.n_peer = sl->n_peer;
             for (int j = 0; j < sl->n_peer; ++j)
                 prm.tmT_peer[j] = make_tmap_bf16(sl->peer_bT[j], (uint64_t)F.R, (uint64_t)F.rowsT, (uint64_t)F.ldT, KP);
+            if (mode == 1 || mode == 6)
+                for (int o = 0; o < sl->G; ++o)
+                    prm.tmNum[o] = make_tmap_f32(sl->num_peer[o], KP, (uint64_t)sl->slot_rows, KP, (uint32_t)F.tile_rows);
+            prm.num_wait = sl->num_wait;
+            prm.den_flag = sl->den_flag;
+            prm.rank = sl->rank;
+            prm.hbt_cnt = sl->hbt_cnt;
+            for (int j = 0; j < XCHG_MAX_RANKS; ++j) prm.hbt_flag[j] = sl->hbt_flag[j];
+            prm.hbt_wait = sl->hbt_wait;
         }
         prm.tmB = make_tmap_bf16(O.bT, (uint64_t)Kdim, KP, (uint64_t)O.ldT, KP);
         prm.tmFhi = make_tmap_bf16(F.hi, KP, (uint64_t)F.R, KP, (uint32_t)F.tile_rows);
@@ -102,14 +119,15 @@ struct TcSolver {
         prm.state = state;
         prm.R = F.R; prm.Kdim = Kdim; prm.lambda = lambda; prm.delta = delta;
         const int smem = UpdCfg<KP>::SMEM_BYTES;
-        const bool timed = h->time_kernels == 1 && mode != 2;
+        const bool timed = h->time_kernels == 1 && mode != 2 && mode != 6;
         if (timed) NMF_CUDA(cudaEventRecord(h->next_event(), st));
         void (*kern)(const UpdateParams) = mode == 0   ? mu_update_kernel<KP, 0>
                                            : mode == 1 ? mu_update_kernel<KP, 1>
                                            : mode == 2 ? mu_update_kernel<KP, 2>
                                            : mode == 3 ? mu_update_kernel<KP, 3>
                                            : mode == 4 ? mu_update_kernel<KP, 4>
-                                                       : mu_update_kernel<KP, 5>;
+                                           : mode == 5 ? mu_update_kernel<KP, 5>
+                                                       : mu_update_kernel<KP, 6>;
         // pdl: programmatic dependent launch -- start streaming X while the preceding reduce kernel is still running
         launch_k(kern, dim3((unsigned)F.tiles), dim3(UpdCfg<KP>::THREADS), (size_t)smem, st, pdl, prm);
         if (timed) NMF_CUDA(cudaEventRecord(h->next_event(), st));
@@ -134,7 +152,7 @@ struct TcSolver {
         // ~128 CTAs at most, each a multiple of 64 rows and at least 256
         g.chunk = (int)std::max<int64_t>(256, round_up(ceil_div(std::max(k1 - k0, 1), 128), 64));
         const int grid = (int)std::max<int64_t>(1, ceil_div(k1 - k0, g.chunk));
-        g.part = h->buf_t<float>(pfx + ".gram_part", (size_t)grid * KP * KP);
+        g.part = h->buf_t<float>(pfx + "." + gram_tag, (size_t)grid * KP * KP);
         g.state = state;
         g.R = F.R;
         g.k0 = k0;
@@ -162,6 +180,7 @@ struct TcSolver {
         NMF_CUDA(cudaFuncSetAttribute(mu_update_kernel<KP, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, UpdCfg<KP>::SMEM_BYTES));
         NMF_CUDA(cudaFuncSetAttribute(mu_update_kernel<KP, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, UpdCfg<KP>::SMEM_BYTES));
         NMF_CUDA(cudaFuncSetAttribute(mu_update_kernel<KP, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, UpdCfg<KP>::SMEM_BYTES));
+        NMF_CUDA(cudaFuncSetAttribute(mu_update_kernel<KP, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, UpdCfg<KP>::SMEM_BYTES));
         NMF_CUDA(cudaFuncSetAttribute(gram_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, GramCfg<KP>::SMEM_BYTES));
         done = true;
     }
@@ -720,6 +739,12 @@ void tc_solve(nmfb200_handle* h, const SolveArgs& a, float* W, int64_t ldw, floa
     }
 }
 
-void tc_release(nmfb200_handle* h) { xchg_teardown(h); }
+void tc_release(nmfb200_handle* h) {
+    xchg_teardown(h);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    h->side_stream = nullptr;
+    for (cudaStream_t vs : h->vstreams) cudaStreamDestroy(vs);
+    h->vstreams.clear();
+}
 
 }  // namespace nmfb200

@@ -6,11 +6,12 @@
 // Ownership.  W rows and the matching rows of X belong to one rank.  The rows of H' (128-row tiles) are divided too:
 // rank o OWNS tiles [o*tpo, (o+1)*tpo) -- it alone applies the multiplicative ratio to them -- and every rank keeps a
 // complete bf16 copy of H' transposed (the B operand of its W-step).  One iteration (multupd.jl:95-115), per rank:
-//   K1  mu_update_kernel<KP,1>   partial numerators (W_g' X_g)' of ALL H tiles, each tile stored straight into the slot its
-//                                 OWNER keeps for this rank (peer stores over NVLink); the last tile for an owner raises NUM
-//   K2  shard_post_kernel        waits NUM (all ranks) and PW; W'W = sum of the ranks' partial Grams (rank order), bf16 hi/lo;
-//                                 stop_condition of the PREVIOUS iteration (its W-side sums travelled with PW)
-//   K3  mu_update_kernel<KP,2>   own tiles only: numerators = sum of the G slots in rank order, Den by tcgen05, ratio,
+//   K2  shard_post_kernel        waits PW; W'W = sum of the ranks' partial Grams (rank order), bf16 hi/lo; stop_condition of the
+//                                 PREVIOUS iteration (its W-side sums travelled with PW).  Overlaps K7 in front and K1 behind (PDL)
+//   K1  mu_update_kernel<KP,1>   partial numerators (W_g' X_g)' of ALL H tiles; each tile is staged in shared memory and sent by
+//                                 bulk TMA stores into the slot its OWNER keeps for this rank (NVLink); the last tile for an
+//                                 owner raises NUM
+//   K3  mu_update_kernel<KP,2>   own tiles only: waits NUM (all ranks); numerators = sum of the G slots in rank order, Den by tcgen05, ratio,
 //                                 new rows -> local fp32 / hi / lo, and the transposed bf16 tile by TMA store into EVERY
 //                                 rank's copy of H'^T (the all-gather); per-tile Gram by tcgen05
 //   K4  shard_push_kernel        partial Gram H'H over the own tiles + H-side stop sums -> every rank's slot; raises H
@@ -89,16 +90,19 @@ __device__ __forceinline__ void shard_signal(const ShardDev& x, int phase, unsig
 
 // ---- K4 / K7: partial Gram of this rank's tiles + its stop_condition partial sums -> every rank's slot ----------------
 // blocks [0, gram_blocks): 4 lanes per Gram element (as gram_reduce_kernel); the next 2*KP/32 blocks: quantity q (0 = dev,
-// 1 = sum) of 32 components over this rank's tiles, in Float64.  The last block to finish raises `phase`.
+// 1 = sum) of 32 components over this rank's tiles, in Float64.  Everything is reduced into THIS rank's copy of its slot;
+// the last block to finish then copies the finished slot (KP*KP floats + 2*KP doubles) to every peer with coalesced 16-byte
+// stores and raises `phase` -- one burst per peer instead of 4-byte stores and a system-scope fence per block.
 __global__ void __launch_bounds__(256) shard_push_kernel(ShardDev x, int phase, unsigned int epoch, const float* __restrict__ gpart,
-                                                         int nparts, int KP, int gram_blocks, size_t slot_off,
+                                                         int nparts, int KP, int gram_blocks, size_t slot_off, size_t slot_bytes,
                                                          const float* __restrict__ conv_part, int tiles, unsigned int* ticket,
                                                          const TcState* st) {
-    pdl_launch_dependents();  // the next H-step may start streaming X now; it waits for us before it reads anything we write
+    pdl_launch_dependents();  // the kernel behind us may set itself up now; it synchronises with us through flags / griddepcontrol.wait
     if (st->converged) return;
     __shared__ double red[8][32];
     __shared__ int is_last;
     const int nelem = KP * KP;
+    char* mine = x.arena[x.rank] + slot_off;
     if ((int)blockIdx.x < gram_blocks) {
         const int t = blockIdx.x * blockDim.x + threadIdx.x;
         const int sub = t & 3, i = t >> 2;
@@ -115,8 +119,7 @@ __global__ void __launch_bounds__(256) shard_push_kernel(ShardDev x, int phase, 
         }
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        if (i < nelem && sub == 0)
-            for (int j = 0; j < x.G; ++j) ((float*)(x.arena[j] + slot_off))[i] = acc;
+        if (i < nelem && sub == 0) ((float*)mine)[i] = acc;
     } else {
         const int cblock = blockIdx.x - gram_blocks, cbs = KP / 32;
         const int q = cblock / cbs, cb = cblock % cbs;
@@ -131,15 +134,34 @@ __global__ void __launch_bounds__(256) shard_push_kernel(ShardDev x, int phase, 
             double tot = red[0][lane];
 #pragma unroll
             for (int i = 1; i < 8; ++i) tot += red[i][lane];
-            for (int j = 0; j < x.G; ++j) ((double*)(x.arena[j] + slot_off + (size_t)nelem * sizeof(float)))[q * KP + c] = tot;
+            ((double*)(mine + (size_t)nelem * sizeof(float)))[q * KP + c] = tot;
         }
     }
-    __threadfence_system();
+    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
     __syncthreads();
     if (!is_last) return;
     if (threadIdx.x == 0) *ticket = 0u;
+    __threadfence();
+    // the slot is complete in local memory: one coalesced copy per peer (gram_blocks == 0: only the sums part is fresh)
+    const size_t first = gram_blocks > 0 ? 0 : (size_t)nelem * sizeof(float);
+    const int n16 = (int)((slot_bytes - first) / 16);
+    const uint4* src = (const uint4*)(mine + first);
+    for (int i0 = threadIdx.x; i0 < n16; i0 += 4 * 256) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (i0 + u * 256 < n16) v[u] = __ldcg(src + i0 + u * 256);
+        for (int j = 0; j < x.G; ++j) {
+            if (j == x.rank) continue;
+            uint4* dst = (uint4*)(x.arena[j] + slot_off + first);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i0 + u * 256 < n16) dst[i0 + u * 256] = v[u];
+        }
+    }
+    __syncthreads();
     shard_signal(x, phase, epoch);
 }
 
@@ -150,13 +172,13 @@ __global__ void __launch_bounds__(256) shard_post_kernel(ShardDev x, int phaseA,
                                                          size_t slots_off, size_t slot_stride, int KP, int k, int do_P,
                                                          float* __restrict__ P, bf16* __restrict__ Phi, bf16* __restrict__ Plo,
                                                          double* __restrict__ acc, int acc_off, int h_fixed, int decide, float tol,
-                                                         TcState* st) {
+                                                         TcState* st, unsigned int* done_flag, unsigned int* done_ticket) {
     pdl_launch_dependents();  // a dependent update kernel may set itself up; it waits for our completion before it reads
     if (st->converged) return;
     if (phaseA >= 0) shard_wait(x, phaseA, epochA);
     if (phaseB >= 0) shard_wait(x, phaseB, epochB);
     __shared__ float devs[256];
-    __shared__ int fail;
+    __shared__ int fail, is_last;
     const int nelem = KP * KP;
     const char* base = x.arena[x.rank] + slots_off;
     if (blockIdx.x == 0) {
@@ -168,17 +190,27 @@ __global__ void __launch_bounds__(256) shard_post_kernel(ShardDev x, int phaseA,
         }
         __syncthreads();
         if (decide) conv_decide(acc, KP, k, tol, st, devs, &fail);
-        return;
+    } else if (do_P) {
+        const int i = (blockIdx.x - 1) * blockDim.x + threadIdx.x;
+        if (i < nelem) {
+            float v = 0.f;
+            for (int j = 0; j < x.G; ++j) v += __ldcg((const float*)(base + (size_t)j * slot_stride) + i);
+            P[i] = v;
+            const bf16 hi = __float2bfloat16_rn(v);
+            Phi[i] = hi;
+            Plo[i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        }
     }
-    if (!do_P) return;
-    const int i = (blockIdx.x - 1) * blockDim.x + threadIdx.x;
-    if (i < nelem) {
-        float v = 0.f;
-        for (int j = 0; j < x.G; ++j) v += __ldcg((const float*)(base + (size_t)j * slot_stride) + i);
-        P[i] = v;
-        const bf16 hi = __float2bfloat16_rn(v);
-        Phi[i] = hi;
-        Plo[i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    if (done_flag == nullptr) return;
+    // side-stream use: the W-step running concurrently polls done_flag before its denominator blocks
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(done_ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        *done_ticket = 0u;
+        __threadfence();
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(done_flag), "r"(epochA) : "memory");
     }
 }
 
@@ -186,7 +218,11 @@ __global__ void __launch_bounds__(256) shard_post_kernel(ShardDev x, int phaseA,
 // <<<1, 32>>> each; signal for every hosted rank first, then wait (logical ranks share one stream: a kernel that waited
 // for a flag raised by a kernel queued behind it would never finish)
 __global__ void shard_signal_kernel(ShardDev x, int phase, unsigned int epoch) { shard_signal(x, phase, epoch); }
-__global__ void shard_wait_kernel(ShardDev x, int phase, unsigned int epoch) { shard_wait(x, phase, epoch); }  // <<<1, 32>>>
+__global__ void shard_wait_kernel(ShardDev x, int phase, unsigned int epoch, const TcState* st) {  // <<<1, 32>>>
+    pdl_launch_dependents();  // a dependent W-step may set itself up; its producer waits for our completion before the first load
+    if (st != nullptr && st->converged) return;  // the loop has stopped: nobody raises this flag any more
+    shard_wait(x, phase, epoch);
+}
 
 // copy a 2D region of this rank's arena (rows x width bytes at byte offset off, row pitch `pitch`; 16-byte granules) into
 // every other rank's arena at the same place; the last block raises `phase` (phase < 0: no flag)
@@ -297,14 +333,16 @@ struct ShardRank {  // one (logical) rank hosted by this process
     int64_t p = 0, ldx = 0, row0 = 0;    // this rank's rows [row0, row0 + p) of the (logical) whole
     bf16 *Xr = nullptr, *Xc = nullptr;
     Factor W, H, Hown;
+    float* h_gram_part = nullptr;        // tile Grams of the own H rows (K3 -> K4)
+    int h_gram_parts = 0;
     int own_tiles = 0;                   // H tiles (of height geom.trH) this rank owns
     int64_t own_r0 = 0, own_r1 = 0;
     TcState* state = nullptr;
     double* acc = nullptr;
-    unsigned int* ticket = nullptr;      // arena-resident counters
-    unsigned int* own_cnt = nullptr;
+    unsigned int* ticket = nullptr;      // arena-resident counters: [0] K7, [1] K4, [2] K3 (PH_HBT), [3] K5 done, [4] copy kernels,
+    unsigned int* own_cnt = nullptr;     //   [5] the "Gram of H is in place" flag itself; own_cnt: K1's per-owner tile counters
     ShardDev dev;
-    ShardLaunch sl1, sl3, sl6;
+    ShardLaunch sl1, sl3, sl6, slf;
     TcSolver<KP> s;
 };
 
@@ -343,8 +381,8 @@ void tc_solve_sharded_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64
 
     const int V = emulate ? G : 1;  // logical ranks hosted here
     std::vector<ShardRank<KP>> R(V);
-    // K3 works on its own H rows in tiles of 64 when there are many ranks (more CTAs for the same rows)
-    const int tr3 = (geom.trH == 128 && G >= 4 && KP <= 128) ? 64 : geom.trH;
+    // K3 works on its own H rows in tiles of 64 (twice the CTAs for the same rows: K3 is latency-, not bandwidth-bound)
+    const int tr3 = (geom.trH == 128 && KP <= 128) ? 64 : geom.trH;
     for (int v = 0; v < V; ++v) {
         ShardRank<KP>& r = R[v];
         r.g = emulate ? v : h->rank;
@@ -397,6 +435,7 @@ void tc_solve_sharded_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64
         // K1: where this rank's partial numerators go
         ShardLaunch& s1 = r.sl1;
         s1.G = G; s1.tiles_per_owner = geom.tpo; s1.tiles_total = geom.tilesH; s1.own_cnt = r.own_cnt;
+        s1.slot_rows = (int64_t)geom.slot_rows;
         for (int o = 0; o < G; ++o) {
             s1.num_peer[o] = (float*)((char*)xc.arena[o] + geom.off_num) + (size_t)r.g * geom.slot_rows * KP;
             s1.num_flag[o] = (unsigned int*)xc.arena[o] + PH_NUM * XCHG_MAX_RANKS + r.g;
@@ -405,11 +444,31 @@ void tc_solve_sharded_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64
         ShardLaunch& s3 = r.sl3;
         s3.tile0 = (int)(r.own_r0 / tr3);
         s3.num_row0 = (int)r.own_r0;
+        s3.G = G;
+        s3.num_wait = (const unsigned int*)arena + PH_NUM * XCHG_MAX_RANKS;
+        s3.own_cnt = r.ticket + 2;
+        for (int j = 0; j < G; ++j) s3.num_flag[j] = (unsigned int*)xc.arena[j] + PH_HBT * XCHG_MAX_RANKS + r.g;
         s3.n_peer = 0;
         for (int j = 0; j < G; ++j)
             if (j != r.g) s3.peer_bT[s3.n_peer++] = (bf16*)((char*)xc.arena[j] + geom.off_hbt);
         if (KP > 128) s3.n_peer = 0;  // no staged epilogue at KP = 256: the slab is pushed by shard_copy2d_kernel
         r.sl6.wait_first = 1;
+        r.sl6.den_flag = r.ticket + 5;
+        r.sl6.G = G;
+        s3.rank = r.g;
+        s3.hbt_cnt = r.ticket + 2;
+        for (int j = 0; j < G; ++j) s3.hbt_flag[j] = (unsigned int*)xc.arena[j] + PH_HBT * XCHG_MAX_RANKS + r.g;
+        // fused H-step (MODE 6): K1's and K3's arguments in one launch; tiles are visited starting behind the own range
+        ShardLaunch& sf = r.slf;
+        sf = s1;
+        sf.rank = r.g;
+        sf.tile0 = (r.g + 1) * geom.tpo < geom.tilesH ? (r.g + 1) * geom.tpo : 0;
+        sf.num_row0 = (int)r.own_r0;
+        sf.num_wait = s3.num_wait;
+        sf.hbt_cnt = s3.hbt_cnt;
+        for (int j = 0; j < G; ++j) sf.hbt_flag[j] = s3.hbt_flag[j];
+        sf.n_peer = s3.n_peer;
+        for (int j = 0; j < XCHG_MAX_RANKS - 1; ++j) sf.peer_bT[j] = s3.peer_bT[j];
         r.s = TcSolver<KP>{h, st, r.state};
         r.s.pfx = r.pfx;
 
@@ -431,13 +490,15 @@ void tc_solve_sharded_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64
     auto push_W = [&](ShardRank<KP>& r, unsigned int e, bool with_gram, bool with_conv) {
         launch_k(shard_push_kernel, dim3((with_gram ? gram_blocks : 0) + 2 * (KP / 32)), dim3(256), 0, st, false, r.dev, (int)PH_PW, e,
                  (const float*)r.s.last_gram_part, with_gram ? r.s.last_gram_parts : 0, KP, with_gram ? gram_blocks : 0,
-                 pw_off(e) + (size_t)r.g * gslot, (const float*)r.W.conv, with_conv ? r.W.tiles : 0, r.ticket, (const TcState*)r.state);
+                 pw_off(e) + (size_t)r.g * gslot, gslot, (const float*)r.W.conv, with_conv ? r.W.tiles : 0, r.ticket, (const TcState*)r.state);
         h->launches += 1;
     };
-    auto post_W = [&](ShardRank<KP>& r, unsigned int e_pw, bool wait_num, unsigned int e_num, bool do_P, bool decide) {
-        launch_k(shard_post_kernel, dim3(do_P ? post_blocks : 1), dim3(256), 0, st, false, r.dev, (int)PH_PW, e_pw, wait_num ? (int)PH_NUM : -1,
-                 e_num, pw_off(e_pw), gslot, KP, (int)k, do_P ? 1 : 0, r.W.P, r.W.Phi, r.W.Plo, r.acc, 0, a.update_H ? 0 : 1, decide ? 1 : 0, tol,
-                 r.state);
+    // K2: W'W of all ranks (epoch e_pw) -> P_W hi/lo, W-side stop sums, optionally the stop decision.  `chain`: launched as a
+    // programmatic dependent of the push kernel in front of it (it synchronises with that kernel through the PW flag)
+    auto post_W = [&](ShardRank<KP>& r, unsigned int e_pw, bool do_P, bool decide, bool chain) {
+        launch_k(shard_post_kernel, dim3(do_P ? post_blocks : 1), dim3(256), 0, st, chain, r.dev, (int)PH_PW, e_pw, -1, 0u, pw_off(e_pw), gslot, KP,
+                 (int)k, do_P ? 1 : 0, r.W.P, r.W.Phi, r.W.Plo, r.acc, 0, a.update_H ? 0 : 1, decide ? 1 : 0, tol, r.state, (unsigned int*)nullptr,
+                 (unsigned int*)nullptr);
         h->launches += 1;
     };
 
@@ -452,7 +513,7 @@ void tc_solve_sharded_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64
     {
         const unsigned int eb = ++xc.epoch;
         for (auto& r : R) shard_signal_kernel<<<1, 32, 0, st>>>(r.dev, (int)PH_BAR, eb);
-        for (auto& r : R) shard_wait_kernel<<<1, 32, 0, st>>>(r.dev, (int)PH_BAR, eb);
+        for (auto& r : R) shard_wait_kernel<<<1, 32, 0, st>>>(r.dev, (int)PH_BAR, eb, (const TcState*)nullptr);
         h->launches += 2 * V;
     }
     NMF_CUDA(cudaEventRecord(e1, st));
@@ -463,6 +524,26 @@ void tc_solve_sharded_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64
     bool converged = false;
     float devmax = 0.f;
     std::vector<TcState> hs(V);
+    // logical ranks: one stream each for the fused H-step launch (see `fused` below)
+    cudaEvent_t ev_vfork = nullptr, ev_vjoin[XCHG_MAX_RANKS] = {};
+    if (emulate) {
+        while ((int)h->vstreams.size() < V) {
+            cudaStream_t vs;
+            NMF_CUDA(cudaStreamCreateWithFlags(&vs, cudaStreamNonBlocking));
+            h->vstreams.push_back(vs);
+        }
+        NMF_CUDA(cudaEventCreateWithFlags(&ev_vfork, cudaEventDisableTiming));
+        for (int v = 0; v < V; ++v) NMF_CUDA(cudaEventCreateWithFlags(&ev_vjoin[v], cudaEventDisableTiming));
+    }
+    // side stream for K4 / K5 (real ranks only; option tc_side_stream=0 keeps everything in stream order)
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    if (!emulate && h->tc_side_stream && a.update_H && h->time_kernels != 2) {
+        if (!h->side_stream) NMF_CUDA(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+        side = h->side_stream;
+        NMF_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        NMF_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    }
     const bool covers = [&] {
         bool ok = true;
         for (auto& r : R) ok = ok && tc_objective_covers(r.X, r.p, n, r.ldx);
@@ -476,10 +557,10 @@ void tc_solve_sharded_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64
             const int64_t rows = r.own_r1 - r.own_r0;
             const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(148, ceil_div(rows * KP / 4, 256)));
             shard_copy2d_kernel<<<blocks, 256, 0, st>>>(r.dev, geom.off_hm + (size_t)r.own_r0 * KP * sizeof(float), (size_t)KP * sizeof(float),
-                                                        (int)rows, KP / 4, (int)PH_GATHER, eg, r.ticket, (const TcState*)nullptr);
+                                                        (int)rows, KP / 4, (int)PH_GATHER, eg, r.ticket + 4, (const TcState*)nullptr);
         }
         for (auto& r : R) {
-            shard_wait_kernel<<<1, 32, 0, st>>>(r.dev, (int)PH_GATHER, eg);
+            shard_wait_kernel<<<1, 32, 0, st>>>(r.dev, (int)PH_GATHER, eg, (const TcState*)nullptr);
             split_hi_lo_kernel<<<ew_grid(n * KP), 256, 0, st>>>(r.H.m, n * KP, r.H.hi, r.H.lo);
         }
         h->launches += 3 * V;
@@ -521,22 +602,70 @@ void tc_solve_sharded_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64
         for (int64_t i = 0; i < batch; ++i) {
             const unsigned int e = ++xc.epoch;
             h->mark("start");
+            // fused H-step (MODE 6): CTAs of own tiles WAIT inside the kernel for the other ranks' partials.  Real ranks run
+            // concurrently by construction.  Logical ranks must be made concurrent: one stream each, and only when every CTA of
+            // every logical rank fits on the GPU at once (one CTA per SM) -- otherwise the emulation keeps K1 and K3 separate.
+            const bool fused = a.update_H && KP <= 128 && h->tc_fused_hstep != 0 && (!emulate || (int64_t)G * geom.tilesH <= 120);
             if (a.update_H) {
+                // K2 first: its inputs (the PW slots of the previous iteration) are ready long before K1 ends, and K1 only needs
+                // its results in the epilogue of K3
+                for (auto& r : R) post_W(r, e_prev, true, i > 0, pdl && V == 1);
+                h->mark("K2 W'W + decision");
+                if (fused && emulate) NMF_CUDA(cudaEventRecord(ev_vfork, st));
+                for (auto& r : R) {  // K1 + K3 in one launch (MODE 6): CTAs of own tiles finish the update themselves
+                    if (!fused) break;
+                    if (emulate) {
+                        NMF_CUDA(cudaStreamWaitEvent(h->vstreams[r.g], ev_vfork, 0));
+                        r.s.st = h->vstreams[r.g];
+                    }
+                    r.slf.epoch = e;
+                    r.s.sl = &r.slf;
+                    r.s.defer_gram_reduce = true;
+                    r.s.num_splits = G;
+                    r.s.num_split_stride = (int64_t)geom.slot_rows * KP;
+                    r.s.gram_tag = "gram_partH";
+                    r.s.launch_update(6, r.H, r.W, r.Xr, (int)r.p, lh, delta, (float*)((char*)xc.arena[r.g] + geom.off_num), nullptr, 1, nullptr,
+                                      pdl && !emulate);
+                    if (emulate) {
+                        NMF_CUDA(cudaEventRecord(ev_vjoin[r.g], r.s.st));
+                        r.s.st = st;
+                    }
+                    r.s.num_splits = 1;
+                    r.s.num_split_stride = 0;
+                    r.s.defer_gram_reduce = false;
+                    r.s.sl = nullptr;
+                    r.h_gram_part = r.s.last_gram_part;
+                    r.h_gram_parts = r.own_tiles;
+                    r.s.gram_tag = "gram_part";
+                    if (r.own_tiles == 0) {  // the other ranks wait for this rank's PH_HBT too
+                        shard_signal_kernel<<<1, 32, 0, st>>>(r.dev, (int)PH_HBT, e);
+                        h->launches += 1;
+                    }
+                }
+                if (fused && emulate)
+                    for (auto& r : R) NMF_CUDA(cudaStreamWaitEvent(st, ev_vjoin[r.g], 0));
+                if (fused) h->mark("K1+K3 fused H-step");
                 for (auto& r : R) {  // K1
+                    if (fused) break;
                     r.sl1.epoch = e;
                     r.s.sl = &r.sl1;
                     r.s.launch_update(1, r.H, r.W, r.Xr, (int)r.p, lh, delta, nullptr, nullptr, -1, nullptr, pdl);
                     r.s.sl = nullptr;
                 }
-                h->mark("K1 numerators");
-                for (auto& r : R) post_W(r, e_prev, r.own_tiles > 0, e, true, i > 0);  // K2
-                h->mark("K2 W'W + decision");
+                if (!fused) h->mark("K1 numerators");
                 for (auto& r : R) {  // K3
-                    if (r.own_tiles == 0) continue;
+                    if (fused) break;
+                    if (r.own_tiles == 0) {  // nothing to update here, but the other ranks wait for this rank's PH_HBT too
+                        shard_signal_kernel<<<1, 32, 0, st>>>(r.dev, (int)PH_HBT, e);
+                        h->launches += 1;
+                        continue;
+                    }
+                    r.sl3.epoch = e;
                     r.s.sl = &r.sl3;
                     r.s.defer_gram_reduce = true;
                     r.s.num_splits = G;
                     r.s.num_split_stride = (int64_t)geom.slot_rows * KP;
+                    r.s.gram_tag = "gram_partH";   // K4 reads these on the side stream while K6 fills the W-step's tile Grams
                     r.s.launch_update(2, r.Hown, r.W, r.Xr, (int)r.p, lh, delta, (float*)((char*)xc.arena[r.g] + geom.off_num), nullptr,
                                       KP <= 128 ? 1 : -1, nullptr, false);
                     r.s.num_splits = 1;
@@ -547,45 +676,67 @@ void tc_solve_sharded_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64
                         r.s.launch_gram_parts(r.H, (int)r.own_r0, (int)r.own_r1);
                         const int w16 = (int)(round_up((r.own_r1 - r.own_r0) * sizeof(bf16), 16) / 16);
                         shard_copy2d_kernel<<<64, 256, 0, st>>>(r.dev, geom.off_hbt + (size_t)r.own_r0 * sizeof(bf16), (size_t)geom.ldT * sizeof(bf16),
-                                                                KP, w16, -1, 0u, r.ticket, (const TcState*)r.state);
+                                                                KP, w16, (int)PH_HBT, e, r.ticket + 4, (const TcState*)r.state);
                         h->launches += 1;
                     }
+                    r.h_gram_part = r.s.last_gram_part;
+                    r.h_gram_parts = r.s.last_gram_parts;
+                    r.s.gram_tag = "gram_part";
                 }
-                h->mark("K3 own rows of H");
+                if (!fused) h->mark("K3 own rows of H");
+                // K4 + K5 only feed the denominator blocks at the END of the W-step: a real rank runs them on a side stream,
+                // concurrently with the W-step's main loop (logical ranks share one stream; the flags are then already up)
+                cudaStream_t sk = side ? side : st;
+                if (side) {
+                    NMF_CUDA(cudaEventRecord(ev_fork, st));
+                    NMF_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+                }
                 for (auto& r : R) {  // K4
                     const bool any = r.own_tiles > 0;
-                    launch_k(shard_push_kernel, dim3(gram_blocks + 2 * (KP / 32)), dim3(256), 0, st, false, r.dev, (int)PH_H, e,
-                             (const float*)r.s.last_gram_part, any ? r.s.last_gram_parts : 0, KP, gram_blocks, geom.off_ph + (size_t)r.g * gslot,
-                             (const float*)r.Hown.conv, any ? r.Hown.tiles : 0, r.ticket, (const TcState*)r.state);
+                    launch_k(shard_push_kernel, dim3(gram_blocks + 2 * (KP / 32)), dim3(256), 0, sk, false, r.dev, (int)PH_H, e,
+                             (const float*)r.h_gram_part, any ? r.h_gram_parts : 0, KP, gram_blocks, geom.off_ph + (size_t)r.g * gslot,
+                             gslot, (const float*)r.Hown.conv, any ? (fused ? r.own_tiles : r.Hown.tiles) : 0, r.ticket + 1, (const TcState*)r.state);
                     h->launches += 1;
                 }
-                h->mark("K4 push H'H");
+                if (!side) h->mark("K4 push H'H");
                 for (auto& r : R) {  // K5
-                    launch_k(shard_post_kernel, dim3(post_blocks), dim3(256), 0, st, false, r.dev, (int)PH_H, e, -1, 0u, geom.off_ph, gslot, KP,
-                             (int)k, 1, r.H.P, r.H.Phi, r.H.Plo, r.acc, 2 * KP, 0, 0, tol, r.state);
+                    launch_k(shard_post_kernel, dim3(post_blocks), dim3(256), 0, sk, false, r.dev, (int)PH_H, e, -1, 0u, geom.off_ph, gslot, KP,
+                             (int)k, 1, r.H.P, r.H.Phi, r.H.Plo, r.acc, 2 * KP, 0, 0, tol, r.state, r.ticket + 5, r.ticket + 3);
                     h->launches += 1;
                 }
-                h->mark("K5 HH'");
+                if (!side) h->mark("K5 HH'");
+                if (side) NMF_CUDA(cudaEventRecord(ev_join, side));
+                // every rank's rows of H'^T must be in this rank's copy before the W-step streams it: its producer thread polls
+                // the PH_HBT flags itself (real ranks); logical ranks share a stream, a wait kernel keeps the order simple there
+                for (auto& r : R) {
+                    if (!emulate) break;
+                    launch_k(shard_wait_kernel, dim3(1), dim3(32), 0, st, false, r.dev, (int)PH_HBT, e, (const TcState*)r.state);
+                    h->launches += 1;
+                }
             }
             for (auto& r : R) {  // K6
+                r.sl6.epoch = e;
+                r.sl6.den_flag = a.update_H ? r.ticket + 5 : nullptr;
+                r.sl6.hbt_wait = a.update_H ? (const unsigned int*)xc.arena[r.g] + PH_HBT * XCHG_MAX_RANKS : nullptr;
                 r.s.sl = &r.sl6;
                 r.s.defer_gram_reduce = true;
                 const int gramW = (a.update_H && KP <= 128) ? 1 : -1;
-                r.s.launch_update(0, r.W, r.H, r.Xc, (int)n, lw, delta, nullptr, nullptr, gramW, nullptr, pdl && a.update_H);
+                r.s.launch_update(0, r.W, r.H, r.Xc, (int)n, lw, delta, nullptr, nullptr, gramW, nullptr, pdl && a.update_H && emulate);
                 r.s.defer_gram_reduce = false;
                 r.s.sl = nullptr;
                 if (a.update_H && KP > 128) r.s.launch_gram_parts(r.W);
             }
             h->mark("K6 W-step");
+            if (side && a.update_H) NMF_CUDA(cudaStreamWaitEvent(st, ev_join, 0));  // everything later on the main stream sees K5's results
             for (auto& r : R) push_W(r, e, a.update_H, true);  // K7
             h->mark("K7 push W'W");
             e_prev = e;
             if (!a.update_H)
-                for (auto& r : R) post_W(r, e_prev, false, 0u, false, true);  // H fixed: nothing to ride on, decide every iteration
+                for (auto& r : R) post_W(r, e_prev, false, true, false);  // H fixed: nothing to ride on, decide every iteration
         }
         NMF_CUDA(cudaEventRecord(e2, st));  // end of the timed loop (re-recorded per batch; the last one counts)
         if (a.update_H)
-            for (auto& r : R) post_W(r, e_prev, false, 0u, false, true);  // decision of the last iteration of the batch
+            for (auto& r : R) post_W(r, e_prev, false, true, false);  // decision of the last iteration of the batch
         enq += batch;
         NMF_CUDA(cudaGetLastError());
         for (int v = 0; v < V; ++v) NMF_CUDA(cudaMemcpyAsync(&hs[v], R[v].state, sizeof(TcState), cudaMemcpyDeviceToHost, st));
@@ -633,6 +784,12 @@ void tc_solve_sharded_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64
         NMF_CUDA(cudaMemcpy2DAsync(Hc, ldh * sizeof(float), Hd, k * sizeof(float), k * sizeof(float), n, cudaMemcpyDeviceToHost, st));
     }
     NMF_CUDA(cudaStreamSynchronize(st));
+    if (side) NMF_CUDA(cudaStreamSynchronize(side));
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (ev_vfork) cudaEventDestroy(ev_vfork);
+    for (cudaEvent_t ev : ev_vjoin)
+        if (ev) cudaEventDestroy(ev);
     float ms_up = 0, ms_loop = 0;
     cudaEventElapsedTime(&ms_up, e0, e1);
     cudaEventElapsedTime(&ms_loop, e1, e2);

@@ -17,7 +17,8 @@ constexpr int PH_H = 1;       // src's updated H rows (bf16 transposed slab), it
 constexpr int PH_PW = 2;      // src's partial Gram W'W and W-side stop sums are here
 constexpr int PH_BAR = 3;     // plain barrier (rank alignment before a timed region)
 constexpr int PH_GATHER = 4;  // src's fp32 H rows are here (end of solve / verbose)
-constexpr int N_PHASES = 5;
+constexpr int PH_HBT = 5;     // src's updated rows of H'^T (bf16 slab) are in my copy: the W-step may start streaming
+constexpr int N_PHASES = 6;
 
 // ---- kernel parameter block (tensor maps must live in __grid_constant__ param space) ---------------
 struct UpdateParams {
@@ -59,6 +60,15 @@ struct UpdateParams {
     unsigned int* own_cnt;                     // MODE 1: [G] local counters "tiles of owner o finished"
     int n_peer;                                // MODE 2: transposed tile is also stored into n_peer peer copies of F^T
     CUtensorMap tmT_peer[XCHG_MAX_RANKS - 1];
+    CUtensorMap tmNum[XCHG_MAX_RANKS];         // MODE 1: [owner] -> this rank's slot in the owner's arena, fp32 [slot_rows][KP], box 32 x tile_rows
+    const unsigned int* num_wait;              // MODE 2: this rank's PH_NUM flag row (G entries): wait for `epoch` before reading the slots
+    int rank;                                  // this rank
+    unsigned int* hbt_cnt;                     // MODE 2 / 6: local counter "own tiles finished"
+    unsigned int* hbt_flag[XCHG_MAX_RANKS];    // MODE 2 / 6: [j] -> flags[PH_HBT][my rank] in rank j's arena
+    const unsigned int* hbt_wait;              // MODE 0 (W-step): this rank's PH_HBT flag row: the producer waits for `epoch` from every
+                                               // rank before its first operand load (the rows of H'^T arrive from the peers)
+    const unsigned int* den_flag;              // MODE 0 (W-step): local flag "the Gram of the other factor for `epoch` is in place" -- set by
+                                               // shard_post_kernel, which runs on a side stream concurrently with this kernel's main loop
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
@@ -109,6 +119,11 @@ __device__ __forceinline__ uint32_t pack_bf16x2(bf16 lo, bf16 hi) {
 // MODE 4: MultUpdate(:div): Xs is the quotient panel Q, no denominator MMAs; F <- F * Num / (colsum + lambda) (multupd.jl:177-179,189-191).
 // MODE 3: GreedyCD gradient: G = F*P - Xs*O (+lambda) -> num_io, per-CTA max_r D[i,r] -> conv_part (greedycd.jl:117-137).
 // MODE 5: MultUpdate(:div) after div_fused_kernel: no main loop, numerators = sum of the k-split partials in num_io, then as MODE 4.
+// MODE 6: row-sharded fused H-step (tc_shard.cuh): every CTA computes the partial numerators of one H tile over this rank's rows of
+//         X; a CTA whose tile belongs to ANOTHER rank sends it there (as MODE 1) and exits; a CTA whose tile this rank OWNS waits
+//         for the other ranks' partials, adds them to its own (rank order) and finishes like MODE 0 -- ratio, the new rows in all
+//         forms (the transposed bf16 tile also into every peer's copy), tile Gram, stop sums.  Tiles are visited starting behind
+//         the own range, so the CTAs that only send are dispatched before the CTAs that wait.
 template <int KP, int MODE>
 __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const __grid_constant__ UpdateParams prm) {
     using C = UpdCfg<KP>;
@@ -123,7 +138,8 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
     uint32_t* stop_slot = tmem_slot + 1;
     float* conv_s = (float*)(smem + C::RING_BYTES + 1024);  // [4 warps][2][KP]
     // Staged epilogue (KP <= 128, modes that write the factor): the ring is idle once the accumulators are complete
-    constexpr bool STAGED = (KP <= 128) && (MODE == 0 || MODE == 2 || MODE == 4 || MODE == 5);
+    constexpr bool STAGED = (KP <= 128) && (MODE == 0 || MODE == 2 || MODE == 4 || MODE == 5 || MODE == 6);
+    constexpr bool FUSED = (MODE == 6);
     uint8_t* const SF = smem;                              // fp32 tile:  KP/32 boxes of 128 rows x 128 B
     uint8_t* const SH = SF + (KP / 32) * 16384;            // bf16 hi:    KP/64 boxes
     uint8_t* const SL = SH + (KP / 64) * 16384;            // bf16 lo
@@ -139,7 +155,12 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
         prm.timing[16 + 2 * blockIdx.x] = gt;
     }
     const int tile_rows = prm.tile_rows;
-    const int tile = (int)blockIdx.x + prm.tile0;
+    int tile_ = (int)blockIdx.x + prm.tile0;
+    if (FUSED && tile_ >= prm.tiles_total) tile_ -= prm.tiles_total;
+    const int tile = tile_;
+    const bool owner = !FUSED || (tile / prm.tiles_per_owner == prm.rank);     // CTA-uniform
+    const bool push = (MODE == 1) || (FUSED && !owner);                         // this CTA only sends its numerators away
+    const int out_idx = FUSED ? tile - prm.rank * prm.tiles_per_owner : (int)blockIdx.x;   // index into gram_part / conv_part
     const int r0 = tile * tile_rows;
     const uint32_t a_bytes = (uint32_t)tile_rows * 128u;
     const int nkb = (MODE == 2 || MODE == 5) ? 0 : (prm.Kdim + 63) / 64;
@@ -189,6 +210,15 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
             int arow = tile * nkb * tile_rows;   // tile-contiguous X: k-block kb of this tile starts at panel row arow0 + kb*tile_rows
             const uint32_t num_tx = a_bytes + (uint32_t)C::B_BYTES;
             if (prm.wait_first) pdl_wait();   // sharded W-step: the other factor's rows arrive from peers, confirmed by the kernel in front
+            if (MODE == 0 && prm.hbt_wait != nullptr) {   // ... or by the peers' PH_HBT flags themselves
+                for (int j = 0; j < prm.G; ++j) {
+                    const long long t0 = clock64();
+                    while ((int)(ld_acquire_sys(prm.hbt_wait + j) - prm.epoch) < 0) {
+                        if (clock64() - t0 > 20000000000LL) { printf("nmfb200: H'^T flag wait timed out (rank %d, epoch %u)\n", j, prm.epoch); __trap(); }
+                    }
+                }
+                asm volatile("fence.proxy.async;" ::: "memory");   // the peers' writes -> the TMA loads below
+            }
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(&empty_bar[s], ph ^ 1u);
                 mbar_arrive_expect_tx(&full_bar[s], num_tx);
@@ -198,8 +228,17 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                 dst += C::STAGE_BYTES;
                 if (++s == C::STAGES) { s = 0; ph ^= 1u; dst = smem; }
             }
-            if (NPRE > 0) {
+            if (NPRE > 0 && owner) {
                 pdl_wait();  // the Gram of the other factor comes from the preceding (reduce) kernel
+                if (MODE == 0 && prm.den_flag != nullptr) {   // ... or, row-sharded, from a kernel on the side stream: wait for its flag
+                    const long long t0 = clock64();
+                    unsigned int seen;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(prm.den_flag) : "memory");
+                        if (clock64() - t0 > 20000000000LL) { printf("nmfb200: Gram flag wait timed out (epoch %u)\n", prm.epoch); __trap(); }
+                    } while ((int)(seen - prm.epoch) < 0);
+                    asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy writes of P hi/lo -> the TMA loads below
+                }
 #pragma unroll
                 for (int bd = 0; bd < NPRE; ++bd) {  // Den = Fhi*Phi + Fhi*Plo + Flo*Phi
                     mbar_wait(&empty_bar[s], ph ^ 1u);
@@ -238,7 +277,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
             if (nkb > 0) { block(tmem_base, 0u); kb = 1; TSTAMP(1); }   // first operands have landed
             for (; kb < nkb; ++kb) block(tmem_base, 1u);
             TSTAMP(2);                                                   // numerator blocks issued
-            if (NPRE > 0) {
+            if (NPRE > 0 && owner) {
                 block(tmem_base + KP, 0u);
 #pragma unroll 1
                 for (int bd = 1; bd < NPRE; ++bd) block(tmem_base + KP, 1u);
@@ -262,6 +301,21 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
         if (threadIdx.x == 64) TSTAMP(5);    // accumulators complete
         do {
         if (stop) break;  // converged while this kernel was streaming (PDL): leave F untouched
+        if ((MODE == 2 || (FUSED && owner)) && prm.G > 0) {
+            // row-sharded H-step: every rank's partial numerators for these rows must have landed in this rank's slots
+            // (MODE 6: every OTHER rank's -- this rank's own partial is in TMEM)
+            const int t = (int)threadIdx.x - 64;
+            if (t < prm.G && !(FUSED && t == prm.rank)) {
+                const long long t0 = clock64();
+                while ((int)(ld_acquire_sys(prm.num_wait + t) - prm.epoch) < 0) {
+                    if (clock64() - t0 > 20000000000LL) {
+                        printf("nmfb200: numerator flag wait timed out (waiting for rank %d, epoch %u)\n", t, prm.epoch);
+                        __trap();
+                    }
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
         float* convw = conv_s + q * 2 * KP;
         const float lambda = prm.lambda, delta = prm.delta;
         float gcd_rowmax = -1.0f;
@@ -274,15 +328,19 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
             uint32_t num_u[32], den_u[32];
             float f[32];
             if (MODE != 2 && MODE != 5) tmem_ld32(t_lane + c0, num_u);
-            if (MODE != 1 && MODE != 4 && MODE != 5) tmem_ld32(t_lane + KP + c0, den_u);
-            if (MODE == 1) {
+            if (MODE != 1 && MODE != 4 && MODE != 5 && !push) tmem_ld32(t_lane + KP + c0, den_u);
+            if (push) {
                 tmem_ld_wait();
-                if (valid) {
-                    // sharded: straight into the slot the OWNER of this tile keeps for this rank (peer memory over NVLink)
-                    float* base = prm.G > 0 ? prm.num_peer[tile / prm.tiles_per_owner] +
-                                                  ((size_t)(tile % prm.tiles_per_owner) * tile_rows + (32 * q + lane)) * KP
-                                            : prm.num_io + (size_t)row * KP;
-                    float4* dst = (float4*)(base + c0);
+                if (prm.G > 0) {
+                    // row-sharded: the tile goes to the slot its OWNER keeps for this rank.  Staged in the (idle) ring as the
+                    // SWIZZLE_128B image and sent by bulk TMA stores below: NVLink carries 16 KB bursts, not 16-byte stores.
+                    const int rr = 32 * q + lane;
+                    uint8_t* sf = SF + (c0 >> 5) * 16384 + rr * 128;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *(uint4*)(sf + ((j ^ (rr & 7)) << 4)) = make_uint4(num_u[4 * j], num_u[4 * j + 1], num_u[4 * j + 2], num_u[4 * j + 3]);
+                } else if (valid) {
+                    float4* dst = (float4*)(prm.num_io + (size_t)row * KP + c0);
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         dst[j] = make_float4(__uint_as_float(num_u[4 * j]), __uint_as_float(num_u[4 * j + 1]),
@@ -307,7 +365,20 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                         float4 v = __ldcg((const float4*)nbase + j);
                         acc[4 * j] = v.x; acc[4 * j + 1] = v.y; acc[4 * j + 2] = v.z; acc[4 * j + 3] = v.w;
                     }
-                    for (int sp = 1; sp < prm.num_splits; ++sp) {
+                    int sp = 1;
+                    for (; sp + 1 < prm.num_splits; sp += 2) {   // two slots per trip: 16 independent 16-byte loads in flight
+                        const float4* n0 = (const float4*)(nbase + (size_t)sp * prm.num_split_stride);
+                        const float4* n1 = (const float4*)(nbase + (size_t)(sp + 1) * prm.num_split_stride);
+                        float4 v0[8], v1[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { v0[j] = __ldcg(n0 + j); v1[j] = __ldcg(n1 + j); }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {   // slot order is kept: (acc + slot sp) + slot sp+1
+                            acc[4 * j] = (acc[4 * j] + v0[j].x) + v1[j].x; acc[4 * j + 1] = (acc[4 * j + 1] + v0[j].y) + v1[j].y;
+                            acc[4 * j + 2] = (acc[4 * j + 2] + v0[j].z) + v1[j].z; acc[4 * j + 3] = (acc[4 * j + 3] + v0[j].w) + v1[j].w;
+                        }
+                    }
+                    for (; sp < prm.num_splits; ++sp) {
                         const float4* ns = (const float4*)(nbase + (size_t)sp * prm.num_split_stride);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
@@ -323,6 +394,30 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                 for (int j = 0; j < 32; ++j) { f[j] = 0.f; if (MODE == 2 || MODE == 5) num_u[j] = 0u; }
             }
             tmem_ld_wait();
+            if (FUSED) {
+                // numerator = sum over the ranks IN RANK ORDER of their partials: slot s for s != rank, TMEM for s == rank
+                if (valid) {
+                    const float* nbase = prm.num_io + (size_t)(row - prm.num_row0) * KP + c0;
+                    float acc[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+                    for (int sp = 0; sp < prm.num_splits; ++sp) {
+                        if (sp == prm.rank) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(num_u[j]);
+                        } else {
+                            const float4* ns = (const float4*)(nbase + (size_t)sp * prm.num_split_stride);
+                            float4 v[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = __ldcg(ns + j);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) { acc[4 * j] += v[j].x; acc[4 * j + 1] += v[j].y; acc[4 * j + 2] += v[j].z; acc[4 * j + 3] += v[j].w; }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) num_u[j] = __float_as_uint(acc[j]);
+                }
+            }
             if (MODE == 3) {
                 float g[32];
 #pragma unroll
@@ -419,18 +514,25 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
             convw[c0 + lane] = d2[0];
             convw[KP + c0 + lane] = s2[0];
         }
-        if (MODE == 1 && prm.G > 0) {
-            // this tile's partial numerators are in the owner's slot: count it, and the last tile for an owner raises the flag
-            __threadfence_system();
+        if (push && prm.G > 0) {
+            // send the staged tile, count it, and the last tile for an owner raises that owner's NUM flag
+            fence_proxy_async();
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (threadIdx.x == 64) {
-                const int owner = tile / prm.tiles_per_owner;
-                const int owned = min(prm.tiles_per_owner, prm.tiles_total - owner * prm.tiles_per_owner);
-                const unsigned prev = atomicAdd(prm.own_cnt + owner, 1u);
+                const int owner_rank = tile / prm.tiles_per_owner;
+                const int srow = (tile % prm.tiles_per_owner) * tile_rows;
+#pragma unroll
+                for (int b = 0; b < KP / 32; ++b) tma_store_2d(&prm.tmNum[owner_rank], SF + b * 16384, 32 * b, srow);
+                tma_store_commit();
+                tma_store_wait_all<0>();
+                asm volatile("fence.proxy.async;" ::: "memory");
+                __threadfence_system();
+                const int owned = min(prm.tiles_per_owner, prm.tiles_total - owner_rank * prm.tiles_per_owner);
+                const unsigned prev = atomicAdd(prm.own_cnt + owner_rank, 1u);
                 if (prev == (unsigned)owned - 1u) {
-                    prm.own_cnt[owner] = 0u;
+                    prm.own_cnt[owner_rank] = 0u;
                     __threadfence_system();
-                    st_release_sys(prm.num_flag[owner], prm.epoch);
+                    st_release_sys(prm.num_flag[owner_rank], prm.epoch);
                 }
             }
         }
@@ -445,7 +547,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                 for (int i = 1; i < 8; ++i) m = fmaxf(m, conv_s[i]);
                 prm.conv_part[blockIdx.x] = m;
             }
-        } else if (MODE != 1) {
+        } else if (MODE != 1 && !push) {
             if constexpr (STAGED) {
                 fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA / tensor-core (async) proxy
                 tc_fence_before();     // our TMEM reads are complete (the Gram below reuses the Num columns)
@@ -465,7 +567,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                     }
                     tma_store_2d(&prm.tmT, ST, r0, 0);
                     if (tile_rows > 64) tma_store_2d(&prm.tmT, ST + KP * 128, r0 + 64, 0);
-                    if (MODE == 2) {   // row-sharded H-step: the all-gather of the new rows is these stores into the peers' copies
+                    if (MODE == 2 || FUSED) {   // row-sharded H-step: the all-gather of the new rows is these stores into the peers' copies
                         for (int j = 0; j < prm.n_peer; ++j) {
                             tma_store_2d(&prm.tmT_peer[j], ST, r0, 0);
                             if (tile_rows > 64) tma_store_2d(&prm.tmT_peer[j], ST + KP * 128, r0 + 64, 0);
@@ -488,7 +590,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
             const int t = threadIdx.x - 64;  // 0..255
             for (int i = t; i < 2 * KP; i += 256) {
                 float s = conv_s[i] + conv_s[2 * KP + i] + conv_s[4 * KP + i] + conv_s[6 * KP + i];
-                prm.conv_part[(size_t)blockIdx.x * 2 * KP + i] = s;
+                prm.conv_part[(size_t)out_idx * 2 * KP + i] = s;
             }
             if constexpr (STAGED) {
                 if (prm.gram_part != nullptr) {
@@ -496,7 +598,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                     tc_fence_after();
                     if (threadIdx.x == 64) TSTAMP(8);  // tile Gram MMAs complete
                     const int a = 32 * q + lane;
-                    float* gp = prm.gram_part + ((size_t)blockIdx.x * KP + a) * KP;
+                    float* gp = prm.gram_part + ((size_t)out_idx * KP + a) * KP;
 #pragma unroll 1
                     for (int c0 = chalf * (KP / 2); c0 < (chalf + 1) * (KP / 2); c0 += 32) {
                         uint32_t v[32];
@@ -515,9 +617,17 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                 if (threadIdx.x == 64) {
                     TSTAMP(9);                 // tile Gram written
                     tma_store_wait_all<0>();
-                    if (MODE == 2 && prm.n_peer > 0) {   // peer copies written through the async proxy: order them before the flag
-                        asm volatile("fence.proxy.async;" ::: "memory");   // that the following kernel publishes at system scope
+                    if ((MODE == 2 || FUSED) && prm.G > 0) {
+                        // the peers' copies were written through the async proxy: order them, count this tile, and the last own
+                        // tile tells every rank that this rank's rows of H'^T are in place (PH_HBT)
+                        asm volatile("fence.proxy.async;" ::: "memory");
                         __threadfence_system();
+                        const unsigned own_n = FUSED ? (unsigned)min(prm.tiles_per_owner, prm.tiles_total - prm.rank * prm.tiles_per_owner) : gridDim.x;
+                        if (atomicAdd(prm.hbt_cnt, 1u) == own_n - 1u) {
+                            *prm.hbt_cnt = 0u;
+                            __threadfence_system();
+                            for (int j = 0; j < prm.G; ++j) st_release_sys(prm.hbt_flag[j], prm.epoch);
+                        }
                     }
                     TSTAMP(10);                // bulk stores have read their staging buffers
                 }

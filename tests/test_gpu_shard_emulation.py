@@ -43,11 +43,16 @@ def _solve(NMF, X, W0, H0, G, alg, check_every=7, opts=()):
     (515, 640, 32, 9, 4),       # the shape the round-1 multi-GPU check used (p % G != 0)
     (640, 300, 200, 6, 2),      # KP = 256: no staged epilogue, slab pushed by the copy kernel, Gram by gram_kernel
     (700, 200, 24, 8, 8),       # fewer H tiles (2) than ranks: six ranks own nothing
+    (1536, 4224, 64, 4, 4),     # 33 H tiles x 4 ranks > 120 CTAs: the emulation keeps K1 and K3 as separate launches (see tc_shard.cuh)
+    (1024, 768, 96, 12, -4),    # negative G: option tc_fused_hstep=0, the unfused H-step (K1 + K3) on the small shape as well
 ])
 def test_emulated_shards_vs_oracle_and_unsharded(NMF, oracle, p, n, k, iters, G):
+    opts = ()
+    if G < 0:
+        G, opts = -G, (("tc_fused_hstep", 0),)
     X, W0, H0 = _problem(NMF, p, n, k, seed=p + n + k + G)
     alg = NMF.MultUpdate(np.float32, obj="mse", maxiter=iters, tol=1e-9)
-    r, W, H = _solve(NMF, X, W0, H0, G, alg)
+    r, W, H = _solve(NMF, X, W0, H0, G, alg, opts=opts)
     r1, W1, H1 = _solve(NMF, X, W0, H0, 0, alg)
     Wo, Ho = W0.copy(order="F"), H0.copy(order="F")
     ro = oracle.solve(oracle.MultUpdate(np.float32, obj="mse", maxiter=iters, tol=1e-9), X, Wo, Ho)
