@@ -114,7 +114,8 @@ struct nmfb200_handle {
     int tc_tile_rows = 0;  // 0 = auto
     int tc_debug = 0;      // diagnostics: bit 3 (8) = record and print the phase clocks of the update kernel
     int tc_xchg = 1;       // multi-GPU on the tensor-core engine needs peer memory; 0 = keep multi-GPU solves on the exact engine (NCCL)
-    int tc_fused_hstep = 1;  // row-sharded solves, k <= 128: one launch for the H-step (own tiles finish the update in the numerator kernel)
+    int tc_fused_hstep = -1; // row-sharded solves, k <= 128: 1 = one launch for the H-step (own tiles finish the update in the numerator
+                             // kernel), 0 = numerators / slot sum / ratio as three launches, -1 = auto (fused for two ranks)
     int tc_side_stream = 1;  // row-sharded solves: run the H-Gram exchange (K4/K5) on a side stream, concurrently with the W-step
     cudaStream_t side_stream = nullptr;
     std::vector<cudaStream_t> vstreams;  // logical ranks (emulate_shards): one stream each for launches that wait on each other

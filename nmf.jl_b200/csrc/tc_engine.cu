@@ -83,8 +83,10 @@ struct TcSolver {
         prm.tmT = make_tmap_bf16(F.bT, (uint64_t)F.R, (uint64_t)F.rowsT, (uint64_t)F.ldT, KP);
         prm.tile_rows = F.tile_rows;
         prm.timing = (h->tc_debug & 8) ? (long long*)h->buf("tc.timing", (16 + 2 * 4096) * sizeof(long long)) : nullptr;
+        if ((h->tc_debug & 64) && mode == 0) prm.timing = nullptr;   // bit 6: keep the H-step's clocks (the W-step would overwrite them)
         const uint64_t nkb = (uint64_t)ceil_div(Kdim, 64);
         const int tile0 = sl ? sl->tile0 : 0;
+        prm.timing_cta = mode == 6 ? F.tiles - 1 : 0;   // fused sharded H-step: the last CTA works on a tile this rank owns
         prm.tmA = make_tmap_bf16(Xs, 64, (uint64_t)(tile0 + F.tiles) * nkb * F.tile_rows, 64, (uint32_t)F.tile_rows);
         if (sl) {
             prm.tile0 = sl->tile0; prm.wait_first = sl->wait_first; prm.num_row0 = sl->num_row0;

@@ -214,6 +214,28 @@ __global__ void __launch_bounds__(256) shard_post_kernel(ShardDev x, int phaseA,
     }
 }
 
+// ---- Ksum: the partial numerators of this rank's own H rows, summed over the ranks' slots in rank order ----------------
+// One coalesced 16-byte load per slot and thread (the epilogue of the update kernel would read the same data row by row,
+// 16 bytes per lane at a 512-byte stride: measured ~2.3 us per slot there, ~3 us for ALL slots here).
+__global__ void __launch_bounds__(256) shard_slot_sum_kernel(ShardDev x, unsigned int epoch, size_t num_off, size_t slot_stride4, int64_t n4,
+                                                             float4* __restrict__ out, const TcState* st) {
+    pdl_launch_dependents();  // the ratio kernel behind us may set itself up; it waits for our completion before it reads `out`
+    if (st->converged) return;
+    shard_wait(x, PH_NUM, epoch);
+    const float4* base = (const float4*)(x.arena[x.rank] + num_off);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 v[XCHG_MAX_RANKS];
+#pragma unroll
+        for (int j = 0; j < XCHG_MAX_RANKS; ++j)
+            if (j < x.G) v[j] = __ldcg(base + (size_t)j * slot_stride4 + i);
+        float4 a = v[0];
+#pragma unroll
+        for (int j = 1; j < XCHG_MAX_RANKS; ++j)
+            if (j < x.G) { a.x += v[j].x; a.y += v[j].y; a.z += v[j].z; a.w += v[j].w; }
+        out[i] = a;
+    }
+}
+
 // ---- small helpers ----------------------------------------------------------------------------------------------
 // <<<1, 32>>> each; signal for every hosted rank first, then wait (logical ranks share one stream: a kernel that waited
 // for a flag raised by a kernel queued behind it would never finish)
@@ -333,6 +355,7 @@ struct ShardRank {  // one (logical) rank hosted by this process
     int64_t p = 0, ldx = 0, row0 = 0;    // this rank's rows [row0, row0 + p) of the (logical) whole
     bf16 *Xr = nullptr, *Xc = nullptr;
     Factor W, H, Hown;
+    float* numsum = nullptr;             // [slot_rows][KP]: numerators of the own H rows, summed over the ranks (Ksum -> K3)
     float* h_gram_part = nullptr;        // tile Grams of the own H rows (K3 -> K4)
     int h_gram_parts = 0;
     int own_tiles = 0;                   // H tiles (of height geom.trH) this rank owns
@@ -424,6 +447,7 @@ void tc_solve_sharded_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64
         r.Hown.tiles = (int)ceil_div(r.own_r1 - r.own_r0, tr3);
         r.Hown.conv = h->buf_t<float>(r.pfx + ".H.conv", (size_t)std::max(r.Hown.tiles, 1) * 2 * KP);
         H.conv = r.Hown.conv;
+        r.numsum = h->buf_t<float>(r.pfx + ".numsum", std::max<size_t>(geom.slot_rows, 1) * KP);
         r.state = (TcState*)h->buf(r.pfx + ".state", sizeof(TcState));
         r.acc = h->buf_t<double>(r.pfx + ".acc", 4 * KP);
         r.ticket = (unsigned int*)(arena + geom.off_cnt + 64);
@@ -445,7 +469,7 @@ void tc_solve_sharded_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64
         s3.tile0 = (int)(r.own_r0 / tr3);
         s3.num_row0 = (int)r.own_r0;
         s3.G = G;
-        s3.num_wait = (const unsigned int*)arena + PH_NUM * XCHG_MAX_RANKS;
+        s3.num_wait = nullptr;   // Ksum has waited for the NUM flags and summed the slots
         s3.own_cnt = r.ticket + 2;
         for (int j = 0; j < G; ++j) s3.num_flag[j] = (unsigned int*)xc.arena[j] + PH_HBT * XCHG_MAX_RANKS + r.g;
         s3.n_peer = 0;
@@ -464,7 +488,7 @@ void tc_solve_sharded_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64
         sf.rank = r.g;
         sf.tile0 = (r.g + 1) * geom.tpo < geom.tilesH ? (r.g + 1) * geom.tpo : 0;
         sf.num_row0 = (int)r.own_r0;
-        sf.num_wait = s3.num_wait;
+        sf.num_wait = (const unsigned int*)arena + PH_NUM * XCHG_MAX_RANKS;
         sf.hbt_cnt = s3.hbt_cnt;
         for (int j = 0; j < G; ++j) sf.hbt_flag[j] = s3.hbt_flag[j];
         sf.n_peer = s3.n_peer;
@@ -605,7 +629,11 @@ void tc_solve_sharded_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64
             // fused H-step (MODE 6): CTAs of own tiles WAIT inside the kernel for the other ranks' partials.  Real ranks run
             // concurrently by construction.  Logical ranks must be made concurrent: one stream each, and only when every CTA of
             // every logical rank fits on the GPU at once (one CTA per SM) -- otherwise the emulation keeps K1 and K3 separate.
-            const bool fused = a.update_H && KP <= 128 && h->tc_fused_hstep != 0 && (!emulate || (int64_t)G * geom.tilesH <= 120);
+            // Measured (profiles/r2_scaling.md): the fused form wins at G = 2 (0.239 vs 0.251 ms per iteration) and loses from
+            // G = 4 on (0.300 vs 0.277 ms at G = 8): its 128/G owner CTAs sum the G slots row by row, 2.3 us per slot.  Default
+            // (tc_fused_hstep = -1): fused for two ranks, K1 + Ksum + K3 for more.
+            const bool want_fused = h->tc_fused_hstep < 0 ? G == 2 : h->tc_fused_hstep != 0;
+            const bool fused = a.update_H && KP <= 128 && want_fused && (!emulate || (int64_t)G * geom.tilesH <= 120);
             if (a.update_H) {
                 // K2 first: its inputs (the PW slots of the previous iteration) are ready long before K1 ends, and K1 only needs
                 // its results in the epilogue of K3
@@ -653,6 +681,15 @@ void tc_solve_sharded_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64
                     r.s.sl = nullptr;
                 }
                 if (!fused) h->mark("K1 numerators");
+                for (auto& r : R) {  // Ksum
+                    if (fused || r.own_tiles == 0) continue;
+                    const int64_t n4 = (r.own_r1 - r.own_r0) * KP / 4;
+                    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(148 * 4, ceil_div(n4, 256)));
+                    launch_k(shard_slot_sum_kernel, dim3(blocks), dim3(256), 0, st, false, r.dev, e, geom.off_num, geom.slot_rows * KP / 4, n4,
+                             (float4*)r.numsum, (const TcState*)r.state);
+                    h->launches += 1;
+                }
+                if (!fused) h->mark("Ksum slots");
                 for (auto& r : R) {  // K3
                     if (fused) break;
                     if (r.own_tiles == 0) {  // nothing to update here, but the other ranks wait for this rank's PH_HBT too
@@ -663,11 +700,9 @@ void tc_solve_sharded_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64
                     r.sl3.epoch = e;
                     r.s.sl = &r.sl3;
                     r.s.defer_gram_reduce = true;
-                    r.s.num_splits = G;
-                    r.s.num_split_stride = (int64_t)geom.slot_rows * KP;
+                    r.s.num_splits = 1;
                     r.s.gram_tag = "gram_partH";   // K4 reads these on the side stream while K6 fills the W-step's tile Grams
-                    r.s.launch_update(2, r.Hown, r.W, r.Xr, (int)r.p, lh, delta, (float*)((char*)xc.arena[r.g] + geom.off_num), nullptr,
-                                      KP <= 128 ? 1 : -1, nullptr, false);
+                    r.s.launch_update(2, r.Hown, r.W, r.Xr, (int)r.p, lh, delta, r.numsum, nullptr, KP <= 128 ? 1 : -1, nullptr, pdl);
                     r.s.num_splits = 1;
                     r.s.num_split_stride = 0;
                     r.s.defer_gram_reduce = false;
@@ -807,4 +842,20 @@ void tc_solve_sharded_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64
     out->kernel_launches = h->launches;
     out->hot_kernel_ms = h->drain_event_pairs(&out->hot_kernel_launches);
     h->report_marks(iters);
+    if ((h->tc_debug & 8) && h->rank == 0) {  // diagnostics: the LAST update launch (a W-step); and see tc_debug & 64 for the H-step
+        std::vector<long long> tv(16 + 2 * 4096);
+        NMF_CUDA(cudaMemcpy(tv.data(), h->buf("tc.timing", tv.size() * sizeof(long long)), tv.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        const long long* t = tv.data();
+        const int nct = std::min(geom.tilesH, 4096);
+        long long s_min = LLONG_MAX;
+        for (int c = 0; c < nct; ++c) s_min = std::min(s_min, t[16 + 2 * c]);
+        fprintf(stderr, "[nmfb200] last timed launch: per-CTA exit (us after the first entry):");
+        for (int c = 0; c < nct; c += std::max(1, nct / 16)) fprintf(stderr, " %d:%.1f", c, (t[17 + 2 * c] - s_min) * 1e-3);
+        fprintf(stderr, " last:%.1f\n", (t[17 + 2 * (nct - 1)] - s_min) * 1e-3);
+        static const char* names[13] = {"entry", "first_operands", "numerators_issued", "mma_issued", "pred_complete", "accum_complete",
+                                        "ratio_done", "all_warps_done", "gram_mma_done", "gram_written", "stores_done", "exit", "peers_arrived"};
+        fprintf(stderr, "[nmfb200] timed CTA phase clocks (cycles since entry):");
+        for (int i = 1; i < 13; ++i) fprintf(stderr, " %s=%lld", names[i], t[i] - t[0]);
+        fprintf(stderr, "\n");
+    }
 }

@@ -45,7 +45,8 @@ struct UpdateParams {
     int64_t ldT;
     int R, Kdim;
     int tile_rows;      // rows of F owned by one CTA (<= 128, multiple of 8); the TMA boxes of A / Fhi / Flo have this many rows
-    long long* timing;  // diagnostics (tc_debug bit 3): CTA 0 records clock64() at its phase boundaries, see TSTAMP
+    long long* timing;  // diagnostics (tc_debug bit 3): CTA timing_cta records clock64() at its phase boundaries, see TSTAMP
+    int timing_cta;
     float lambda, delta;
     // ---- row-sharded solves (tc_shard.cuh); all zero for a single-GPU launch
     int tile0;          // first tile of this launch (MODE 2: the rank's own H rows only)
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
     static_assert(!STAGED || (KP / 32 + 2 * (KP / 64)) * 16384 + 2 * KP * 128 <= C::RING_BYTES, "staging does not fit in the ring");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#define TSTAMP(i) do { if (prm.timing != nullptr && blockIdx.x == 0) prm.timing[i] = clock64(); } while (0)
+#define TSTAMP(i) do { if (prm.timing != nullptr && (int)blockIdx.x == prm.timing_cta) prm.timing[i] = clock64(); } while (0)
     if (threadIdx.x == 0) TSTAMP(0);
     if (prm.timing != nullptr && threadIdx.x == 0) {  // every CTA: global timer at entry (and exit, below)
         long long gt;
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
         if (threadIdx.x == 64) TSTAMP(5);    // accumulators complete
         do {
         if (stop) break;  // converged while this kernel was streaming (PDL): leave F untouched
-        if ((MODE == 2 || (FUSED && owner)) && prm.G > 0) {
+        if ((MODE == 2 || (FUSED && owner)) && prm.G > 0 && prm.num_wait != nullptr) {
             // row-sharded H-step: every rank's partial numerators for these rows must have landed in this rank's slots
             // (MODE 6: every OTHER rank's -- this rank's own partial is in TMEM)
             const int t = (int)threadIdx.x - 64;
@@ -315,6 +316,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                 }
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (threadIdx.x == 64) TSTAMP(12);   // the other ranks' partial numerators have arrived
         }
         float* convw = conv_s + q * 2 * KP;
         const float lambda = prm.lambda, delta = prm.delta;

@@ -36,20 +36,22 @@ def _solve(NMF, X, W0, H0, G, alg, check_every=7, opts=()):
 
 
 @pytest.mark.parametrize("p,n,k,iters,G", [
-    (1024, 768, 96, 12, 2),     # KP = 128, 6 H tiles over 2 owners
+    (1024, 768, 96, 12, 2),     # KP = 128, 6 H tiles over 2 owners (two ranks: the fused H-step is the default)
+    (1024, 768, 96, 12, -2),    # negative G: the other H-step form than the default (here: K1 + Ksum + K3 for two ranks)
     (1024, 768, 96, 12, 4),     # ... over 4 owners: 2 own two tiles, 2 own one; K3 runs 64-row tiles
     (1000, 1100, 64, 10, 3),    # ragged rows (1000 = 334 + 333 + 333: shards 2, 3 start at rows not divisible by 4), ragged H tail
     (2048, 1024, 128, 8, 8),    # 8 H tiles, 8 owners
     (515, 640, 32, 9, 4),       # the shape the round-1 multi-GPU check used (p % G != 0)
     (640, 300, 200, 6, 2),      # KP = 256: no staged epilogue, slab pushed by the copy kernel, Gram by gram_kernel
     (700, 200, 24, 8, 8),       # fewer H tiles (2) than ranks: six ranks own nothing
-    (1536, 4224, 64, 4, 4),     # 33 H tiles x 4 ranks > 120 CTAs: the emulation keeps K1 and K3 as separate launches (see tc_shard.cuh)
-    (1024, 768, 96, 12, -4),    # negative G: option tc_fused_hstep=0, the unfused H-step (K1 + K3) on the small shape as well
+    (1536, 4224, 64, 4, 4),     # 33 H tiles, KP = 64
+    (1024, 768, 96, 12, -4),    # ... and the fused H-step (MODE 6: own tiles finish inside the numerator kernel) for more than two
+    (2048, 1024, 128, 8, -8),
 ])
 def test_emulated_shards_vs_oracle_and_unsharded(NMF, oracle, p, n, k, iters, G):
     opts = ()
     if G < 0:
-        G, opts = -G, (("tc_fused_hstep", 0),)
+        G, opts = -G, (("tc_fused_hstep", 0 if G == -2 else 1),)
     X, W0, H0 = _problem(NMF, p, n, k, seed=p + n + k + G)
     alg = NMF.MultUpdate(np.float32, obj="mse", maxiter=iters, tol=1e-9)
     r, W, H = _solve(NMF, X, W0, H0, G, alg, opts=opts)
