@@ -120,6 +120,7 @@ struct nmfb200_handle {
     cudaStream_t side_stream = nullptr;
     std::vector<cudaStream_t> vstreams;  // logical ranks (emulate_shards): one stream each for launches that wait on each other
     int emulate_shards = 0;  // > 1: run the row-sharded tensor-core algorithm with this many LOGICAL ranks on this one GPU
+    int tc_flush = -1;     // k-blocks per TMEM accumulation chunk of the update kernel (0 = one long chain; -1 = default: 8)
     int tc_precision = 0;  // 0 = bf16 operands; 1 = bf16x3 (hi/lo split of X and of the streamed factor: fp32-class products)
     nmfb200::Xchg xchg;
     int tc_pdl = 1;        // 1 = launch the update kernels as programmatic dependents of the reduce kernel before them
@@ -140,7 +141,10 @@ struct nmfb200_handle {
         const void* X = nullptr;
         int64_t p = 0;
         int trH = 0, trW = 0;
-        bool operator==(const XCacheKey& o) const { return epoch == o.epoch && X == o.X && p == o.p && trH == o.trH && trW == o.trW; }
+        int with_lo = 0;  // precision mode bf16x3: the remainder caches were built too
+        bool operator==(const XCacheKey& o) const {
+            return epoch == o.epoch && X == o.X && p == o.p && trH == o.trH && trW == o.trW && with_lo == o.with_lo;
+        }
     };
     std::map<std::string, XCacheKey> tc_x_cache;
 

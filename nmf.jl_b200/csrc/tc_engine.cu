@@ -63,6 +63,7 @@ struct TcSolver {
     std::string pfx = "tc";          // prefix of the handle's named buffers (one set per logical rank)
     std::string gram_tag = "gram_part";  // name of the tile-Gram buffer the next launch fills
     const ShardLaunch* sl = nullptr; // row-sharded launch extras for the NEXT launch_update (reset by the caller)
+    const bf16* Xs_lo = nullptr;     // precision mode bf16x3: the remainder panel matching the Xs of the NEXT launch_update
     bool defer_gram_reduce = false;  // the caller will run gram_conv_reduce_kernel itself
     bool last_fused_gram = false;
     float* last_gram_part = nullptr;
@@ -76,7 +77,10 @@ struct TcSolver {
     void launch_update(int mode, const Factor& F, const Factor& O, const bf16* Xs, int Kdim, float lambda, float delta,
                        float* num_io, float* conv_override = nullptr, int gram = -1, float* gram_dst = nullptr, bool pdl = false) {
         UpdateParams prm;
-        const bool fused_gram = gram >= 0 && KP <= 128 && (mode == 0 || mode == 2 || mode == 6);
+        // precision mode bf16x3 (MultUpdate :mse and the GreedyCD gradient): three passes over the k-blocks with the bf16
+        // remainders of X and of the other factor; the Gram then comes from the split stand-alone kernel, not the tile epilogue
+        const bool x3 = h->tc_precision == 1 && Xs_lo != nullptr && O.bTlo != nullptr && (mode == 0 || mode == 3);
+        const bool fused_gram = gram >= 0 && KP <= 128 && (mode == 0 || mode == 2 || mode == 6) && !x3;
         std::memset(&prm, 0, sizeof(prm));
         prm.gram_part = fused_gram ? h->buf_t<float>(pfx + "." + gram_tag, (size_t)std::max(F.tiles, 1) * KP * KP) : nullptr;
         prm.tmF32 = make_tmap_f32(F.m, KP, (uint64_t)F.R, KP, (uint32_t)F.tile_rows);
@@ -107,6 +111,13 @@ struct TcSolver {
             prm.hbt_wait = sl->hbt_wait;
         }
         prm.tmB = make_tmap_bf16(O.bT, (uint64_t)Kdim, KP, (uint64_t)O.ldT, KP);
+        if (KP <= 128 && (mode == 0 || mode == 1 || mode == 3 || mode == 6))
+            prm.flush_chunk = h->tc_flush >= 0 ? h->tc_flush : 8;   // chunked accumulation (costs nothing measurable: 4784 vs 4781 it/s at config 2)
+        if (x3) {
+            prm.x3 = 1;
+            prm.tmAlo = make_tmap_bf16(Xs_lo, 64, (uint64_t)(tile0 + F.tiles) * nkb * F.tile_rows, 64, (uint32_t)F.tile_rows);
+            prm.tmBlo = make_tmap_bf16(O.bTlo, (uint64_t)Kdim, KP, (uint64_t)O.ldT, KP);
+        }
         prm.tmFhi = make_tmap_bf16(F.hi, KP, (uint64_t)F.R, KP, (uint32_t)F.tile_rows);
         prm.tmFlo = make_tmap_bf16(F.lo, KP, (uint64_t)F.R, KP, (uint32_t)F.tile_rows);
         prm.tmPhi = make_tmap_bf16(O.Phi, KP, KP, KP, KP);
@@ -134,6 +145,7 @@ struct TcSolver {
         launch_k(kern, dim3((unsigned)F.tiles), dim3(UpdCfg<KP>::THREADS), (size_t)smem, st, pdl, prm);
         if (timed) NMF_CUDA(cudaEventRecord(h->next_event(), st));
         h->launches += 1;
+        if (x3 && mode == 0) refresh_bTlo(F);   // the new remainder, transposed, for the other factor's next hi*lo pass
         last_fused_gram = fused_gram;
         last_gram_part = prm.gram_part;
         last_gram_parts = F.tiles;
@@ -146,11 +158,20 @@ struct TcSolver {
         }
     }
 
+    void refresh_bTlo(const Factor& F) {
+        transpose_lo_kernel<<<dim3((unsigned)ceil_div(F.R, 32), KP / 32), dim3(32, 8), 0, st>>>(F.lo, F.R, KP, F.bTlo, F.ldT);
+        h->launches += 1;
+    }
     // partial Grams of rows [k0, k1) of F (k1 < 0: all rows) -> last_gram_part / last_gram_parts; no reduce
     void launch_gram_parts(const Factor& F, int k0 = 0, int k1 = -1) {
         GramParams g;
         if (k1 < 0) k1 = F.R;
+        std::memset(&g, 0, sizeof(g));
         g.tmT = make_tmap_bf16(F.bT, (uint64_t)F.R, (uint64_t)F.rowsT, (uint64_t)F.ldT, 128);
+        if (h->tc_precision == 1 && F.bTlo != nullptr) {   // T T' = hi hi' + hi lo' + lo hi'
+            g.split = 1;
+            g.tmTlo = make_tmap_bf16(F.bTlo, (uint64_t)F.R, (uint64_t)F.rowsT, (uint64_t)F.ldT, 128);
+        }
         // ~128 CTAs at most, each a multiple of 64 rows and at least 256
         g.chunk = (int)std::max<int64_t>(256, round_up(ceil_div(std::max(k1 - k0, 1), 128), 64));
         const int grid = (int)std::max<int64_t>(1, ceil_div(k1 - k0, g.chunk));
@@ -204,8 +225,8 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
     NMF_CUDA(cudaEventCreate(&e1));
     NMF_CUDA(cudaEventCreate(&e2));
 
-    bf16 *Xr = nullptr, *Xc = nullptr;
-    build_x_caches(h, &Xr, &Xc);
+    bf16 *Xr = nullptr, *Xc = nullptr, *Xr_lo = nullptr, *Xc_lo = nullptr;
+    build_x_caches(h, &Xr, &Xc, &Xr_lo, &Xc_lo);
     NMF_CUDA(cudaEventRecord(e0, st));
 
     Factor W = alloc_factor(h, "W", (int)p, KP), H = alloc_factor(h, "H", (int)n, KP);
@@ -232,6 +253,7 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
     NMF_CUDA(cudaGetLastError());
 
     TcSolver<KP> s{h, st, state};
+    if (h->tc_precision == 1) { s.refresh_bTlo(W); s.refresh_bTlo(H); }
     s.launch_gram(W, true);                   // P_W = W'W for the first H-step
     if (!a.update_H) s.launch_gram(H, true);  // H never changes: P_H once
     NMF_CUDA(cudaEventRecord(e1, st));
@@ -268,12 +290,14 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
         for (int64_t i = 0; i < batch; ++i) {
             h->mark("start");
             if (a.update_H) {
+                s.Xs_lo = Xr_lo;
                 s.launch_update(0, H, W, Xr, (int)p, lh, delta, nullptr, nullptr, 1, nullptr, pdl);  // H-step (+ tile Grams of the new H)
                 h->mark("updH");
             }
             // W-step + W'W for the next H-step (not needed if H is fixed)
             const int gramW = a.update_H ? 1 : -1;
             s.defer_gram_reduce = true;
+            s.Xs_lo = Xc_lo;
             s.launch_update(0, W, H, Xc, (int)n, lw, delta, nullptr, nullptr, gramW, nullptr, pdl);
             s.defer_gram_reduce = false;
             h->mark("updW");
@@ -587,8 +611,8 @@ void tc_solve_gcd_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t l
     NMF_CUDA(cudaEventCreate(&e0));
     NMF_CUDA(cudaEventCreate(&e1));
     NMF_CUDA(cudaEventCreate(&e2));
-    bf16 *Xr = nullptr, *Xc = nullptr;
-    build_x_caches(h, &Xr, &Xc);
+    bf16 *Xr = nullptr, *Xc = nullptr, *Xr_lo = nullptr, *Xc_lo = nullptr;
+    build_x_caches(h, &Xr, &Xc, &Xr_lo, &Xc_lo);
     NMF_CUDA(cudaEventRecord(e0, st));
 
     Factor W = alloc_factor(h, "W", (int)p, KP), H = alloc_factor(h, "H", (int)n, KP);
@@ -623,16 +647,19 @@ void tc_solve_gcd_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t l
     pack_factor_kernel<<<ew_grid(n * KP), 256, 0, st>>>(Hd, ldhd, 1, (int)n, (int)k, KP, H.m, H.hi, H.lo, H.bT, H.ldT);
     h->launches += 2;
     TcSolver<KP> s{h, st, state};
+    if (h->tc_precision == 1) { s.refresh_bTlo(W); s.refresh_bTlo(H); }
     s.launch_gram(H, true);  // P = HH' for the first W-step (greedycd.jl:117)
     NMF_CUDA(cudaEventRecord(e1, st));
 
-    auto half_step = [&](Factor& F, Factor& O, const bf16* Xs, int Kdim, float lambda, int tiles128) {
+    auto half_step = [&](Factor& F, Factor& O, const bf16* Xs, const bf16* Xs_lo, int Kdim, float lambda, int tiles128) {
         NMF_CUDA(cudaMemcpyAsync(prev, F.m, (size_t)F.R * KP * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        s.Xs_lo = Xs_lo;
         s.launch_update(3, F, O, Xs, Kdim, lambda, 0.f, G, bmax);                                  // G = F P - X O (+lambda), per-CTA max D
         max_partials_kernel<float><<<1, 256, 0, st>>>(bmax, F.tiles, bmax + maxtiles);            // p_init (:132-137)
         gcd_rows_tc_kernel<KP><<<(unsigned)ceil_div(F.R, 8), 256, 0, st>>>(F.m, G, O.P, F.R, (int)k, bmax + maxtiles, d_updates);  // :139-165
         gcd_repack_kernel<<<tiles128, 256, 0, st>>>(F.m, prev, F.R, KP, F.hi, F.lo, F.bT, F.ldT, F.conv);
         h->launches += 3;
+        if (h->tc_precision == 1) s.refresh_bTlo(F);
         s.launch_gram(F, true);                                                                   // Gram of the updated factor
     };
 
@@ -641,8 +668,8 @@ void tc_solve_gcd_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t l
     float devmax = 0.f;
     TcState hs;
     while (iters < a.maxiter && !converged) {  // one host check per iteration: the row kernel has no early-exit flag
-        half_step(W, H, Xc, (int)n, lw, tilesW);                                                   // W first (greedycd.jl:169-171)
-        if (a.update_H) half_step(H, W, Xr, (int)p, lh, tilesH);                                   // then H (:173-177)
+        half_step(W, H, Xc, Xc_lo, (int)n, lw, tilesW);                                            // W first (greedycd.jl:169-171)
+        if (a.update_H) half_step(H, W, Xr, Xr_lo, (int)p, lh, tilesH);                            // then H (:173-177)
         conv_reduce_kernel<<<4 * (KP / 32), 256, 0, st>>>(W.conv, tilesW, H.conv, tilesH, KP, (int)k, a.update_H, acc, tol, state, 1, nullptr);
         h->launches += 1;
         NMF_CUDA(cudaGetLastError());
@@ -697,6 +724,7 @@ bool tc_supported(const nmfb200_handle* h, const SolveArgs& a) {
         if (h->engine_opt != 2 && h->p * h->n < ((int64_t)1 << 20)) return false;
     }
     const bool sharded = h->comm != nullptr || h->emulate_shards > 1;
+    if (sharded && h->tc_precision == 1 && h->engine_opt != 2) return false;   // parity mode on several ranks: the exact engine
     if (a.alg == 0 && h->comm != nullptr && !h->tc_xchg) return false;   // option tc_xchg=nccl: multi-GPU solves stay on the exact engine
     if (a.alg == 0 && sharded && (h->comm ? h->nranks : h->emulate_shards) > XCHG_MAX_RANKS) return false;
     if (a.alg == 2) {                     // GreedyCD: bf16 gradients; single GPU; auto-selected for large problems only

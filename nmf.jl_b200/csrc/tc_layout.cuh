@@ -9,20 +9,24 @@
 // sequential region of HBM (instead of gathering 128-B segments from TR rows a full row pitch apart).
 // Padding rows / columns are written as zeros.  element(r, c) = X[r*sr + c*sc].
 // (a) contraction index contiguous in the source (sc == 1): direct
+// dst_lo (optional): the bf16 remainder X - bf16(X) in the same layout (precision mode bf16x3)
 __global__ void cvt_tiled_direct_kernel(const float* __restrict__ X, int64_t sr, int R, int Kdim, int TR, int nkb,
-                                        bf16* __restrict__ dst) {
+                                        bf16* __restrict__ dst, bf16* __restrict__ dst_lo) {
     const int64_t row_slot = blockIdx.x;            // tile * TR + row-in-tile (x: up to 2^31-1 rows)
     const int tile = (int)(row_slot / TR), rr = (int)(row_slot % TR);
     const int64_t r = (int64_t)tile * TR + rr;
     for (int c = blockIdx.y * blockDim.x + threadIdx.x; c < nkb * 64; c += gridDim.y * blockDim.x) {
         float v = (r < R && c < Kdim) ? X[r * sr + c] : 0.f;
         const int kb = c >> 6, cc = c & 63;
-        dst[(((int64_t)tile * nkb + kb) * TR + rr) * 64 + cc] = __float2bfloat16_rn(v);
+        const bf16 hi = __float2bfloat16_rn(v);
+        const int64_t o = (((int64_t)tile * nkb + kb) * TR + rr) * 64 + cc;
+        dst[o] = hi;
+        if (dst_lo != nullptr) dst_lo[o] = __float2bfloat16_rn(v - __bfloat162float(hi));
     }
 }
 // (b) row index contiguous in the source (sr == 1): 64 x 64 transpose through shared memory
 __global__ void cvt_tiled_transpose_kernel(const float* __restrict__ X, int64_t sc, int R, int Kdim, int TR, int nkb, int tiles,
-                                           bf16* __restrict__ dst) {
+                                           bf16* __restrict__ dst, bf16* __restrict__ dst_lo) {
     __shared__ float tile_s[64][65];
     const int kb = blockIdx.x;
     const int64_t r_base = (int64_t)blockIdx.y * 64;   // 64 consecutive logical rows
@@ -39,8 +43,12 @@ __global__ void cvt_tiled_transpose_kernel(const float* __restrict__ X, int64_t 
         int64_t r = r_base + y;
         const int tile = (int)(r / TR), rr = (int)(r % TR);
         if (tile >= tiles) continue;  // the grid is rounded up to 64-row groups
-        __nv_bfloat162 pk = __floats2bfloat162_rn(tile_s[y][threadIdx.x * 2], tile_s[y][threadIdx.x * 2 + 1]);
-        *(__nv_bfloat162*)(dst + (((int64_t)tile * nkb + kb) * TR + rr) * 64 + threadIdx.x * 2) = pk;
+        const float v0 = tile_s[y][threadIdx.x * 2], v1 = tile_s[y][threadIdx.x * 2 + 1];
+        __nv_bfloat162 pk = __floats2bfloat162_rn(v0, v1);
+        const int64_t o = (((int64_t)tile * nkb + kb) * TR + rr) * 64 + threadIdx.x * 2;
+        *(__nv_bfloat162*)(dst + o) = pk;
+        if (dst_lo != nullptr)
+            *(__nv_bfloat162*)(dst_lo + o) = __floats2bfloat162_rn(v0 - __bfloat162float(pk.x), v1 - __bfloat162float(pk.y));
     }
 }
 
@@ -58,6 +66,22 @@ __global__ void pack_factor_kernel(const float* __restrict__ S, int64_t sr, int6
         Fhi[idx] = hi;
         Flo[idx] = __float2bfloat16_rn(v - __bfloat162float(hi));
         FbT[(int64_t)a * ldT + r] = hi;
+    }
+}
+// FbTlo[a][r] = Flo[r][a]: the transposed copy of the bf16 remainder (B operand of the hi*lo pass, precision mode bf16x3)
+__global__ void transpose_lo_kernel(const bf16* __restrict__ Flo, int R, int KP, bf16* __restrict__ FbTlo, int64_t ldT) {
+    __shared__ unsigned short t[32][33];
+    const unsigned short* src = (const unsigned short*)Flo;
+    unsigned short* dst = (unsigned short*)FbTlo;
+    const int r0 = blockIdx.x * 32, a0 = blockIdx.y * 32;
+    for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+        const int r = r0 + y, a = a0 + threadIdx.x;
+        t[y][threadIdx.x] = (r < R) ? src[(size_t)r * KP + a] : (unsigned short)0;
+    }
+    __syncthreads();
+    for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+        const int a = a0 + y, r = r0 + threadIdx.x;
+        if (r < R) dst[(size_t)a * ldT + r] = t[threadIdx.x][y];
     }
 }
 __global__ void unpack_factor_kernel(const float* __restrict__ Fm, int R, int k, int KP, float* __restrict__ D, int64_t sr, int64_t sa) {
@@ -124,6 +148,7 @@ struct Factor {  // one factor in row-factor layout
     int64_t ldT = 0;
     float* m = nullptr;
     bf16 *hi = nullptr, *lo = nullptr, *bT = nullptr;
+    bf16* bTlo = nullptr;  // precision mode bf16x3 only: transposed copy of lo
     float* P = nullptr;  // Gram of THIS factor (k x k), fp32 accumulator
     bf16 *Phi = nullptr, *Plo = nullptr;
     float* conv = nullptr;
@@ -171,6 +196,10 @@ Factor alloc_factor(nmfb200_handle* h, const std::string& tag, int R, int KP) {
     f.lo = h->buf_t<bf16>("tc." + t + ".lo", (size_t)R * KP);
     f.rowsT = KP < 128 ? 128 : KP;  // gram_kernel loads 128-row M tiles: keep zero rows behind KP = 64
     f.bT = h->buf_t<bf16>("tc." + t + ".bT", (size_t)f.rowsT * f.ldT);
+    if (h->tc_precision == 1) {
+        f.bTlo = h->buf_t<bf16>("tc." + t + ".bTlo", (size_t)f.rowsT * f.ldT);
+        NMF_CUDA(cudaMemsetAsync(f.bTlo, 0, (size_t)f.rowsT * f.ldT * sizeof(bf16), h->stream));
+    }
     f.P = h->buf_t<float>("tc." + t + ".P", (size_t)KP * KP);
     f.Phi = h->buf_t<bf16>("tc." + t + ".Phi", (size_t)KP * KP);
     f.Plo = h->buf_t<bf16>("tc." + t + ".Plo", (size_t)KP * KP);
@@ -182,29 +211,34 @@ Factor alloc_factor(nmfb200_handle* h, const std::string& tag, int R, int KP) {
 // bf16 tile-contiguous caches of X in both orientations (built once per set_X / tile shape / shard geometry).
 // X, p, ldx describe the rows this (logical) rank works on: the whole matrix, or a row shard of it (pfx names the buffers).
 void build_x_caches(nmfb200_handle* h, const std::string& pfx, const float* X, int64_t p, int64_t n, int64_t ldx, bf16** Xr_out,
-                    bf16** Xc_out) {
+                    bf16** Xc_out, bf16** Xr_lo_out = nullptr, bf16** Xc_lo_out = nullptr) {
     cudaStream_t st = h->stream;
     const int trH = pick_tile_rows((int)n, h->tc_tile_rows), trW = pick_tile_rows((int)p, h->tc_tile_rows);
     const int64_t tilesH = ceil_div(n, trH), tilesW = ceil_div(p, trW);
     const int nkbH = (int)ceil_div(p, 64), nkbW = (int)ceil_div(n, 64);
     bf16* Xr_ = h->buf_t<bf16>(pfx + ".Xr", (size_t)tilesH * nkbH * trH * 64);  // rows = columns of X, contraction over p
     bf16* Xc_ = h->buf_t<bf16>(pfx + ".Xc", (size_t)tilesW * nkbW * trW * 64);  // rows = rows of X, contraction over n
-    nmfb200_handle::XCacheKey key{h->x_epoch, (const void*)X, p, trH, trW};
+    const bool x3 = h->tc_precision == 1 && Xr_lo_out != nullptr;
+    bf16* Xr_lo = x3 ? h->buf_t<bf16>(pfx + ".Xr_lo", (size_t)tilesH * nkbH * trH * 64) : nullptr;
+    bf16* Xc_lo = x3 ? h->buf_t<bf16>(pfx + ".Xc_lo", (size_t)tilesW * nkbW * trW * 64) : nullptr;
+    nmfb200_handle::XCacheKey key{h->x_epoch, (const void*)X, p, trH, trW, x3 ? 1 : 0};
     nmfb200_handle::XCacheKey& have = h->tc_x_cache[pfx];
     if (!(have == key)) {
         cvt_tiled_direct_kernel<<<dim3((unsigned)(tilesH * trH), (unsigned)std::min<int64_t>(ceil_div((int64_t)nkbH * 64, 256), 64)), 256, 0, st>>>(
-            X, ldx, (int)n, (int)p, trH, nkbH, Xr_);
+            X, ldx, (int)n, (int)p, trH, nkbH, Xr_, Xr_lo);
         NMF_REQUIRE(trW % 8 == 0, NMFB200_EINVAL, "tile rows must be a multiple of 8");
         // the transpose kernel walks 64 logical rows per block; cover the padded row range of the last tile too
         cvt_tiled_transpose_kernel<<<dim3((unsigned)nkbW, (unsigned)ceil_div(tilesW * trW, 64)), dim3(32, 8), 0, st>>>(
-            X, ldx, (int)p, (int)n, trW, nkbW, (int)tilesW, Xc_);
+            X, ldx, (int)p, (int)n, trW, nkbW, (int)tilesW, Xc_, Xc_lo);
         h->launches += 2;
         NMF_CUDA(cudaGetLastError());
         have = key;
     }
     *Xr_out = Xr_;
     *Xc_out = Xc_;
+    if (Xr_lo_out) *Xr_lo_out = Xr_lo;
+    if (Xc_lo_out) *Xc_lo_out = Xc_lo;
 }
-void build_x_caches(nmfb200_handle* h, bf16** Xr_out, bf16** Xc_out) {
-    build_x_caches(h, "tc", (const float*)h->dX, h->p, h->n, h->ldx, Xr_out, Xc_out);
+void build_x_caches(nmfb200_handle* h, bf16** Xr_out, bf16** Xc_out, bf16** Xr_lo_out = nullptr, bf16** Xc_lo_out = nullptr) {
+    build_x_caches(h, "tc", (const float*)h->dX, h->p, h->n, h->ldx, Xr_out, Xc_out, Xr_lo_out, Xc_lo_out);
 }

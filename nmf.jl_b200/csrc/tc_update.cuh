@@ -30,6 +30,13 @@ struct UpdateParams {
     CUtensorMap tmPlo;  // P lo
     CUtensorMap tmF32;  // F fp32 [R][KP]          box 32 x tile_rows (staged epilogue store)
     CUtensorMap tmT;    // F^T bf16 [KP][R]        box 64 x KP        (staged epilogue store of the transposed copy)
+    CUtensorMap tmAlo;  // precision mode bf16x3: the remainder panel Xs - bf16(Xs), same geometry as tmA
+    CUtensorMap tmBlo;  //   ... and the transposed remainder of the other factor, same geometry as tmB
+    int flush_chunk;    // > 0 (KP <= 128): the numerator MMAs accumulate at most this many k-blocks in TMEM; the epilogue warps add
+                        // each finished chunk to fp32 register sums (round to nearest) while the next chunk accumulates.  The
+                        // tensor core's accumulator TRUNCATES (measured: ~0.5 ulp lost per MMA, a relative bias of ~3e-8 per
+                        // step that adds up over the 1000+ steps of a long contraction); short chains keep the bias at 1e-6.
+    int x3;             // 1: numerators = A*B + A*Blo + Alo*B (three passes over the k-blocks), ~2^-16 relative instead of 2^-8
     float* gram_part;   // staged epilogue: [tiles][KP][KP] fp32 Gram contribution of each tile (nullptr = skip)
     float* F;           // [R][KP] fp32 master, updated in place
     bf16* Fhi;          // [R][KP]
@@ -135,7 +142,9 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
     uint64_t* empty_bar = full_bar + C::STAGES;
     uint64_t* tmem_full = empty_bar + C::STAGES;
     uint64_t* gram_bar = tmem_full + 1;
-    uint32_t* tmem_slot = (uint32_t*)(gram_bar + 1);
+    uint64_t* acc_full = gram_bar + 1;    // [2] chunk buffer b holds a finished chunk of the numerator (flush_chunk mode)
+    uint64_t* acc_empty = acc_full + 2;   // [2] ... has been added to the register sums
+    uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
     uint32_t* stop_slot = tmem_slot + 1;
     float* conv_s = (float*)(smem + C::RING_BYTES + 1024);  // [4 warps][2][KP]
     // Staged epilogue (KP <= 128, modes that write the factor): the ring is idle once the accumulators are complete
@@ -165,6 +174,13 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
     const int r0 = tile * tile_rows;
     const uint32_t a_bytes = (uint32_t)tile_rows * 128u;
     const int nkb = (MODE == 2 || MODE == 5) ? 0 : (prm.Kdim + 63) / 64;
+    const int npass = prm.x3 ? 3 : 1;   // precision mode bf16x3: hi*hi, hi*lo, lo*hi
+    const int flush_ch = (KP <= 128 && nkb > 0) ? prm.flush_chunk : 0;
+    const int nchunks = flush_ch > 0 ? (nkb * npass + flush_ch - 1) / flush_ch : 0;
+    // TMEM columns of the finished numerators / denominators: [0, KP) / [KP, 2KP), or -- chunked -- the buffer of the last chunk
+    // (the register sums are written back there) / the other one
+    const uint32_t num_col = flush_ch > 0 ? (uint32_t)(((nchunks - 1) & 1) * KP) : 0u;
+    const uint32_t den_col = (uint32_t)KP - num_col;
     constexpr int NPRE = (MODE == 1 || MODE == 4 || MODE == 5) ? 0 : 3 * C::NSLAB;
 
     if (warp == 0 && lane == 0) {
@@ -186,6 +202,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
         }
         mbar_init(tmem_full, 1);
         mbar_init(gram_bar, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
@@ -220,14 +237,20 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                 }
                 asm volatile("fence.proxy.async;" ::: "memory");   // the peers' writes -> the TMA loads below
             }
-            for (int kb = 0; kb < nkb; ++kb) {
-                mbar_wait(&empty_bar[s], ph ^ 1u);
-                mbar_arrive_expect_tx(&full_bar[s], num_tx);
-                tma_load_2d(dst, &prm.tmA, &full_bar[s], 0, arow);
-                tma_load_2d(dst + C::A_BYTES, &prm.tmB, &full_bar[s], 64 * kb, 0);
-                arow += tile_rows;
-                dst += C::STAGE_BYTES;
-                if (++s == C::STAGES) { s = 0; ph ^= 1u; dst = smem; }
+            const int arow0 = arow;
+            for (int pass = 0; pass < npass; ++pass) {   // one pass unless precision mode bf16x3
+                const CUtensorMap* mA = pass == 2 ? &prm.tmAlo : &prm.tmA;
+                const CUtensorMap* mB = pass == 1 ? &prm.tmBlo : &prm.tmB;
+                arow = arow0;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    mbar_arrive_expect_tx(&full_bar[s], num_tx);
+                    tma_load_2d(dst, mA, &full_bar[s], 0, arow);
+                    tma_load_2d(dst + C::A_BYTES, mB, &full_bar[s], 64 * kb, 0);
+                    arow += tile_rows;
+                    dst += C::STAGE_BYTES;
+                    if (++s == C::STAGES) { s = 0; ph ^= 1u; dst = smem; }
+                }
             }
             if (NPRE > 0 && owner) {
                 pdl_wait();  // the Gram of the other factor comes from the preceding (reduce) kernel
@@ -275,13 +298,35 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                 if (++s == C::STAGES) { s = 0; ph ^= 1u; adesc = adesc0; bdesc = bdesc0; }
             };
             int kb = 0;
+            const int nkb_all = nkb * npass;
+            if (flush_ch > 0) {
+                // chunked accumulation: chunk c goes to buffer c & 1; a buffer is reused once the epilogue warps have drained it
+                int buf = 0;
+                for (int c = 0; c < nchunks; ++c) {
+                    const int kend = min(kb + flush_ch, nkb_all);
+                    if (c >= 2) { mbar_wait(&acc_empty[buf], (uint32_t)((c >> 1) - 1) & 1u); tc_fence_after(); }
+                    block(tmem_base + buf * KP, 0u);
+                    if (c == 0) TSTAMP(1);
+                    for (++kb; kb < kend; ++kb) block(tmem_base + buf * KP, 1u);
+                    umma_commit(&acc_full[buf]);
+                    buf ^= 1;
+                }
+                TSTAMP(2);
+                if (NPRE > 0 && owner) {   // denominators: the buffer that does NOT hold the last chunk (= den_col)
+                    if (nchunks >= 2) { mbar_wait(&acc_empty[buf], (uint32_t)(((nchunks - 2) >> 1)) & 1u); tc_fence_after(); }
+                    block(tmem_base + den_col, 0u);
+#pragma unroll 1
+                    for (int bd = 1; bd < NPRE; ++bd) block(tmem_base + den_col, 1u);
+                }
+            } else {
             if (nkb > 0) { block(tmem_base, 0u); kb = 1; TSTAMP(1); }   // first operands have landed
-            for (; kb < nkb; ++kb) block(tmem_base, 1u);
+            for (; kb < nkb_all; ++kb) block(tmem_base, 1u);
             TSTAMP(2);                                                   // numerator blocks issued
             if (NPRE > 0 && owner) {
                 block(tmem_base + KP, 0u);
 #pragma unroll 1
                 for (int bd = 1; bd < NPRE; ++bd) block(tmem_base + KP, 1u);
+            }
             }
             if (MODE != 5) umma_commit(tmem_full);
             TSTAMP(3);                                                   // all MMAs issued
@@ -294,6 +339,41 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
         const int row = r0 + 32 * q + lane;
         const bool valid = (32 * q + lane) < tile_rows && row < prm.R;
         const uint32_t t_lane = tmem_base + ((uint32_t)(32 * q) << 16);
+        if constexpr (KP <= 128) {
+            if (flush_ch > 0) {
+                // chunked accumulation: add every finished chunk to fp32 register sums (this thread: its row, its column half)
+                float nsum[KP / 2];
+#pragma unroll
+                for (int j = 0; j < KP / 2; ++j) nsum[j] = 0.f;
+                int buf = 0;
+                for (int c = 0; c < nchunks; ++c) {
+                    mbar_wait(&acc_full[buf], (uint32_t)(c >> 1) & 1u);
+                    tc_fence_after();
+#pragma unroll
+                    for (int cc = 0; cc < KP / 2; cc += 32) {
+                        uint32_t v[32];
+                        tmem_ld32(t_lane + buf * KP + chalf * (KP / 2) + cc, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) nsum[cc + j] += __uint_as_float(v[j]);
+                    }
+                    if (c + 1 < nchunks) {   // the last chunk's buffer stays with us (the sums go back into it)
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                    }
+                    buf ^= 1;
+                }
+#pragma unroll
+                for (int cc = 0; cc < KP / 2; cc += 32) {
+                    uint32_t v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(nsum[cc + j]);
+                    tmem_st32(t_lane + num_col + chalf * (KP / 2) + cc, v);
+                }
+                tmem_st_wait();
+            }
+        }
         pdl_wait();  // from here on we read / overwrite what the preceding kernel wrote / read
         const bool stop = __ldcg(&prm.state->converged) != 0;  // uniform: the preceding kernel is complete
         if (threadIdx.x == 64) TSTAMP(4);    // preceding kernel complete
@@ -329,8 +409,8 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
         for (int c0 = chalf * (KP / 2); c0 < (chalf + 1) * (KP / 2); c0 += 32) {
             uint32_t num_u[32], den_u[32];
             float f[32];
-            if (MODE != 2 && MODE != 5) tmem_ld32(t_lane + c0, num_u);
-            if (MODE != 1 && MODE != 4 && MODE != 5 && !push) tmem_ld32(t_lane + KP + c0, den_u);
+            if (MODE != 2 && MODE != 5) tmem_ld32(t_lane + num_col + c0, num_u);
+            if (MODE != 1 && MODE != 4 && MODE != 5 && !push) tmem_ld32(t_lane + den_col + c0, den_u);
             if (push) {
                 tmem_ld_wait();
                 if (prm.G > 0) {
@@ -654,6 +734,8 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
 
 // ---- Gram: P += T T'  for T = FbT ([KP][R] bf16, rows of length R contiguous) ------------------------
 struct GramParams {
+    CUtensorMap tmTlo;  // precision mode bf16x3: the transposed remainder, same geometry as tmT
+    int split;        // 1: T T' = hi hi' + hi lo' + lo hi'
     CUtensorMap tmT;  // bf16 [KP][R], box 64 x 128
     float* part;      // [gridDim.x][KP][KP] fp32 partial Grams (plain stores, reduced by gram_reduce_kernel)
     const TcState* state;
@@ -664,8 +746,9 @@ struct GramParams {
 template <int KP>
 struct GramCfg {
     static constexpr int MT = (KP + 127) / 128;         // 128-row M tiles
-    static constexpr int STAGE_BYTES = MT * 128 * 128;  // the tile is both A and B operand
-    static constexpr int STAGES = 4;
+    static constexpr int TILE_BYTES = MT * 128 * 128;   // the tile is both A and B operand
+    static constexpr int STAGE_BYTES = 2 * TILE_BYTES;  // hi tile | lo tile (the lo half is only filled in split mode)
+    static constexpr int STAGES = KP == 256 ? 3 : 4;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
     static constexpr int TMEM_COLS = (MT * KP) < 32 ? 32 : (MT * KP);  // 64, 128, 512
 };
@@ -707,11 +790,14 @@ __global__ void __launch_bounds__(192, 1) gram_kernel(const __grid_constant__ Gr
                 const int s = b % C::STAGES;
                 const uint32_t ph = (uint32_t)(b / C::STAGES) & 1u;
                 mbar_wait(&empty_bar[s], ph ^ 1u);
-                mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
+                mbar_arrive_expect_tx(&full_bar[s], prm.split ? C::STAGE_BYTES : C::TILE_BYTES);
                 // NOTE: columns >= k_end inside the last 64-block belong to the next CTA's chunk only if
                 // chunk % 64 != 0; chunk, k0 and k1 (unless k1 = R) are multiples of 64, and columns >= R are zero-filled by TMA.
-                for (int m = 0; m < C::MT; ++m)
+                for (int m = 0; m < C::MT; ++m) {
                     tma_load_2d(smem + s * C::STAGE_BYTES + m * 128 * 128, &prm.tmT, &full_bar[s], k_begin + 64 * b, 128 * m);
+                    if (prm.split)
+                        tma_load_2d(smem + s * C::STAGE_BYTES + C::TILE_BYTES + m * 128 * 128, &prm.tmTlo, &full_bar[s], k_begin + 64 * b, 128 * m);
+                }
             }
         }
         __syncwarp();
@@ -724,13 +810,17 @@ __global__ void __launch_bounds__(192, 1) gram_kernel(const __grid_constant__ Gr
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
                 const uint32_t base = smem_u32(smem + s * C::STAGE_BYTES);
-                const uint64_t bdesc = make_kmajor_sw128_desc(base);  // B = first KP rows of the tile
+                const int nterm = prm.split ? 3 : 1;   // (A, B) = (hi, hi), (hi, lo), (lo, hi)
+                for (int term = 0; term < nterm; ++term) {
+                    const uint32_t abase = base + (term == 2 ? C::TILE_BYTES : 0), bbase = base + (term == 1 ? C::TILE_BYTES : 0);
+                    const uint64_t bdesc = make_kmajor_sw128_desc(bbase);  // B = first KP rows of the tile
 #pragma unroll
-                for (int m = 0; m < C::MT; ++m) {
-                    const uint64_t adesc = make_kmajor_sw128_desc(base + m * 128 * 128);
+                    for (int m = 0; m < C::MT; ++m) {
+                        const uint64_t adesc = make_kmajor_sw128_desc(abase + m * 128 * 128);
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        umma_bf16(tmem_base + m * KP, adesc + 2 * kk, bdesc + 2 * kk, idesc, (b > 0 || kk > 0) ? 1u : 0u);
+                        for (int kk = 0; kk < 4; ++kk)
+                            umma_bf16(tmem_base + m * KP, adesc + 2 * kk, bdesc + 2 * kk, idesc, (b > 0 || kk > 0 || term > 0) ? 1u : 0u);
+                    }
                 }
                 umma_commit(&empty_bar[s]);
             }

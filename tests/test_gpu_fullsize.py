@@ -125,7 +125,7 @@ def test_config4_greedycd_32768_k256_properties(NMF):
             objs.append(r.objvalue)
             updates.append(int(r.coordinate_updates))
         obj = _objective_mse(dX, dW, dH)
-        # KP = 256: the objective kernel forms W*H from the bf16 hi parts only (no room for the hi/lo split): 1e-3
-        assert abs(objs[-1] - obj) <= 1e-3 * obj, (objs[-1], obj)
+        # the objective kernel splits both factors into bf16 hi + lo at every KP (round 2; hi only gave 1e-3 here)
+        assert abs(objs[-1] - obj) <= 2e-5 * obj, (objs[-1], obj)
     obj0 = _objective_mse(dX, dW0, dH0)
     assert obj0 > objs[0] > objs[1] > 0 and updates[1] > updates[0] > 0
