@@ -1,6 +1,6 @@
 """BASELINE.json's full-size configurations through the C ABI, checked by what does not need a CPU run of the same
-size: (1) two iterations of config 2 against the oracle itself (the as-written update costs ~0.3 s per iteration on
-the host), (2) size-independent properties -- non-negativity, the monotone decrease of the objective that the
+size: (1) two iterations of EVERY BASELINE configuration against the oracle itself at full size (the as-written updates
+cost 0.3 s ... 30 s per iteration on the host), (2) size-independent properties -- non-negativity, the monotone decrease of the objective that the
 multiplicative updates guarantee (Lee & Seung; multupd.jl:83-116, :150-193) and that GreedyCD's exact coordinate steps
 imply (greedycd.jl:94-166), agreement of the returned objvalue with an independent evaluation of the objective from the
 returned factors, equivariance under a permutation of the rows of X, bit-repeatability.
@@ -88,12 +88,32 @@ def test_config2_multmse_16384_k128_vs_oracle_and_properties(NMF, oracle):
     assert float(torch.linalg.norm(dHp - dH) / torch.linalg.norm(dH)) <= 2e-3
 
 
-def test_config3_multdiv_8192x65536_k64_properties(NMF):
+def _to_host(dX, dW, dH):
+    return (np.asfortranarray(dX.cpu().numpy().T), np.asfortranarray(dW.cpu().numpy().T), np.asfortranarray(dH.cpu().numpy().T))
+
+
+def _rel(a, b):
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+def test_config3_multdiv_8192x65536_k64_vs_oracle_and_properties(NMF, oracle):
     p, n, k = 8192, 65536, 64
     dX, dW0, dH0 = _device_problem(p, n, k, seed=3)
     objs = []
     with NMF.Session(engine="tc") as s:
         s.set_X_device(dX.data_ptr(), p, n, p, np.float32, keepalive=dX)
+        # (1) two iterations at full size against the oracle (the as-written :div update: materialised WH and Q, 6 GiB on the host)
+        dW, dH = dW0.clone(), dH0.clone()
+        r = _solve(NMF, s, "multdiv", dW, dH, p, k, 2)
+        assert r.engine == 1 and r.niters == 2
+        X, Wo, Ho = _to_host(dX, dW0, dH0)
+        ro = oracle.solve(oracle.MultUpdate(np.float32, obj="div", maxiter=2, tol=1e-30), X, Wo, Ho)
+        ew, eh = _rel(dW.cpu().numpy().T, Wo), _rel(dH.cpu().numpy().T, Ho)
+        eo = abs(r.objvalue - float(ro.objvalue)) / float(ro.objvalue)
+        print(f"config 3, 2 iterations vs oracle: errW={ew:.2e} errH={eh:.2e} errObj={eo:.2e}")
+        assert ew <= 5e-3 and eh <= 5e-3
+        assert eo <= 1e-4                                              # north-star bar
+        del X, Wo, Ho
         for iters in (2, 5, 9):
             dW, dH = dW0.clone(), dH0.clone()
             r = _solve(NMF, s, "multdiv", dW, dH, p, k, iters)
@@ -110,11 +130,29 @@ def test_config3_multdiv_8192x65536_k64_properties(NMF):
     assert objs[0] >= objs[1] >= objs[2] > 0           # the KL updates never increase the divergence
 
 
-def test_config4_greedycd_32768_k256_properties(NMF):
+def test_config4_greedycd_32768_k256_vs_oracle_and_properties(NMF, oracle):
     p = n = 32768
     k = 256
     dX, dW0, dH0 = _device_problem(p, n, k, seed=4, planted_rank=64)
     objs, updates = [], []
+    # (1) two iterations at full size against the oracle (two 550-GFLOP sgemm per half-step plus the serial coordinate loops: ~1 min
+    # on the host).  GreedyCD's coordinate choices are discrete, so W / H are not comparable element-wise; the bars are objvalue and
+    # the number of coordinate steps, for the default bf16 gradients and for the split-operand parity mode.
+    X, Wo, Ho = _to_host(dX, dW0, dH0)
+    ro = oracle.solve(oracle.GreedyCD(np.float32, maxiter=2, tol=1e-30), X, Wo, Ho)
+    del X
+    for mode, bar_obj, bar_upd in (("bf16", 5e-3, 0.15), ("bf16x3", 5e-4, 0.02)):
+        with NMF.Session(engine="tc") as s:
+            s.set_option("precision", mode)
+            s.set_X_device(dX.data_ptr(), p, n, p, np.float32, keepalive=dX)
+            dW, dH = dW0.clone(), dH0.clone()
+            r = _solve(NMF, s, "greedycd", dW, dH, p, k, 2)
+        eo = abs(r.objvalue - float(ro.objvalue)) / float(ro.objvalue)
+        du = abs(int(r.coordinate_updates) - ro.coordinate_updates) / ro.coordinate_updates
+        print(f"config 4, 2 iterations vs oracle [{mode}]: errObj={eo:.2e} updates {int(r.coordinate_updates)}/{ro.coordinate_updates} ({du:.2%})")
+        assert r.engine == 1 and r.niters == 2
+        assert eo <= bar_obj and du <= bar_upd
+    del Wo, Ho
     with NMF.Session(engine="tc") as s:
         s.set_X_device(dX.data_ptr(), p, n, p, np.float32, keepalive=dX)
         for iters in (2, 4):
