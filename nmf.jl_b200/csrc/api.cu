@@ -195,6 +195,8 @@ int nmfb200_set_option(nmfb200_handle* h, const char* key, const char* value) {
             if (v == "p2p") h->tc_xchg = 1;
             else if (v == "nccl") h->tc_xchg = 0;
             else throw Error{NMFB200_EINVAL, "tc_xchg must be p2p|nccl"};
+        } else if (k == "tc_xmul") {
+            h->tc_xmul_opt = atoi(value);
         } else if (k == "tc_flush") {
             h->tc_flush = atoi(value);
         } else if (k == "tc_fused_hstep") {

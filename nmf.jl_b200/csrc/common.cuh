@@ -120,6 +120,7 @@ struct nmfb200_handle {
     cudaStream_t side_stream = nullptr;
     std::vector<cudaStream_t> vstreams;  // logical ranks (emulate_shards): one stream each for launches that wait on each other
     int emulate_shards = 0;  // > 1: run the row-sharded tensor-core algorithm with this many LOGICAL ranks on this one GPU
+    int tc_xmul_opt = 1;   // ProjectedALS / CoordinateDescent / ALSPGrad (Float32): X-sized products on the tensor cores (split operands)
     int tc_flush = -1;     // k-blocks per TMEM accumulation chunk of the update kernel (0 = one long chain; -1 = default: 8)
     int tc_precision = 0;  // 0 = bf16 operands; 1 = bf16x3 (hi/lo split of X and of the streamed factor: fp32-class products)
     nmfb200::Xchg xchg;
@@ -142,8 +143,8 @@ struct nmfb200_handle {
         int64_t p = 0;
         int trH = 0, trW = 0;
         int with_lo = 0;  // precision mode bf16x3: the remainder caches were built too
-        bool operator==(const XCacheKey& o) const {
-            return epoch == o.epoch && X == o.X && p == o.p && trH == o.trH && trW == o.trW && with_lo == o.with_lo;
+        bool covers(const XCacheKey& want) const {   // a cache built with the remainders also serves a request without them
+            return epoch == want.epoch && X == want.X && p == want.p && trH == want.trH && trW == want.trW && with_lo >= want.with_lo;
         }
     };
     std::map<std::string, XCacheKey> tc_x_cache;
@@ -281,6 +282,11 @@ double simt_objective_f32(nmfb200_handle* h, int alg, const float* W, int64_t ld
 template <typename T>
 void simt_mul_X(nmfb200_handle* h, int transpose_X, const T* B, int64_t ldb, int64_t c, T* C, int64_t ldc);
 bool tc_supported(const nmfb200_handle* h, const SolveArgs& a);
+// out(r, a) = sum_c Xs(r, c) * O(c, a) on the tensor cores with split (bf16 hi + lo) operands, for the algorithms whose remaining
+// arithmetic stays on the exact engine (ProjectedALS, CoordinateDescent, ALSPGrad).  side 0: Xs = X' (rows = columns of X,
+// O is p x k); side 1: Xs = X (O is n x k).  O(c, a) = O[c*sOr + a*sOc], out(r, a) = out[r*sNr + a*sNc]; device pointers.
+// Returns false (nothing done) when the shape is not covered; the caller then uses its own GEMM.
+bool tc_xmul(nmfb200_handle* h, int side, const float* O, int64_t sOr, int64_t sOc, int64_t k, float* out, int64_t sNr, int64_t sNc);
 void tc_solve(nmfb200_handle* h, const SolveArgs& a, float* W, int64_t ldw, float* H, int64_t ldh, nmfb200_result* out);
 void tc_release(nmfb200_handle* h);
 

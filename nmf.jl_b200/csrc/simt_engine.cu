@@ -431,6 +431,22 @@ struct Simt {
         NMF_CUDA(cudaGetLastError());
     }
 
+    // The two X-sized products of every iterative algorithm: side 0: out (n x k) = X' O with O p x k; side 1: out (p x k) = X O
+    // with O n x k.  O(c, a) = O[c*sOr + a*sOc], out(r, a) = out[r*sNr + a*sNc].  Float32 problems from 2^20 cells on go to the
+    // tcgen05 mainloop of the tensor-core engine with split (bf16 hi + lo) operands (tc_xmul, ~2^-16 relative per product,
+    // fp32 accumulation); everything else, and every k x k product, stays on the fp32 / fp64 CUDA-core GEMM.
+    bool used_tc = false;
+    void xprod(int side, const T* O, int64_t sOr, int64_t sOc, T* out, int64_t sNr, int64_t sNc) {
+        if constexpr (sizeof(T) == 4) {
+            if (tc_xmul(h, side, (const float*)O, sOr, sOc, k, (float*)out, sNr, sNc)) {
+                used_tc = true;
+                return;
+            }
+        }
+        if (side == 0) gemm((int)n, (int)k, (int)p, X, ldx, 1, O, sOr, sOc, out, sNr, sNc);
+        else gemm((int)p, (int)k, (int)n, X, 1, ldx, O, sOr, sOc, out, sNr, sNc);
+    }
+
     double reduce_objective(int mode, const T* Xp, int64_t rows, int64_t cols, int64_t ld, const T* Y) {
         int nb = ew_blocks(rows * cols);
         double* part = h->buf_t<double>("simt.obj_part", (size_t)nb + 1);
@@ -593,7 +609,7 @@ struct Simt {
         T* gram = num_h + (size_t)k * n;
         T* inv = h->buf_t<T>("simt.inv", (size_t)k * k);
         if (update_H) {
-            gemm((int)k, (int)n, (int)p, W, p, 1, X, 1, ldx, num_h, 1, k);   // W'X        (projals.jl:92)
+            xprod(0, W, 1, p, num_h, k, 1);                                  // W'X        (projals.jl:92)
             gemm((int)k, (int)k, (int)p, W, p, 1, W, 1, p, gram, 1, k);     // W'W        (:91)
             h->allreduce_sum(num_h, (size_t)k * n + (size_t)k * k);
             if (lh != T(0)) { add_diag_kernel<T><<<(unsigned)ceil_div(k, 256), 256, 0, st>>>(gram, (int)k, lh); h->launches += 1; }
@@ -606,7 +622,7 @@ struct Simt {
         T* num_w = h->buf_t<T>("simt.num_w", (size_t)p * k);
         gemm((int)k, (int)k, (int)n, H, 1, k, H, k, 1, gramh, 1, k);         // HH'        (:99)
         if (lw != T(0)) { add_diag_kernel<T><<<(unsigned)ceil_div(k, 256), 256, 0, st>>>(gramh, (int)k, lw); h->launches += 1; }
-        gemm((int)p, (int)k, (int)n, X, 1, ldx, H, k, 1, num_w, 1, p);       // XH'        (:100)
+        xprod(1, H, k, 1, num_w, 1, p);                                      // XH'        (:100)
         spd_inverse(gramh, inv, info);                                       // pdrsolve!  (:101)
         gemm((int)p, (int)k, (int)k, num_w, 1, p, inv, 1, k, W, 1, p);
         clamp_nn_kernel<T><<<ew_blocks(p * k), 256, 0, st>>>(W, p * k);      // projectnn! (:102)
@@ -621,7 +637,7 @@ struct Simt {
         T* Z = h->buf_t<T>("simt.gcd_Z", (size_t)std::max(p, n) * k + (size_t)k * k);
         T* HHt = Z + (size_t)rows * k;
         gemm((int)k, (int)k, (int)cols, O, sOc, sOr, O, sOr, sOc, HHt, 1, k);        // :112
-        gemm((int)rows, (int)k, (int)cols, X, sXr, sXc, O, sOr, sOc, Z, k, 1);      // :118
+        xprod(sXr == 1 ? 1 : 0, O, sOr, sOc, Z, k, 1);                              // :118
         if (contraction_sharded) h->allreduce_sum(Z, (size_t)rows * k + (size_t)k * k);
         if (l2 > T(0)) { add_diag_kernel<T><<<(unsigned)ceil_div(k, 256), 256, 0, st>>>(HHt, (int)k, l2); h->launches += 1; }  // :123-125
         std::vector<int> perm;
@@ -725,14 +741,14 @@ struct Simt {
         if (update_H) {
             T* wtx = h->buf_t<T>("simt.num_h", (size_t)k * n + (size_t)k * k);
             gemm((int)k, (int)k, (int)p, W, p, 1, W, 1, p, gram, 1, k);              // set_w! (:55-59)
-            gemm((int)k, (int)n, (int)p, W, p, 1, X, 1, ldx, wtx, 1, k);
+            xprod(0, W, 1, p, wtx, k, 1);
             const int64_t itH = pg_subsolve(H, gram, wtx, true, maxsub, 20, *tolg, T(0.2), T(0.01));   // :405-407
             sub += itH;
             if (itH == 1) *tolg = (T)((double)*tolg * 0.1);                          // :409-411
         }
         T* xht = h->buf_t<T>("simt.num_w", (size_t)p * k);
         gemm((int)k, (int)k, (int)n, H, 1, k, H, k, 1, gram, 1, k);                  // set_h! (:211-215)
-        gemm((int)p, (int)k, (int)n, X, 1, ldx, H, k, 1, xht, 1, p);
+        xprod(1, H, k, 1, xht, 1, p);
         const int64_t itW = pg_subsolve(W, gram, xht, false, maxsub, 20, *tolg, T(0.2), T(0.01));      // :415-417
         sub += itW;
         if (itW == 1) *tolg = (T)((double)*tolg * 0.1);                              // :419-421
@@ -804,6 +820,10 @@ void simt_solve(nmfb200_handle* h, const SolveArgs& a, T* Wc, int64_t ldw, T* Hc
     }
     unsigned long long* d_updates = (unsigned long long*)h->buf("simt.gcd_updates", 16);
     NMF_CUDA(cudaMemsetAsync(d_updates, 0, sizeof(unsigned long long), st));
+    if (sizeof(T) == 4 && a.alg >= 3) {   // tensor-core products (xprod): bf16 caches of X and buffers, built outside the timed loop
+        tc_xmul(h, 0, nullptr, 0, 0, k, nullptr, 0, 0);
+        tc_xmul(h, 1, nullptr, 0, 0, k, nullptr, 0, 0);
+    }
     NMF_CUDA(cudaEventRecord(e1, st));
 
     double objv = std::numeric_limits<double>::quiet_NaN();
@@ -865,7 +885,7 @@ void simt_solve(nmfb200_handle* h, const SolveArgs& a, T* Wc, int64_t ldw, T* Hc
     cudaEventDestroy(e2);
     out->niters = t;
     out->converged = converged ? 1 : 0;
-    out->engine = 0;
+    out->engine = s.used_tc ? 1 : 0;   // 1: the X-sized products ran on the tensor cores (split operands); the rest is exact fp32
     out->objvalue = objv;
     out->last_dev = dev;
     out->solve_ms = ms_loop;

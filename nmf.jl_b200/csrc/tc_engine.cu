@@ -64,6 +64,7 @@ struct TcSolver {
     std::string gram_tag = "gram_part";  // name of the tile-Gram buffer the next launch fills
     const ShardLaunch* sl = nullptr; // row-sharded launch extras for the NEXT launch_update (reset by the caller)
     const bf16* Xs_lo = nullptr;     // precision mode bf16x3: the remainder panel matching the Xs of the NEXT launch_update
+    bool force_x3 = false;           // split operands whatever the handle's precision option says (tc_xmul)
     bool defer_gram_reduce = false;  // the caller will run gram_conv_reduce_kernel itself
     bool last_fused_gram = false;
     float* last_gram_part = nullptr;
@@ -79,7 +80,7 @@ struct TcSolver {
         UpdateParams prm;
         // precision mode bf16x3 (MultUpdate :mse and the GreedyCD gradient): three passes over the k-blocks with the bf16
         // remainders of X and of the other factor; the Gram then comes from the split stand-alone kernel, not the tile epilogue
-        const bool x3 = h->tc_precision == 1 && Xs_lo != nullptr && O.bTlo != nullptr && (mode == 0 || mode == 3);
+        const bool x3 = (h->tc_precision == 1 || force_x3) && Xs_lo != nullptr && O.bTlo != nullptr && (mode == 0 || mode == 3 || (mode == 1 && sl == nullptr));
         const bool fused_gram = gram >= 0 && KP <= 128 && (mode == 0 || mode == 2 || mode == 6) && !x3;
         std::memset(&prm, 0, sizeof(prm));
         prm.gram_part = fused_gram ? h->buf_t<float>(pfx + "." + gram_tag, (size_t)std::max(F.tiles, 1) * KP * KP) : nullptr;
@@ -766,6 +767,60 @@ void tc_solve(nmfb200_handle* h, const SolveArgs& a, float* W, int64_t ldw, floa
         case 128: tc_solve_kp<128>(h, a, W, ldw, H, ldh, out); break;
         case 256: tc_solve_kp<256>(h, a, W, ldw, H, ldh, out); break;
         default: throw Error{NMFB200_ENOTSUP, "k > 256 is not covered by the tensor-core engine"};
+    }
+}
+
+namespace {
+template <int KP>
+void tc_xmul_kp(nmfb200_handle* h, int side, const float* O, int64_t sOr, int64_t sOc, int64_t k, float* out, int64_t sNr, int64_t sNc,
+                bool prepare_only) {
+    TcSolver<KP>::set_attrs(h->device);
+    cudaStream_t st = h->stream;
+    const int saved = h->tc_precision;
+    h->tc_precision = 1;   // the remainder caches / transposed remainders below exist only in the split-operand mode
+    try {
+        bf16 *Xr = nullptr, *Xc = nullptr, *Xr_lo = nullptr, *Xc_lo = nullptr;
+        build_x_caches(h, &Xr, &Xc, &Xr_lo, &Xc_lo);
+        const int R = (int)(side == 0 ? h->n : h->p), Kdim = (int)(side == 0 ? h->p : h->n);
+        Factor F = alloc_factor(h, side == 0 ? "xm.F0" : "xm.F1", R, KP);     // rows of the result (only their geometry is used)
+        Factor Of = alloc_factor(h, side == 0 ? "xm.O0" : "xm.O1", Kdim, KP);  // the factor being contracted against
+        TcState* state = (TcState*)h->buf("xm.state", sizeof(TcState));
+        float* num = h->buf_t<float>("xm.num", (size_t)std::max(h->n, h->p) * KP);
+        NMF_CUDA(cudaMemsetAsync(state, 0, sizeof(TcState), st));
+        if (prepare_only) {   // bf16 caches of X and every buffer now exist: the first product inside the timed loop allocates nothing
+            h->tc_precision = saved;
+            return;
+        }
+        pack_factor_kernel<<<ew_grid((int64_t)Kdim * KP), 256, 0, st>>>(O, sOr, sOc, Kdim, (int)k, KP, Of.m, Of.hi, Of.lo, Of.bT, Of.ldT);
+        h->launches += 1;
+        TcSolver<KP> s{h, st, state};
+        s.pfx = "xm";
+        s.refresh_bTlo(Of);
+        s.Xs_lo = side == 0 ? Xr_lo : Xc_lo;
+        s.force_x3 = true;
+        s.launch_update(1, F, Of, side == 0 ? Xr : Xc, Kdim, 0.f, 0.f, num, nullptr, -1, nullptr, false);
+        unpack_factor_kernel<<<ew_grid((int64_t)R * k), 256, 0, st>>>(num, R, (int)k, KP, out, sNr, sNc);
+        h->launches += 1;
+        NMF_CUDA(cudaGetLastError());
+    } catch (...) {
+        h->tc_precision = saved;
+        throw;
+    }
+    h->tc_precision = saved;
+}
+}  // namespace
+
+bool tc_xmul(nmfb200_handle* h, int side, const float* O, int64_t sOr, int64_t sOc, int64_t k, float* out, int64_t sNr, int64_t sNc) {
+    const bool prepare_only = O == nullptr;   // tc_xmul(h, side, nullptr, ...): allocate and build the caches, compute nothing
+    if (h->engine_opt == 1 || h->x_elt != 4 || h->tc_xmul_opt == 0) return false;
+    if (h->p < 128 || h->n < 128 || pick_kp(k) == 0) return false;
+    if (h->engine_opt != 2 && h->p * h->n < ((int64_t)1 << 20)) return false;   // small problems: the exact engine, as for MultUpdate
+    if (h->p > (int64_t)INT32_MAX / 256 || h->n > (int64_t)INT32_MAX / 256) return false;
+    switch (pick_kp(k)) {
+        case 64: tc_xmul_kp<64>(h, side, O, sOr, sOc, k, out, sNr, sNc, prepare_only); return true;
+        case 128: tc_xmul_kp<128>(h, side, O, sOr, sOc, k, out, sNr, sNc, prepare_only); return true;
+        case 256: tc_xmul_kp<256>(h, side, O, sOr, sOc, k, out, sNr, sNc, prepare_only); return true;
+        default: return false;
     }
 }
 

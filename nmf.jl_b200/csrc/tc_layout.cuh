@@ -197,8 +197,10 @@ Factor alloc_factor(nmfb200_handle* h, const std::string& tag, int R, int KP) {
     f.rowsT = KP < 128 ? 128 : KP;  // gram_kernel loads 128-row M tiles: keep zero rows behind KP = 64
     f.bT = h->buf_t<bf16>("tc." + t + ".bT", (size_t)f.rowsT * f.ldT);
     if (h->tc_precision == 1) {
+        const size_t before = h->bufs["tc." + t + ".bTlo"].bytes;
         f.bTlo = h->buf_t<bf16>("tc." + t + ".bTlo", (size_t)f.rowsT * f.ldT);
-        NMF_CUDA(cudaMemsetAsync(f.bTlo, 0, (size_t)f.rowsT * f.ldT * sizeof(bf16), h->stream));
+        if (h->bufs["tc." + t + ".bTlo"].bytes != before)   // fresh allocation: rows behind k (KP = 64: up to 128) must read as zero
+            NMF_CUDA(cudaMemsetAsync(f.bTlo, 0, (size_t)f.rowsT * f.ldT * sizeof(bf16), h->stream));
     }
     f.P = h->buf_t<float>("tc." + t + ".P", (size_t)KP * KP);
     f.Phi = h->buf_t<bf16>("tc." + t + ".Phi", (size_t)KP * KP);
@@ -223,7 +225,7 @@ void build_x_caches(nmfb200_handle* h, const std::string& pfx, const float* X, i
     bf16* Xc_lo = x3 ? h->buf_t<bf16>(pfx + ".Xc_lo", (size_t)tilesW * nkbW * trW * 64) : nullptr;
     nmfb200_handle::XCacheKey key{h->x_epoch, (const void*)X, p, trH, trW, x3 ? 1 : 0};
     nmfb200_handle::XCacheKey& have = h->tc_x_cache[pfx];
-    if (!(have == key)) {
+    if (!have.covers(key)) {
         cvt_tiled_direct_kernel<<<dim3((unsigned)(tilesH * trH), (unsigned)std::min<int64_t>(ceil_div((int64_t)nkbH * 64, 256), 64)), 256, 0, st>>>(
             X, ldx, (int)n, (int)p, trH, nkbH, Xr_, Xr_lo);
         NMF_REQUIRE(trW % 8 == 0, NMFB200_EINVAL, "tile rows must be a multiple of 8");

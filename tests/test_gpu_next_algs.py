@@ -179,3 +179,46 @@ def test_nnmf_dispatches_next_algs(NMF, oracle):
         r = NMF.nnmf(X, 3, alg=alg, init="random", maxiter=30, rng=np.random.default_rng(1))
         assert r.W.shape == (12, 3) and r.H.shape == (3, 10) and np.isfinite(float(r.objvalue))
         assert float(r.objvalue) <= 0.5 * float(np.sum(X * X))
+
+
+# ---- the X-sized products of ProjectedALS / CoordinateDescent / ALSPGrad on the tcgen05 mainloop --------------------
+# Float32 problems from 2^20 cells on compute W'X and XH' with the update kernel of the tensor-core engine (split bf16 hi + lo
+# operands, fp32 accumulation; tc_xmul in csrc/tc_engine.cu); the k x k algebra (Cholesky-equivalent inverse, sweeps, Armijo
+# control flow) is unchanged.  Checked against the oracle AND against the same solve with the products on the exact engine
+# (option tc_xmul=0): the tensor-core products must not cost more than a small multiple of the exact engine's own distance.
+def _solve_opt(NMF, alg, X, W0, H0, opts=()):
+    W, H = W0.copy(order="F"), H0.copy(order="F")
+    with NMF.Session(engine="auto") as s:
+        for key, val in opts:
+            s.set_option(key, val)
+        s.set_X(X)
+        r = s.solve(alg, W, H)
+    return r, W, H
+
+
+@pytest.mark.parametrize("name,p,n,k,iters", [("projals", 1536, 1024, 32, 8), ("projals", 1100, 1300, 100, 5), ("cd", 1280, 1024, 24, 6),
+                                              ("cd", 1024, 1536, 150, 3), ("alspgrad", 1200, 1024, 16, 3), ("projals", 6144, 4096, 64, 4),
+                                              ("cd", 4096, 6144, 64, 3)])
+def test_next_algorithms_with_tensor_core_products(NMF, oracle, name, p, n, k, iters):
+    X, W0, H0 = _problem(NMF, p, n, k, np.float32, seed=p + k, zeroh=(name == "projals"))
+    if name == "projals":
+        alg, oalg = NMF.ProjectedALS(np.float32, maxiter=iters, tol=1e-30), oracle.ProjectedALS(np.float32, maxiter=iters, tol=1e-30)
+    elif name == "cd":
+        alg = NMF.CoordinateDescent(np.float32, maxiter=iters, tol=1e-30, alpha=1e-3, l1ratio=0.5)
+        oalg = oracle.CoordinateDescent(np.float32, maxiter=iters, tol=1e-30, alpha=1e-3, l1ratio=0.5)
+    else:
+        alg, oalg = NMF.ALSPGrad(np.float32, maxiter=iters, tol=1e-30), oracle.ALSPGrad(np.float32, maxiter=iters, tol=1e-30)
+    r, W, H = _solve_opt(NMF, alg, X, W0, H0)
+    re, We, He = _solve_opt(NMF, alg, X, W0, H0, opts=(("tc_xmul", 0),))
+    Wo, Ho = W0.copy(order="F"), H0.copy(order="F")
+    ro = oracle.solve(oalg, X, Wo, Ho)
+    assert r.info["engine"] == "tc" and re.info["engine"] == "simt"          # "tc" here = tensor-core products, exact rest
+    assert r.niters == ro.niters == iters
+    e_tc = max(_relerr(W, Wo), _relerr(H, Ho))
+    e_ex = max(_relerr(We, Wo), _relerr(He, Ho))
+    eo = abs(float(r.objvalue) - float(ro.objvalue)) / float(ro.objvalue)
+    print(f"{name} p={p} n={n} k={k} it={iters}: W/H vs oracle: tensor-core products {e_tc:.1e}, exact products {e_ex:.1e}; objvalue {eo:.1e}; "
+          f"loop {r.info['solve_ms']:.2f} ms vs {re.info['solve_ms']:.2f} ms")
+    assert (W >= 0).all() and (H >= 0).all() and np.isfinite(W).all() and np.isfinite(H).all()
+    assert e_tc <= 10 * e_ex + 1e-4
+    assert eo <= 1e-4
