@@ -51,7 +51,8 @@ typedef enum nmfb200_status {
 typedef struct nmfb200_result {
     int64_t niters;             /* Result.niters    (common.jl:24) */
     int32_t converged;          /* Result.converged (common.jl:25) */
-    int32_t engine;             /* 0 = SIMT fp32/fp64 kernels, 1 = tcgen05 bf16 tensor-core kernels */
+    int32_t engine;             /* 0 = exact fp32/fp64 CUDA-core kernels, 1 = tcgen05 tensor-core kernels (ProjectedALS / CD / ALSPGrad:
+                                   1 = their X-sized products ran on the tensor cores with split operands, the rest is exact) */
     double objvalue;            /* Result.objvalue  (common.jl:26), already rounded to T */
     double last_dev;            /* `dev` of the last stop_condition call (common.jl:73); full max, not partial */
     double solve_ms;            /* device time of the iteration loop (CUDA events), excl. transfers */
@@ -83,13 +84,28 @@ int nmfb200_set_stream(nmfb200_handle* h, void* stream);
 /* Options (key, value):
  *   "engine"      = "auto" | "simt" | "tc"   -- simt: exact fp32/fp64 CUDA-core kernels;
  *                                               tc: tcgen05 bf16-operand / fp32-accumulate kernels
- *                                               (Float32 only); auto = tc when shape allows.
+ *                                               (Float32 only); auto = tc for Float32 problems of at least
+ *                                               2^20 cells (2^24 for GreedyCD), the exact engine below that.
  *   "check_every" = "<int>"                  -- host polls the device convergence flag every N
  *                                               iterations (results are independent of N).
  *   "tc_tile_rows" = "<int>"                 -- rows of a factor owned by one CTA of the tensor-core
  *                                               update kernel (multiple of 8 in [8,128]; 0 = auto).
- *   "tc_xchg"      = "p2p" | "nccl"          -- multi-GPU exchange of the tensor-core engine: fused peer-memory
- *                                               reduce-scatter/all-gather over NVLink (default) or ncclAllReduce.
+ *   "precision"   = "bf16" | "bf16x3"        -- tensor-core engine, MultUpdate(:mse) and the GreedyCD gradient: bf16 = X and the
+ *                                               streamed factor rounded to bf16 (default); bf16x3 = plus their bf16 remainders
+ *                                               (hi*hi + hi*lo + lo*hi, three passes over X, split Gram): fp32-class products,
+ *                                               W/H within ~2x the exact engine's distance to the reference, 2.65x the time.
+ *   "emulate_shards" = "<G>"                 -- G in 2..8: run MultUpdate(:mse) as the ROW-SHARDED algorithm with G logical ranks on
+ *                                               this one GPU (same kernels, arenas and flags as a G-GPU run; the caller passes the
+ *                                               whole X, W, H); 0 (default) = off.  The 1-GPU test of the multi-GPU mathematics.
+ *   "tc_xchg"      = "p2p" | "nccl"          -- multi-GPU MultUpdate(:mse): p2p (default) = tensor-core engine over NVLink peer
+ *                                               memory (csrc/tc_shard.cuh); nccl = stay on the exact engine (ncclAllReduce).
+ *   "tc_fused_hstep" = "-1" | "0" | "1"      -- row-sharded H-step as one launch (1), as numerators / slot sum / ratio (0), or
+ *                                               auto (-1, default: one launch for two ranks).  Results are identical.
+ *   "tc_side_stream" = "0" | "1"             -- row-sharded: H-Gram exchange on a side stream under the W-step (1, default).
+ *   "tc_flush"     = "<int>"                 -- k-blocks per TMEM accumulation chunk of the update kernel (default 8; 0 = one chain:
+ *                                               the tensor core's accumulator truncates, long chains bias the sums by ~3e-8 per MMA).
+ *   "tc_xmul"      = "0" | "1"               -- ProjectedALS / CoordinateDescent / ALSPGrad (Float32, >= 2^20 cells): X-sized products
+ *                                               on the tensor cores with split operands (1, default) or on the exact engine (0).
  *   "tc_pdl"       = "0" | "1"               -- 1 (default): the tensor-core update kernels are launched as programmatic
  *                                               dependents of the small reduce kernel in front of them (their X streaming
  *                                               overlaps it); 0: plain stream order.  Results are identical.
@@ -186,8 +202,10 @@ int nmfb200_mul_X_f64(nmfb200_handle* h, int transpose_X, const double* B, int64
  * No counterpart in the reference (single process).  One handle per rank/GPU.  The unique id is an
  * opaque 128-byte blob (an ncclUniqueId) created on rank 0 and distributed by the host program
  * (torch.distributed / MPI / sockets).  After comm_init every solve on the handle treats its X, W
- * as the rank's row shard and all-reduces the k x k Gram, the k x n accumulator and the
- * convergence partial sums once per iteration over NCCL. */
+ * as the rank's row shard; H, niters, converged and objvalue come back identical on all ranks.
+ * MultUpdate(:mse) Float32 exchanges the k x n numerators, the k x k Grams and the convergence partial
+ * sums once per iteration through NVLink peer memory (CUDA IPC, no NCCL call in the loop); the other
+ * algorithms all-reduce the same quantities over NCCL on the exact engine. */
 #define NMFB200_UNIQUE_ID_BYTES 128
 int nmfb200_comm_unique_id(void* out_id_128);
 int nmfb200_comm_init(nmfb200_handle* h, int rank, int nranks, const void* id_128);
