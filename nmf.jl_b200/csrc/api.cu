@@ -201,6 +201,8 @@ int nmfb200_set_option(nmfb200_handle* h, const char* key, const char* value) {
             h->tc_flush = atoi(value);
         } else if (k == "tc_fused_hstep") {
             h->tc_fused_hstep = atoi(value);
+        } else if (k == "tc_defer_signal") {
+            h->tc_defer_signal = atoi(value);
         } else if (k == "tc_side_stream") {
             h->tc_side_stream = atoi(value);
         } else if (k == "emulate_shards") {

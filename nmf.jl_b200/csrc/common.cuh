@@ -116,6 +116,8 @@ struct nmfb200_handle {
     int tc_xchg = 1;       // multi-GPU on the tensor-core engine needs peer memory; 0 = keep multi-GPU solves on the exact engine (NCCL)
     int tc_fused_hstep = -1; // row-sharded solves, k <= 128: 1 = one launch for the H-step (own tiles finish the update in the numerator
                              // kernel), 0 = numerators / slot sum / ratio as three launches, -1 = auto (fused for two ranks)
+    int tc_defer_signal = 1; // row-sharded, > 2 ranks: the numerator / ratio kernels do not wait for their peer stores; the next kernel in
+                             // the stream (kernel boundary) raises the NUM / HBT flags
     int tc_side_stream = 1;  // row-sharded solves: run the H-Gram exchange (K4/K5) on a side stream, concurrently with the W-step
     cudaStream_t side_stream = nullptr;
     std::vector<cudaStream_t> vstreams;  // logical ranks (emulate_shards): one stream each for launches that wait on each other

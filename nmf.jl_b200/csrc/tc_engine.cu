@@ -53,6 +53,7 @@ struct ShardLaunch {
     unsigned int* hbt_cnt = nullptr;          // MODE 2 / 6: counter of finished own tiles
     unsigned int* hbt_flag[XCHG_MAX_RANKS] = {};
     const unsigned int* hbt_wait = nullptr;   // MODE 0: this rank's PH_HBT flag row
+    int defer_signal = 0, signal_hbt = 0;
 };
 
 template <int KP>
@@ -110,6 +111,8 @@ struct TcSolver {
             prm.hbt_cnt = sl->hbt_cnt;
             for (int j = 0; j < XCHG_MAX_RANKS; ++j) prm.hbt_flag[j] = sl->hbt_flag[j];
             prm.hbt_wait = sl->hbt_wait;
+            prm.defer_signal = sl->defer_signal;
+            prm.signal_hbt = sl->signal_hbt;
         }
         prm.tmB = make_tmap_bf16(O.bT, (uint64_t)Kdim, KP, (uint64_t)O.ldT, KP);
         if (KP <= 128 && (mode == 0 || mode == 1 || mode == 3 || mode == 6))

@@ -218,9 +218,12 @@ __global__ void __launch_bounds__(256) shard_post_kernel(ShardDev x, int phaseA,
 // One coalesced 16-byte load per slot and thread (the epilogue of the update kernel would read the same data row by row,
 // 16 bytes per lane at a 512-byte stride: measured ~2.3 us per slot there, ~3 us for ALL slots here).
 __global__ void __launch_bounds__(256) shard_slot_sum_kernel(ShardDev x, unsigned int epoch, size_t num_off, size_t slot_stride4, int64_t n4,
-                                                             float4* __restrict__ out, const TcState* st) {
+                                                             float4* __restrict__ out, const TcState* st, int signal_first) {
     pdl_launch_dependents();  // the ratio kernel behind us may set itself up; it waits for our completion before it reads `out`
     if (st->converged) return;
+    // deferred NUM flag: the numerator kernel in front of us (same stream, complete) pushed this rank's partials into the owners'
+    // slots without waiting for the stores; the kernel boundary has performed them, publish
+    if (signal_first && blockIdx.x == 0) shard_signal(x, PH_NUM, epoch);
     shard_wait(x, PH_NUM, epoch);
     const float4* base = (const float4*)(x.arena[x.rank] + num_off);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -676,17 +679,25 @@ void tc_solve_sharded_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64
                 for (auto& r : R) {  // K1
                     if (fused) break;
                     r.sl1.epoch = e;
+                    r.sl1.defer_signal = (h->tc_defer_signal != 0) ? 1 : 0;
                     r.s.sl = &r.sl1;
                     r.s.launch_update(1, r.H, r.W, r.Xr, (int)r.p, lh, delta, nullptr, nullptr, -1, nullptr, pdl);
                     r.s.sl = nullptr;
                 }
+                if (!fused && h->tc_defer_signal != 0 && emulate)   // logical ranks share a stream: every NUM flag before any Ksum
+                    for (auto& r : R) { shard_signal_kernel<<<1, 32, 0, st>>>(r.dev, (int)PH_NUM, e); h->launches += 1; }
                 if (!fused) h->mark("K1 numerators");
+                const bool defer = !fused && h->tc_defer_signal != 0;
                 for (auto& r : R) {  // Ksum
-                    if (fused || r.own_tiles == 0) continue;
+                    if (fused) break;
+                    if (r.own_tiles == 0) {  // nothing to sum here, but the owners wait for this rank's NUM flag
+                        if (defer) { shard_signal_kernel<<<1, 32, 0, st>>>(r.dev, (int)PH_NUM, e); h->launches += 1; }
+                        continue;
+                    }
                     const int64_t n4 = (r.own_r1 - r.own_r0) * KP / 4;
                     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(148 * 4, ceil_div(n4, 256)));
                     launch_k(shard_slot_sum_kernel, dim3(blocks), dim3(256), 0, st, false, r.dev, e, geom.off_num, geom.slot_rows * KP / 4, n4,
-                             (float4*)r.numsum, (const TcState*)r.state);
+                             (float4*)r.numsum, (const TcState*)r.state, defer && !emulate ? 1 : 0);
                     h->launches += 1;
                 }
                 if (!fused) h->mark("Ksum slots");
@@ -698,25 +709,29 @@ void tc_solve_sharded_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64
                         continue;
                     }
                     r.sl3.epoch = e;
+                    r.sl3.defer_signal = (defer && KP <= 128) ? 1 : 0;
                     r.s.sl = &r.sl3;
                     r.s.defer_gram_reduce = true;
                     r.s.num_splits = 1;
                     r.s.gram_tag = "gram_partH";   // K4 reads these on the side stream while K6 fills the W-step's tile Grams
-                    r.s.launch_update(2, r.Hown, r.W, r.Xr, (int)r.p, lh, delta, r.numsum, nullptr, KP <= 128 ? 1 : -1, nullptr, pdl);
+                    // no tile Gram in the ratio kernel: H'H over the own rows comes from gram_kernel on the side stream (below), which
+                    // takes the TMEM read-back and a 64 KB store per CTA out of the critical path
+                    r.s.launch_update(2, r.Hown, r.W, r.Xr, (int)r.p, lh, delta, r.numsum, nullptr, -1, nullptr, pdl);
                     r.s.num_splits = 1;
                     r.s.num_split_stride = 0;
                     r.s.defer_gram_reduce = false;
                     r.s.sl = nullptr;
-                    if (KP > 128) {  // no staged epilogue: Gram of the own rows by gram_kernel, slab to the peers by a copy kernel
-                        r.s.launch_gram_parts(r.H, (int)r.own_r0, (int)r.own_r1);
+                    if (KP > 128) {  // no staged epilogue: slab to the peers by a copy kernel
                         const int w16 = (int)(round_up((r.own_r1 - r.own_r0) * sizeof(bf16), 16) / 16);
                         shard_copy2d_kernel<<<64, 256, 0, st>>>(r.dev, geom.off_hbt + (size_t)r.own_r0 * sizeof(bf16), (size_t)geom.ldT * sizeof(bf16),
                                                                 KP, w16, (int)PH_HBT, e, r.ticket + 4, (const TcState*)r.state);
                         h->launches += 1;
                     }
-                    r.h_gram_part = r.s.last_gram_part;
-                    r.h_gram_parts = r.s.last_gram_parts;
                     r.s.gram_tag = "gram_part";
+                    if (defer && KP <= 128 && emulate) {  // deferred HBT flag (a real rank's W-step raises it at its start)
+                        shard_signal_kernel<<<1, 32, 0, st>>>(r.dev, (int)PH_HBT, e);
+                        h->launches += 1;
+                    }
                 }
                 if (!fused) h->mark("K3 own rows of H");
                 // K4 + K5 only feed the denominator blocks at the END of the W-step: a real rank runs them on a side stream,
@@ -725,6 +740,16 @@ void tc_solve_sharded_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64
                 if (side) {
                     NMF_CUDA(cudaEventRecord(ev_fork, st));
                     NMF_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+                }
+                for (auto& r : R) {  // partial Grams H'H of the own rows (the fused H-step made them in its epilogue)
+                    if (fused || r.own_tiles == 0) continue;
+                    r.s.st = sk;
+                    r.s.gram_tag = "gram_partH";
+                    r.s.launch_gram_parts(r.H, (int)r.own_r0, (int)r.own_r1);
+                    r.s.gram_tag = "gram_part";
+                    r.s.st = st;
+                    r.h_gram_part = r.s.last_gram_part;
+                    r.h_gram_parts = r.s.last_gram_parts;
                 }
                 for (auto& r : R) {  // K4
                     const bool any = r.own_tiles > 0;
@@ -753,6 +778,8 @@ void tc_solve_sharded_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64
                 r.sl6.epoch = e;
                 r.sl6.den_flag = a.update_H ? r.ticket + 5 : nullptr;
                 r.sl6.hbt_wait = a.update_H ? (const unsigned int*)xc.arena[r.g] + PH_HBT * XCHG_MAX_RANKS : nullptr;
+                r.sl6.signal_hbt = (a.update_H && !fused && h->tc_defer_signal != 0 && KP <= 128 && !emulate && r.own_tiles > 0) ? 1 : 0;
+                for (int j = 0; j < G; ++j) r.sl6.hbt_flag[j] = r.sl3.hbt_flag[j];
                 r.s.sl = &r.sl6;
                 r.s.defer_gram_reduce = true;
                 const int gramW = (a.update_H && KP <= 128) ? 1 : -1;

@@ -75,6 +75,9 @@ struct UpdateParams {
     unsigned int* hbt_flag[XCHG_MAX_RANKS];    // MODE 2 / 6: [j] -> flags[PH_HBT][my rank] in rank j's arena
     const unsigned int* hbt_wait;              // MODE 0 (W-step): this rank's PH_HBT flag row: the producer waits for `epoch` from every
                                                // rank before its first operand load (the rows of H'^T arrive from the peers)
+    int defer_signal;                          // MODE 1 / 2: do not wait for the peer stores and raise no flag here -- the kernel behind
+                                               // this one (kernel boundary = all stores performed) publishes NUM / HBT
+    int signal_hbt;                            // MODE 0 (W-step): CTA 0 raises PH_HBT for this rank at its start (deferred from MODE 2)
     const unsigned int* den_flag;              // MODE 0 (W-step): local flag "the Gram of the other factor for `epoch` is in place" -- set by
                                                // shard_post_kernel, which runs on a side stream concurrently with this kernel's main loop
 };
@@ -219,6 +222,12 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
     // The two single-thread loops below are the latency-critical part of the kernel: no per-block branches, no
     // div/mod, everything loop-invariant is hoisted (an extra compare per block is measurable at 256 blocks).
 
+    if (MODE == 0 && prm.signal_hbt && blockIdx.x == 0 && threadIdx.x == 96) {
+        // row-sharded W-step: the ratio kernel in front of us (same stream, complete) stored this rank's rows of H'^T into every
+        // rank's copy without waiting for the stores; publish them now (one thread of an epilogue warp, off the producer's path)
+        __threadfence_system();
+        for (int j = 0; j < prm.G; ++j) st_release_sys(prm.hbt_flag[j], prm.epoch);
+    }
     if (warp == 0) {
         // ===== TMA producer =====
         if (elect_one()) {
@@ -606,15 +615,19 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
 #pragma unroll
                 for (int b = 0; b < KP / 32; ++b) tma_store_2d(&prm.tmNum[owner_rank], SF + b * 16384, 32 * b, srow);
                 tma_store_commit();
-                tma_store_wait_all<0>();
-                asm volatile("fence.proxy.async;" ::: "memory");
-                __threadfence_system();
-                const int owned = min(prm.tiles_per_owner, prm.tiles_total - owner_rank * prm.tiles_per_owner);
-                const unsigned prev = atomicAdd(prm.own_cnt + owner_rank, 1u);
-                if (prev == (unsigned)owned - 1u) {
-                    prm.own_cnt[owner_rank] = 0u;
+                if (MODE == 1 && prm.defer_signal) {
+                    tma_store_wait_read<0>();   // the staging buffers have been read; completion is the kernel boundary's business
+                } else {
+                    tma_store_wait_all<0>();
+                    asm volatile("fence.proxy.async;" ::: "memory");
                     __threadfence_system();
-                    st_release_sys(prm.num_flag[owner_rank], prm.epoch);
+                    const int owned = min(prm.tiles_per_owner, prm.tiles_total - owner_rank * prm.tiles_per_owner);
+                    const unsigned prev = atomicAdd(prm.own_cnt + owner_rank, 1u);
+                    if (prev == (unsigned)owned - 1u) {
+                        prm.own_cnt[owner_rank] = 0u;
+                        __threadfence_system();
+                        st_release_sys(prm.num_flag[owner_rank], prm.epoch);
+                    }
                 }
             }
         }
@@ -698,8 +711,9 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                 // .read, measured the same)
                 if (threadIdx.x == 64) {
                     TSTAMP(9);                 // tile Gram written
-                    tma_store_wait_all<0>();
-                    if ((MODE == 2 || FUSED) && prm.G > 0) {
+                    if (MODE == 2 && prm.defer_signal) tma_store_wait_read<0>();
+                    else tma_store_wait_all<0>();
+                    if ((MODE == 2 || FUSED) && prm.G > 0 && !(MODE == 2 && prm.defer_signal)) {
                         // the peers' copies were written through the async proxy: order them, count this tile, and the last own
                         // tile tells every rank that this rank's rows of H'^T are in place (PH_HBT)
                         asm volatile("fence.proxy.async;" ::: "memory");

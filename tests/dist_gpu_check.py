@@ -43,6 +43,8 @@ def main():
         Wl, Hl = np.asfortranarray(W0[lo:hi]), H0.copy(order="F")
         with NMF.Session(device=local, engine=engine) as s:
             s.set_option("check_every", 7)
+            for kv in filter(None, os.environ.get("NMFB200_TEST_OPTS", "").split(",")):   # e.g. tc_fused_hstep=0,tc_defer_signal=0
+                s.set_option(*kv.split("="))
             NMF.dist.init_comm(s)
             r = NMF.dist.solve_sharded(alg, s, np.asfortranarray(X[lo:hi]), Wl, Hl)
         Wo, Ho = W0.copy(order="F"), H0.copy(order="F")
