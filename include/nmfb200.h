@@ -208,6 +208,11 @@ int nmfb200_mul_X_f64(nmfb200_handle* h, int transpose_X, const double* B, int64
  * algorithms all-reduce the same quantities over NCCL on the exact engine. */
 #define NMFB200_UNIQUE_ID_BYTES 128
 int nmfb200_comm_unique_id(void* out_id_128);
+/* Host-only helper (no GPU needed): which rows of H' (columns of H) rank `rank` of `ranks` OWNS in the row-sharded tensor-core
+ * MultUpdate(:mse) solve -- it alone applies the multiplicative ratio to them; everybody else receives them (csrc/tc_shard.cuh).
+ * H' is cut into tiles of `tile_rows` rows (128 for n >= 128, else n rounded up to 8), ceil(tiles / ranks) consecutive tiles per rank;
+ * trailing ranks may own nothing (own_row0 == own_row1).  EINVAL for ranks outside 1..8 or rank outside 0..ranks-1. */
+int nmfb200_shard_geometry(int64_t n, int ranks, int rank, int64_t* own_row0, int64_t* own_row1, int64_t* tile_rows);
 int nmfb200_comm_init(nmfb200_handle* h, int rank, int nranks, const void* id_128);
 int nmfb200_comm_destroy(nmfb200_handle* h);
 

@@ -78,6 +78,7 @@ SIGNATURES = {
     "nmfb200_mul_X_f32": (_i, [_vp, _i, _vp, _i64, _i64, _vp, _i64]),
     "nmfb200_mul_X_f64": (_i, [_vp, _i, _vp, _i64, _i64, _vp, _i64]),
     "nmfb200_comm_unique_id": (_i, [_vp]),
+    "nmfb200_shard_geometry": (_i, [_i64, _i, _i, ctypes.POINTER(_i64), ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),
     "nmfb200_comm_init": (_i, [_vp, _i, _i, _vp]),
     "nmfb200_comm_destroy": (_i, [_vp]),
 }

@@ -313,6 +313,16 @@ int nmfb200_comm_unique_id(void* out_id_128) {
     }
 }
 
+int nmfb200_shard_geometry(int64_t n, int ranks, int rank, int64_t* own_row0, int64_t* own_row1, int64_t* tile_rows) {
+    if (!own_row0 || !own_row1 || !tile_rows || n < 1 || ranks < 1 || ranks > XCHG_MAX_RANKS || rank < 0 || rank >= ranks) return NMFB200_EINVAL;
+    try {
+        tc_shard_geometry(n, ranks, rank, own_row0, own_row1, tile_rows);
+        return NMFB200_OK;
+    } catch (...) {
+        return NMFB200_EINVAL;
+    }
+}
+
 int nmfb200_comm_init(nmfb200_handle* h, int rank, int nranks, const void* id_128) {
     return guarded(h, [&] {
         NMF_REQUIRE(id_128 && nranks >= 1 && rank >= 0 && rank < nranks, NMFB200_EINVAL, "invalid rank/nranks/id");

@@ -291,6 +291,7 @@ bool tc_supported(const nmfb200_handle* h, const SolveArgs& a);
 bool tc_xmul(nmfb200_handle* h, int side, const float* O, int64_t sOr, int64_t sOc, int64_t k, float* out, int64_t sNr, int64_t sNc);
 void tc_solve(nmfb200_handle* h, const SolveArgs& a, float* W, int64_t ldw, float* H, int64_t ldh, nmfb200_result* out);
 void tc_release(nmfb200_handle* h);
+void tc_shard_geometry(int64_t n, int ranks, int rank, int64_t* own_row0, int64_t* own_row1, int64_t* tile_rows);
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -827,6 +827,13 @@ bool tc_xmul(nmfb200_handle* h, int side, const float* O, int64_t sOr, int64_t s
     }
 }
 
+void tc_shard_geometry(int64_t n, int ranks, int rank, int64_t* own_row0, int64_t* own_row1, int64_t* tile_rows) {
+    const ShardGeom g = shard_geom(ranks, 128, n, 0);   // KP does not enter the ownership
+    *own_row0 = g.own_row0(rank);
+    *own_row1 = g.own_row1(rank);
+    *tile_rows = g.trH;
+}
+
 void tc_release(nmfb200_handle* h) {
     xchg_teardown(h);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);

@@ -17,6 +17,30 @@ def row_shard(p: int, rank: int, world: int) -> Tuple[int, int]:
     return start, start + base + (1 if rank < extra else 0)
 
 
+def h_row_ownership(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Rows [start, stop) of H' (= columns of H) that `rank` OWNS in the row-sharded tensor-core MultUpdate(:mse) solve: it alone
+    applies the multiplicative ratio to them (csrc/tc_shard.cuh).  H' is cut into tiles of 128 rows (n < 128: one tile), each rank
+    owns ceil(tiles / world) consecutive tiles; trailing ranks may own nothing.  Python mirror of nmfb200_shard_geometry."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    tile = 128 if n >= 128 else -(-max(n, 8) // 8) * 8
+    tiles = -(-n // tile)
+    tpo = -(-tiles // world)
+    return min(n, rank * tpo * tile), min(n, (rank + 1) * tpo * tile)
+
+
+def shard_geometry(n: int, rank: int, world: int) -> Tuple[int, int, int]:
+    """The library's own answer (host-only C entry point nmfb200_shard_geometry): (own_row0, own_row1, tile_rows)."""
+    import ctypes
+
+    from . import _lib
+    a, b, t = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+    st = _lib.load().nmfb200_shard_geometry(n, world, rank, ctypes.byref(a), ctypes.byref(b), ctypes.byref(t))
+    if st != _lib.OK:
+        raise ValueError("nmfb200_shard_geometry: invalid arguments")
+    return a.value, b.value, t.value
+
+
 def init_comm(session, group=None) -> None:
     """Create the library's NCCL communicator over the ranks of `group` (default: WORLD)."""
     import torch.distributed as dist

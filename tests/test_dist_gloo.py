@@ -99,3 +99,113 @@ def test_sharded_iteration_world2_gloo():
     for pr in procs:
         pr.join(timeout=60)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+# ---- round 2: the OWNERSHIP protocol of the row-sharded tensor-core solver (csrc/tc_shard.cuh), restated with gloo + NumPy ----------
+def test_h_row_ownership_mirror_matches_library(NMF):
+    """dist.h_row_ownership (Python) == nmfb200_shard_geometry (the C++ geometry the kernels use; host-only entry point)."""
+    for n in (5, 96, 128, 129, 640, 1030, 16384, 65536):
+        for world in (1, 2, 3, 4, 8):
+            spans = []
+            for r in range(world):
+                a, b, t = NMF.dist.shard_geometry(n, r, world)
+                assert (a, b) == NMF.dist.h_row_ownership(n, r, world)
+                assert t == (128 if n >= 128 else -(-max(n, 8) // 8) * 8) and (a % t == 0 or a == n)
+                spans.append((a, b))
+            assert spans[0][0] == 0 and spans[-1][1] == n and all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+    with pytest.raises(ValueError):
+        NMF.dist.shard_geometry(100, 3, 3)
+
+
+def _owner_worker(rank, world, port, q):
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        sys.path.insert(0, p)
+    import nmf_jl_b200 as NMF
+    import nmf_oracle as O
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def gather(x):  # every rank's array, in rank order
+        out = [torch.empty_like(torch.from_numpy(x)) for _ in range(world)]
+        dist.all_gather(out, torch.from_numpy(np.ascontiguousarray(x)))
+        return [o.numpy() for o in out]
+
+    try:
+        rng = np.random.default_rng(1)
+        p, n, k = 301, 389, 6                       # 389 rows of H': 4 tiles of 128 -> world 3 owns 2 / 2 / 0 tiles
+        T = np.float64
+        X = np.asfortranarray(rng.random((p, n)))
+        W, H = O.randinit(p, n, k, T, rng, normalize=True)
+        Wref, Href = W.copy(order="F"), H.copy(order="F")
+        lo, hi = NMF.dist.row_shard(p, rank, world)
+        Xg, Wg = X[lo:hi], np.asfortranarray(W[lo:hi])
+        Ht = np.ascontiguousarray(H.T)              # H' (n x k): the rows this rank owns are the only ones it ever updates
+        o0, o1 = NMF.dist.h_row_ownership(n, rank, world)
+        owners = [NMF.dist.h_row_ownership(n, r, world) for r in range(world)]
+        delta = np.sqrt(np.finfo(T).eps)
+        tol, maxiter = 5e-3, 400
+        converged, updates = False, 0
+        Pw_parts = gather(Wg.T @ Wg)                # set-up: partial Grams W'W (PH_PW of the epoch before the loop)
+        wsums_parts = None
+        while True:
+            # K2: W'W = sum of the ranks' partial Grams in rank order; stop_condition of the PREVIOUS iteration (also run
+            # stand-alone after the last iteration of a host batch)
+            Pw = sum(Pw_parts[1:], Pw_parts[0].copy())
+            if wsums_parts is not None:
+                ws = sum(wsums_parts[1:], wsums_parts[0].copy())
+                hs = sum(hsums_parts[1:], hsums_parts[0].copy())
+                if all(np.sqrt(ws[0, j]) <= tol * np.sqrt(ws[1, j]) and np.sqrt(hs[0, j]) <= tol * np.sqrt(hs[1, j]) for j in range(k)):
+                    converged = True
+                    break
+            if updates == maxiter:
+                break
+            updates += 1
+            preW, preHt = Wg.copy(), Ht.copy()
+            # K1: partial numerators of ALL H rows over this rank's rows of X; every owner receives one slot per rank
+            slots = gather(np.ascontiguousarray((Wg.T @ Xg).T))        # slots[s] = rank s's partial (n x k)
+            # Ksum + K3: the OWNER sums its rows over the slots in rank order and applies the ratio to them -- nobody else does
+            if o1 > o0:
+                num = sum((s[o0:o1] for s in slots[1:]), slots[0][o0:o1].copy())
+                Ht[o0:o1] *= np.maximum(0, num) / (Ht[o0:o1] @ Pw + delta)
+            # the all-gather: every rank receives the owners' new rows (K3's epilogue stores)
+            mine = np.ascontiguousarray(Ht[o0:o1]) if o1 > o0 else np.zeros((0, k))
+            pad = np.zeros((max(b - a for a, b in owners), k))
+            pad[: o1 - o0] = mine
+            for r, rows in enumerate(gather(pad)):
+                a, b = owners[r]
+                Ht[a:b] = rows[: b - a]
+            # K4 / K5: partial Gram H'H and H-side stop sums of the own rows, summed over ranks in rank order
+            Ph = sum((g for g in gather(Ht[o0:o1].T @ Ht[o0:o1])[1:]), gather(Ht[o0:o1].T @ Ht[o0:o1])[0].copy())
+            hsums_parts = gather(np.stack([((Ht[o0:o1] - preHt[o0:o1]) ** 2).sum(0), ((Ht[o0:o1] + preHt[o0:o1]) ** 2).sum(0)]))
+            # K6: W-step on the local rows; K7: partial Gram W'W + W-side stop sums to everybody
+            Wg *= np.maximum(0, Xg @ Ht) / (Wg @ Ph + delta)
+            Pw_parts = gather(Wg.T @ Wg)
+            wsums_parts = gather(np.stack([((Wg - preW) ** 2).sum(0), ((Wg + preW) ** 2).sum(0)]))
+        ref = O.solve(O.MultUpdate(T, maxiter=maxiter, tol=tol), X, Wref, Href)
+        assert ref.converged and converged and ref.niters == updates, (ref.niters, updates, ref.converged, converged)
+        np.testing.assert_allclose(Ht.T, Href, rtol=1e-9)
+        np.testing.assert_allclose(Wg, Wref[lo:hi], rtol=1e-9)
+        same = gather(Ht)
+        assert all((s == same[0]).all() for s in same)      # the replicated H is bit-identical on every rank
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, f"FAIL {type(e).__name__}: {e} {traceback.format_exc()[-400:]}"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_ownership_protocol_gloo(world):
+    """The sharded algorithm of tc_shard.cuh, step for step (K1 ... K7, stop decision one iteration late), with gloo collectives
+    in place of the peer-memory stores: same iteration count, `converged`, W and H as the unsharded oracle; H identical everywhere."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + (os.getpid() + world) % 90
+    procs = [ctx.Process(target=_owner_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for pr in procs:
+        pr.join(timeout=60)
+    assert sorted(res) == [(r, "ok") for r in range(world)], res
