@@ -198,6 +198,20 @@ int nmfb200_solve_alspgrad_f64(nmfb200_handle* h, double* W, int64_t ldw, double
 int nmfb200_mul_X_f32(nmfb200_handle* h, int transpose_X, const float* B, int64_t ldb, int64_t c, float* C, int64_t ldc);
 int nmfb200_mul_X_f64(nmfb200_handle* h, int transpose_X, const double* B, int64_t ldb, int64_t c, double* C, int64_t ldc);
 
+/* ---- initialisation on the device: NMF.randinit (initialization.jl:4-17) ------------------------
+ * W ~ U[0,1)^(p x k), columns scaled to sum 1 when normalize != 0 (normalize1_cols!, utils.jl:26-32 -- what nnmf does for
+ * init=:random, interf.jl:43); H ~ U[0,1)^(k x n), or zeros when zeroh != 0.  p, n are those of the X set on the handle.
+ * The reference draws from Julia's global RNG, which nothing outside Julia can reproduce; this entry point is counter-based
+ * instead: element e (column-major linear index; for W the index in the UNSHARDED matrix: row_offset + i + j * p_total) is
+ * output word 0 (Float32: >> 8, * 2^-24) or words 0,1 (Float64: 53 bits, * 2^-53) of Philox4x32-10 with counter (e_lo, e_hi,
+ * stream, 0) -- stream 0 for W, 1 for H -- and key (seed_lo, seed_hi).  So the draw does not depend on the launch geometry or
+ * on how the rows are sharded (multi-GPU: pass the rank's row_offset and the total row count; column sums are all-reduced),
+ * and a host can regenerate it (tests/test_gpu_init.py does).  W, H: column-major, host or (on_device != 0) device pointers. */
+int nmfb200_randinit_f32(nmfb200_handle* h, float* W, int64_t ldw, float* H, int64_t ldh, int64_t k, uint64_t seed,
+                         int64_t row_offset, int64_t p_total, int normalize, int zeroh, int on_device);
+int nmfb200_randinit_f64(nmfb200_handle* h, double* W, int64_t ldw, double* H, int64_t ldh, int64_t k, uint64_t seed,
+                         int64_t row_offset, int64_t p_total, int normalize, int zeroh, int on_device);
+
 /* ---- multi-GPU: rows of X / W sharded over ranks, H replicated -----------
  * No counterpart in the reference (single process).  One handle per rank/GPU.  The unique id is an
  * opaque 128-byte blob (an ncclUniqueId) created on rank 0 and distributed by the host program

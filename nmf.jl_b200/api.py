@@ -287,6 +287,22 @@ class Session:
         buf = ctypes.create_string_buffer(unique_id, _lib.UNIQUE_ID_BYTES)
         self._check(self._lib.nmfb200_comm_init(self._h, rank, nranks, buf))
 
+    # -- initialisation on the device
+    def randinit(self, k: int, *, seed: int = 0, normalize: bool = False, zeroh: bool = False, row_offset: int = 0,
+                 p_total: Optional[int] = None):
+        """NMF.randinit (initialization.jl:4-17) generated on the GPU for the X that is resident: counter-based Philox4x32-10
+        keyed by `seed` (nmfb200_randinit_*; the draw of element (i, j) depends only on its index in the unsharded matrix, so
+        row-sharded ranks that pass their row_offset / p_total get the rows of the same W).  Returns (W, H), column-major."""
+        if self.dtype is None:
+            raise NmfB200Error("set_X must precede randinit")
+        p, n = self.shape
+        W = np.empty((p, k), dtype=self.dtype, order="F")
+        H = np.empty((k, n), dtype=self.dtype, order="F")
+        fn = getattr(self._lib, "nmfb200_randinit_" + _SFX[self.dtype])
+        self._check(fn(self._h, W.ctypes.data, p, H.ctypes.data, k, k, int(seed) & ((1 << 64) - 1), int(row_offset),
+                       int(p if p_total is None else p_total), int(normalize), int(zeroh), 0))
+        return W, H
+
     # -- solve
     def mul_X(self, B: np.ndarray, transpose: bool = False) -> np.ndarray:
         """X * B (transpose=False) or X' * B on the resident X (nmfb200_mul_X_*): the two X-sized products of the
@@ -484,13 +500,17 @@ def nndsvd(X: np.ndarray, k: int, *, zeroh: bool = False, variant: str = "std", 
 
 
 def solve_replicates(alg, session: Session, W, H, *, replicates: int, initH: bool, rng=None) -> Result:
-    """interf.jl:85-101; X stays resident on the GPU across replicates."""
+    """interf.jl:85-101; X stays resident on the GPU across replicates.  `rng`: a NumPy Generator (restarts drawn on the host) or an
+    int seed (restarts drawn on the GPU, Session.randinit with seed + replicate number)."""
     ret = session.solve(alg, W, H)
     p, n = session.shape
     k = W.shape[1]
     minobjv = ret.objvalue
-    for _ in range(2, replicates + 1):
-        Wr, Hr = randinit(p, n, k, alg.T, normalize=True, zeroh=not initH, rng=rng)
+    for rep in range(2, replicates + 1):
+        if isinstance(rng, (int, np.integer)):
+            Wr, Hr = session.randinit(k, seed=int(rng) + rep - 1, normalize=True, zeroh=not initH)
+        else:
+            Wr, Hr = randinit(p, n, k, alg.T, normalize=True, zeroh=not initH, rng=rng)
         tmp = session.solve(alg, Wr, Hr)
         if minobjv > tmp.objvalue:
             ret, minobjv = tmp, tmp.objvalue
@@ -506,7 +526,8 @@ def nnmf(X: np.ndarray, k: int, *, init: str = "nndsvdar", initdata=None, alg: s
          tol=None, replicates: int = 1, W0=None, H0=None, update_H: bool = True, verbose: bool = False, rng=None,
          device: int = 0, engine: str = "auto") -> Result:
     """interf.jl:3-83.  Same keyword names, defaults, validation order and messages.  `rng`, `device`
-    and `engine` are additions (Julia's global RNG has no NumPy counterpart)."""
+    and `engine` are additions (Julia's global RNG has no NumPy counterpart).  `rng` = a NumPy Generator: random factors are drawn
+    on the host; `rng` = an int: init=:random and the random restarts of `replicates` are drawn on the GPU (Philox keyed by it)."""
     X = np.asarray(X)
     T = X.dtype
     if T not in _SFX:
@@ -535,7 +556,10 @@ def nnmf(X: np.ndarray, k: int, *, init: str = "nndsvdar", initdata=None, alg: s
     elif W0 is not None or H0 is not None:  # :35
         warnings.warn("Ignore W0 and H0 except for :custom initialization.")
     initH = alg != "projals"  # :39
-    if init == "random":  # :42-43
+    device_seed = int(rng) if isinstance(rng, (int, np.integer)) else None
+    if init == "random" and device_seed is not None:  # :42-43, drawn on the GPU once the session holds X (below)
+        W = H = None
+    elif init == "random":  # :42-43
         W, H = randinit(p, n, k, T, normalize=True, zeroh=not initH, rng=rng)
     elif init == "custom":  # :52-53
         W, H = W0, H0
@@ -568,7 +592,9 @@ def nnmf(X: np.ndarray, k: int, *, init: str = "nndsvdar", initdata=None, alg: s
         raise ArgumentError("Invalid algorithm.")  # :79
     with Session(device=device, engine=engine) as s:
         s.set_X(X)
-        if W is None:
-            rng = rng if rng is not None else np.random.default_rng()
-            W, H = nndsvd(X, k, zeroh=not initH, variant=_NNDSVD_VARIANT[init], initdata=initdata, rng=rng, session=s)
+        if W is None and init == "random":
+            W, H = s.randinit(k, seed=device_seed, normalize=True, zeroh=not initH)
+        elif W is None:
+            nrng = np.random.default_rng(device_seed) if device_seed is not None else (rng if rng is not None else np.random.default_rng())
+            W, H = nndsvd(X, k, zeroh=not initH, variant=_NNDSVD_VARIANT[init], initdata=initdata, rng=nrng, session=s)
         return solve_replicates(inst, s, W, H, replicates=replicates, initH=initH, rng=rng)

@@ -19,6 +19,102 @@ __global__ void count_not_nonneg_kernel(const T* __restrict__ X, int64_t p, int6
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
+// ---- NMF.randinit on the device (initialization.jl:4-17): counter-based Philox4x32-10, one counter per element -----------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t& o0,
+                                              uint32_t& o1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    o0 = c0;
+    o1 = c1;
+}
+template <typename T> __device__ __forceinline__ T philox_uniform(uint64_t e, uint32_t stream, uint64_t seed);
+template <> __device__ __forceinline__ float philox_uniform<float>(uint64_t e, uint32_t stream, uint64_t seed) {
+    uint32_t a, b;
+    philox4x32_10((uint32_t)e, (uint32_t)(e >> 32), stream, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), a, b);
+    return (float)(a >> 8) * 5.9604644775390625e-08f;   // 24 bits -> [0, 1)
+}
+template <> __device__ __forceinline__ double philox_uniform<double>(uint64_t e, uint32_t stream, uint64_t seed) {
+    uint32_t a, b;
+    philox4x32_10((uint32_t)e, (uint32_t)(e >> 32), stream, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), a, b);
+    return (double)((((uint64_t)a << 32) | b) >> 11) * 1.1102230246251565e-16;   // 53 bits -> [0, 1)
+}
+// A(i, j) = U(e), e = e0 + i + j * e_ld  (rows x cols, column-major with leading dimension ld)
+template <typename T>
+__global__ void philox_fill_kernel(T* __restrict__ A, int64_t rows, int64_t cols, int64_t ld, uint64_t e0, uint64_t e_ld, uint32_t stream,
+                                   uint64_t seed) {
+    const int64_t total = rows * cols;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t % rows, j = t / rows;
+        A[i + j * ld] = philox_uniform<T>(e0 + (uint64_t)i + (uint64_t)j * e_ld, stream, seed);
+    }
+}
+// column sums in T, sequentially per column like `sum(view(W, :, j))` would not be (Julia sums pairwise): one block per column,
+// fixed tree => deterministic; the result is only a scale factor
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ A, int64_t rows, int64_t ld, T* __restrict__ out) {
+    __shared__ T red[256];
+    const T* col = A + (int64_t)blockIdx.x * ld;
+    T s = T(0);
+    for (int64_t i = threadIdx.x; i < rows; i += 256) s += col[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = red[0];
+}
+template <typename T>
+__global__ void colscale_kernel(T* __restrict__ A, int64_t rows, int64_t cols, int64_t ld, const T* __restrict__ sums) {
+    const int64_t total = rows * cols;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t % rows, j = t / rows;
+        A[i + j * ld] *= T(1) / sums[j];   // `W[:, j] .*= 1 / sum(W[:, j])` (utils.jl:28-32)
+    }
+}
+
+template <typename T>
+void randinit_impl(nmfb200_handle* h, T* W, int64_t ldw, T* H, int64_t ldh, int64_t k, uint64_t seed, int64_t row_offset, int64_t p_total,
+                   int normalize, int zeroh, int on_device) {
+    NMF_REQUIRE(W != nullptr && H != nullptr, NMFB200_EINVAL, "NULL argument");
+    NMF_REQUIRE(h->x_elt != 0, NMFB200_ESTATE, "nmfb200_set_X must precede randinit (it defines p and n)");
+    const int64_t p = h->p, n = h->n;
+    NMF_REQUIRE(k >= 1 && ldw >= p && ldh >= k && row_offset >= 0 && p_total >= row_offset + p, NMFB200_EDIM, "inconsistent dimensions");
+    cudaStream_t st = h->stream;
+    T* dW = on_device ? W : h->buf_t<T>("init.W", (size_t)p * k);
+    T* dH = on_device ? H : h->buf_t<T>("init.H", (size_t)k * n);
+    const int64_t lw = on_device ? ldw : p, lh = on_device ? ldh : k;
+    const int grid = 148 * 8;
+    philox_fill_kernel<T><<<grid, 256, 0, st>>>(dW, p, k, lw, (uint64_t)row_offset, (uint64_t)p_total, 0u, seed);
+    h->launches += 1;
+    if (normalize) {
+        T* sums = h->buf_t<T>("init.colsum", (size_t)k);
+        colsum_kernel<T><<<(unsigned)k, 256, 0, st>>>(dW, p, lw, sums);
+        h->allreduce_sum(sums, (size_t)k);   // row-sharded: the column sum runs over all ranks' rows
+        colscale_kernel<T><<<grid, 256, 0, st>>>(dW, p, k, lw, sums);
+        h->launches += 2;
+    }
+    if (zeroh) {
+        NMF_CUDA(cudaMemset2DAsync(dH, lh * sizeof(T), 0, k * sizeof(T), n, st));
+    } else {
+        philox_fill_kernel<T><<<grid, 256, 0, st>>>(dH, k, n, lh, 0, (uint64_t)k, 1u, seed);
+        h->launches += 1;
+    }
+    NMF_CUDA(cudaGetLastError());
+    if (!on_device) {
+        NMF_CUDA(cudaMemcpy2DAsync(W, ldw * sizeof(T), dW, p * sizeof(T), p * sizeof(T), k, cudaMemcpyDeviceToHost, st));
+        NMF_CUDA(cudaMemcpy2DAsync(H, ldh * sizeof(T), dH, k * sizeof(T), k * sizeof(T), n, cudaMemcpyDeviceToHost, st));
+    }
+    NMF_CUDA(cudaStreamSynchronize(st));
+}
+
 template <typename F>
 int guarded(nmfb200_handle* h, F&& f) {
     if (!h) return NMFB200_EINVAL;
@@ -298,6 +394,15 @@ int nmfb200_mul_X_f64(nmfb200_handle* h, int transpose_X, const double* B, int64
         NMF_REQUIRE(h->x_elt == 8, NMFB200_ESTATE, h->x_elt ? "X was set with a different element type" : "nmfb200_set_X must precede mul_X");
         simt_mul_X<double>(h, transpose_X, B, ldb, c, C, ldc);
     });
+}
+
+int nmfb200_randinit_f32(nmfb200_handle* h, float* W, int64_t ldw, float* H, int64_t ldh, int64_t k, uint64_t seed, int64_t row_offset,
+                         int64_t p_total, int normalize, int zeroh, int on_device) {
+    return guarded(h, [&] { randinit_impl<float>(h, W, ldw, H, ldh, k, seed, row_offset, p_total, normalize, zeroh, on_device); });
+}
+int nmfb200_randinit_f64(nmfb200_handle* h, double* W, int64_t ldw, double* H, int64_t ldh, int64_t k, uint64_t seed, int64_t row_offset,
+                         int64_t p_total, int normalize, int zeroh, int on_device) {
+    return guarded(h, [&] { randinit_impl<double>(h, W, ldw, H, ldh, k, seed, row_offset, p_total, normalize, zeroh, on_device); });
 }
 
 int nmfb200_comm_unique_id(void* out_id_128) {

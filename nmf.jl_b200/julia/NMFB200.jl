@@ -211,6 +211,18 @@ for (T, sfx) in ((Float32, "f32"), (Float64, "f64"))
     end
 end
 
+# randinit on the device (nmfb200_randinit_*): counter-based Philox keyed by `seed`, for the X resident on the handle
+for (T, sfx) in ((Float32, "f32"), (Float64, "f64"))
+    rinit = Symbol("nmfb200_randinit_", sfx)
+    @eval function randinit!(h::Handle, W::Matrix{$T}, H::Matrix{$T}; seed::Integer=0, normalize::Bool=false, zeroh::Bool=false,
+                             row_offset::Integer=0, p_total::Integer=size(W, 1))
+        GC.@preserve W H check(h, ccall(($(QuoteNode(rinit)), libnmfb200), Cint,
+            (Ptr{Cvoid}, Ptr{$T}, Int64, Ptr{$T}, Int64, Int64, UInt64, Int64, Int64, Cint, Cint, Cint),
+            h.ptr, W, stride(W, 2), H, stride(H, 2), size(W, 2), seed % UInt64, row_offset, p_total, normalize, zeroh, 0))
+        return W, H
+    end
+end
+
 function nmf_checksize(X, W::AbstractMatrix, H::AbstractMatrix)   # src/common.jl:5-16
     p, n = size(X); k = size(W, 2)
     (size(W, 1) == p && size(H) == (k, n)) || throw(DimensionMismatch("Dimensions of X, W, and H are inconsistent."))

@@ -73,3 +73,67 @@ def test_nnmf_reference_defaults_run_on_the_gpu(NMF, oracle):
     ro = oracle.nnmf(X, 4, alg="multmse", init="nndsvd", initdata=(U, s, Vt.T), maxiter=300)
     assert r.niters == ro.niters
     assert abs(float(r.objvalue) - float(ro.objvalue)) <= 1e-8 * float(ro.objvalue) + 1e-14
+
+
+# ---- randinit on the device (nmfb200_randinit_*): counter-based Philox4x32-10, regenerated here on the host --------------------
+def _philox_words(e, stream, seed):
+    """Words 0 and 1 of Philox4x32-10 with counter (e_lo, e_hi, stream, 0) and key (seed_lo, seed_hi); e: uint64 array."""
+    M0, M1, W0, W1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), 0x9E3779B9, 0xBB67AE85
+    mask = np.uint64(0xFFFFFFFF)
+    c0, c1 = e & mask, e >> np.uint64(32)
+    c2, c3 = np.full_like(e, stream), np.zeros_like(e)
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2                        # 32 x 32 -> 64 bit products
+        c0, c1, c2, c3 = (p1 >> np.uint64(32)) ^ c1 ^ np.uint64(k0), p1 & mask, (p0 >> np.uint64(32)) ^ c3 ^ np.uint64(k1), p0 & mask
+        k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+    return c0, c1
+
+
+def _philox_uniform(shape, T, stream, seed, e0=0, e_ld=None):
+    rows, cols = shape
+    e_ld = rows if e_ld is None else e_ld
+    i, j = np.meshgrid(np.arange(rows, dtype=np.uint64), np.arange(cols, dtype=np.uint64), indexing="ij")
+    a, b = _philox_words(np.uint64(e0) + i + j * np.uint64(e_ld), stream, seed)
+    if np.dtype(T) == np.float32:
+        return ((a >> np.uint64(8)).astype(np.float32) * np.float32(2.0 ** -24)).astype(np.float32)
+    return (((a << np.uint64(32)) | b) >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
+
+
+@pytest.mark.parametrize("T", [np.float32, np.float64])
+def test_device_randinit_is_the_documented_philox_stream(NMF, T):
+    p, n, k, seed = 301, 257, 7, 0x1234567890ABCDEF
+    X = np.asfortranarray(np.random.default_rng(0).random((p, n)), dtype=T)
+    with NMF.Session() as s:
+        s.set_X(X)
+        W, H = s.randinit(k, seed=seed)
+        assert (W == _philox_uniform((p, k), T, 0, seed)).all() and (H == _philox_uniform((k, n), T, 1, seed)).all()
+        assert W.min() >= 0 and W.max() < 1 and H.min() >= 0 and H.max() < 1 and abs(W.mean() - 0.5) < 0.05
+        Wn, Hz = s.randinit(k, seed=seed, normalize=True, zeroh=True)                 # what nnmf asks for with alg=:projals
+        np.testing.assert_allclose(Wn.sum(axis=0), 1.0, rtol=1e-5 if T == np.float32 else 1e-12)   # test/initialization.jl:22-27
+        np.testing.assert_allclose(Wn * W.sum(axis=0, keepdims=True, dtype=np.float64), W, rtol=2e-5 if T == np.float32 else 1e-12)
+        assert (Hz == 0).all()
+    # a row shard draws the rows of the unsharded W (row_offset / p_total) and the same H
+    lo, hi = 100, 230
+    with NMF.Session() as s:
+        s.set_X(np.asfortranarray(X[lo:hi]))
+        Ws, Hs = s.randinit(k, seed=seed, row_offset=lo, p_total=p)
+    assert (Ws == W[lo:hi]).all() and (Hs == H).all()
+
+
+def test_nnmf_with_device_seed(NMF, oracle):
+    """nnmf(..., init=:random, rng=<int>): the initial factors and the random restarts of `replicates` come from the device
+    generator; the run is reproducible and equals a solve from the same (regenerated) factors."""
+    rng = np.random.default_rng(3)
+    X = np.asfortranarray(rng.random((96, 80)), dtype=np.float64)
+    r1 = NMF.nnmf(X, 4, init="random", alg="multmse", maxiter=30, rng=77, replicates=3)
+    r2 = NMF.nnmf(X, 4, init="random", alg="multmse", maxiter=30, rng=77, replicates=3)
+    assert r1 == r2 and np.isfinite(float(r1.objvalue))
+    objs = []
+    for rep in range(3):
+        W0 = _philox_uniform((96, 4), np.float64, 0, 77 + rep)
+        W0 = np.asfortranarray(W0 * (1.0 / W0.sum(axis=0, keepdims=True)))
+        H0 = np.asfortranarray(_philox_uniform((4, 80), np.float64, 1, 77 + rep))
+        ro = oracle.solve(oracle.MultUpdate(np.float64, maxiter=30, tol=np.cbrt(np.finfo(np.float64).eps / 100)), X, W0, H0)
+        objs.append(float(ro.objvalue))
+    assert abs(float(r1.objvalue) - min(objs)) <= 1e-9 * min(objs)          # interf.jl:91-98 keeps the best replicate
