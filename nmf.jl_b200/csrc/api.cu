@@ -297,6 +297,8 @@ int nmfb200_set_option(nmfb200_handle* h, const char* key, const char* value) {
             h->tc_flush = atoi(value);
         } else if (k == "tc_fused_hstep") {
             h->tc_fused_hstep = atoi(value);
+        } else if (k == "tc_trace_identity") {
+            h->tc_trace_identity = atoi(value);
         } else if (k == "tc_defer_signal") {
             h->tc_defer_signal = atoi(value);
         } else if (k == "tc_side_stream") {

@@ -150,6 +150,9 @@ struct nmfb200_handle {
         }
     };
     std::map<std::string, XCacheKey> tc_x_cache;
+    double x_norm2 = 0;            // ||X||^2 of the resident X (verbose trace-identity objective)
+    uint64_t x_norm2_epoch = ~0ull;
+    int tc_trace_identity = 1;     // verbose on the tensor-core engine: per-iteration objective by the trace identity (0 = a pass over X)
 
     // multi-GPU
     ncclComm_t comm = nullptr;

@@ -66,6 +66,7 @@ struct TcSolver {
     const ShardLaunch* sl = nullptr; // row-sharded launch extras for the NEXT launch_update (reset by the caller)
     const bf16* Xs_lo = nullptr;     // precision mode bf16x3: the remainder panel matching the Xs of the NEXT launch_update
     bool force_x3 = false;           // split operands whatever the handle's precision option says (tc_xmul)
+    float* cross_part = nullptr;     // verbose W-step: per-tile sums of Num .* F_new for the NEXT launch_update (trace identity)
     bool defer_gram_reduce = false;  // the caller will run gram_conv_reduce_kernel itself
     bool last_fused_gram = false;
     float* last_gram_part = nullptr;
@@ -128,6 +129,7 @@ struct TcSolver {
         prm.tmPlo = make_tmap_bf16(O.Plo, KP, KP, KP, KP);
         prm.F = F.m; prm.Fhi = F.hi; prm.Flo = F.lo; prm.FbT = F.bT; prm.ldT = F.ldT;
         prm.num_io = num_io;
+        prm.cross_part = mode == 0 ? cross_part : nullptr;
         prm.num_splits = num_splits;
         prm.num_split_stride = num_split_stride;
         prm.conv_part = conv_override ? conv_override : F.conv;
@@ -284,6 +286,18 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
         NMF_REQUIRE(tc_objective<KP>(h, 0, W, H, 0.0, 0.0, &v), NMFB200_ENOTSUP, "verbose on the tensor-core engine needs the tensor-core objective");
         return v;
     };
+    // verbose: the objective after every iteration comes from the trace identity 0.5*(||X||^2 - 2<XH',W> + <W'W,HH'>) -- the W-step's
+    // numerators times the new W, and the two Grams, are on hand -- instead of a pass over X (311 us at config 2 = 1.5 iterations);
+    // the line before the loop and the last one (= Result.objvalue) use the objective kernel
+    const bool trace_id = a.verbose && h->tc_trace_identity != 0;
+    TraceObj tr;
+    std::memset(&tr, 0, sizeof(tr));
+    if (trace_id) {
+        tr.cross_part = h->buf_t<float>("tc.cross_part", (size_t)std::max(W.tiles, 1));
+        tr.ntiles = W.tiles;
+        tr.P_other = H.P;
+        tr.xnorm2 = x_norm2(h);
+    }
     if (a.verbose) {
         v_t0 = wall();
         v_objv = objective_now();
@@ -302,7 +316,9 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
             const int gramW = a.update_H ? 1 : -1;
             s.defer_gram_reduce = true;
             s.Xs_lo = Xc_lo;
+            s.cross_part = const_cast<float*>(tr.cross_part);
             s.launch_update(0, W, H, Xc, (int)n, lw, delta, nullptr, nullptr, gramW, nullptr, pdl);
+            s.cross_part = nullptr;
             s.defer_gram_reduce = false;
             h->mark("updW");
             const int gram_blocks = (s.last_fused_gram && gramW >= 0) ? (4 * KP * KP + 255) / 256 : 0;
@@ -310,7 +326,7 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
             // launch_update) + stop_condition reduce / decision
             launch_k(gram_conv_reduce_kernel, dim3(gram_blocks + 4 * (KP / 32)), dim3(256), 0, st, false, (const float*)s.last_gram_part,
                      W.tiles, KP * KP, W.P, W.Phi, W.Plo, 1, gram_blocks, (const float*)W.conv, W.tiles, (const float*)H.conv, H.tiles,
-                     KP, (int)k, (int)a.update_H, acc, tol, state, 1, (float*)nullptr);
+                     KP, (int)k, (int)a.update_H, acc, tol, state, 1, (float*)nullptr, tr);
             h->launches += 1;
             h->mark("conv");
         }
@@ -322,7 +338,8 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
         devmax = hs.devmax;
         if (a.verbose) {
             const double pre = v_objv;
-            v_objv = objective_now();
+            const bool last = hs.converged != 0 || enq >= a.maxiter;
+            v_objv = (trace_id && !last && a.update_H) ? hs.objv : objective_now();
             if (h->trace) h->trace(h->trace_user, iters, wall() - v_t0, v_objv, v_objv - pre, (double)devmax);
         }
         if (hs.converged) {

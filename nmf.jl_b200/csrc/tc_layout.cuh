@@ -210,6 +210,39 @@ Factor alloc_factor(nmfb200_handle* h, const std::string& tag, int R, int KP) {
     return f;
 }
 
+// ||X||^2 in Float64 (trace-identity objective of the verbose path), once per set_X
+__global__ void sumsq_kernel(const float* __restrict__ X, int64_t p, int64_t n, int64_t ldx, double* __restrict__ part) {
+    __shared__ double red[256];
+    double s = 0.0;
+    const int64_t total = p * n;
+    for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
+        const float v = X[(t % p) + (t / p) * ldx];
+        s += (double)v * (double)v;
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part[blockIdx.x] = red[0];
+}
+double x_norm2(nmfb200_handle* h) {
+    if (h->x_norm2_epoch == h->x_epoch) return h->x_norm2;
+    const int nb = 148 * 8;
+    double* part = h->buf_t<double>("tc.xnorm_part", nb);
+    sumsq_kernel<<<nb, 256, 0, h->stream>>>((const float*)h->dX, h->p, h->n, h->ldx, part);
+    h->launches += 1;
+    std::vector<double> hp(nb);
+    NMF_CUDA(cudaMemcpyAsync(hp.data(), part, nb * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    NMF_CUDA(cudaStreamSynchronize(h->stream));
+    double s = 0.0;
+    for (double v : hp) s += v;
+    h->x_norm2 = s;
+    h->x_norm2_epoch = h->x_epoch;
+    return s;
+}
+
 // bf16 tile-contiguous caches of X in both orientations (built once per set_X / tile shape / shard geometry).
 // X, p, ldx describe the rows this (logical) rank works on: the whole matrix, or a row shard of it (pfx names the buffers).
 void build_x_caches(nmfb200_handle* h, const std::string& pfx, const float* X, int64_t p, int64_t n, int64_t ldx, bf16** Xr_out,

@@ -110,57 +110,94 @@ __device__ __forceinline__ void gram_reduce_body(const float* __restrict__ part,
     }
 }
 
+// Trace-identity objective (verbose): 0.5*||X - WH||^2 = 0.5*(||X||^2 - 2<XH', W> + <W'W, HH'>) from quantities the
+// iteration has on hand -- the W-step's numerators times the new W (per-tile sums in cross_part), the two k x k Grams -- instead
+// of a pass over X.  Evaluated by the last block of gram_conv_reduce_kernel to finish (all-blocks ticket).
+struct TraceObj {
+    const float* cross_part;  // nullptr = off
+    int ntiles;
+    const float* P_other;     // Gram of the other factor (H H'), KP x KP fp32
+    double xnorm2;            // ||X||^2 (Float64, once per set_X)
+};
+
 __global__ void __launch_bounds__(256) gram_conv_reduce_kernel(const float* __restrict__ gpart, int nparts, int nelem, float* __restrict__ P,
                                                                bf16* __restrict__ Phi, bf16* __restrict__ Plo, int do_split, int gram_blocks,
                                                                const float* __restrict__ partW, int tilesW, const float* __restrict__ partH,
                                                                int tilesH, int KP, int k, int update_H, double* __restrict__ acc, float tol,
-                                                               TcState* st, int do_decide, float* __restrict__ wsums_f32) {
+                                                               TcState* st, int do_decide, float* __restrict__ wsums_f32, TraceObj tr) {
     pdl_launch_dependents();  // the next H-step may start streaming X now; it waits for us before it reads P / `converged`
     if (st->converged) return;
-    if ((int)blockIdx.x < gram_blocks) {
-        gram_reduce_body(gpart, nparts, nelem, P, Phi, Plo, do_split, blockIdx.x);
-        return;
-    }
     __shared__ double red[8][32];
     __shared__ float devs[256];
-    __shared__ int fail, is_last;
-    const int cblock = blockIdx.x - gram_blocks, nconv = gridDim.x - gram_blocks;
-    const int cbs = KP / 32;
-    const int q = cblock / cbs, cb = cblock % cbs;
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c = cb * 32 + lane;
-    const float* part = (q < 2 ? partW : partH) + (size_t)(q & 1) * KP + c;
-    const int tiles = q < 2 ? tilesW : (update_H ? tilesH : 0);
-    double s = 0.0;
-    int t = w;
-    for (; t + 56 < tiles; t += 64) {
-        float v[8];
+    __shared__ int fail, is_last, is_last_all;
+    if ((int)blockIdx.x < gram_blocks) {
+        gram_reduce_body(gpart, nparts, nelem, P, Phi, Plo, do_split, blockIdx.x);
+    } else {
+        const int cblock = blockIdx.x - gram_blocks, nconv = gridDim.x - gram_blocks;
+        const int cbs = KP / 32;
+        const int q = cblock / cbs, cb = cblock % cbs;
+        const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int c = cb * 32 + lane;
+        const float* part = (q < 2 ? partW : partH) + (size_t)(q & 1) * KP + c;
+        const int tiles = q < 2 ? tilesW : (update_H ? tilesH : 0);
+        double s = 0.0;
+        int t = w;
+        for (; t + 56 < tiles; t += 64) {
+            float v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = __ldcg(part + (size_t)(t + 8 * u) * 2 * KP);
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(part + (size_t)(t + 8 * u) * 2 * KP);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) s += (double)v[u];
+            for (int u = 0; u < 8; ++u) s += (double)v[u];
+        }
+        for (; t < tiles; t += 8) s += (double)__ldcg(part + (size_t)t * 2 * KP);
+        red[w][lane] = s;
+        __syncthreads();
+        if (w == 0) {
+            double tot = red[0][lane];
+#pragma unroll
+            for (int i = 1; i < 8; ++i) tot += red[i][lane];
+            if (q >= 2 && !update_H) tot = (q == 2) ? 0.0 : 1.0;
+            acc[(size_t)q * KP + c] = tot;
+            if (wsums_f32 && q < 2) wsums_f32[(size_t)q * KP + c] = (float)tot;
+        }
+        if (do_decide) {
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned int prev = atomicAdd(&st->ticket, 1u);
+                is_last = (prev == (unsigned)nconv - 1) ? 1 : 0;
+            }
+            __syncthreads();
+            if (is_last) {
+                __threadfence();
+                if (threadIdx.x == 0) st->ticket = 0u;
+                conv_decide(acc, KP, k, tol, st, devs, &fail);
+            }
+        }
     }
-    for (; t < tiles; t += 8) s += (double)__ldcg(part + (size_t)t * 2 * KP);
-    red[w][lane] = s;
-    __syncthreads();
-    if (w == 0) {
-        double tot = red[0][lane];
-#pragma unroll
-        for (int i = 1; i < 8; ++i) tot += red[i][lane];
-        if (q >= 2 && !update_H) tot = (q == 2) ? 0.0 : 1.0;
-        acc[(size_t)q * KP + c] = tot;
-        if (wsums_f32 && q < 2) wsums_f32[(size_t)q * KP + c] = (float)tot;
-    }
-    if (!do_decide) return;
+    if (tr.cross_part == nullptr) return;
+    // ---- trace-identity objective: the last of ALL blocks sees the complete Gram P of this factor
     __threadfence();
     __syncthreads();
+    if (threadIdx.x == 0) is_last_all = (atomicAdd(&st->ticket2, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!is_last_all) return;
+    __threadfence();
+    double part = 0.0;
+    for (int i = threadIdx.x; i < nelem; i += 256) part += (double)__ldcg(P + i) * (double)__ldcg(tr.P_other + i);   // <W'W, HH'>
+    double cross = 0.0;
+    for (int i = threadIdx.x; i < tr.ntiles; i += 256) cross += (double)__ldcg(tr.cross_part + i);                    // <XH', W>
+    part -= 2.0 * cross;
+    double* sred = &red[0][0];
+    sred[threadIdx.x] = part;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sred[threadIdx.x] += sred[threadIdx.x + o];
+        __syncthreads();
+    }
     if (threadIdx.x == 0) {
-        unsigned int prev = atomicAdd(&st->ticket, 1u);
-        is_last = (prev == (unsigned)nconv - 1) ? 1 : 0;
+        st->ticket2 = 0u;
+        const double d = tr.xnorm2 + sred[0];
+        st->objv = (double)(0.5f * (float)(d > 0.0 ? d : 0.0));   // convert(T, 0.5) * sqL2dist (multupd.jl:81)
     }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    if (threadIdx.x == 0) st->ticket = 0u;
-    conv_decide(acc, KP, k, tol, st, devs, &fail);
 }

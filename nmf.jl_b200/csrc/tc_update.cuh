@@ -8,6 +8,9 @@ struct TcState {
     int iters;
     float devmax;
     unsigned int ticket;
+    unsigned int ticket2;  // all-blocks ticket of gram_conv_reduce_kernel (trace-identity objective)
+    unsigned int pad_;
+    double objv;           // verbose: objective of the iteration just finished, by the trace identity (tc_reduce.cuh)
 };
 
 // ---- row-sharded solves (multi-GPU, or G logical shards on one GPU): see tc_shard.cuh -----------------------
@@ -36,6 +39,7 @@ struct UpdateParams {
                         // each finished chunk to fp32 register sums (round to nearest) while the next chunk accumulates.  The
                         // tensor core's accumulator TRUNCATES (measured: ~0.5 ulp lost per MMA, a relative bias of ~3e-8 per
                         // step that adds up over the 1000+ steps of a long contraction); short chains keep the bias at 1e-6.
+    float* cross_part;  // verbose W-step: [tiles] per-CTA sums of Num .* F_new = this tile's share of <X H', W> (trace identity; nullptr = skip)
     int x3;             // 1: numerators = A*B + A*Blo + Alo*B (three passes over the k-blocks), ~2^-16 relative instead of 2^-8
     float* gram_part;   // staged epilogue: [tiles][KP][KP] fp32 Gram contribution of each tile (nullptr = skip)
     float* F;           // [R][KP] fp32 master, updated in place
@@ -408,6 +412,8 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
             if (threadIdx.x == 64) TSTAMP(12);   // the other ranks' partial numerators have arrived
         }
         float* convw = conv_s + q * 2 * KP;
+        float cross_acc = 0.f;
+        float* cross_s = (float*)(smem + C::RING_BYTES + 512);   // [8 epilogue warps], behind the barriers
         const float lambda = prm.lambda, delta = prm.delta;
         float gcd_rowmax = -1.0f;
         if (MODE == 3) {  // diagonal of P into shared memory (conv scratch is free in this mode)
@@ -532,6 +538,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
             }
             float d2[32], s2[32];
             uint32_t hi_p[16], lo_p[16];
+            const bool want_cross = MODE == 0 && prm.cross_part != nullptr;
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
                 float fn[2];
@@ -547,6 +554,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                         v = f[j + e] * __fdividef(num, den);                 // multupd.jl:102 / :113 (2-ulp divide; operands are bf16-derived)
                     }
                     fn[e] = valid ? v : 0.f;
+                    if (want_cross) cross_acc += __uint_as_float(num_u[j + e]) * fn[e];   // <X H', W_new>, this row, this column
                     float dd = fn[e] - f[j + e], ss = fn[e] + f[j + e];      // common.jl:98-99 / :103-104
                     d2[j + e] = dd * dd;
                     s2[j + e] = ss * ss;
@@ -648,8 +656,18 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                 tc_fence_before();     // our TMEM reads are complete (the Gram below reuses the Num columns)
             }
             if (threadIdx.x == 64) TSTAMP(6);  // this warp's ratio / staging done
+            if (MODE == 0 && prm.cross_part != nullptr) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) cross_acc += __shfl_xor_sync(0xffffffffu, cross_acc, o);
+                if (lane == 0) cross_s[warp - 2] = cross_acc;
+            }
             // combine the four lane quarters: named barrier over the 256 epilogue threads
             asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (MODE == 0 && prm.cross_part != nullptr && threadIdx.x == 64) {
+                float c = 0.f;
+                for (int i = 0; i < 8; ++i) c += cross_s[i];   // fixed order
+                prm.cross_part[out_idx] = c;
+            }
             if constexpr (STAGED) {
                 if (threadIdx.x == 64) {
                     TSTAMP(7);                 // all epilogue warps done

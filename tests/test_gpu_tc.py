@@ -294,3 +294,31 @@ def test_tc_objective_kp256_split(NMF, oracle):
     r, W, H = _solve_mode(NMF, X, W0, H0, NMF.MultUpdate(np.float32, maxiter=4, tol=1e-30), None)
     obj = 0.5 * float(np.sum((X.astype(np.float64) - W.astype(np.float64) @ H.astype(np.float64)) ** 2))
     assert abs(float(r.objvalue) - obj) <= 1e-5 * obj
+
+
+@pytest.mark.parametrize("p,n,k", [(1024, 1152, 64), (700, 1500, 100), (1280, 1024, 200)])
+def test_tc_verbose_trace_identity_objective(NMF, oracle, p, n, k):
+    """The per-iteration objective of the verbose path comes from the trace identity 0.5*(||X||^2 - 2<XH',W> + <W'W,HH'>) (quantities the
+    iteration has on hand) instead of a pass over X; it must agree with the objective kernel (option tc_trace_identity=0) to 3e-4 on
+    every line (measured 1.1e-4 at 1.2 M cells: the bf16 rounding of the k*n entries of H enters <XH',W> un-averaged and the
+    objective is a difference of terms 8x its size; the error falls like 1/sqrt(k*n)) -- it is a progress display, as in the reference --
+    and the first and last lines ARE the objective kernel's (last == Result.objvalue)."""
+    X, W0, H0 = _problem(NMF, p, n, k, seed=p + 7)
+    out = {}
+    for ident in (1, 0):
+        lines = []
+        Wg, Hg = W0.copy(order="F"), H0.copy(order="F")
+        with NMF.Session(engine="tc") as s:
+            s.set_option("tc_trace_identity", ident)
+            s.set_X(X)
+            s.set_trace(lambda it, el, ob, ch, dv: lines.append((it, ob, ch, dv)))
+            r = s.solve(NMF.MultUpdate(np.float32, maxiter=8, tol=1e-9, verbose=True), Wg, Hg)
+        assert [l[0] for l in lines] == list(range(9)) and lines[-1][1] == float(r.objvalue)
+        out[ident] = (lines, Wg, Hg, r)
+    li, lk = out[1][0], out[0][0]
+    rel = [abs(a[1] - b[1]) / b[1] for a, b in zip(li, lk)]
+    print(f"trace identity vs objective kernel p={p} n={n} k={k}: max rel {max(rel):.2e}")
+    assert max(rel) <= 3e-4
+    assert li[0][1] == lk[0][1] and li[-1][1] == lk[-1][1]                  # same kernel for the first and the last line
+    assert (out[1][1] == out[0][1]).all() and (out[1][2] == out[0][2]).all()  # the factors do not depend on how the trace is computed
+    assert all(li[i + 1][1] <= li[i][1] * (1 + 1e-5) for i in range(8))
