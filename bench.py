@@ -400,6 +400,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 except Exception as e:  # never lose the headline line to a secondary workload
                     sec[wl] = {"error": repr(e)}
                 torch.cuda.empty_cache()
+            sec["batched_replicates"] = []
+            for R, kk in ((2, 128), (8, 32)):
+                try:
+                    sec["batched_replicates"].append(batched_line(R, kk, steps=20, warmup=3))
+                except Exception as e:
+                    sec["batched_replicates"].append({"error": repr(e), "replicates": R, "k": kk})
+                torch.cuda.empty_cache()
             line["secondary"] = sec
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -469,6 +476,55 @@ def secondary_line(workload, engine, steps, warmup, opts):
     return line
 
 
+def batched_line(R, k, steps, warmup):
+    """Batched replicates (interf.jl:85-101) on the configs[1] matrix: R MultUpdate(:mse) solves as one stacked
+    iteration (nmfb200_solve_multmse_batched_f32, device-resident) next to ONE solve of the same k timed the same way."""
+    import ctypes
+    import torch
+    import nmf_jl_b200 as NMF
+
+    p = n = 16384
+    torch.cuda.set_device(0)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(0)
+    dX = torch.rand((n, p), device="cuda", generator=g)
+    dW = torch.rand((R * k, p), device="cuda", generator=g)
+    dW /= dW.sum(dim=1, keepdim=True)
+    dH = torch.rand((n, R * k), device="cuda", generator=g)
+    W0, H0 = dW.clone(), dH.clone()
+    sess = NMF.Session(device=0, engine="tc")
+    sess.set_X_device(dX.data_ptr(), p, n, p, np.float32, keepalive=dX)
+    sess.set_option("check_every", max(steps, 1))
+    lib = sess._lib
+    res = (NMF._lib.NmfResult * R)()
+    ms_b = None
+    for iters in (max(warmup, 2), max(steps, 2)):
+        dW.copy_(W0)
+        dH.copy_(H0)
+        torch.cuda.synchronize()
+        sess._check(lib.nmfb200_solve_multmse_batched_f32(sess._h, ctypes.c_void_p(dW.data_ptr()), p, ctypes.c_void_p(dH.data_ptr()), R * k, k, R,
+                                                          iters, 1e-30, 0.0, 0.0, 1, 1, res))
+        ms_b = res[0].solve_ms / res[0].niters
+    objs = [res[r].objvalue for r in range(R)]
+    ms_1 = None
+    for iters in (max(warmup, 2), max(steps, 2)):   # one solve of the first replicate's factors (columns / rows [0, k))
+        w1 = W0[:k].contiguous()
+        h1 = H0[:, :k].contiguous()
+        torch.cuda.synchronize()
+        r1 = sess.solve_raw("multmse", np.float32, w1.data_ptr(), p, h1.data_ptr(), k, k, iters, 1e-30, 0.0, 0.0, True, False, True)
+        ms_1 = r1.solve_ms / r1.niters
+    hbm_peak, tf_peak, src = peaks()
+    flops = R * (4.0 * p * n * k + 4.0 * k * k * (p + n))
+    sess.close()
+    del dX, dW, dH, W0, H0
+    return {"workload": f"{R} replicates of MultUpdate(:mse) k={k} on dense fp32 X {p}x{n} as one stacked iteration",
+            "replicates": R, "k": k, "steps": int(res[0].niters), "ms_per_stacked_iteration": ms_b,
+            "replicate_iters_per_sec": R * 1e3 / ms_b, "one_solve_ms_per_iteration": ms_1, "one_by_one_replicate_iters_per_sec": 1e3 / ms_1,
+            "speedup_vs_one_by_one": R * ms_1 / ms_b, "tflops": flops / (ms_b * 1e-3) / 1e12,
+            "tensor_frac_of_sustained_bf16": flops / (ms_b * 1e-3) / 1e12 / tf_peak,
+            "objvalue_first_replicate": objs[0], "objvalue_one_solve": r1.objvalue}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -478,7 +534,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="experiments only: skip the end-to-end (host buffers) leg")
     ap.add_argument("--no-secondary", action="store_true", help="skip the configs[2] / configs[3] legs of the default run")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4"], help="cfg2 = headline (default); cfg3/cfg4 = secondary")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "batched"],
+                    help="cfg2 = headline (default); cfg3/cfg4 = secondary; batched = batched replicates on the cfg2 matrix")
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc"])
     ap.add_argument("--timeline", action="store_true", help="print the per-phase event timeline of the iteration (stderr)")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value for experiments (device-resident leg)")
@@ -489,6 +546,9 @@ def main():
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload == "batched":
+        print(json.dumps([batched_line(R, kk, args.steps, args.warmup) for R, kk in ((2, 128), (8, 32), (4, 64))]), flush=True)
         return
     if args.workload != "cfg2":
         run_secondary(args)

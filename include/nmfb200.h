@@ -128,6 +128,17 @@ int nmfb200_set_X_f64(nmfb200_handle* h, const double* X, int64_t p, int64_t n, 
 int nmfb200_set_X_dev_f32(nmfb200_handle* h, const float* dX, int64_t p, int64_t n, int64_t ldx, int check_nonneg);
 int nmfb200_set_X_dev_f64(nmfb200_handle* h, const double* dX, int64_t p, int64_t n, int64_t ldx, int check_nonneg);
 
+/* X as a SparseMatrixCSC{T,Int64} (README.md:22 "Sparse NMF": the reference's solvers reach X only through mul!, so sparse X works
+ * there).  colptr [n+1], rowval [nnz], nzval [nnz] are the three arrays of the Julia type (index_base = 1) or of a scipy csc_matrix
+ * with int64 indices (index_base = 0).  Only the stored entries cross PCIe; they are expanded on the device into the dense
+ * column-major matrix the kernels stream (p * n * sizeof(T) must fit in HBM -- the tensor-core path reads dense bf16 tiles whatever
+ * the sparsity).  Duplicate entries are summed.  EINVAL: colptr not non-decreasing / not starting at index_base, a row index out of
+ * range, or (check_nonneg != 0) a stored entry that is not >= 0. */
+int nmfb200_set_X_csc_f32(nmfb200_handle* h, const int64_t* colptr, const int64_t* rowval, const float* nzval,
+                          int64_t p, int64_t n, int index_base, int check_nonneg);
+int nmfb200_set_X_csc_f64(nmfb200_handle* h, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+                          int64_t p, int64_t n, int index_base, int check_nonneg);
+
 /* ---- solve!: one entry point per (algorithm, eltype) -------------------------------------------
  * Common arguments: W (p x k, ldw), H (k x n, ldh) initialised by the caller, updated in place.
  * `on_device` != 0: W and H are device pointers on this handle's GPU (no PCIe traffic).
@@ -143,6 +154,16 @@ int nmfb200_solve_multmse_f32(nmfb200_handle* h, float* W, int64_t ldw, float* H
 int nmfb200_solve_multmse_f64(nmfb200_handle* h, double* W, int64_t ldw, double* H, int64_t ldh, int64_t k,
                               int64_t maxiter, double tol, double lambda_w, double lambda_h, int update_H,
                               int verbose, int on_device, nmfb200_result* out);
+/* solve_replicates! (interf.jl:85-101) for MultUpdate{Float32} with obj=:mse as ONE stacked iteration: `replicates` independent
+ * solves of the resident X, replicate r initialised from columns [r*k, (r+1)*k) of W (p x replicates*k, ldw) and rows [r*k, (r+1)*k)
+ * of H (replicates*k x n, ldh), all updated in place.  Every pass over X serves all replicates (the HBM-bound operand is read once
+ * per half-step whatever `replicates` is); they do not interact (block-diagonal Grams), stop_condition is applied per replicate, and
+ * out[r] (r < replicates) carries the niters / converged / objvalue that replicate's own solve! returns -- the caller picks the
+ * smallest objvalue as interf.jl:94-98 does.  Tensor-core engine, one GPU, replicates * k <= 256, replicates <= 32; ENOTSUP otherwise
+ * (the caller then loops over nmfb200_solve_multmse_f32).  solve_ms / upload_ms / kernel_launches of every out[r] describe the batch. */
+int nmfb200_solve_multmse_batched_f32(nmfb200_handle* h, float* W, int64_t ldw, float* H, int64_t ldh, int64_t k,
+                                      int32_t replicates, int64_t maxiter, float tol, float lambda_w, float lambda_h,
+                                      int update_H, int on_device, nmfb200_result* out);
 /* NMF.solve!(::MultUpdate{T} with obj=:div, X, W, H)  -- multupd.jl:45-51, :150-193.
  * The lambda floor max(lambda, sqrt(eps(T))) of the constructor (multupd.jl:37-40) is applied here. */
 int nmfb200_solve_multdiv_f32(nmfb200_handle* h, float* W, int64_t ldw, float* H, int64_t ldh, int64_t k,

@@ -63,8 +63,12 @@ SIGNATURES = {
     "nmfb200_set_X_f64": (_i, [_vp, _vp, _i64, _i64, _i64, _i]),
     "nmfb200_set_X_dev_f32": (_i, [_vp, _vp, _i64, _i64, _i64, _i]),
     "nmfb200_set_X_dev_f64": (_i, [_vp, _vp, _i64, _i64, _i64, _i]),
+    "nmfb200_set_X_csc_f32": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _i, _i]),
+    "nmfb200_set_X_csc_f64": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _i, _i]),
     "nmfb200_solve_multmse_f32": _solve_sig(_f),
     "nmfb200_solve_multmse_f64": _solve_sig(_d),
+    "nmfb200_solve_multmse_batched_f32": (_i, [_vp, _vp, _i64, _vp, _i64, _i64, ctypes.c_int32, _i64, _f, _f, _f, _i, _i,
+                                               ctypes.POINTER(NmfResult)]),
     "nmfb200_solve_multdiv_f32": _solve_sig(_f),
     "nmfb200_solve_multdiv_f64": _solve_sig(_d),
     "nmfb200_solve_greedycd_f32": _solve_sig(_f),

@@ -197,6 +197,11 @@ class SPA:
 _SFX = {np.dtype(np.float32): "f32", np.dtype(np.float64): "f64"}
 
 
+def _is_sparse(X) -> bool:
+    """A scipy.sparse matrix / array (duck-typed: scipy is imported only if the caller already holds one)."""
+    return hasattr(X, "tocsc") and hasattr(X, "nnz") and not isinstance(X, np.ndarray)
+
+
 def _col_major(a: np.ndarray, dtype) -> np.ndarray:
     return np.asfortranarray(a, dtype=dtype)
 
@@ -252,7 +257,11 @@ class Session:
         self._check(self._lib.nmfb200_set_trace(self._h, self._trace_cb, None))
 
     # -- X
-    def set_X(self, X: np.ndarray, check_nonneg: bool = False) -> None:
+    def set_X(self, X, check_nonneg: bool = False) -> None:
+        """X: a NumPy matrix, or a scipy.sparse matrix (README.md:22 "Sparse NMF") -- its CSC arrays are uploaded and expanded on
+        the device (nmfb200_set_X_csc_*)."""
+        if _is_sparse(X):
+            return self._set_X_csc(X, check_nonneg)
         X = np.asarray(X)
         if X.ndim != 2:
             raise DimensionMismatch("X must be a matrix")
@@ -265,6 +274,21 @@ class Session:
         self._check(fn(self._h, Xf.ctypes.data_as(ctypes.c_void_p), p, n, p, int(check_nonneg)))
         self.dtype, self.shape = T, (p, n)
         self._x_host = X  # identity of the matrix that is resident (solve(alg, X, ..., session=s) compares against it)
+
+    def _set_X_csc(self, X, check_nonneg: bool) -> None:
+        Xc = X.tocsc()
+        T = np.dtype(Xc.dtype)
+        if T not in _SFX:
+            raise ArgumentError(f"eltype {T} not supported (Float32 / Float64)")
+        p, n = Xc.shape
+        colptr = np.ascontiguousarray(Xc.indptr, dtype=np.int64)
+        rowval = np.ascontiguousarray(Xc.indices, dtype=np.int64)
+        nzval = np.ascontiguousarray(Xc.data, dtype=T)
+        fn = getattr(self._lib, f"nmfb200_set_X_csc_{_SFX[T]}")
+        self._check(fn(self._h, colptr.ctypes.data_as(ctypes.c_void_p), rowval.ctypes.data_as(ctypes.c_void_p),
+                       nzval.ctypes.data_as(ctypes.c_void_p), p, n, 0, int(check_nonneg)))
+        self.dtype, self.shape = T, (p, n)
+        self._x_host = X
 
     def set_X_device(self, ptr: int, p: int, n: int, ldx: int, dtype, check_nonneg: bool = False, keepalive=None) -> None:
         """X already resident on this GPU (column-major p x n at device address `ptr`)."""
@@ -387,6 +411,43 @@ class Session:
         return Result(W, H, r.niters, bool(r.converged), r.objvalue, info)
 
 
+    def solve_batched(self, alg, Ws, Hs):
+        """`len(Ws)` independent MultUpdate(:mse) solves of the resident X as ONE stacked iteration
+        (nmfb200_solve_multmse_batched_f32: every pass over X serves all of them; block-diagonal Grams keep them independent;
+        stop_condition per replicate).  Ws[r] (p x k) and Hs[r] (k x n) are updated in place like `solve!`; returns one Result per
+        replicate.  Raises NotImplementedError when the library does not cover the request (Float32, tensor-core engine, one GPU,
+        len(Ws) * k <= 256) -- callers then loop over solve()."""
+        if not (isinstance(alg, MultUpdate) and alg.obj == "mse"):
+            raise NotImplementedError("batched replicates cover MultUpdate(:mse) only")
+        if self.shape is None:
+            raise NmfB200Error("set_X must precede solve")
+        T = alg.T
+        if T != np.dtype(np.float32) or alg.verbose:
+            raise NotImplementedError("batched replicates: Float32, verbose=false")
+        p, n = self.shape
+        R = len(Ws)
+        k = Ws[0].shape[1]
+        for W, H in zip(Ws, Hs):
+            if W.dtype != T or H.dtype != T or self.dtype != T:
+                raise TypeError("element types differ")
+            if not (W.shape == (p, k) and H.shape == (k, n)):
+                raise DimensionMismatch("Dimensions of X, W, and H are inconsistent.")
+        Wst = np.asfortranarray(np.concatenate(Ws, axis=1))   # p x R*k: replicate r = columns [r*k, (r+1)*k)
+        Hst = np.asfortranarray(np.concatenate(Hs, axis=0))   # R*k x n: replicate r = rows [r*k, (r+1)*k)
+        res = (_lib.NmfResult * R)()
+        self._check(self._lib.nmfb200_solve_multmse_batched_f32(
+            self._h, ctypes.c_void_p(Wst.ctypes.data), p, ctypes.c_void_p(Hst.ctypes.data), R * k, k, R, alg.maxiter, float(alg.tol),
+            float(alg.lambda_w), float(alg.lambda_h), int(alg.update_H), 0, res))
+        out = []
+        for r in range(R):
+            Ws[r][...] = Wst[:, r * k:(r + 1) * k]
+            Hs[r][...] = Hst[r * k:(r + 1) * k, :]
+            info = {"engine": "tc", "solve_ms": res[r].solve_ms, "upload_ms": res[r].upload_ms, "last_dev": res[r].last_dev,
+                    "kernel_launches": res[r].kernel_launches, "batched": R}
+            out.append(Result(Ws[r], Hs[r], res[r].niters, bool(res[r].converged), res[r].objvalue, info))
+        return out
+
+
 def _print_trace(it, elapsed, objv, change, dev):
     if it == 0:  # common.jl:57-58
         print("%-5s    %-13s    %-13s    %-13s    %-13s" % ("Iter", "Elapsed time", "objv", "objv.change", "(W & H).relchange"))
@@ -453,8 +514,8 @@ def nndsvd(X: np.ndarray, k: int, *, zeroh: bool = False, variant: str = "std", 
     """NMF.nndsvd (initialization.jl:70-101) with `_nndsvd!` (:26-68).  `initdata` = (U, S, V) of an SVD of X (the
     reference takes an `SVD` object); without it the triplets come from `rsvd`, whose X-sized products run on the
     GPU (`session` with X resident; one is opened on device 0 if none is given).  variant: "std" | "a" | "ar"."""
-    X = np.asarray(X)
-    T = X.dtype
+    X = X if _is_sparse(X) else np.asarray(X)
+    T = np.dtype(X.dtype)
     p, n = X.shape
     if variant not in ("std", "a", "ar"):
         raise ArgumentError("Invalid value for variant")
@@ -499,21 +560,42 @@ def nndsvd(X: np.ndarray, k: int, *, zeroh: bool = False, variant: str = "std", 
     return W, H
 
 
-def solve_replicates(alg, session: Session, W, H, *, replicates: int, initH: bool, rng=None) -> Result:
+def solve_replicates(alg, session: Session, W, H, *, replicates: int, initH: bool, rng=None, batched: bool = True) -> Result:
     """interf.jl:85-101; X stays resident on the GPU across replicates.  `rng`: a NumPy Generator (restarts drawn on the host) or an
-    int seed (restarts drawn on the GPU, Session.randinit with seed + replicate number)."""
-    ret = session.solve(alg, W, H)
+    int seed (restarts drawn on the GPU, Session.randinit with seed + replicate number).
+
+    MultUpdate(:mse) in Float32 runs its replicates in groups of up to 256 // k as ONE stacked iteration each (Session.solve_batched:
+    one pass over X per half-step serves the whole group -- SURVEY 8f-3).  The restarts are drawn in the reference's order (solve!
+    of MultUpdate consumes no random numbers, so drawing a group's factors up front is the same stream), and the first replicate with
+    the smallest objvalue wins as at interf.jl:94-98.  batched=False, or a request the library does not cover, loops one by one."""
     p, n = session.shape
     k = W.shape[1]
-    minobjv = ret.objvalue
-    for rep in range(2, replicates + 1):
+
+    def restart(rep):
         if isinstance(rng, (int, np.integer)):
-            Wr, Hr = session.randinit(k, seed=int(rng) + rep - 1, normalize=True, zeroh=not initH)
-        else:
-            Wr, Hr = randinit(p, n, k, alg.T, normalize=True, zeroh=not initH, rng=rng)
-        tmp = session.solve(alg, Wr, Hr)
-        if minobjv > tmp.objvalue:
-            ret, minobjv = tmp, tmp.objvalue
+            return session.randinit(k, seed=int(rng) + rep - 1, normalize=True, zeroh=not initH)
+        return randinit(p, n, k, alg.T, normalize=True, zeroh=not initH, rng=rng)
+
+    group = min(replicates, 256 // max(k, 1), 32)
+    use_batch = (batched and replicates > 1 and group >= 2 and isinstance(alg, MultUpdate) and alg.obj == "mse"
+                 and alg.T == np.dtype(np.float32) and not alg.verbose)
+    ret, minobjv = None, None
+    rep = 1
+    while rep <= replicates:
+        g = min(group, replicates - rep + 1) if use_batch else 1
+        facs = [(W, H) if r == 1 else restart(r) for r in range(rep, rep + g)]
+        results = None
+        if g >= 2:
+            try:
+                results = session.solve_batched(alg, [f[0] for f in facs], [f[1] for f in facs])
+            except NotImplementedError:   # small problem / exact engine / sharded handle: one by one below, same factors
+                use_batch = False
+        if results is None:
+            results = [session.solve(alg, fw, fh) for fw, fh in facs]
+        for tmp in results:
+            if ret is None or minobjv > tmp.objvalue:
+                ret, minobjv = tmp, tmp.objvalue
+        rep += g
     return ret
 
 
@@ -528,12 +610,13 @@ def nnmf(X: np.ndarray, k: int, *, init: str = "nndsvdar", initdata=None, alg: s
     """interf.jl:3-83.  Same keyword names, defaults, validation order and messages.  `rng`, `device`
     and `engine` are additions (Julia's global RNG has no NumPy counterpart).  `rng` = a NumPy Generator: random factors are drawn
     on the host; `rng` = an int: init=:random and the random restarts of `replicates` are drawn on the GPU (Philox keyed by it)."""
-    X = np.asarray(X)
-    T = X.dtype
+    sparse = _is_sparse(X)
+    X = X if sparse else np.asarray(X)
+    T = np.dtype(X.dtype)
     if T not in _SFX:
         raise ArgumentError(f"eltype {T} not supported (Float32 / Float64)")
     tol = np.cbrt(_eps(T) / 100) if tol is None else tol
-    if not bool((X >= 0).all()):  # interf.jl:15
+    if not bool(((X.data if sparse else X) >= 0).all()):  # interf.jl:15 (sparse: the stored entries; implicit zeros pass)
         raise ArgumentError("The elements of X must be non-negative.")
     p, n = X.shape
     if not k <= min(p, n):  # :18

@@ -174,6 +174,70 @@ void set_X_impl(nmfb200_handle* h, const T* X, int64_t p, int64_t n, int64_t ldx
     h->x_epoch += 1;
 }
 
+// ---- sparse X (README.md:22 "Sparse NMF": the reference's solvers only touch X through mul!, so a SparseMatrixCSC works there) ----
+// The compressed columns cross PCIe (12 or 16 bytes per stored entry instead of 4 or 8 per cell) and are expanded ON THE DEVICE into
+// the dense column-major matrix every engine works on -- the tensor-core path streams dense bf16 tiles whatever the sparsity, and
+// p * n * sizeof(T) has to fit in HBM.  Duplicate (row, column) entries are summed, as `sparse(I, J, V)` / scipy's toarray() do.
+template <typename T>
+__global__ void csc_scatter_kernel(const int64_t* __restrict__ colptr, const int64_t* __restrict__ rowval, const T* __restrict__ nzval,
+                                   int64_t p, int64_t n, int64_t base, T* __restrict__ X, unsigned long long* __restrict__ bad) {
+    for (int64_t col = blockIdx.x; col < n; col += gridDim.x) {
+        const int64_t e0 = colptr[col] - base, e1 = colptr[col + 1] - base;
+        for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+            const int64_t r = rowval[e] - base;
+            if (r < 0 || r >= p) { atomicAdd(bad, 1ull); continue; }
+            atomicAdd(X + r + col * p, nzval[e]);
+        }
+    }
+}
+
+template <typename T>
+void set_X_csc_impl(nmfb200_handle* h, const int64_t* colptr, const int64_t* rowval, const T* nzval, int64_t p, int64_t n, int index_base,
+                    int check_nonneg) {
+    NMF_REQUIRE(colptr != nullptr, NMFB200_EINVAL, "colptr is NULL");
+    NMF_REQUIRE(p > 0 && n > 0, NMFB200_EDIM, "invalid dimensions for X");
+    NMF_REQUIRE(index_base == 0 || index_base == 1, NMFB200_EINVAL, "index_base must be 0 or 1");
+    const int64_t base = index_base;
+    NMF_REQUIRE(colptr[0] == base, NMFB200_EINVAL, "colptr[0] must equal index_base");
+    for (int64_t j = 0; j < n; ++j) NMF_REQUIRE(colptr[j + 1] >= colptr[j], NMFB200_EINVAL, "colptr must be non-decreasing");
+    const int64_t nnz = colptr[n] - base;
+    NMF_REQUIRE(nnz == 0 || (rowval != nullptr && nzval != nullptr), NMFB200_EINVAL, "rowval / nzval is NULL");
+    cudaStream_t st = h->stream;
+    h->x_owned = false;
+    h->dX = nullptr;
+    h->x_elt = 0;
+    T* X = h->buf_t<T>("X", (size_t)p * n);
+    int64_t* d_colptr = h->buf_t<int64_t>("X.csc_colptr", (size_t)n + 1);
+    int64_t* d_rowval = h->buf_t<int64_t>("X.csc_rowval", (size_t)std::max<int64_t>(nnz, 1));
+    T* d_nzval = h->buf_t<T>("X.csc_nzval", (size_t)std::max<int64_t>(nnz, 1));
+    unsigned long long* cnt = (unsigned long long*)h->buf("X.nonneg_count", 16);
+    NMF_CUDA(cudaMemsetAsync(X, 0, (size_t)p * n * sizeof(T), st));
+    NMF_CUDA(cudaMemsetAsync(cnt, 0, 2 * sizeof(unsigned long long), st));
+    NMF_CUDA(cudaMemcpyAsync(d_colptr, colptr, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    if (nnz > 0) {
+        NMF_CUDA(cudaMemcpyAsync(d_rowval, rowval, (size_t)nnz * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        NMF_CUDA(cudaMemcpyAsync(d_nzval, nzval, (size_t)nnz * sizeof(T), cudaMemcpyHostToDevice, st));
+        csc_scatter_kernel<T><<<(unsigned)std::min<int64_t>(n, 148 * 16), 128, 0, st>>>(d_colptr, d_rowval, d_nzval, p, n, base, X, cnt + 1);
+        h->launches += 1;
+        if (check_nonneg) {   // interf.jl:15 on the stored entries (the implicit zeros pass)
+            count_not_nonneg_kernel<T><<<148 * 8, 256, 0, st>>>(d_nzval, nnz, 1, nnz, cnt);
+            h->launches += 1;
+        }
+    }
+    unsigned long long c[2] = {0, 0};
+    NMF_CUDA(cudaMemcpyAsync(c, cnt, sizeof(c), cudaMemcpyDeviceToHost, st));
+    NMF_CUDA(cudaStreamSynchronize(st));
+    NMF_REQUIRE(c[1] == 0, NMFB200_EINVAL, "rowval holds a row index outside 1..p (index_base .. index_base + p - 1)");
+    NMF_REQUIRE(c[0] == 0, NMFB200_EINVAL, "The elements of X must be non-negative.");
+    h->dX = X;
+    h->ldx = p;
+    h->p = p;
+    h->n = n;
+    h->x_elt = (int)sizeof(T);
+    h->x_owned = true;
+    h->x_epoch += 1;
+}
+
 template <typename T>
 void solve_args(nmfb200_handle* h, const SolveArgs& a, T* W, int64_t ldw, T* H, int64_t ldh, nmfb200_result* out) {
     NMF_REQUIRE(out != nullptr && W != nullptr && H != nullptr, NMFB200_EINVAL, "NULL argument");
@@ -293,6 +357,10 @@ int nmfb200_set_option(nmfb200_handle* h, const char* key, const char* value) {
             else throw Error{NMFB200_EINVAL, "tc_xchg must be p2p|nccl"};
         } else if (k == "tc_xmul") {
             h->tc_xmul_opt = atoi(value);
+        } else if (k == "tc_prefetch_next") {
+            int c = atoi(value);
+            NMF_REQUIRE(c >= 0 && c <= 4096, NMFB200_EINVAL, "tc_prefetch_next must be 0..4096");
+            h->tc_prefetch_next = c;
         } else if (k == "tc_flush") {
             h->tc_flush = atoi(value);
         } else if (k == "tc_fused_hstep") {
@@ -338,6 +406,15 @@ int nmfb200_set_X_dev_f64(nmfb200_handle* h, const double* X, int64_t p, int64_t
     return guarded(h, [&] { set_X_impl<double>(h, X, p, n, ldx, check_nonneg, true); });
 }
 
+int nmfb200_set_X_csc_f32(nmfb200_handle* h, const int64_t* colptr, const int64_t* rowval, const float* nzval, int64_t p, int64_t n,
+                          int index_base, int check_nonneg) {
+    return guarded(h, [&] { set_X_csc_impl<float>(h, colptr, rowval, nzval, p, n, index_base, check_nonneg); });
+}
+int nmfb200_set_X_csc_f64(nmfb200_handle* h, const int64_t* colptr, const int64_t* rowval, const double* nzval, int64_t p, int64_t n,
+                          int index_base, int check_nonneg) {
+    return guarded(h, [&] { set_X_csc_impl<double>(h, colptr, rowval, nzval, p, n, index_base, check_nonneg); });
+}
+
 #define NMFB200_DEFINE_SOLVE(NAME, ALG, T)                                                                                   \
     int NAME(nmfb200_handle* h, T* W, int64_t ldw, T* H, int64_t ldh, int64_t k, int64_t maxiter, T tol, T lambda_w,         \
              T lambda_h, int update_H, int verbose, int on_device, nmfb200_result* out) {                                    \
@@ -355,6 +432,27 @@ NMFB200_DEFINE_SOLVE(nmfb200_solve_greedycd_f32, 2, float)
 NMFB200_DEFINE_SOLVE(nmfb200_solve_greedycd_f64, 2, double)
 NMFB200_DEFINE_SOLVE(nmfb200_solve_projals_f32, 3, float)
 NMFB200_DEFINE_SOLVE(nmfb200_solve_projals_f64, 3, double)
+
+int nmfb200_solve_multmse_batched_f32(nmfb200_handle* h, float* W, int64_t ldw, float* H, int64_t ldh, int64_t k, int32_t replicates,
+                                      int64_t maxiter, float tol, float lambda_w, float lambda_h, int update_H, int on_device,
+                                      nmfb200_result* out) {
+    return guarded(h, [&] {
+        NMF_REQUIRE(out != nullptr && W != nullptr && H != nullptr, NMFB200_EINVAL, "NULL argument");
+        NMF_REQUIRE(h->x_elt != 0, NMFB200_ESTATE, "nmfb200_set_X must precede solve");
+        NMF_REQUIRE(h->x_elt == 4, NMFB200_ESTATE, "X was set with a different element type");
+        NMF_REQUIRE(replicates >= 1, NMFB200_EINVAL, "The value of replicates must be positive.");   // interf.jl:20
+        NMF_REQUIRE(maxiter > 1, NMFB200_EINVAL, "maxiter must be greater than 1.");               // multupd.jl:28
+        NMF_REQUIRE(tol > 0, NMFB200_EINVAL, "tol must be positive.");
+        NMF_REQUIRE(lambda_w >= 0, NMFB200_EINVAL, "lambda_w must be non-negative.");
+        NMF_REQUIRE(lambda_h >= 0, NMFB200_EINVAL, "lambda_h must be non-negative.");
+        NMF_REQUIRE(k >= 1 && ldw >= h->p && ldh >= k * replicates, NMFB200_EDIM, "Dimensions of X, W, and H are inconsistent.");
+        SolveArgs a{0, k, maxiter, (double)tol, (double)lambda_w, (double)lambda_h, update_H, 0, on_device};
+        NMF_REQUIRE(tc_batched_supported(h, a, replicates), NMFB200_ENOTSUP,
+                    "batched replicates need the tensor-core engine on one GPU: Float32, replicates * k <= 256, replicates <= 32, "
+                    "at least 2^20 cells unless engine=tc");
+        tc_solve_batched(h, a, replicates, W, ldw, H, ldh, out);
+    });
+}
 
 #define NMFB200_DEFINE_SOLVE_CD(NAME, T)                                                                                     \
     int NAME(nmfb200_handle* h, T* W, int64_t ldw, T* H, int64_t ldh, int64_t k, int64_t maxiter, T tol, T alpha, T l1ratio, \

@@ -124,6 +124,8 @@ struct nmfb200_handle {
     int emulate_shards = 0;  // > 1: run the row-sharded tensor-core algorithm with this many LOGICAL ranks on this one GPU
     int tc_xmul_opt = 1;   // ProjectedALS / CoordinateDescent / ALSPGrad (Float32): X-sized products on the tensor cores (split operands)
     int tc_flush = -1;     // k-blocks per TMEM accumulation chunk of the update kernel (0 = one long chain; -1 = default: 8)
+    int tc_prefetch_next = 0;  // update kernel (single GPU, bf16 mode): k-blocks of the NEXT launch's X panel each CTA prefetches into L2
+                               // while it sits in its epilogue (0 = off)
     int tc_precision = 0;  // 0 = bf16 operands; 1 = bf16x3 (hi/lo split of X and of the streamed factor: fp32-class products)
     nmfb200::Xchg xchg;
     int tc_pdl = 1;        // 1 = launch the update kernels as programmatic dependents of the reduce kernel before them
@@ -293,6 +295,9 @@ bool tc_supported(const nmfb200_handle* h, const SolveArgs& a);
 // Returns false (nothing done) when the shape is not covered; the caller then uses its own GEMM.
 bool tc_xmul(nmfb200_handle* h, int side, const float* O, int64_t sOr, int64_t sOc, int64_t k, float* out, int64_t sNr, int64_t sNc);
 void tc_solve(nmfb200_handle* h, const SolveArgs& a, float* W, int64_t ldw, float* H, int64_t ldh, nmfb200_result* out);
+// batched replicates: nrep MultUpdate(:mse) solves stacked along the component axis (W p x nrep*k, H nrep*k x n), one pass over X for all
+bool tc_batched_supported(const nmfb200_handle* h, const SolveArgs& a, int nrep);
+void tc_solve_batched(nmfb200_handle* h, const SolveArgs& a, int nrep, float* W, int64_t ldw, float* H, int64_t ldh, nmfb200_result* out);
 void tc_release(nmfb200_handle* h);
 void tc_shard_geometry(int64_t n, int ranks, int rank, int64_t* own_row0, int64_t* own_row1, int64_t* tile_rows);
 

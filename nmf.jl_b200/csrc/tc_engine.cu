@@ -67,6 +67,8 @@ struct TcSolver {
     const bf16* Xs_lo = nullptr;     // precision mode bf16x3: the remainder panel matching the Xs of the NEXT launch_update
     bool force_x3 = false;           // split operands whatever the handle's precision option says (tc_xmul)
     float* cross_part = nullptr;     // verbose W-step: per-tile sums of Num .* F_new for the NEXT launch_update (trace identity)
+    const bf16* pf_X = nullptr;      // option tc_prefetch_next: the X panel of the launch AFTER the next launch_update ...
+    int pf_tiles = 0, pf_tile_rows = 0, pf_nkb = 0;   // ... and its geometry (reset by the caller)
     bool defer_gram_reduce = false;  // the caller will run gram_conv_reduce_kernel itself
     bool last_fused_gram = false;
     float* last_gram_part = nullptr;
@@ -122,6 +124,13 @@ struct TcSolver {
             prm.x3 = 1;
             prm.tmAlo = make_tmap_bf16(Xs_lo, 64, (uint64_t)(tile0 + F.tiles) * nkb * F.tile_rows, 64, (uint32_t)F.tile_rows);
             prm.tmBlo = make_tmap_bf16(O.bTlo, (uint64_t)Kdim, KP, (uint64_t)O.ldT, KP);
+        }
+        if (mode == 0 && !x3 && sl == nullptr && pf_X != nullptr && h->tc_prefetch_next > 0 && pf_tiles > 0) {
+            prm.tmAnext = make_tmap_bf16(pf_X, 64, (uint64_t)pf_tiles * pf_nkb * pf_tile_rows, 64, (uint32_t)pf_tile_rows);
+            prm.pf_blocks = std::min(h->tc_prefetch_next, pf_nkb);
+            prm.pf_tiles = pf_tiles;
+            prm.pf_tile_rows = pf_tile_rows;
+            prm.pf_panel_rows = pf_nkb * pf_tile_rows;
         }
         prm.tmFhi = make_tmap_bf16(F.hi, KP, (uint64_t)F.R, KP, (uint32_t)F.tile_rows);
         prm.tmFlo = make_tmap_bf16(F.lo, KP, (uint64_t)F.R, KP, (uint32_t)F.tile_rows);
@@ -309,6 +318,7 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
             h->mark("start");
             if (a.update_H) {
                 s.Xs_lo = Xr_lo;
+                s.pf_X = Xc; s.pf_tiles = W.tiles; s.pf_tile_rows = W.tile_rows; s.pf_nkb = (int)ceil_div(n, 64);   // next: the W-step's panel
                 s.launch_update(0, H, W, Xr, (int)p, lh, delta, nullptr, nullptr, 1, nullptr, pdl);  // H-step (+ tile Grams of the new H)
                 h->mark("updH");
             }
@@ -317,7 +327,10 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
             s.defer_gram_reduce = true;
             s.Xs_lo = Xc_lo;
             s.cross_part = const_cast<float*>(tr.cross_part);
+            if (a.update_H) { s.pf_X = Xr; s.pf_tiles = H.tiles; s.pf_tile_rows = H.tile_rows; s.pf_nkb = (int)ceil_div(p, 64); }   // next: an H-step
+            else { s.pf_X = Xc; s.pf_tiles = W.tiles; s.pf_tile_rows = W.tile_rows; s.pf_nkb = (int)ceil_div(n, 64); }
             s.launch_update(0, W, H, Xc, (int)n, lw, delta, nullptr, nullptr, gramW, nullptr, pdl);
+            s.pf_X = nullptr;
             s.cross_part = nullptr;
             s.defer_gram_reduce = false;
             h->mark("updW");
@@ -406,6 +419,160 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
         for (int i = 1; i < 12; ++i) fprintf(stderr, " %s=%lld", names[i], t[i] - t[0]);
         fprintf(stderr, "\n");
     }
+}
+
+// ---- batched replicates (interf.jl:85-101) --------------------------------------------------------------
+// `nrep` independent MultUpdate(:mse) solves of the same X advance TOGETHER: their factors are stacked along the component axis
+// (W p x nrep*k, H nrep*k x n), so every pass over X feeds nrep numerators at once -- the contraction X'W_stack is the same kernel with
+// a wider B operand (nrep x the arithmetic intensity of one solve; X is the HBM-bound operand).  The replicates do not interact because
+// the k x k Grams of the denominators are kept BLOCK DIAGONAL (gram_masked, tc_update.cuh): Den_r = H_r (W_r'W_r).  stop_condition is
+// evaluated per replicate (conv_decide_batched); a replicate that meets it is snapshotted at that iteration (batch_snapshot_kernel) while
+// the stacked iteration carries on for the others, and the loop ends when all have passed or at maxiter -- each replicate returns the
+// niters / converged / factors its own solve! would have produced.
+template <int KPr>
+double batched_objective(nmfb200_handle* h, const float* Wd, int64_t ldwd, const float* Hd, int64_t ldhd, int64_t k) {
+    cudaStream_t st = h->stream;
+    const int64_t p = h->p, n = h->n;
+    Factor Wr = alloc_factor(h, "Wrep", (int)p, KPr), Hr = alloc_factor(h, "Hrep", (int)n, KPr);
+    pack_factor_kernel<<<ew_grid(p * KPr), 256, 0, st>>>(Wd, 1, ldwd, (int)p, (int)k, KPr, Wr.m, Wr.hi, Wr.lo, Wr.bT, Wr.ldT);
+    pack_factor_kernel<<<ew_grid(n * KPr), 256, 0, st>>>(Hd, ldhd, 1, (int)n, (int)k, KPr, Hr.m, Hr.hi, Hr.lo, Hr.bT, Hr.ldT);
+    h->launches += 2;
+    double v = 0;
+    if (!tc_objective<KPr>(h, 0, Wr, Hr, 0.0, 0.0, &v)) v = simt_objective_f32(h, 0, Wd, ldwd, Hd, ldhd, k, 0.0, 0.0);
+    return v;
+}
+
+template <int KP>
+void tc_solve_batched_kp(nmfb200_handle* h, const SolveArgs& a, int nrep, float* Wc, int64_t ldw, float* Hc, int64_t ldh, nmfb200_result* out) {
+    TcSolver<KP>::set_attrs(h->device);
+    cudaStream_t st = h->stream;
+    const int64_t p = h->p, n = h->n, k = a.k, kt = a.k * nrep;
+    const float delta = std::sqrt(std::numeric_limits<float>::epsilon());
+    const float lw = (float)a.lambda_w, lh = (float)a.lambda_h, tol = (float)a.tol;
+    cudaEvent_t e0, e1, e2;
+    NMF_CUDA(cudaEventCreate(&e0));
+    NMF_CUDA(cudaEventCreate(&e1));
+    NMF_CUDA(cudaEventCreate(&e2));
+    bf16 *Xr = nullptr, *Xc = nullptr, *Xr_lo = nullptr, *Xc_lo = nullptr;
+    build_x_caches(h, &Xr, &Xc, &Xr_lo, &Xc_lo);
+    NMF_CUDA(cudaEventRecord(e0, st));
+
+    Factor W = alloc_factor(h, "W", (int)p, KP), H = alloc_factor(h, "H", (int)n, KP);
+    TcState* state = (TcState*)h->buf("tc.state", sizeof(TcState));
+    BatchState* bs = (BatchState*)h->buf("tc.batch", sizeof(BatchState));
+    float* Wsnap = h->buf_t<float>("tc.W.snap", (size_t)p * KP);
+    float* Hsnap = h->buf_t<float>("tc.H.snap", (size_t)n * KP);
+    double* acc = h->buf_t<double>("tc.acc", 4 * KP);
+    TcState hs0;
+    std::memset(&hs0, 0, sizeof(hs0));
+    hs0.blk = (int)k;
+    hs0.kp = KP;
+    hs0.nrep = nrep;
+    hs0.bs = bs;
+    NMF_CUDA(cudaMemcpyAsync(state, &hs0, sizeof(TcState), cudaMemcpyHostToDevice, st));
+    NMF_CUDA(cudaMemsetAsync(bs, 0, sizeof(BatchState), st));
+    NMF_CUDA(cudaMemsetAsync(W.bT, 0, (size_t)W.rowsT * W.ldT * sizeof(bf16), st));
+    NMF_CUDA(cudaMemsetAsync(H.bT, 0, (size_t)H.rowsT * H.ldT * sizeof(bf16), st));
+
+    float *Wd = Wc, *Hd = Hc;
+    int64_t ldwd = ldw, ldhd = ldh;
+    if (!a.on_device) {
+        Wd = h->buf_t<float>("tc.Wstage", (size_t)p * kt);
+        Hd = h->buf_t<float>("tc.Hstage", (size_t)kt * n);
+        ldwd = p;
+        ldhd = kt;
+        NMF_CUDA(cudaMemcpy2DAsync(Wd, p * sizeof(float), Wc, ldw * sizeof(float), p * sizeof(float), kt, cudaMemcpyHostToDevice, st));
+        NMF_CUDA(cudaMemcpy2DAsync(Hd, kt * sizeof(float), Hc, ldh * sizeof(float), kt * sizeof(float), n, cudaMemcpyHostToDevice, st));
+    }
+    pack_factor_kernel<<<ew_grid(p * KP), 256, 0, st>>>(Wd, 1, ldwd, (int)p, (int)kt, KP, W.m, W.hi, W.lo, W.bT, W.ldT);
+    pack_factor_kernel<<<ew_grid(n * KP), 256, 0, st>>>(Hd, ldhd, 1, (int)n, (int)kt, KP, H.m, H.hi, H.lo, H.bT, H.ldT);
+    h->launches += 2;
+    NMF_CUDA(cudaGetLastError());
+
+    TcSolver<KP> s{h, st, state};
+    if (h->tc_precision == 1) { s.refresh_bTlo(W); s.refresh_bTlo(H); }
+    s.launch_gram(W, true);                   // block-diagonal W'W for the first H-step
+    if (!a.update_H) s.launch_gram(H, true);
+    NMF_CUDA(cudaEventRecord(e1, st));
+
+    h->ev_used = 0;
+    int64_t enq = 0;
+    TcState hs;
+    std::memset(&hs, 0, sizeof(hs));
+    const bool pdl = h->tc_pdl != 0;
+    const int snap_grid = ew_grid((p + n) * KP);
+    while (enq < a.maxiter) {
+        const int64_t batch = std::min<int64_t>(h->check_every, a.maxiter - enq);
+        for (int64_t i = 0; i < batch; ++i) {
+            if (a.update_H) {
+                s.Xs_lo = Xr_lo;
+                s.launch_update(0, H, W, Xr, (int)p, lh, delta, nullptr, nullptr, 1, nullptr, pdl);
+            }
+            const int gramW = a.update_H ? 1 : -1;
+            s.defer_gram_reduce = true;
+            s.Xs_lo = Xc_lo;
+            s.launch_update(0, W, H, Xc, (int)n, lw, delta, nullptr, nullptr, gramW, nullptr, pdl);
+            s.defer_gram_reduce = false;
+            const int gram_blocks = (s.last_fused_gram && gramW >= 0) ? (4 * KP * KP + 255) / 256 : 0;
+            TraceObj tr;
+            std::memset(&tr, 0, sizeof(tr));
+            launch_k(gram_conv_reduce_kernel, dim3(gram_blocks + 4 * (KP / 32)), dim3(256), 0, st, false, (const float*)s.last_gram_part,
+                     W.tiles, KP * KP, W.P, W.Phi, W.Plo, 1, gram_blocks, (const float*)W.conv, W.tiles, (const float*)H.conv, H.tiles,
+                     KP, (int)kt, (int)a.update_H, acc, tol, state, 1, (float*)nullptr, tr);
+            launch_k(batch_snapshot_kernel, dim3(snap_grid), dim3(256), 0, st, false, (const TcState*)state, KP, (const float*)W.m, Wsnap,
+                     (int64_t)p * KP, (const float*)H.m, Hsnap, (int64_t)n * KP, 0);
+            h->launches += 2;
+        }
+        enq += batch;
+        NMF_CUDA(cudaGetLastError());
+        NMF_CUDA(cudaMemcpyAsync(&hs, state, sizeof(TcState), cudaMemcpyDeviceToHost, st));
+        NMF_CUDA(cudaStreamSynchronize(st));
+        if (hs.converged) break;
+    }
+    NMF_CUDA(cudaEventRecord(e2, st));
+    // replicates that never met stop_condition: their factors are the current ones
+    batch_snapshot_kernel<<<snap_grid, 256, 0, st>>>(state, KP, W.m, Wsnap, (int64_t)p * KP, H.m, Hsnap, (int64_t)n * KP, 1);
+    unpack_factor_kernel<<<ew_grid(p * kt), 256, 0, st>>>(Wsnap, (int)p, (int)kt, KP, Wd, 1, ldwd);
+    unpack_factor_kernel<<<ew_grid(n * kt), 256, 0, st>>>(Hsnap, (int)n, (int)kt, KP, Hd, ldhd, 1);
+    h->launches += 3;
+    NMF_CUDA(cudaGetLastError());
+    BatchState hb;
+    NMF_CUDA(cudaMemcpyAsync(&hb, bs, sizeof(BatchState), cudaMemcpyDeviceToHost, st));
+    NMF_CUDA(cudaStreamSynchronize(st));
+    float ms_up = 0, ms_loop = 0;
+    cudaEventElapsedTime(&ms_up, e0, e1);
+    cudaEventElapsedTime(&ms_loop, e1, e2);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaEventDestroy(e2);
+    for (int r = 0; r < nrep; ++r) {   // objective of every replicate from ITS factors (multupd.jl:81)
+        const float* Wr = Wd + (size_t)r * k * ldwd;
+        const float* Hr = Hd + (size_t)r * k;
+        double objv = 0;
+        switch (pick_kp(k)) {
+            case 64: objv = batched_objective<64>(h, Wr, ldwd, Hr, ldhd, k); break;
+            case 128: objv = batched_objective<128>(h, Wr, ldwd, Hr, ldhd, k); break;
+            default: objv = batched_objective<256>(h, Wr, ldwd, Hr, ldhd, k); break;
+        }
+        std::memset(&out[r], 0, sizeof(nmfb200_result));
+        out[r].niters = hb.done[r] ? hb.niters[r] : hs.iters;
+        out[r].converged = hb.done[r] ? 1 : 0;
+        out[r].engine = 1;
+        out[r].objvalue = objv;
+        out[r].last_dev = hb.devmax[r];
+        out[r].solve_ms = ms_loop;       // the loop is shared: device time of the whole batch
+        out[r].upload_ms = ms_up;
+    }
+    if (!a.on_device) {
+        NMF_CUDA(cudaMemcpy2DAsync(Wc, ldw * sizeof(float), Wd, p * sizeof(float), p * sizeof(float), kt, cudaMemcpyDeviceToHost, st));
+        NMF_CUDA(cudaMemcpy2DAsync(Hc, ldh * sizeof(float), Hd, kt * sizeof(float), kt * sizeof(float), n, cudaMemcpyDeviceToHost, st));
+    }
+    NMF_CUDA(cudaStreamSynchronize(st));
+    for (int r = 0; r < nrep; ++r) out[r].kernel_launches = h->launches;
+    int64_t npairs = 0;
+    const double hot = h->drain_event_pairs(&npairs);
+    out[0].hot_kernel_ms = hot;
+    out[0].hot_kernel_launches = npairs;
 }
 
 #include "tc_div.cuh"
@@ -787,6 +954,23 @@ void tc_solve(nmfb200_handle* h, const SolveArgs& a, float* W, int64_t ldw, floa
         case 128: tc_solve_kp<128>(h, a, W, ldw, H, ldh, out); break;
         case 256: tc_solve_kp<256>(h, a, W, ldw, H, ldh, out); break;
         default: throw Error{NMFB200_ENOTSUP, "k > 256 is not covered by the tensor-core engine"};
+    }
+}
+
+bool tc_batched_supported(const nmfb200_handle* h, const SolveArgs& a, int nrep) {
+    if (a.alg != 0 || a.verbose || nrep < 1 || nrep > MAX_BATCH || a.k * nrep > 256) return false;
+    if (h->x_elt != 4 || h->engine_opt == 1 || h->comm != nullptr || h->emulate_shards > 1) return false;
+    if (h->engine_opt != 2 && h->p * h->n < ((int64_t)1 << 20)) return false;   // small problems stay on the exact engine, one by one
+    if (h->p > (int64_t)INT32_MAX / 256 || h->n > (int64_t)INT32_MAX / 256) return false;
+    return true;
+}
+
+void tc_solve_batched(nmfb200_handle* h, const SolveArgs& a, int nrep, float* W, int64_t ldw, float* H, int64_t ldh, nmfb200_result* out) {
+    switch (pick_kp(a.k * nrep)) {
+        case 64: tc_solve_batched_kp<64>(h, a, nrep, W, ldw, H, ldh, out); break;
+        case 128: tc_solve_batched_kp<128>(h, a, nrep, W, ldw, H, ldh, out); break;
+        case 256: tc_solve_batched_kp<256>(h, a, nrep, W, ldw, H, ldh, out); break;
+        default: throw Error{NMFB200_ENOTSUP, "replicates * k > 256 is not covered by the batched tensor-core solve"};
     }
 }
 

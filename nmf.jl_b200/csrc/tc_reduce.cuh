@@ -8,7 +8,57 @@
 // block (q, cb) sums quantity q of components [32cb, 32cb+32) over all tiles (warp w takes tiles w, w+8, ...;
 // 8 loads in flight; fixed combination order => deterministic).  With do_decide the last block to finish
 // (atomic ticket) applies the reference's test; row-sharded solves decide in shard_post_kernel (tc_shard.cuh).
+// Batched replicates: the reference's test per replicate (components [r*blk, (r+1)*blk)).  A replicate that passes for the first
+// time is marked `newly` (batch_snapshot_kernel then keeps its factors as they are now -- the stacked iteration goes on for the
+// others, and the replicates do not interact: block-diagonal Grams); the loop ends when every replicate has passed.
+__device__ void conv_decide_batched(const double* acc, int KP, float tol, TcState* st, float* devs) {
+    __shared__ int failc[256];
+    const int a = threadIdx.x;
+    const int blk = st->blk, nrep = st->nrep;
+    BatchState* bs = st->bs;
+    float dev = 0.f;
+    int f = 0;
+    if (a < blk * nrep) {
+        float dw = (float)__ldcg(acc + a), sw = (float)__ldcg(acc + KP + a), dh = (float)__ldcg(acc + 2 * KP + a),
+              sh = (float)__ldcg(acc + 3 * KP + a);
+        float rw = dw / sw, rh = dh / sh;
+        float m = (rw != rw) ? rw : ((rh != rh) ? rh : fmaxf(rw, rh));
+        dev = sqrtf(m);
+        f = (sqrtf(dw) > tol * sqrtf(sw) || sqrtf(dh) > tol * sqrtf(sh)) ? 1 : 0;
+    }
+    if (a < 256) { devs[a] = dev; failc[a] = f; }
+    __syncthreads();
+    if (a < nrep) {
+        float dm = 0.f;
+        int any = 0;
+        for (int i = a * blk; i < (a + 1) * blk; ++i) {
+            dm = (dm != dm) ? dm : ((devs[i] != devs[i]) ? devs[i] : fmaxf(dm, devs[i]));
+            any |= failc[i];
+        }
+        int nw = 0;
+        if (!bs->done[a]) {
+            bs->devmax[a] = dm;
+            if (!any) { bs->done[a] = 1; bs->niters[a] = st->iters + 1; nw = 1; }
+        }
+        bs->newly[a] = nw;
+    }
+    __syncthreads();
+    if (a == 0) {
+        int all = 1;
+        float dm = 0.f;
+        for (int r = 0; r < nrep; ++r) {
+            all &= bs->done[r];
+            const float d = bs->devmax[r];
+            dm = (dm != dm) ? dm : ((d != d) ? d : fmaxf(dm, d));
+        }
+        st->devmax = dm;
+        st->iters += 1;
+        if (all) st->converged = 1;
+    }
+}
+
 __device__ void conv_decide(const double* acc, int KP, int k, float tol, TcState* st, float* devs, int* fail) {
+    if (st->bs != nullptr) { conv_decide_batched(acc, KP, tol, st, devs); return; }
     const int a = threadIdx.x;
     if (a == 0) *fail = 0;
     __syncthreads();
@@ -83,7 +133,7 @@ __global__ void __launch_bounds__(256) conv_reduce_kernel(const float* __restric
 // contributions (gram_reduce_kernel's work), the remaining 4*KP/32 blocks reduce the stop_condition partial sums and the
 // last of them decides (conv_reduce_kernel's work).
 __device__ __forceinline__ void gram_reduce_body(const float* __restrict__ part, int nparts, int nelem, float* __restrict__ P,
-                                                 bf16* __restrict__ Phi, bf16* __restrict__ Plo, int do_split, int block) {
+                                                 bf16* __restrict__ Phi, bf16* __restrict__ Plo, int do_split, int block, const TcState* st) {
     const int t = block * blockDim.x + threadIdx.x;
     const int sub = t & 3;
     const int i = t >> 2;
@@ -101,6 +151,7 @@ __device__ __forceinline__ void gram_reduce_body(const float* __restrict__ part,
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
     if (i < nelem && sub == 0) {
+        if (gram_masked(st, i)) acc = 0.f;   // batched replicates: block-diagonal Gram
         P[i] = acc;
         if (do_split) {
             bf16 hi = __float2bfloat16_rn(acc);
@@ -131,7 +182,7 @@ __global__ void __launch_bounds__(256) gram_conv_reduce_kernel(const float* __re
     __shared__ float devs[256];
     __shared__ int fail, is_last, is_last_all;
     if ((int)blockIdx.x < gram_blocks) {
-        gram_reduce_body(gpart, nparts, nelem, P, Phi, Plo, do_split, blockIdx.x);
+        gram_reduce_body(gpart, nparts, nelem, P, Phi, Plo, do_split, blockIdx.x, st);
     } else {
         const int cblock = blockIdx.x - gram_blocks, nconv = gridDim.x - gram_blocks;
         const int cbs = KP / 32;
@@ -199,5 +250,37 @@ __global__ void __launch_bounds__(256) gram_conv_reduce_kernel(const float* __re
         st->ticket2 = 0u;
         const double d = tr.xnorm2 + sred[0];
         st->objv = (double)(0.5f * (float)(d > 0.0 ? d : 0.0));   // convert(T, 0.5) * sqL2dist (multupd.jl:81)
+    }
+}
+
+// Batched replicates: keep the factors of every replicate that met stop_condition in the iteration just decided (final != 0: of
+// every replicate that never did -- the end of the loop).  Fm / snap: [rows][KP] fp32 masters, W rows then H rows as two calls' worth
+// of work in one launch.  Launched behind gram_conv_reduce_kernel every iteration; copies nothing unless a flag is up.
+__global__ void __launch_bounds__(256) batch_snapshot_kernel(const TcState* __restrict__ st, int KP, const float* __restrict__ Wm,
+                                                             float* __restrict__ Wsnap, int64_t lenW, const float* __restrict__ Hm,
+                                                             float* __restrict__ Hsnap, int64_t lenH, int final) {
+    pdl_launch_dependents();   // the next H-step may start streaming; it waits for this kernel's completion before it touches H
+    __shared__ int flag[MAX_BATCH];
+    __shared__ int any;
+    const BatchState* bs = st->bs;
+    const int nrep = st->nrep, blk = st->blk;
+    if (threadIdx.x == 0) any = 0;
+    __syncthreads();
+    if ((int)threadIdx.x < nrep) {
+        const int f = final ? (bs->done[threadIdx.x] ? 0 : 1) : bs->newly[threadIdx.x];
+        flag[threadIdx.x] = f;
+        if (f) any = 1;
+    }
+    __syncthreads();
+    if (!any) return;
+    const int64_t total = lenW + lenH;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const bool w = i < lenW;
+        const int64_t j = w ? i : i - lenW;
+        const int r = (int)(j % KP) / blk;
+        if (r < nrep && flag[r]) {
+            if (w) Wsnap[j] = Wm[j];
+            else Hsnap[j] = Hm[j];
+        }
     }
 }

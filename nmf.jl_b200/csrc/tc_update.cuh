@@ -3,6 +3,16 @@
 // anonymous namespace.
 #pragma once
 
+// Batched replicates (interf.jl:85-101 as ONE pass over X per half-step for all replicates, tc_engine.cu::tc_solve_batched_kp):
+// replicate r owns components [r*blk, (r+1)*blk) of the stacked factors; stop_condition (common.jl:92-111) is applied per replicate.
+constexpr int MAX_BATCH = 32;
+struct BatchState {
+    int done[MAX_BATCH];     // the replicate has met stop_condition (its factors were snapshotted at that iteration)
+    int newly[MAX_BATCH];    // ... in the iteration just decided
+    int niters[MAX_BATCH];   // iteration count at which it did
+    float devmax[MAX_BATCH]; // `dev` of its last stop_condition call
+};
+
 struct TcState {
     int converged;
     int iters;
@@ -11,7 +21,19 @@ struct TcState {
     unsigned int ticket2;  // all-blocks ticket of gram_conv_reduce_kernel (trace-identity objective)
     unsigned int pad_;
     double objv;           // verbose: objective of the iteration just finished, by the trace identity (tc_reduce.cuh)
+    // batched replicates (all zero otherwise): the Gram reduce keeps only the diagonal blk x blk blocks of the KP x KP Gram (kp = KP),
+    // and the stop decision is taken per replicate in *bs; `converged` is raised once every replicate is done
+    int blk, kp, nrep, pad2_;
+    BatchState* bs;
 };
+
+// Gram element i = row * kp + col of a stacked factor: does it couple two different replicates?
+__device__ __forceinline__ bool gram_masked(const TcState* st, int i) {
+    const int blk = st->blk;
+    if (blk <= 0) return false;
+    const int kp = st->kp;
+    return (i / kp) / blk != (i % kp) / blk;
+}
 
 // ---- row-sharded solves (multi-GPU, or G logical shards on one GPU): see tc_shard.cuh -----------------------
 // Flag phases of the per-rank arena (flags[phase * XCHG_MAX_RANKS + src] = last epoch `src` has published):
@@ -35,6 +57,10 @@ struct UpdateParams {
     CUtensorMap tmT;    // F^T bf16 [KP][R]        box 64 x KP        (staged epilogue store of the transposed copy)
     CUtensorMap tmAlo;  // precision mode bf16x3: the remainder panel Xs - bf16(Xs), same geometry as tmA
     CUtensorMap tmBlo;  //   ... and the transposed remainder of the other factor, same geometry as tmB
+    CUtensorMap tmAnext; // MODE 0, pf_blocks > 0: the X panel the NEXT update launch streams (same geometry rules as tmA)
+    int pf_blocks;      // > 0: once its own loads are issued, the producer asks L2 for the first pf_blocks k-blocks of the tile that CTA
+                        // blockIdx.x of the next launch will stream -- HBM is otherwise idle while all CTAs sit in their epilogues
+    int pf_tiles, pf_tile_rows, pf_panel_rows;   // next launch: tiles, rows per tile, rows of the tile-contiguous panel per tile (nkb * tile_rows)
     int flush_chunk;    // > 0 (KP <= 128): the numerator MMAs accumulate at most this many k-blocks in TMEM; the epilogue warps add
                         // each finished chunk to fp32 register sums (round to nearest) while the next chunk accumulates.  The
                         // tensor core's accumulator TRUNCATES (measured: ~0.5 ulp lost per MMA, a relative bias of ~3e-8 per
@@ -285,6 +311,15 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                     tma_load_2d(dst + C::A_BYTES, t == 1 ? &prm.tmPlo : &prm.tmPhi, &full_bar[s], 64 * sl, 0);
                     dst += C::STAGE_BYTES;
                     if (++s == C::STAGES) { s = 0; ph ^= 1u; dst = smem; }
+                }
+            }
+            if (MODE == 0 && prm.pf_blocks > 0 && (int)blockIdx.x < prm.pf_tiles) {
+                // every load of this launch is in flight: warm L2 with the head of the next launch's panel (no smem destination,
+                // no completion tracking; a converged solve wastes them harmlessly)
+                int prow = (int)blockIdx.x * prm.pf_panel_rows;
+                for (int i = 0; i < prm.pf_blocks; ++i) {
+                    tma_prefetch_2d(&prm.tmAnext, 0, prow);
+                    prow += prm.pf_tile_rows;
                 }
             }
         }
@@ -917,6 +952,7 @@ __global__ void __launch_bounds__(256) gram_reduce_kernel(const float* __restric
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
     if (i < nelem && sub == 0) {
+        if (gram_masked(st, i)) acc = 0.f;   // batched replicates: block-diagonal Gram
         P[i] = acc;
         if (do_split) {
             bf16 hi = __float2bfloat16_rn(acc);

@@ -20,6 +20,7 @@ module NMFB200
 
 using LinearAlgebra
 using LinearAlgebra: qr!, svd!
+using SparseArrays
 
 export nnmf
 
@@ -177,6 +178,13 @@ for (T, sfx) in ((Float32, "f32"), (Float64, "f64"))
         GC.@preserve X check(h, ccall(($(QuoteNode(setx)), libnmfb200), Cint,
             (Ptr{Cvoid}, Ptr{$T}, Int64, Int64, Int64, Cint), h.ptr, X, size(X, 1), size(X, 2), stride(X, 2), check_nonneg))
     end
+    setcsc = Symbol("nmfb200_set_X_csc_", sfx)
+    # README.md:22 "Sparse NMF": the three arrays of the SparseMatrixCSC cross PCIe and are expanded on the device
+    @eval function set_X!(h::Handle, X::SparseMatrixCSC{$T,Int64}; check_nonneg::Bool=false)
+        GC.@preserve X check(h, ccall(($(QuoteNode(setcsc)), libnmfb200), Cint,
+            (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{$T}, Int64, Int64, Cint, Cint),
+            h.ptr, X.colptr, X.rowval, X.nzval, size(X, 1), size(X, 2), 1, check_nonneg))
+    end
     cd = Symbol("nmfb200_solve_cd_", sfx)
     @eval function _solve_cd(h::Handle, W::Matrix{$T}, H::Matrix{$T}, a::CoordinateDescent{$T})
         res = Ref{CResult}()
@@ -230,32 +238,54 @@ function nmf_checksize(X, W::AbstractMatrix, H::AbstractMatrix)   # src/common.j
 end
 
 """    solve!(alg, X, W, H; handle=Handle()) -> Result{T}   (NMF.solve!, src/multupd.jl:45, src/greedycd.jl:33)"""
-function solve!(alg::MultUpdate{T}, X::Matrix{T}, W::Matrix{T}, H::Matrix{T}; handle::Handle=Handle(), x_resident::Bool=false) where T
+function solve!(alg::MultUpdate{T}, X::Union{Matrix{T},SparseMatrixCSC{T,Int64}}, W::Matrix{T}, H::Matrix{T}; handle::Handle=Handle(), x_resident::Bool=false) where T
     nmf_checksize(X, W, H)
     x_resident || set_X!(handle, X)
     f = alg.obj == :mse ? _solve_multmse : _solve_multdiv
     f(handle, W, H, alg.maxiter, alg.tol, alg.lambda_w, alg.lambda_h, alg.update_H, alg.verbose)
 end
-function solve!(alg::GreedyCD{T}, X::Matrix{T}, W::Matrix{T}, H::Matrix{T}; handle::Handle=Handle(), x_resident::Bool=false) where T
+function solve!(alg::GreedyCD{T}, X::Union{Matrix{T},SparseMatrixCSC{T,Int64}}, W::Matrix{T}, H::Matrix{T}; handle::Handle=Handle(), x_resident::Bool=false) where T
     nmf_checksize(X, W, H)
     x_resident || set_X!(handle, X)
     _solve_greedycd(handle, W, H, alg.maxiter, alg.tol, alg.lambda_w, alg.lambda_h, alg.update_H, alg.verbose)
 end
 
-function solve!(alg::ProjectedALS{T}, X::Matrix{T}, W::Matrix{T}, H::Matrix{T}; handle::Handle=Handle(), x_resident::Bool=false) where T
+function solve!(alg::ProjectedALS{T}, X::Union{Matrix{T},SparseMatrixCSC{T,Int64}}, W::Matrix{T}, H::Matrix{T}; handle::Handle=Handle(), x_resident::Bool=false) where T
     nmf_checksize(X, W, H)                                    # src/projals.jl:37-39
     x_resident || set_X!(handle, X)
     _solve_projals(handle, W, H, alg.maxiter, alg.tol, alg.lambda_w, alg.lambda_h, alg.update_H, alg.verbose)
 end
-function solve!(alg::CoordinateDescent{T}, X::Matrix{T}, W::Matrix{T}, H::Matrix{T}; handle::Handle=Handle(), x_resident::Bool=false) where T
+function solve!(alg::CoordinateDescent{T}, X::Union{Matrix{T},SparseMatrixCSC{T,Int64}}, W::Matrix{T}, H::Matrix{T}; handle::Handle=Handle(), x_resident::Bool=false) where T
     nmf_checksize(X, W, H)                                    # src/coorddesc.jl:49-51
     x_resident || set_X!(handle, X)
     _solve_cd(handle, W, H, alg)
 end
-function solve!(alg::ALSPGrad{T}, X::Matrix{T}, W::Matrix{T}, H::Matrix{T}; handle::Handle=Handle(), x_resident::Bool=false) where T
+function solve!(alg::ALSPGrad{T}, X::Union{Matrix{T},SparseMatrixCSC{T,Int64}}, W::Matrix{T}, H::Matrix{T}; handle::Handle=Handle(), x_resident::Bool=false) where T
     nmf_checksize(X, W, H)                                    # src/alspgrad.jl:381-383
     x_resident || set_X!(handle, X)
     _solve_alspgrad(handle, W, H, alg)
+end
+
+"""    solve_batched!(alg::MultUpdate{Float32}, Ws, Hs; handle) -> Vector{Result{Float32}} or `nothing`
+
+`length(Ws)` independent `MultUpdate(obj=:mse)` solves of the X resident on `handle` as ONE stacked iteration
+(`nmfb200_solve_multmse_batched_f32`: every pass over X serves all replicates; stop_condition per replicate).  `Ws[r]`, `Hs[r]` are
+updated in place.  Returns `nothing` when the library does not cover the request (status ENOTSUP): the caller loops over `solve!`."""
+function solve_batched!(alg::MultUpdate{Float32}, Ws::Vector{Matrix{Float32}}, Hs::Vector{Matrix{Float32}}; handle::Handle)
+    R = length(Ws); k = size(Ws[1], 2)
+    Wst = reduce(hcat, Ws); Hst = reduce(vcat, Hs)            # replicate r: columns / rows (r-1)*k+1 : r*k
+    res = Vector{CResult}(undef, R)
+    st = GC.@preserve Wst Hst res ccall((:nmfb200_solve_multmse_batched_f32, libnmfb200), Cint,
+        (Ptr{Cvoid}, Ptr{Float32}, Int64, Ptr{Float32}, Int64, Int64, Int32, Int64, Float32, Float32, Float32, Cint, Cint, Ref{CResult}),
+        handle.ptr, Wst, stride(Wst, 2), Hst, stride(Hst, 2), k, R, alg.maxiter, alg.tol, alg.lambda_w, alg.lambda_h, alg.update_H, 0, res)
+    st == ENOTSUP && return nothing
+    check(handle, st)
+    out = Vector{Result{Float32}}(undef, R)
+    for r in 1:R
+        copyto!(Ws[r], view(Wst, :, (r-1)*k+1:r*k)); copyto!(Hs[r], view(Hst, (r-1)*k+1:r*k, :))
+        out[r] = Result{Float32}(Ws[r], Hs[r], Int(res[r].niters), res[r].converged != 0, Float32(res[r].objvalue))
+    end
+    return out
 end
 
 # ---- randinit (src/initialization.jl:4-17, src/utils.jl:26-32) and nnmf (src/interf.jl:3-101) -------------------
@@ -361,11 +391,27 @@ function nnmf(X::AbstractMatrix{T}, k::Integer; init::Symbol=:nndsvdar, initdata
            alg == :spa ? error("alg=:spa is not on the accelerated path") :
            throw(ArgumentError("Invalid algorithm."))
     h = Handle(device)
-    Xm = Matrix{T}(X)
+    Xm = X isa SparseMatrixCSC{T,Int64} ? X : Matrix{T}(X)   # sparse X: only the stored entries cross PCIe (set_X! expands them on the GPU)
     set_X!(h, Xm)                                      # X stays resident on the GPU across init, solve and replicates
     W, H = init == :random ? randinit(p, n, k, T; normalize=true, zeroh=!initH) :
            init == :custom ? (W0::Matrix{T}, H0::Matrix{T}) :     # aliased and updated in place, like `W = W::Matrix{T}` at src/interf.jl:57-58
            nndsvd(Xm, k; zeroh=!initH, variant=(init == :nndsvd ? :std : init == :nndsvda ? :a : :ar), initdata=initdata, handle=h)
+    if replicates > 1 && inst isa MultUpdate{Float32} && inst.obj == :mse && !verbose && 2k <= 256
+        # src/interf.jl:85-101 in groups of up to 256 ÷ k replicates per stacked iteration (one pass over X per half-step for the group);
+        # solve! of MultUpdate draws no random numbers, so drawing a group's restarts up front is the reference's stream
+        ret = nothing; rep = 1
+        while rep <= replicates
+            g = min(256 ÷ k, 32, replicates - rep + 1)
+            facs = [r == 1 ? (W, H) : randinit(p, n, k, T; normalize=true, zeroh=!initH) for r in rep:rep+g-1]
+            rs = g >= 2 ? solve_batched!(inst, [f[1] for f in facs], [f[2] for f in facs]; handle=h) : nothing
+            rs === nothing && (rs = [solve!(inst, Xm, f[1], f[2]; handle=h, x_resident=true) for f in facs])
+            for tmp in rs
+                (ret === nothing || ret.objvalue > tmp.objvalue) && (ret = tmp)
+            end
+            rep += g
+        end
+        return ret
+    end
     ret = solve!(inst, Xm, W, H; handle=h, x_resident=true)
     for _ in 2:replicates                              # src/interf.jl:91-98
         Wr, Hr = randinit(p, n, k, T; normalize=true, zeroh=!initH)

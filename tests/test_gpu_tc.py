@@ -322,3 +322,20 @@ def test_tc_verbose_trace_identity_objective(NMF, oracle, p, n, k):
     assert li[0][1] == lk[0][1] and li[-1][1] == lk[-1][1]                  # same kernel for the first and the last line
     assert (out[1][1] == out[0][1]).all() and (out[1][2] == out[0][2]).all()  # the factors do not depend on how the trace is computed
     assert all(li[i + 1][1] <= li[i][1] * (1 + 1e-5) for i in range(8))
+
+
+def test_tc_prefetch_next_option_changes_no_result(NMF):
+    """Option tc_prefetch_next: while a CTA of the update kernel sits in its epilogue, its producer thread asks L2 for the head of the
+    panel the NEXT launch will stream.  Pure L2 prefetches: the factors, niters and objvalue must be bit-identical."""
+    X, W0, H0 = _problem(NMF, 1280, 1536, 96, seed=77)
+    out = []
+    for pf in (0, 4, 64):       # 64 > the 20 / 24 k-blocks of these panels: clamped to the panel
+        W, H = W0.copy(order="F"), H0.copy(order="F")
+        with NMF.Session(engine="tc") as s:
+            s.set_option("tc_prefetch_next", pf)
+            s.set_X(X)
+            r = s.solve(NMF.MultUpdate(np.float32, obj="mse", maxiter=12, tol=1e-9), W, H)
+        out.append((W, H, r))
+    for W, H, r in out[1:]:
+        assert (W == out[0][0]).all() and (H == out[0][1]).all()
+        assert r.objvalue == out[0][2].objvalue and r.niters == out[0][2].niters == 12

@@ -192,7 +192,7 @@ _C2JL = {
     "void*": "Ptr{Cvoid}", "const void*": "Ptr{Cvoid}", "const char*": "Cstring", "int": "Cint", "int64_t": "Int64",
     "uint64_t": "UInt64", "float": "Float32", "double": "Float64", "float*": "Ptr{Float32}", "const float*": "Ptr{Float32}",
     "double*": "Ptr{Float64}", "const double*": "Ptr{Float64}", "nmfb200_result*": "Ref{CResult}", "nmfb200_trace_fn": "Ptr{Cvoid}",
-    "int64_t*": "Ref{Int64}",
+    "int64_t*": "Ref{Int64}", "int32_t": "Int32", "const int64_t*": "Ptr{Int64}",
 }
 
 
