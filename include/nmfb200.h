@@ -233,6 +233,23 @@ int nmfb200_randinit_f32(nmfb200_handle* h, float* W, int64_t ldw, float* H, int
 int nmfb200_randinit_f64(nmfb200_handle* h, double* W, int64_t ldw, double* H, int64_t ldh, int64_t k, uint64_t seed,
                          int64_t row_offset, int64_t p_total, int normalize, int zeroh, int on_device);
 
+/* ---- initialisation on the device: NMF.nndsvd (initialization.jl:70-101) ------------------------
+ * nmfb200_rsvd_*: RandomizedLinAlg.rsvd(X, k) as called at initialization.jl:78 on the resident X, entirely on the GPU:
+ * Omega = randn(n, k) (Philox4x32-10 as above, stream 2, element e = i + j*n, Box-Muller in Float64 on words 0 and 1:
+ * sqrt(-2 ln((w0 + 0.5) 2^-32)) cos(2 pi w1 2^-32)), Y = X*Omega, Q = qr(Y).Q by CholeskyQR2 in Float64, B' = X'*Q, svd(B) by
+ * one-sided Jacobi in Float64, U = Q*U_B.  Outputs: U (p x k, ldu), S (k, decreasing), V (n x k, ldv), column-major HOST arrays.
+ * ENUMERIC: the sample is numerically rank deficient (k > rank(X)): orthogonalise on the host instead (LAPACK Householder QR, which
+ * is what the reference runs) -- the Python / Julia layers do that.  ENOTSUP on a row-sharded handle.
+ * nmfb200_nndsvd_*: rsvd as above, then _nndsvd! (initialization.jl:26-68) -> W (p x k, ldw), H (k x n, ldh); host pointers, or
+ * device pointers when on_device != 0.  variant: 0 :nndsvd, 1 :nndsvda (fill = mean(X)), 2 :nndsvdar (fill = mean(X)/100 * rand,
+ * rand = Philox stream 3, element j); zeroh != 0: H = 0 (interf.jl:39,45-49 for :projals). */
+int nmfb200_rsvd_f32(nmfb200_handle* h, int64_t k, uint64_t seed, float* U, int64_t ldu, float* S, float* V, int64_t ldv);
+int nmfb200_rsvd_f64(nmfb200_handle* h, int64_t k, uint64_t seed, double* U, int64_t ldu, double* S, double* V, int64_t ldv);
+int nmfb200_nndsvd_f32(nmfb200_handle* h, float* W, int64_t ldw, float* H, int64_t ldh, int64_t k, int variant, int zeroh,
+                       uint64_t seed, int on_device);
+int nmfb200_nndsvd_f64(nmfb200_handle* h, double* W, int64_t ldw, double* H, int64_t ldh, int64_t k, int variant, int zeroh,
+                       uint64_t seed, int on_device);
+
 /* ---- multi-GPU: rows of X / W sharded over ranks, H replicated -----------
  * No counterpart in the reference (single process).  One handle per rank/GPU.  The unique id is an
  * opaque 128-byte blob (an ncclUniqueId) created on rank 0 and distributed by the host program

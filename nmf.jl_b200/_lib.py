@@ -83,6 +83,10 @@ SIGNATURES = {
     "nmfb200_mul_X_f64": (_i, [_vp, _i, _vp, _i64, _i64, _vp, _i64]),
     "nmfb200_randinit_f32": (_i, [_vp, _vp, _i64, _vp, _i64, _i64, _u64, _i64, _i64, _i, _i, _i]),
     "nmfb200_randinit_f64": (_i, [_vp, _vp, _i64, _vp, _i64, _i64, _u64, _i64, _i64, _i, _i, _i]),
+    "nmfb200_rsvd_f32": (_i, [_vp, _i64, _u64, _vp, _i64, _vp, _vp, _i64]),
+    "nmfb200_rsvd_f64": (_i, [_vp, _i64, _u64, _vp, _i64, _vp, _vp, _i64]),
+    "nmfb200_nndsvd_f32": (_i, [_vp, _vp, _i64, _vp, _i64, _i64, _i, _i, _u64, _i]),
+    "nmfb200_nndsvd_f64": (_i, [_vp, _vp, _i64, _vp, _i64, _i64, _i, _i, _u64, _i]),
     "nmfb200_comm_unique_id": (_i, [_vp]),
     "nmfb200_shard_geometry": (_i, [_i64, _i, _i, ctypes.POINTER(_i64), ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),
     "nmfb200_comm_init": (_i, [_vp, _i, _i, _vp]),

@@ -327,6 +327,36 @@ class Session:
                        int(p if p_total is None else p_total), int(normalize), int(zeroh), 0))
         return W, H
 
+    def rsvd(self, k: int, *, seed: int = 0):
+        """RandomizedLinAlg.rsvd(X, k) as called at initialization.jl:78, entirely on the GPU for the resident X (nmfb200_rsvd_*:
+        Philox Gaussian test matrix keyed by `seed`, CholeskyQR2 and a one-sided Jacobi SVD in Float64, csrc/init_device.cuh).
+        Returns (U p x k, S k, V n x k).  Raises NumericalError when the sample is numerically rank deficient (k > rank(X)): use the
+        host range finder (`rsvd(session, k, rng)`, LAPACK Householder QR) then."""
+        if self.dtype is None:
+            raise NmfB200Error("set_X must precede rsvd")
+        p, n = self.shape
+        U = np.empty((p, k), dtype=self.dtype, order="F")
+        S = np.empty(k, dtype=self.dtype)
+        V = np.empty((n, k), dtype=self.dtype, order="F")
+        fn = getattr(self._lib, "nmfb200_rsvd_" + _SFX[self.dtype])
+        self._check(fn(self._h, k, int(seed) & ((1 << 64) - 1), U.ctypes.data, p, S.ctypes.data, V.ctypes.data, n))
+        return U, S, V
+
+    def nndsvd(self, k: int, *, variant: str = "std", zeroh: bool = False, seed: int = 0):
+        """NMF.nndsvd(X, k; zeroh, variant) (initialization.jl:70-101) on the GPU for the resident X: rsvd as above, then `_nndsvd!`
+        (one CTA per component).  The :nndsvdar fill draws come from Philox stream 3 of the same seed.  Returns (W, H)."""
+        if self.dtype is None:
+            raise NmfB200Error("set_X must precede nndsvd")
+        if variant not in ("std", "a", "ar"):
+            raise ArgumentError("Invalid value for variant")
+        p, n = self.shape
+        W = np.empty((p, k), dtype=self.dtype, order="F")
+        H = np.empty((k, n), dtype=self.dtype, order="F")
+        fn = getattr(self._lib, "nmfb200_nndsvd_" + _SFX[self.dtype])
+        self._check(fn(self._h, W.ctypes.data, p, H.ctypes.data, k, k, {"std": 0, "a": 1, "ar": 2}[variant], int(zeroh),
+                       int(seed) & ((1 << 64) - 1), 0))
+        return W, H
+
     # -- solve
     def mul_X(self, B: np.ndarray, transpose: bool = False) -> np.ndarray:
         """X * B (transpose=False) or X' * B on the resident X (nmfb200_mul_X_*): the two X-sized products of the
@@ -677,6 +707,13 @@ def nnmf(X: np.ndarray, k: int, *, init: str = "nndsvdar", initdata=None, alg: s
         s.set_X(X)
         if W is None and init == "random":
             W, H = s.randinit(k, seed=device_seed, normalize=True, zeroh=not initH)
+        elif W is None and device_seed is not None and initdata is None:
+            # rng = <int>: the whole initialiser runs on the GPU (range finder, QR, SVD, split: Session.nndsvd).  A sample that is
+            # numerically rank deficient (k > rank(X)) needs the Householder QR the reference uses: host path with the same seed.
+            try:
+                W, H = s.nndsvd(k, variant=_NNDSVD_VARIANT[init], zeroh=not initH, seed=device_seed)
+            except (NumericalError, NotImplementedError):
+                W, H = nndsvd(X, k, zeroh=not initH, variant=_NNDSVD_VARIANT[init], rng=np.random.default_rng(device_seed), session=s)
         elif W is None:
             nrng = np.random.default_rng(device_seed) if device_seed is not None else (rng if rng is not None else np.random.default_rng())
             W, H = nndsvd(X, k, zeroh=not initH, variant=_NNDSVD_VARIANT[init], initdata=initdata, rng=nrng, session=s)

@@ -2,6 +2,7 @@
 // constructors (multupd.jl:27-31, greedycd.jl:25-28) and nmf_checksize (common.jl:5-16); every C++
 // exception is converted to a status code + message at this boundary.
 #include "common.cuh"
+#include "philox.cuh"
 
 using namespace nmfb200;
 
@@ -19,32 +20,6 @@ __global__ void count_not_nonneg_kernel(const T* __restrict__ X, int64_t p, int6
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
-// ---- NMF.randinit on the device (initialization.jl:4-17): counter-based Philox4x32-10, one counter per element -----------
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t& o0,
-                                              uint32_t& o1) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-    o0 = c0;
-    o1 = c1;
-}
-template <typename T> __device__ __forceinline__ T philox_uniform(uint64_t e, uint32_t stream, uint64_t seed);
-template <> __device__ __forceinline__ float philox_uniform<float>(uint64_t e, uint32_t stream, uint64_t seed) {
-    uint32_t a, b;
-    philox4x32_10((uint32_t)e, (uint32_t)(e >> 32), stream, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), a, b);
-    return (float)(a >> 8) * 5.9604644775390625e-08f;   // 24 bits -> [0, 1)
-}
-template <> __device__ __forceinline__ double philox_uniform<double>(uint64_t e, uint32_t stream, uint64_t seed) {
-    uint32_t a, b;
-    philox4x32_10((uint32_t)e, (uint32_t)(e >> 32), stream, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), a, b);
-    return (double)((((uint64_t)a << 32) | b) >> 11) * 1.1102230246251565e-16;   // 53 bits -> [0, 1)
-}
 // A(i, j) = U(e), e = e0 + i + j * e_ld  (rows x cols, column-major with leading dimension ld)
 template <typename T>
 __global__ void philox_fill_kernel(T* __restrict__ A, int64_t rows, int64_t cols, int64_t ld, uint64_t e0, uint64_t e_ld, uint32_t stream,
@@ -503,6 +478,21 @@ int nmfb200_randinit_f32(nmfb200_handle* h, float* W, int64_t ldw, float* H, int
 int nmfb200_randinit_f64(nmfb200_handle* h, double* W, int64_t ldw, double* H, int64_t ldh, int64_t k, uint64_t seed, int64_t row_offset,
                          int64_t p_total, int normalize, int zeroh, int on_device) {
     return guarded(h, [&] { randinit_impl<double>(h, W, ldw, H, ldh, k, seed, row_offset, p_total, normalize, zeroh, on_device); });
+}
+
+int nmfb200_rsvd_f32(nmfb200_handle* h, int64_t k, uint64_t seed, float* U, int64_t ldu, float* S, float* V, int64_t ldv) {
+    return guarded(h, [&] { simt_rsvd<float>(h, k, seed, U, ldu, S, V, ldv); });
+}
+int nmfb200_rsvd_f64(nmfb200_handle* h, int64_t k, uint64_t seed, double* U, int64_t ldu, double* S, double* V, int64_t ldv) {
+    return guarded(h, [&] { simt_rsvd<double>(h, k, seed, U, ldu, S, V, ldv); });
+}
+int nmfb200_nndsvd_f32(nmfb200_handle* h, float* W, int64_t ldw, float* H, int64_t ldh, int64_t k, int variant, int zeroh, uint64_t seed,
+                       int on_device) {
+    return guarded(h, [&] { simt_nndsvd<float>(h, W, ldw, H, ldh, k, variant, zeroh, seed, on_device); });
+}
+int nmfb200_nndsvd_f64(nmfb200_handle* h, double* W, int64_t ldw, double* H, int64_t ldh, int64_t k, int variant, int zeroh, uint64_t seed,
+                       int on_device) {
+    return guarded(h, [&] { simt_nndsvd<double>(h, W, ldw, H, ldh, k, variant, zeroh, seed, on_device); });
 }
 
 int nmfb200_comm_unique_id(void* out_id_128) {

@@ -288,6 +288,11 @@ double simt_objective_f32(nmfb200_handle* h, int alg, const float* W, int64_t ld
                           double lambda_w, double lambda_h);
 template <typename T>
 void simt_mul_X(nmfb200_handle* h, int transpose_X, const T* B, int64_t ldb, int64_t c, T* C, int64_t ldc);
+// NNDSVD on the device (csrc/init_device.cuh): rsvd(X, k) of initialization.jl:78 and _nndsvd! (:26-68) on the resident X
+template <typename T>
+void simt_rsvd(nmfb200_handle* h, int64_t k, uint64_t seed, T* U, int64_t ldu, T* S, T* V, int64_t ldv);
+template <typename T>
+void simt_nndsvd(nmfb200_handle* h, T* W, int64_t ldw, T* H, int64_t ldh, int64_t k, int variant, int zeroh, uint64_t seed, int on_device);
 bool tc_supported(const nmfb200_handle* h, const SolveArgs& a);
 // out(r, a) = sum_c Xs(r, c) * O(c, a) on the tensor cores with split (bf16 hi + lo) operands, for the algorithms whose remaining
 // arithmetic stays on the exact engine (ProjectedALS, CoordinateDescent, ALSPGrad).  side 0: Xs = X' (rows = columns of X,

@@ -10,6 +10,7 @@
 
 #include "common.cuh"
 #include "gcd_kernels.cuh"
+#include "philox.cuh"
 
 namespace nmfb200 {
 namespace {
@@ -765,7 +766,22 @@ struct Simt {
     }
 };
 
+#include "init_device.cuh"
+
 }  // namespace
+
+template <typename T>
+void simt_rsvd(nmfb200_handle* h, int64_t k, uint64_t seed, T* U, int64_t ldu, T* S, T* V, int64_t ldv) {
+    rsvd_impl<T>(h, k, seed, U, ldu, S, V, ldv);
+}
+template <typename T>
+void simt_nndsvd(nmfb200_handle* h, T* W, int64_t ldw, T* H, int64_t ldh, int64_t k, int variant, int zeroh, uint64_t seed, int on_device) {
+    nndsvd_impl<T>(h, W, ldw, H, ldh, k, variant, zeroh, seed, on_device);
+}
+template void simt_rsvd<float>(nmfb200_handle*, int64_t, uint64_t, float*, int64_t, float*, float*, int64_t);
+template void simt_rsvd<double>(nmfb200_handle*, int64_t, uint64_t, double*, int64_t, double*, double*, int64_t);
+template void simt_nndsvd<float>(nmfb200_handle*, float*, int64_t, float*, int64_t, int64_t, int, int, uint64_t, int);
+template void simt_nndsvd<double>(nmfb200_handle*, double*, int64_t, double*, int64_t, int64_t, int, int, uint64_t, int);
 
 template <typename T>
 void simt_solve(nmfb200_handle* h, const SolveArgs& a, T* Wc, int64_t ldw, T* Hc, int64_t ldh, nmfb200_result* out) {

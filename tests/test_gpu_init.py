@@ -137,3 +137,98 @@ def test_nnmf_with_device_seed(NMF, oracle):
         ro = oracle.solve(oracle.MultUpdate(np.float64, maxiter=30, tol=np.cbrt(np.finfo(np.float64).eps / 100)), X, W0, H0)
         objs.append(float(ro.objvalue))
     assert abs(float(r1.objvalue) - min(objs)) <= 1e-9 * min(objs)          # interf.jl:91-98 keeps the best replicate
+
+
+# ---- NNDSVD entirely on the device (nmfb200_rsvd_* / nmfb200_nndsvd_*, csrc/init_device.cuh) -------------------------------------
+def _philox_normal(rows, cols, T, seed):
+    """The Gaussian test matrix of the device range finder: Philox stream 2, element e = i + j*rows, Box-Muller in Float64."""
+    i, j = np.meshgrid(np.arange(rows, dtype=np.uint64), np.arange(cols, dtype=np.uint64), indexing="ij")
+    a, b = _philox_words(i + j * np.uint64(rows), 2, seed)
+    u1 = (a.astype(np.float64) + 0.5) * 2.0 ** -32
+    u2 = b.astype(np.float64) * 2.0 ** -32
+    return (np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)).astype(T)
+
+
+def _separated(rng, p, n, r, T):
+    """Non-negative X with well separated leading singular values (so individual singular vectors are well conditioned)."""
+    A = np.maximum(rng.random((p, r)) - 0.3, 0) * (2.0 ** -np.arange(r))
+    B = np.maximum(rng.random((r, n)) - 0.3, 0)
+    return np.asfortranarray(A @ B + 1e-3 * rng.random((p, n)), dtype=T)
+
+
+@pytest.mark.parametrize("T,tol", [(np.float64, 1e-9), (np.float32, 5e-4)])
+def test_device_rsvd_matches_the_host_range_finder(NMF, T, tol):
+    rng = np.random.default_rng(41)
+    p, n, k, seed = 300, 220, 6, 2024
+    X = _separated(rng, p, n, 8, T)
+    with NMF.Session() as s:
+        s.set_X(X)
+        U, S, V = s.rsvd(k, seed=seed)
+        U2, S2, V2 = s.rsvd(k, seed=seed)
+    assert (U == U2).all() and (S == S2).all() and (V == V2).all()          # counter-based draw, fixed reduction orders
+    # the same algorithm on the host from the regenerated test matrix (initialization.jl:78: qr(X * randn).Q, svd(Q' * X))
+    Om = _philox_normal(n, k, T, seed).astype(np.float64)
+    X64 = X.astype(np.float64)
+    Q, _ = np.linalg.qr(X64 @ Om)
+    Ub, s_ref, Vt = np.linalg.svd(Q.T @ X64, full_matrices=False)
+    U_ref, V_ref = Q @ Ub, Vt.T
+    assert (np.diff(S) <= 0).all()
+    np.testing.assert_allclose(S, s_ref, rtol=tol)
+    eye_tol = 1e-10 if T == np.float64 else 1e-5
+    assert np.abs(U.astype(np.float64).T @ U - np.eye(k)).max() <= eye_tol and np.abs(V.astype(np.float64).T @ V - np.eye(k)).max() <= eye_tol
+    for j in range(k):                                                     # singular pairs agree up to their joint sign
+        su, sv = np.sign(U[:, j] @ U_ref[:, j]), np.sign(V[:, j] @ V_ref[:, j])
+        assert su == sv
+        assert np.linalg.norm(su * U[:, j] - U_ref[:, j]) <= 50 * tol and np.linalg.norm(sv * V[:, j] - V_ref[:, j]) <= 50 * tol
+    rec, rec_ref = (U * S) @ V.T, (U_ref * s_ref) @ V_ref.T
+    assert np.linalg.norm(rec - rec_ref) <= tol * np.linalg.norm(rec_ref)
+
+
+@pytest.mark.parametrize("T,tol", [(np.float64, 1e-10), (np.float32, 2e-5)])
+def test_device_nndsvd_matches_oracle_split_of_the_same_triplets(NMF, oracle, T, tol):
+    rng = np.random.default_rng(43)
+    p, n, k, seed = 260, 310, 5, 99
+    X = _separated(rng, p, n, 7, T)
+    with NMF.Session() as s:
+        s.set_X(X)
+        U, S, V = s.rsvd(k, seed=seed)
+        out = {(v, z): s.nndsvd(k, variant=v, zeroh=z, seed=seed) for v in ("std", "a", "ar") for z in (False, True)}
+    for v in ("std", "a"):
+        for z in (False, True):
+            W, H = out[(v, z)]
+            Wo, Ho = oracle.nndsvd(X, k, zeroh=z, variant=v, initdata=(U, S, V))     # _nndsvd! on the device's own triplets
+            assert (W >= 0).all() and (H >= 0).all() and W.dtype == T and H.shape == (k, n)   # test/initialization.jl:29-53
+            assert np.linalg.norm(W - Wo) <= tol * np.linalg.norm(Wo)
+            assert np.linalg.norm(H - Ho) <= tol * max(np.linalg.norm(Ho), 1e-300)
+            if z:
+                assert (H == 0).all()
+    # :nndsvdar -- the fill of column j is convert(T, mean(X) * 0.01) * rand(T) with rand = Philox stream 3, element j
+    Ws, Hs = out[("std", False)]
+    War, Har = out[("ar", False)]
+    v0 = T(X.mean(dtype=np.float64) * 0.01)
+    fill = (v0 * _philox_uniform((k, 1), T, 3, seed)[:, 0]).astype(T)
+    for j in range(k):
+        zw, zh = Ws[:, j] == 0, Hs[j, :] == 0
+        assert (War[~zw, j] == Ws[~zw, j]).all() and (Har[j, ~zh] == Hs[j, ~zh]).all()
+        np.testing.assert_allclose(War[zw, j], fill[j], rtol=1e-6)
+        np.testing.assert_allclose(Har[j, zh], fill[j], rtol=1e-6)
+
+
+def test_nnmf_with_device_seed_runs_nndsvd_on_the_gpu(NMF):
+    rng = np.random.default_rng(47)
+    for T in (np.float64, np.float32):
+        X = _separated(rng, 200, 160, 6, T)
+        r = NMF.nnmf(X, 5, maxiter=60, rng=123)                       # defaults: init=:nndsvdar, alg=:greedycd (interf.jl:3-13)
+        r_again = NMF.nnmf(X, 5, maxiter=60, rng=123)
+        r_host = NMF.nnmf(X, 5, maxiter=60, rng=np.random.default_rng(123))
+        assert r == r_again
+        assert (r.W >= 0).all() and (r.H >= 0).all() and np.isfinite(float(r.objvalue))
+        assert float(r.objvalue) <= 2.0 * float(r_host.objvalue) + 1e-12     # another test matrix, the same quality of start
+    # k > rank(X): the sample X * randn(n, k) is rank deficient -- the device QR refuses, nnmf falls back to the host QR
+    Xr = np.asfortranarray(np.maximum(rng.random((80, 3)) - 0.3, 0) @ np.maximum(rng.random((3, 70)) - 0.3, 0))
+    with NMF.Session() as s:
+        s.set_X(Xr)
+        with pytest.raises(NMF.NumericalError):
+            s.rsvd(5, seed=1)
+    r = NMF.nnmf(Xr, 5, maxiter=100, rng=1, alg="multmse")
+    assert np.isfinite(r.W).all() and np.linalg.norm(Xr - r.W @ r.H) <= 0.2 * np.linalg.norm(Xr)
