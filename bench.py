@@ -262,6 +262,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     # iteration's kernels, so a window holds K iterations and nothing else; five windows, each max over ranks, median reported.
     device_solve(max(args.warmup, 3), timed=False)
     barrier()
+    # roofline pass FIRST, right behind the warm-up: CUDA events around every mu_update_kernel launch (the dominant kernel).  The events
+    # serialise the launches (no programmatic-dependent-launch overlap), so this pass is not the throughput number; it runs before the
+    # long timed windows because those drive the board into its software power cap (clocks.reasons), and the peak it is compared with
+    # (MEASURED_PEAKS.json: best of 10 copies) is a burst figure too.
+    res_k = None if args.timeline else device_solve(args.steps, timed=True)
+    barrier()
     windows = []
     with ClockSampler(local_rank) as clk:
         for _ in range(1 if args.timeline else 5):
@@ -272,10 +278,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             if dist is not None:
                 dist.all_reduce(w, op=dist.ReduceOp.MAX)
             windows.append(float(w.item()))
-    # second pass with CUDA events around every mu_update_kernel launch (roofline of the dominant kernel); the events
-    # serialise the launches (no programmatic-dependent-launch overlap), so this pass is not the throughput number
-    res_k = res if args.timeline else device_solve(args.steps, timed=True)
-    barrier()
+    if res_k is None:
+        res_k = res
     loop_ms = float(np.median(windows))
     iters = res.niters
     it_per_s = iters / (loop_ms * 1e-3)

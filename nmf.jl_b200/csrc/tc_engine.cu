@@ -67,10 +67,13 @@ struct TcSolver {
     const bf16* Xs_lo = nullptr;     // precision mode bf16x3: the remainder panel matching the Xs of the NEXT launch_update
     bool force_x3 = false;           // split operands whatever the handle's precision option says (tc_xmul)
     float* cross_part = nullptr;     // verbose W-step: per-tile sums of Num .* F_new for the NEXT launch_update (trace identity)
+    bool chain = false;              // option tc_chain: update and reduce kernels of the loop form one chain of programmatic dependents
+    unsigned int chain_seq = 0;      //   reduce kernels launched so far in this solve (= the value the last one publishes)
     const bf16* pf_X = nullptr;      // option tc_prefetch_next: the X panel of the launch AFTER the next launch_update ...
     int pf_tiles = 0, pf_tile_rows = 0, pf_nkb = 0;   // ... and its geometry (reset by the caller)
     bool defer_gram_reduce = false;  // the caller will run gram_conv_reduce_kernel itself
     bool last_fused_gram = false;
+    bool last_chained = false;       // the last launch_update was part of the chain (its reduce kernel must publish)
     float* last_gram_part = nullptr;
     int last_gram_parts = 0;
     int num_splits = 1;              // MODE 5: k-split partial numerators behind num_io
@@ -132,6 +135,13 @@ struct TcSolver {
             prm.pf_tile_rows = pf_tile_rows;
             prm.pf_panel_rows = pf_nkb * pf_tile_rows;
         }
+        const bool timed_ = h->time_kernels == 1 && mode != 2 && mode != 6;
+        const bool chained = chain && pdl && mode == 0 && fused_gram && sl == nullptr && !timed_;
+        if (chained) {
+            prm.chain_flag = &state->chain;
+            prm.chain_need = chain_seq;
+            prm.early_trigger = 1;
+        }
         prm.tmFhi = make_tmap_bf16(F.hi, KP, (uint64_t)F.R, KP, (uint32_t)F.tile_rows);
         prm.tmFlo = make_tmap_bf16(F.lo, KP, (uint64_t)F.R, KP, (uint32_t)F.tile_rows);
         prm.tmPhi = make_tmap_bf16(O.Phi, KP, KP, KP, KP);
@@ -164,9 +174,12 @@ struct TcSolver {
         last_fused_gram = fused_gram;
         last_gram_part = prm.gram_part;
         last_gram_parts = F.tiles;
+        last_chained = chained;
         if (fused_gram && !defer_gram_reduce) {
-            launch_k(gram_reduce_kernel, dim3((4 * KP * KP + 255) / 256), dim3(256), 0, st, false, (const float*)prm.gram_part, F.tiles, KP * KP,
-                     gram_dst ? gram_dst : F.P, F.Phi, F.Plo, gram, (const TcState*)state);
+            unsigned int* cf = chained ? &state->chain : nullptr;
+            if (chained) ++chain_seq;
+            launch_k(gram_reduce_kernel, dim3((4 * KP * KP + 255) / 256), dim3(256), 0, st, chained, (const float*)prm.gram_part, F.tiles, KP * KP,
+                     gram_dst ? gram_dst : F.P, F.Phi, F.Plo, gram, (const TcState*)state, cf, chain_seq);
             h->launches += 1;
         } else if (gram >= 0 && !fused_gram) {
             launch_gram(F, gram != 0, gram_dst);
@@ -203,7 +216,7 @@ struct TcSolver {
     void launch_gram(const Factor& F, bool split, float* P_dst = nullptr) {
         launch_gram_parts(F);
         gram_reduce_kernel<<<(4 * KP * KP + 255) / 256, 256, 0, st>>>(last_gram_part, last_gram_parts, KP * KP, P_dst ? P_dst : F.P, F.Phi, F.Plo,
-                                                                       split ? 1 : 0, state);
+                                                                       split ? 1 : 0, state, (unsigned int*)nullptr, 0u);
         h->launches += 1;
     }
 
@@ -268,6 +281,7 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
     NMF_CUDA(cudaGetLastError());
 
     TcSolver<KP> s{h, st, state};
+    s.chain = h->tc_chain != 0 && !a.verbose;
     if (h->tc_precision == 1) { s.refresh_bTlo(W); s.refresh_bTlo(H); }
     s.launch_gram(W, true);                   // P_W = W'W for the first H-step
     if (!a.update_H) s.launch_gram(H, true);  // H never changes: P_H once
@@ -337,9 +351,14 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
             const int gram_blocks = (s.last_fused_gram && gramW >= 0) ? (4 * KP * KP + 255) / 256 : 0;
             // one launch: Gram reduce (if the staged epilogue produced tile Grams; KP = 256 ran gram_kernel + reduce inside
             // launch_update) + stop_condition reduce / decision
-            launch_k(gram_conv_reduce_kernel, dim3(gram_blocks + 4 * (KP / 32)), dim3(256), 0, st, false, (const float*)s.last_gram_part,
+            // option tc_chain: a W-step launched with early_trigger expects the kernel behind it to be a programmatic dependent that
+            // publishes the chain flag the next H-step polls
+            const bool chW = s.last_chained;
+            unsigned int* cf = chW ? &state->chain : nullptr;
+            if (chW) ++s.chain_seq;
+            launch_k(gram_conv_reduce_kernel, dim3(gram_blocks + 4 * (KP / 32)), dim3(256), 0, st, chW, (const float*)s.last_gram_part,
                      W.tiles, KP * KP, W.P, W.Phi, W.Plo, 1, gram_blocks, (const float*)W.conv, W.tiles, (const float*)H.conv, H.tiles,
-                     KP, (int)k, (int)a.update_H, acc, tol, state, 1, (float*)nullptr, tr);
+                     KP, (int)k, (int)a.update_H, acc, tol, state, 1, (float*)nullptr, tr, cf, s.chain_seq);
             h->launches += 1;
             h->mark("conv");
         }
@@ -518,7 +537,7 @@ void tc_solve_batched_kp(nmfb200_handle* h, const SolveArgs& a, int nrep, float*
             std::memset(&tr, 0, sizeof(tr));
             launch_k(gram_conv_reduce_kernel, dim3(gram_blocks + 4 * (KP / 32)), dim3(256), 0, st, false, (const float*)s.last_gram_part,
                      W.tiles, KP * KP, W.P, W.Phi, W.Plo, 1, gram_blocks, (const float*)W.conv, W.tiles, (const float*)H.conv, H.tiles,
-                     KP, (int)kt, (int)a.update_H, acc, tol, state, 1, (float*)nullptr, tr);
+                     KP, (int)kt, (int)a.update_H, acc, tol, state, 1, (float*)nullptr, tr, (unsigned int*)nullptr, 0u);
             launch_k(batch_snapshot_kernel, dim3(snap_grid), dim3(256), 0, st, false, (const TcState*)state, KP, (const float*)W.m, Wsnap,
                      (int64_t)p * KP, (const float*)H.m, Hsnap, (int64_t)n * KP, 0);
             h->launches += 2;

@@ -23,7 +23,8 @@ struct TcState {
     double objv;           // verbose: objective of the iteration just finished, by the trace identity (tc_reduce.cuh)
     // batched replicates (all zero otherwise): the Gram reduce keeps only the diagonal blk x blk blocks of the KP x KP Gram (kp = KP),
     // and the stop decision is taken per replicate in *bs; `converged` is raised once every replicate is done
-    int blk, kp, nrep, pad2_;
+    int blk, kp, nrep;
+    unsigned int chain;    // option tc_chain: sequence number of the last reduce kernel whose predecessor (an update launch) is COMPLETE
     BatchState* bs;
 };
 
@@ -61,6 +62,13 @@ struct UpdateParams {
     int pf_blocks;      // > 0: once its own loads are issued, the producer asks L2 for the first pf_blocks k-blocks of the tile that CTA
                         // blockIdx.x of the next launch will stream -- HBM is otherwise idle while all CTAs sit in their epilogues
     int pf_tiles, pf_tile_rows, pf_panel_rows;   // next launch: tiles, rows per tile, rows of the tile-contiguous panel per tile (nkb * tile_rows)
+    // option tc_chain (MODE 0, single GPU): the whole iteration is one chain of programmatic dependents.  This launch lets ITS dependent
+    // (the reduce kernel) become resident as soon as its own loads are issued (early_trigger), and may itself have been made resident
+    // while the update launch two kernels back was still in its epilogues -- so its producer polls chain_flag >= chain_need (published by
+    // the reduce kernel in between, right after that launch completed) before it touches the other factor's transposed copy.
+    const unsigned int* chain_flag;
+    unsigned int chain_need;
+    int early_trigger;
     int flush_chunk;    // > 0 (KP <= 128): the numerator MMAs accumulate at most this many k-blocks in TMEM; the epilogue warps add
                         // each finished chunk to fp32 register sums (round to nearest) while the next chunk accumulates.  The
                         // tensor core's accumulator TRUNCATES (measured: ~0.5 ulp lost per MMA, a relative bias of ~3e-8 per
@@ -276,6 +284,15 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                 }
                 asm volatile("fence.proxy.async;" ::: "memory");   // the peers' writes -> the TMA loads below
             }
+            if (MODE == 0 && prm.chain_flag != nullptr) {
+                const long long t0 = clock64();
+                unsigned int seen;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(prm.chain_flag) : "memory");
+                    if (clock64() - t0 > 20000000000LL) { printf("nmfb200: chain flag wait timed out (need %u, seen %u)\n", prm.chain_need, seen); __trap(); }
+                } while ((int)(seen - prm.chain_need) < 0);
+                asm volatile("fence.proxy.async;" ::: "memory");   // the predecessor's stores -> the TMA loads below
+            }
             const int arow0 = arow;
             for (int pass = 0; pass < npass; ++pass) {   // one pass unless precision mode bf16x3
                 const CUtensorMap* mA = pass == 2 ? &prm.tmAlo : &prm.tmA;
@@ -313,6 +330,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                     if (++s == C::STAGES) { s = 0; ph ^= 1u; dst = smem; }
                 }
             }
+            if (MODE == 0 && prm.early_trigger) pdl_launch_dependents();   // every load is issued: the reduce kernel behind us may take its seats
             if (MODE == 0 && prm.pf_blocks > 0 && (int)blockIdx.x < prm.pf_tiles) {
                 // every load of this launch is in flight: warm L2 with the head of the next launch's panel (no smem destination,
                 // no completion tracking; a converged solve wastes them harmlessly)
@@ -929,11 +947,18 @@ __global__ void __launch_bounds__(192, 1) gram_kernel(const __grid_constant__ Gr
 // (each sums every 4th partial with 8 loads in flight), combined with two shuffles: fixed order => deterministic.
 __global__ void __launch_bounds__(256) gram_reduce_kernel(const float* __restrict__ part, int nparts, int nelem, float* __restrict__ P,
                                                           bf16* __restrict__ Phi, bf16* __restrict__ Plo, int do_split,
-                                                          const TcState* st) {
+                                                          const TcState* st, unsigned int* chain_flag, unsigned int chain_publish) {
     // The update kernel behind us may start streaming X as soon as every block has passed this point; it waits for our
     // completion before it reads P.  (Pre-launching THIS kernel behind the running update kernel was measured too:
     // its resident blocks polling in griddepcontrol.wait slow the single-thread TMA / MMA loops, 4770 -> 4400 it/s.)
     pdl_launch_dependents();
+    if (chain_flag != nullptr) {
+        // option tc_chain: this kernel was itself launched as a programmatic dependent (resident since the update kernel in front of it
+        // issued its last loads); wait for that kernel to complete, then tell the update kernel behind us -- already resident and
+        // polling -- that the other factor is final.  Published even when converged: nobody may be left polling.
+        pdl_wait();
+        if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(chain_flag), "r"(chain_publish) : "memory");
+    }
     if (st->converged) return;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int sub = t & 3;

@@ -313,6 +313,22 @@ for (T, sfx) in ((Float32, "f32"), (Float64, "f64"))
     end
 end
 
+# NNDSVD entirely on the device (nmfb200_nndsvd_*, csrc/init_device.cuh): Philox Gaussian test matrix keyed by `seed`, CholeskyQR2 and a
+# one-sided Jacobi SVD in Float64, `_nndsvd!` as one CTA per component.  Returns `nothing` when the sample is numerically rank deficient
+# (status ENUMERIC, k > rank(X)) or the handle is row-sharded (ENOTSUP): the caller then uses the host range finder below.
+for (T, sfx) in ((Float32, "f32"), (Float64, "f64"))
+    dname = "nmfb200_nndsvd_" * sfx
+    @eval function nndsvd_device!(h::Handle, W::Matrix{$T}, H::Matrix{$T}; variant::Symbol=:std, zeroh::Bool=false, seed::Integer=0)
+        ivar = variant == :std ? 0 : variant == :a ? 1 : variant == :ar ? 2 : throw(ArgumentError("Invalid value for variant"))
+        st = GC.@preserve W H ccall(($dname, libnmfb200), Cint,
+            (Ptr{Cvoid}, Ptr{$T}, Int64, Ptr{$T}, Int64, Int64, Cint, Cint, UInt64, Cint),
+            h.ptr, W, stride(W, 2), H, stride(H, 2), size(W, 2), ivar, zeroh, seed % UInt64, 0)
+        (st == ENUMERIC || st == ENOTSUP) && return nothing
+        check(h, st)
+        return W, H
+    end
+end
+
 function rsvd(h::Handle, ::Type{T}, p::Integer, n::Integer, k::Integer) where T
     Q = Matrix(qr!(mul_X(h, randn(T, n, k), p)).Q)          # Y = X * Omega on the GPU
     Bt = mul_X(h, Q, n; transpose=true)                     # B' = X' * Q on the GPU
@@ -362,7 +378,8 @@ end
 function nnmf(X::AbstractMatrix{T}, k::Integer; init::Symbol=:nndsvdar, initdata=nothing, alg::Symbol=:greedycd,
               maxiter::Integer=100, tol::Real=cbrt(eps(T) / 100), replicates::Integer=1,
               W0::Union{AbstractMatrix{T},Nothing}=nothing, H0::Union{AbstractMatrix{T},Nothing}=nothing,
-              update_H::Bool=true, verbose::Bool=false, device::Integer=0) where T
+              update_H::Bool=true, verbose::Bool=false, device::Integer=0, seed::Union{Integer,Nothing}=nothing) where T
+    # `seed` (an addition): with an integer the NNDSVD initialiser runs entirely on the GPU (nndsvd_device!, counter-based generator)
     eltype(X) <: Number && all(t -> t >= zero(T), X) || throw(ArgumentError("The elements of X must be non-negative."))
     p, n = size(X)
     k <= min(p, n) || throw(ArgumentError("The value of k should not exceed min(size(X))."))
@@ -395,7 +412,12 @@ function nnmf(X::AbstractMatrix{T}, k::Integer; init::Symbol=:nndsvdar, initdata
     set_X!(h, Xm)                                      # X stays resident on the GPU across init, solve and replicates
     W, H = init == :random ? randinit(p, n, k, T; normalize=true, zeroh=!initH) :
            init == :custom ? (W0::Matrix{T}, H0::Matrix{T}) :     # aliased and updated in place, like `W = W::Matrix{T}` at src/interf.jl:57-58
-           nndsvd(Xm, k; zeroh=!initH, variant=(init == :nndsvd ? :std : init == :nndsvda ? :a : :ar), initdata=initdata, handle=h)
+           begin
+               var = init == :nndsvd ? :std : init == :nndsvda ? :a : :ar
+               dev = (seed !== nothing && initdata === nothing) ?
+                     nndsvd_device!(h, Matrix{T}(undef, p, k), Matrix{T}(undef, k, n); variant=var, zeroh=!initH, seed=seed) : nothing
+               dev === nothing ? nndsvd(Xm, k; zeroh=!initH, variant=var, initdata=initdata, handle=h) : dev
+           end
     if replicates > 1 && inst isa MultUpdate{Float32} && inst.obj == :mse && !verbose && 2k <= 256
         # src/interf.jl:85-101 in groups of up to 256 ÷ k replicates per stacked iteration (one pass over X per half-step for the group);
         # solve! of MultUpdate draws no random numbers, so drawing a group's restarts up front is the reference's stream

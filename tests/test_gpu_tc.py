@@ -339,3 +339,31 @@ def test_tc_prefetch_next_option_changes_no_result(NMF):
     for W, H, r in out[1:]:
         assert (W == out[0][0]).all() and (H == out[0][1]).all()
         assert r.objvalue == out[0][2].objvalue and r.niters == out[0][2].niters == 12
+
+
+@pytest.mark.parametrize("p,n,k,planted,tol,maxiter", [
+    (1280, 1536, 96, False, 1e-9, 15),     # maxiter-bound, KP = 128
+    (2048, 2304, 64, False, 1e-9, 10),     # KP = 64, more tiles than one wave of early CTAs
+    (1024, 1152, 16, True, 2e-3, 400),     # tolerance-bound: the stop decision races with the early-launched kernels
+])
+def test_tc_chain_option_changes_no_result(NMF, p, n, k, planted, tol, maxiter):
+    """Option tc_chain: the reduce kernels become programmatic dependents too (resident while the update kernel in front of them is
+    in its epilogues) and publish a flag the next update kernel -- possibly resident even earlier -- polls before it reads the other
+    factor.  Same arithmetic in the same order: factors, niters, converged and objvalue must be bit-identical, for every polling
+    interval of the host."""
+    X, W0, H0 = _problem(NMF, p, n, k, seed=p + k, planted=planted)
+    out = []
+    for chain, check_every in ((0, 8), (1, 8), (1, 1), (1, 5)):
+        for _ in range(2 if chain else 1):
+            W, H = W0.copy(order="F"), H0.copy(order="F")
+            with NMF.Session(engine="tc") as s:
+                s.set_option("tc_chain", chain)
+                s.set_option("check_every", check_every)
+                s.set_X(X)
+                r = s.solve(NMF.MultUpdate(np.float32, obj="mse", maxiter=maxiter, tol=tol), W, H)
+            out.append((W, H, r))
+    r0 = out[0][2]
+    assert r0.converged == (tol > 1e-6)
+    for W, H, r in out[1:]:
+        assert r.niters == r0.niters and r.converged == r0.converged and r.objvalue == r0.objvalue
+        assert (W == out[0][0]).all() and (H == out[0][1]).all()
