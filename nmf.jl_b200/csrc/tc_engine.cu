@@ -68,7 +68,7 @@ struct TcSolver {
     bool force_x3 = false;           // split operands whatever the handle's precision option says (tc_xmul)
     float* cross_part = nullptr;     // verbose W-step: per-tile sums of Num .* F_new for the NEXT launch_update (trace identity)
     bool chain = false;              // option tc_chain: update and reduce kernels of the loop form one chain of programmatic dependents
-    unsigned int chain_seq = 0;      //   reduce kernels launched so far in this solve (= the value the last one publishes)
+    unsigned int chain_tiles = 0;    //   tiles of all chained update launches so far in this solve (what the next one waits for)
     const bf16* pf_X = nullptr;      // option tc_prefetch_next: the X panel of the launch AFTER the next launch_update ...
     int pf_tiles = 0, pf_tile_rows = 0, pf_nkb = 0;   // ... and its geometry (reset by the caller)
     bool defer_gram_reduce = false;  // the caller will run gram_conv_reduce_kernel itself
@@ -139,8 +139,10 @@ struct TcSolver {
         const bool chained = chain && pdl && mode == 0 && fused_gram && sl == nullptr && !timed_;
         if (chained) {
             prm.chain_flag = &state->chain;
-            prm.chain_need = chain_seq;
+            prm.chain_cnt = &state->chain;
+            prm.chain_need = chain_tiles;
             prm.early_trigger = 1;
+            chain_tiles += (unsigned int)F.tiles;
         }
         prm.tmFhi = make_tmap_bf16(F.hi, KP, (uint64_t)F.R, KP, (uint32_t)F.tile_rows);
         prm.tmFlo = make_tmap_bf16(F.lo, KP, (uint64_t)F.R, KP, (uint32_t)F.tile_rows);
@@ -176,10 +178,8 @@ struct TcSolver {
         last_gram_parts = F.tiles;
         last_chained = chained;
         if (fused_gram && !defer_gram_reduce) {
-            unsigned int* cf = chained ? &state->chain : nullptr;
-            if (chained) ++chain_seq;
             launch_k(gram_reduce_kernel, dim3((4 * KP * KP + 255) / 256), dim3(256), 0, st, chained, (const float*)prm.gram_part, F.tiles, KP * KP,
-                     gram_dst ? gram_dst : F.P, F.Phi, F.Plo, gram, (const TcState*)state, cf, chain_seq);
+                     gram_dst ? gram_dst : F.P, F.Phi, F.Plo, gram, (const TcState*)state, chained ? 1 : 0);
             h->launches += 1;
         } else if (gram >= 0 && !fused_gram) {
             launch_gram(F, gram != 0, gram_dst);
@@ -216,7 +216,7 @@ struct TcSolver {
     void launch_gram(const Factor& F, bool split, float* P_dst = nullptr) {
         launch_gram_parts(F);
         gram_reduce_kernel<<<(4 * KP * KP + 255) / 256, 256, 0, st>>>(last_gram_part, last_gram_parts, KP * KP, P_dst ? P_dst : F.P, F.Phi, F.Plo,
-                                                                       split ? 1 : 0, state, (unsigned int*)nullptr, 0u);
+                                                                       split ? 1 : 0, state, 0);
         h->launches += 1;
     }
 
@@ -351,14 +351,11 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
             const int gram_blocks = (s.last_fused_gram && gramW >= 0) ? (4 * KP * KP + 255) / 256 : 0;
             // one launch: Gram reduce (if the staged epilogue produced tile Grams; KP = 256 ran gram_kernel + reduce inside
             // launch_update) + stop_condition reduce / decision
-            // option tc_chain: a W-step launched with early_trigger expects the kernel behind it to be a programmatic dependent that
-            // publishes the chain flag the next H-step polls
+            // option tc_chain: a W-step launched with early_trigger lets this kernel take its seats early; it then waits for the W-step
             const bool chW = s.last_chained;
-            unsigned int* cf = chW ? &state->chain : nullptr;
-            if (chW) ++s.chain_seq;
             launch_k(gram_conv_reduce_kernel, dim3(gram_blocks + 4 * (KP / 32)), dim3(256), 0, st, chW, (const float*)s.last_gram_part,
                      W.tiles, KP * KP, W.P, W.Phi, W.Plo, 1, gram_blocks, (const float*)W.conv, W.tiles, (const float*)H.conv, H.tiles,
-                     KP, (int)k, (int)a.update_H, acc, tol, state, 1, (float*)nullptr, tr, cf, s.chain_seq);
+                     KP, (int)k, (int)a.update_H, acc, tol, state, 1, (float*)nullptr, tr, chW ? 1 : 0);
             h->launches += 1;
             h->mark("conv");
         }
@@ -537,7 +534,7 @@ void tc_solve_batched_kp(nmfb200_handle* h, const SolveArgs& a, int nrep, float*
             std::memset(&tr, 0, sizeof(tr));
             launch_k(gram_conv_reduce_kernel, dim3(gram_blocks + 4 * (KP / 32)), dim3(256), 0, st, false, (const float*)s.last_gram_part,
                      W.tiles, KP * KP, W.P, W.Phi, W.Plo, 1, gram_blocks, (const float*)W.conv, W.tiles, (const float*)H.conv, H.tiles,
-                     KP, (int)kt, (int)a.update_H, acc, tol, state, 1, (float*)nullptr, tr, (unsigned int*)nullptr, 0u);
+                     KP, (int)kt, (int)a.update_H, acc, tol, state, 1, (float*)nullptr, tr, 0);
             launch_k(batch_snapshot_kernel, dim3(snap_grid), dim3(256), 0, st, false, (const TcState*)state, KP, (const float*)W.m, Wsnap,
                      (int64_t)p * KP, (const float*)H.m, Hsnap, (int64_t)n * KP, 0);
             h->launches += 2;

@@ -176,12 +176,9 @@ __global__ void __launch_bounds__(256) gram_conv_reduce_kernel(const float* __re
                                                                const float* __restrict__ partW, int tilesW, const float* __restrict__ partH,
                                                                int tilesH, int KP, int k, int update_H, double* __restrict__ acc, float tol,
                                                                TcState* st, int do_decide, float* __restrict__ wsums_f32, TraceObj tr,
-                                                               unsigned int* chain_flag, unsigned int chain_publish) {
+                                                               int chained) {
     pdl_launch_dependents();  // the next H-step may start streaming X now; it waits for us before it reads P / `converged`
-    if (chain_flag != nullptr) {   // option tc_chain: see gram_reduce_kernel
-        pdl_wait();
-        if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(chain_flag), "r"(chain_publish) : "memory");
-    }
+    if (chained) pdl_wait();   // option tc_chain: launched as a programmatic dependent of the W-step (see gram_reduce_kernel)
     if (st->converged) return;
     __shared__ double red[8][32];
     __shared__ float devs[256];

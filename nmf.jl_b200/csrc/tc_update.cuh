@@ -62,11 +62,14 @@ struct UpdateParams {
     int pf_blocks;      // > 0: once its own loads are issued, the producer asks L2 for the first pf_blocks k-blocks of the tile that CTA
                         // blockIdx.x of the next launch will stream -- HBM is otherwise idle while all CTAs sit in their epilogues
     int pf_tiles, pf_tile_rows, pf_panel_rows;   // next launch: tiles, rows per tile, rows of the tile-contiguous panel per tile (nkb * tile_rows)
-    // option tc_chain (MODE 0, single GPU): the whole iteration is one chain of programmatic dependents.  This launch lets ITS dependent
-    // (the reduce kernel) become resident as soon as its own loads are issued (early_trigger), and may itself have been made resident
-    // while the update launch two kernels back was still in its epilogues -- so its producer polls chain_flag >= chain_need (published by
-    // the reduce kernel in between, right after that launch completed) before it touches the other factor's transposed copy.
+    // option tc_chain (MODE 0, single GPU, staged epilogue): the whole iteration is one chain of programmatic dependents, and the hand-over
+    // from one update launch to the next does not wait for a kernel boundary (measured: griddepcontrol.wait in the kernel behind returns
+    // ~5 us after the last CTA has exited).  Every CTA counts itself in *chain_cnt once its bulk stores -- the new transposed tile among
+    // them -- are complete; the next update launch, whose CTAs take their seats as soon as this launch's loads are issued (early_trigger
+    // lets the reduce kernel in between become resident, and that kernel releases the next launch at its top), polls
+    // *chain_flag >= chain_need (the tiles of all chained update launches before it) before it touches the other factor's transposed copy.
     const unsigned int* chain_flag;
+    unsigned int* chain_cnt;
     unsigned int chain_need;
     int early_trigger;
     int flush_chunk;    // > 0 (KP <= 128): the numerator MMAs accumulate at most this many k-blocks in TMEM; the epilogue warps add
@@ -289,9 +292,12 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                 unsigned int seen;
                 do {
                     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(prm.chain_flag) : "memory");
-                    if (clock64() - t0 > 20000000000LL) { printf("nmfb200: chain flag wait timed out (need %u, seen %u)\n", prm.chain_need, seen); __trap(); }
-                } while ((int)(seen - prm.chain_need) < 0);
-                asm volatile("fence.proxy.async;" ::: "memory");   // the predecessor's stores -> the TMA loads below
+                    if ((int)(seen - prm.chain_need) >= 0) break;
+                    // a predecessor that met stop_condition skips its epilogue and never counts itself: nothing we compute will be kept
+                    if (__ldcg(&prm.state->converged) != 0) break;
+                    if (clock64() - t0 > 20000000000LL) { printf("nmfb200: chain counter wait timed out (need %u, seen %u)\n", prm.chain_need, seen); __trap(); }
+                } while (true);
+                asm volatile("fence.proxy.async;" ::: "memory");   // the predecessor's bulk stores -> the TMA loads below
             }
             const int arow0 = arow;
             for (int pass = 0; pass < npass; ++pass) {   // one pass unless precision mode bf16x3
@@ -784,6 +790,11 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                     TSTAMP(9);                 // tile Gram written
                     if (MODE == 2 && prm.defer_signal) tma_store_wait_read<0>();
                     else tma_store_wait_all<0>();
+                    if (MODE == 0 && prm.chain_cnt != nullptr) {   // option tc_chain: this tile is final in all four forms
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                        __threadfence();
+                        atomicAdd(prm.chain_cnt, 1u);
+                    }
                     if ((MODE == 2 || FUSED) && prm.G > 0 && !(MODE == 2 && prm.defer_signal)) {
                         // the peers' copies were written through the async proxy: order them, count this tile, and the last own
                         // tile tells every rank that this rank's rows of H'^T are in place (PH_HBT)
@@ -947,18 +958,14 @@ __global__ void __launch_bounds__(192, 1) gram_kernel(const __grid_constant__ Gr
 // (each sums every 4th partial with 8 loads in flight), combined with two shuffles: fixed order => deterministic.
 __global__ void __launch_bounds__(256) gram_reduce_kernel(const float* __restrict__ part, int nparts, int nelem, float* __restrict__ P,
                                                           bf16* __restrict__ Phi, bf16* __restrict__ Plo, int do_split,
-                                                          const TcState* st, unsigned int* chain_flag, unsigned int chain_publish) {
+                                                          const TcState* st, int chained) {
     // The update kernel behind us may start streaming X as soon as every block has passed this point; it waits for our
     // completion before it reads P.  (Pre-launching THIS kernel behind the running update kernel was measured too:
     // its resident blocks polling in griddepcontrol.wait slow the single-thread TMA / MMA loops, 4770 -> 4400 it/s.)
     pdl_launch_dependents();
-    if (chain_flag != nullptr) {
-        // option tc_chain: this kernel was itself launched as a programmatic dependent (resident since the update kernel in front of it
-        // issued its last loads); wait for that kernel to complete, then tell the update kernel behind us -- already resident and
-        // polling -- that the other factor is final.  Published even when converged: nobody may be left polling.
-        pdl_wait();
-        if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(chain_flag), "r"(chain_publish) : "memory");
-    }
+    // option tc_chain: this kernel was itself launched as a programmatic dependent (resident since the update kernel in front of it
+    // issued its last loads): wait for that kernel to complete before reading its tile Grams
+    if (chained) pdl_wait();
     if (st->converged) return;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int sub = t & 3;

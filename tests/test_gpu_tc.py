@@ -345,12 +345,13 @@ def test_tc_prefetch_next_option_changes_no_result(NMF):
     (1280, 1536, 96, False, 1e-9, 15),     # maxiter-bound, KP = 128
     (2048, 2304, 64, False, 1e-9, 10),     # KP = 64, more tiles than one wave of early CTAs
     (1024, 1152, 16, True, 2e-3, 400),     # tolerance-bound: the stop decision races with the early-launched kernels
+    (20000, 1100, 32, False, 1e-9, 6),     # 157 W tiles: more CTAs than SMs (two waves), 9 H tiles
 ])
 def test_tc_chain_option_changes_no_result(NMF, p, n, k, planted, tol, maxiter):
-    """Option tc_chain: the reduce kernels become programmatic dependents too (resident while the update kernel in front of them is
-    in its epilogues) and publish a flag the next update kernel -- possibly resident even earlier -- polls before it reads the other
-    factor.  Same arithmetic in the same order: factors, niters, converged and objvalue must be bit-identical, for every polling
-    interval of the host."""
+    """Option tc_chain: the hand-over between the update launches does not wait for a kernel boundary -- every CTA counts itself in
+    once its bulk stores are complete, and the next update launch (resident early: the reduce kernel in between is a programmatic
+    dependent too) polls that counter before it reads the other factor.  Same arithmetic in the same order: factors, niters,
+    converged and objvalue must be bit-identical, for every polling interval of the host."""
     X, W0, H0 = _problem(NMF, p, n, k, seed=p + k, planted=planted)
     out = []
     for chain, check_every in ((0, 8), (1, 8), (1, 1), (1, 5)):
