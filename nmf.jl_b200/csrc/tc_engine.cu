@@ -67,7 +67,9 @@ struct TcSolver {
     const bf16* Xs_lo = nullptr;     // precision mode bf16x3: the remainder panel matching the Xs of the NEXT launch_update
     bool force_x3 = false;           // split operands whatever the handle's precision option says (tc_xmul)
     float* cross_part = nullptr;     // verbose W-step: per-tile sums of Num .* F_new for the NEXT launch_update (trace identity)
+    int gtl_slot = 0;                // diagnostics (tc_debug bit 7): which half of the per-CTA timeline buffer the NEXT launch_update fills
     bool chain = false;              // option tc_chain: update and reduce kernels of the loop form one chain of programmatic dependents
+    int chain_blocks = 40;           //   CTAs of a chained reduce kernel (they walk its virtual blocks; all resident early, none in the way)
     unsigned int chain_tiles = 0;    //   tiles of all chained update launches so far in this solve (what the next one waits for)
     const bf16* pf_X = nullptr;      // option tc_prefetch_next: the X panel of the launch AFTER the next launch_update ...
     int pf_tiles = 0, pf_tile_rows = 0, pf_nkb = 0;   // ... and its geometry (reset by the caller)
@@ -98,6 +100,8 @@ struct TcSolver {
         if ((h->tc_debug & 64) && mode == 0) prm.timing = nullptr;   // bit 6: keep the H-step's clocks (the W-step would overwrite them)
         const uint64_t nkb = (uint64_t)ceil_div(Kdim, 64);
         const int tile0 = sl ? sl->tile0 : 0;
+        if ((h->tc_debug & 128) && mode == 0 && F.tiles <= 4096)
+            prm.gtl = (long long*)h->buf("tc.gtl", 2 * 8 * 4096 * sizeof(long long)) + (size_t)gtl_slot * 8 * 4096;
         prm.timing_cta = mode == 6 ? F.tiles - 1 : 0;   // fused sharded H-step: the last CTA works on a tile this rank owns
         prm.tmA = make_tmap_bf16(Xs, 64, (uint64_t)(tile0 + F.tiles) * nkb * F.tile_rows, 64, (uint32_t)F.tile_rows);
         if (sl) {
@@ -178,8 +182,9 @@ struct TcSolver {
         last_gram_parts = F.tiles;
         last_chained = chained;
         if (fused_gram && !defer_gram_reduce) {
-            launch_k(gram_reduce_kernel, dim3((4 * KP * KP + 255) / 256), dim3(256), 0, st, chained, (const float*)prm.gram_part, F.tiles, KP * KP,
-                     gram_dst ? gram_dst : F.P, F.Phi, F.Plo, gram, (const TcState*)state, chained ? 1 : 0);
+            const int nvb = (4 * KP * KP + 255) / 256;
+            launch_k(gram_reduce_kernel, dim3(chained ? std::min(nvb, chain_blocks) : nvb), dim3(256), 0, st, chained, (const float*)prm.gram_part,
+                     F.tiles, KP * KP, gram_dst ? gram_dst : F.P, F.Phi, F.Plo, gram, (const TcState*)state, chained ? 1 : 0, nvb);
             h->launches += 1;
         } else if (gram >= 0 && !fused_gram) {
             launch_gram(F, gram != 0, gram_dst);
@@ -216,7 +221,7 @@ struct TcSolver {
     void launch_gram(const Factor& F, bool split, float* P_dst = nullptr) {
         launch_gram_parts(F);
         gram_reduce_kernel<<<(4 * KP * KP + 255) / 256, 256, 0, st>>>(last_gram_part, last_gram_parts, KP * KP, P_dst ? P_dst : F.P, F.Phi, F.Plo,
-                                                                       split ? 1 : 0, state, 0);
+                                                                       split ? 1 : 0, state, 0, (4 * KP * KP + 255) / 256);
         h->launches += 1;
     }
 
@@ -282,6 +287,7 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
 
     TcSolver<KP> s{h, st, state};
     s.chain = h->tc_chain != 0 && !a.verbose;
+    if (h->tc_chain > 1) s.chain_blocks = h->tc_chain;   // tc_chain = 1: default CTA count of the chained reduce kernels; > 1: that many
     if (h->tc_precision == 1) { s.refresh_bTlo(W); s.refresh_bTlo(H); }
     s.launch_gram(W, true);                   // P_W = W'W for the first H-step
     if (!a.update_H) s.launch_gram(H, true);  // H never changes: P_H once
@@ -333,6 +339,7 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
             if (a.update_H) {
                 s.Xs_lo = Xr_lo;
                 s.pf_X = Xc; s.pf_tiles = W.tiles; s.pf_tile_rows = W.tile_rows; s.pf_nkb = (int)ceil_div(n, 64);   // next: the W-step's panel
+                s.gtl_slot = 0;
                 s.launch_update(0, H, W, Xr, (int)p, lh, delta, nullptr, nullptr, 1, nullptr, pdl);  // H-step (+ tile Grams of the new H)
                 h->mark("updH");
             }
@@ -341,6 +348,7 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
             s.defer_gram_reduce = true;
             s.Xs_lo = Xc_lo;
             s.cross_part = const_cast<float*>(tr.cross_part);
+            s.gtl_slot = 1;
             if (a.update_H) { s.pf_X = Xr; s.pf_tiles = H.tiles; s.pf_tile_rows = H.tile_rows; s.pf_nkb = (int)ceil_div(p, 64); }   // next: an H-step
             else { s.pf_X = Xc; s.pf_tiles = W.tiles; s.pf_tile_rows = W.tile_rows; s.pf_nkb = (int)ceil_div(n, 64); }
             s.launch_update(0, W, H, Xc, (int)n, lw, delta, nullptr, nullptr, gramW, nullptr, pdl);
@@ -353,9 +361,10 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
             // launch_update) + stop_condition reduce / decision
             // option tc_chain: a W-step launched with early_trigger lets this kernel take its seats early; it then waits for the W-step
             const bool chW = s.last_chained;
-            launch_k(gram_conv_reduce_kernel, dim3(gram_blocks + 4 * (KP / 32)), dim3(256), 0, st, chW, (const float*)s.last_gram_part,
+            const int nvbW = gram_blocks + 4 * (KP / 32);
+            launch_k(gram_conv_reduce_kernel, dim3(chW ? std::min(nvbW, s.chain_blocks) : nvbW), dim3(256), 0, st, chW, (const float*)s.last_gram_part,
                      W.tiles, KP * KP, W.P, W.Phi, W.Plo, 1, gram_blocks, (const float*)W.conv, W.tiles, (const float*)H.conv, H.tiles,
-                     KP, (int)k, (int)a.update_H, acc, tol, state, 1, (float*)nullptr, tr, chW ? 1 : 0);
+                     KP, (int)k, (int)a.update_H, acc, tol, state, 1, (float*)nullptr, tr, chW ? 1 : 0, nvbW);
             h->launches += 1;
             h->mark("conv");
         }
@@ -417,6 +426,20 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
     out->kernel_launches = h->launches;
     out->hot_kernel_ms = h->drain_event_pairs(&out->hot_kernel_launches);
     h->report_marks(iters);
+    if (h->tc_debug & 128) {  // per-CTA life lines of the last H-step and the last W-step launch (ns since the H-step's first entry)
+        std::vector<long long> g(2 * 8 * 4096);
+        NMF_CUDA(cudaMemcpy(g.data(), h->buf("tc.gtl", g.size() * sizeof(long long)), g.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        long long t0 = LLONG_MAX;
+        for (int c = 0; c < std::min(H.tiles, 4096); ++c) t0 = std::min(t0, g[8 * c]);
+        for (int slot = 0; slot < 2; ++slot) {
+            const int nct = std::min(slot == 0 ? H.tiles : W.tiles, 4096);
+            for (int c = 0; c < nct; ++c) {
+                const long long* t = g.data() + (size_t)slot * 8 * 4096 + 8 * c;
+                fprintf(stderr, "[gtl] %c %d %lld %lld %lld %lld %lld %lld %lld %lld\n", slot == 0 ? 'H' : 'W', c, t[0] - t0, t[1] - t0, t[2] - t0, t[3] - t0,
+                        t[4] - t0, t[5] - t0, t[6] - t0, t[7] - t0);
+            }
+        }
+    }
     if (h->tc_debug & 8) {  // phase clocks of CTA 0 in the last update launch (SM cycles since kernel entry)
         std::vector<long long> tv(16 + 2 * 4096);
         NMF_CUDA(cudaMemcpy(tv.data(), h->buf("tc.timing", tv.size() * sizeof(long long)), tv.size() * sizeof(long long), cudaMemcpyDeviceToHost));
@@ -534,7 +557,7 @@ void tc_solve_batched_kp(nmfb200_handle* h, const SolveArgs& a, int nrep, float*
             std::memset(&tr, 0, sizeof(tr));
             launch_k(gram_conv_reduce_kernel, dim3(gram_blocks + 4 * (KP / 32)), dim3(256), 0, st, false, (const float*)s.last_gram_part,
                      W.tiles, KP * KP, W.P, W.Phi, W.Plo, 1, gram_blocks, (const float*)W.conv, W.tiles, (const float*)H.conv, H.tiles,
-                     KP, (int)kt, (int)a.update_H, acc, tol, state, 1, (float*)nullptr, tr, 0);
+                     KP, (int)kt, (int)a.update_H, acc, tol, state, 1, (float*)nullptr, tr, 0, gram_blocks + 4 * (KP / 32));
             launch_k(batch_snapshot_kernel, dim3(snap_grid), dim3(256), 0, st, false, (const TcState*)state, KP, (const float*)W.m, Wsnap,
                      (int64_t)p * KP, (const float*)H.m, Hsnap, (int64_t)n * KP, 0);
             h->launches += 2;

@@ -171,22 +171,19 @@ struct TraceObj {
     double xnorm2;            // ||X||^2 (Float64, once per set_X)
 };
 
-__global__ void __launch_bounds__(256) gram_conv_reduce_kernel(const float* __restrict__ gpart, int nparts, int nelem, float* __restrict__ P,
-                                                               bf16* __restrict__ Phi, bf16* __restrict__ Plo, int do_split, int gram_blocks,
-                                                               const float* __restrict__ partW, int tilesW, const float* __restrict__ partH,
-                                                               int tilesH, int KP, int k, int update_H, double* __restrict__ acc, float tol,
-                                                               TcState* st, int do_decide, float* __restrict__ wsums_f32, TraceObj tr,
-                                                               int chained) {
-    pdl_launch_dependents();  // the next H-step may start streaming X now; it waits for us before it reads P / `converged`
-    if (chained) pdl_wait();   // option tc_chain: launched as a programmatic dependent of the W-step (see gram_reduce_kernel)
-    if (st->converged) return;
+// One VIRTUAL block of the merged reduce (vb in [0, nvb)): a Gram block (vb < gram_blocks) or a stop_condition block.
+__device__ void gram_conv_virtual_block(int vb, int nvb, const float* __restrict__ gpart, int nparts, int nelem, float* __restrict__ P,
+                                        bf16* __restrict__ Phi, bf16* __restrict__ Plo, int do_split, int gram_blocks,
+                                        const float* __restrict__ partW, int tilesW, const float* __restrict__ partH, int tilesH, int KP, int k,
+                                        int update_H, double* __restrict__ acc, float tol, TcState* st, int do_decide,
+                                        float* __restrict__ wsums_f32, const TraceObj& tr) {
     __shared__ double red[8][32];
     __shared__ float devs[256];
     __shared__ int fail, is_last, is_last_all;
-    if ((int)blockIdx.x < gram_blocks) {
-        gram_reduce_body(gpart, nparts, nelem, P, Phi, Plo, do_split, blockIdx.x, st);
+    if (vb < gram_blocks) {
+        gram_reduce_body(gpart, nparts, nelem, P, Phi, Plo, do_split, vb, st);
     } else {
-        const int cblock = blockIdx.x - gram_blocks, nconv = gridDim.x - gram_blocks;
+        const int cblock = vb - gram_blocks, nconv = nvb - gram_blocks;
         const int cbs = KP / 32;
         const int q = cblock / cbs, cb = cblock % cbs;
         const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -229,10 +226,10 @@ __global__ void __launch_bounds__(256) gram_conv_reduce_kernel(const float* __re
         }
     }
     if (tr.cross_part == nullptr) return;
-    // ---- trace-identity objective: the last of ALL blocks sees the complete Gram P of this factor
+    // ---- trace-identity objective: the last of ALL (virtual) blocks sees the complete Gram P of this factor
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) is_last_all = (atomicAdd(&st->ticket2, 1u) == gridDim.x - 1) ? 1 : 0;
+    if (threadIdx.x == 0) is_last_all = (atomicAdd(&st->ticket2, 1u) == (unsigned)nvb - 1u) ? 1 : 0;
     __syncthreads();
     if (!is_last_all) return;
     __threadfence();
@@ -252,6 +249,25 @@ __global__ void __launch_bounds__(256) gram_conv_reduce_kernel(const float* __re
         st->ticket2 = 0u;
         const double d = tr.xnorm2 + sred[0];
         st->objv = (double)(0.5f * (float)(d > 0.0 ? d : 0.0));   // convert(T, 0.5) * sqL2dist (multupd.jl:81)
+    }
+}
+
+// The work is cut into nvb = gram_blocks + 4*KP/32 VIRTUAL blocks; a launch with gridDim.x == nvb gives each its own CTA (the default),
+// a smaller grid walks them (option tc_chain: a handful of CTAs that are resident early, next to the update kernel's, and whose
+// running time is hidden under the next update launch's 75 us of streaming).
+__global__ void __launch_bounds__(256) gram_conv_reduce_kernel(const float* __restrict__ gpart, int nparts, int nelem, float* __restrict__ P,
+                                                               bf16* __restrict__ Phi, bf16* __restrict__ Plo, int do_split, int gram_blocks,
+                                                               const float* __restrict__ partW, int tilesW, const float* __restrict__ partH,
+                                                               int tilesH, int KP, int k, int update_H, double* __restrict__ acc, float tol,
+                                                               TcState* st, int do_decide, float* __restrict__ wsums_f32, TraceObj tr,
+                                                               int chained, int nvb) {
+    pdl_launch_dependents();  // the next H-step may start streaming X now; it waits for us before it reads P / `converged`
+    if (chained) pdl_wait();   // option tc_chain: launched as a programmatic dependent of the W-step (see gram_reduce_kernel)
+    if (st->converged) return;
+    for (int vb = blockIdx.x; vb < nvb; vb += gridDim.x) {
+        gram_conv_virtual_block(vb, nvb, gpart, nparts, nelem, P, Phi, Plo, do_split, gram_blocks, partW, tilesW, partH, tilesH, KP, k, update_H,
+                                acc, tol, st, do_decide, wsums_f32, tr);
+        __syncthreads();   // the shared scratch of one virtual block is reused by the next
     }
 }
 

@@ -95,6 +95,9 @@ struct UpdateParams {
     int tile_rows;      // rows of F owned by one CTA (<= 128, multiple of 8); the TMA boxes of A / Fhi / Flo have this many rows
     long long* timing;  // diagnostics (tc_debug bit 3): CTA timing_cta records clock64() at its phase boundaries, see TSTAMP
     int timing_cta;
+    long long* gtl;     // diagnostics (tc_debug bit 7): EVERY CTA records %globaltimer at 8 points of its life, [8 * blockIdx.x + i]: 0 entry,
+                        // 1 producer released (chain counter seen), 2 last load issued, 3 last MMA issued, 4 accumulators complete,
+                        // 5 epilogue warps done, 6 bulk stores complete (tile counted), 7 exit
     float lambda, delta;
     // ---- row-sharded solves (tc_shard.cuh); all zero for a single-GPU launch
     int tile0;          // first tile of this launch (MODE 2: the rank's own H rows only)
@@ -202,6 +205,8 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #define TSTAMP(i) do { if (prm.timing != nullptr && (int)blockIdx.x == prm.timing_cta) prm.timing[i] = clock64(); } while (0)
+#define GSTAMP(i) do { if (prm.gtl != nullptr) { long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); prm.gtl[8 * blockIdx.x + (i)] = g_; } } while (0)
+    if (threadIdx.x == 0) GSTAMP(0);
     if (threadIdx.x == 0) TSTAMP(0);
     if (prm.timing != nullptr && threadIdx.x == 0) {  // every CTA: global timer at entry (and exit, below)
         long long gt;
@@ -299,6 +304,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                 } while (true);
                 asm volatile("fence.proxy.async;" ::: "memory");   // the predecessor's bulk stores -> the TMA loads below
             }
+            GSTAMP(1);
             const int arow0 = arow;
             for (int pass = 0; pass < npass; ++pass) {   // one pass unless precision mode bf16x3
                 const CUtensorMap* mA = pass == 2 ? &prm.tmAlo : &prm.tmA;
@@ -336,6 +342,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                     if (++s == C::STAGES) { s = 0; ph ^= 1u; dst = smem; }
                 }
             }
+            GSTAMP(2);
             if (MODE == 0 && prm.early_trigger) pdl_launch_dependents();   // every load is issued: the reduce kernel behind us may take its seats
             if (MODE == 0 && prm.pf_blocks > 0 && (int)blockIdx.x < prm.pf_tiles) {
                 // every load of this launch is in flight: warm L2 with the head of the next launch's panel (no smem destination,
@@ -402,6 +409,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
             }
             if (MODE != 5) umma_commit(tmem_full);
             TSTAMP(3);                                                   // all MMAs issued
+            GSTAMP(3);
         }
         __syncwarp();
     } else if (warp >= 2) {
@@ -451,7 +459,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
         if (threadIdx.x == 64) TSTAMP(4);    // preceding kernel complete
         if (MODE != 5) mbar_wait(tmem_full, 0);   // (parking the epilogue warps in a named barrier instead of this poll was measured: no difference)
         tc_fence_after();
-        if (threadIdx.x == 64) TSTAMP(5);    // accumulators complete
+        if (threadIdx.x == 64) { TSTAMP(5); GSTAMP(4); }   // accumulators complete
         do {
         if (stop) break;  // converged while this kernel was streaming (PDL): leave F untouched
         if ((MODE == 2 || (FUSED && owner)) && prm.G > 0 && prm.num_wait != nullptr) {
@@ -730,6 +738,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
             if constexpr (STAGED) {
                 if (threadIdx.x == 64) {
                     TSTAMP(7);                 // all epilogue warps done
+                    GSTAMP(5);
 #pragma unroll
                     for (int b = 0; b < KP / 32; ++b) tma_store_2d(&prm.tmF32, SF + b * 16384, 32 * b, r0);
 #pragma unroll
@@ -808,6 +817,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                         }
                     }
                     TSTAMP(10);                // bulk stores have read their staging buffers
+                    GSTAMP(6);
                 }
             }
         }
@@ -815,13 +825,14 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
         tc_fence_before();
     }
     __syncthreads();
-    if (threadIdx.x == 0) TSTAMP(11);
+    if (threadIdx.x == 0) { TSTAMP(11); GSTAMP(7); }
     if (prm.timing != nullptr && threadIdx.x == 0) {
         long long gt;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         prm.timing[16 + 2 * blockIdx.x + 1] = gt;
     }
 #undef TSTAMP
+#undef GSTAMP
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -958,38 +969,41 @@ __global__ void __launch_bounds__(192, 1) gram_kernel(const __grid_constant__ Gr
 // (each sums every 4th partial with 8 loads in flight), combined with two shuffles: fixed order => deterministic.
 __global__ void __launch_bounds__(256) gram_reduce_kernel(const float* __restrict__ part, int nparts, int nelem, float* __restrict__ P,
                                                           bf16* __restrict__ Phi, bf16* __restrict__ Plo, int do_split,
-                                                          const TcState* st, int chained) {
+                                                          const TcState* st, int chained, int nvb) {
     // The update kernel behind us may start streaming X as soon as every block has passed this point; it waits for our
     // completion before it reads P.  (Pre-launching THIS kernel behind the running update kernel was measured too:
     // its resident blocks polling in griddepcontrol.wait slow the single-thread TMA / MMA loops, 4770 -> 4400 it/s.)
     pdl_launch_dependents();
     // option tc_chain: this kernel was itself launched as a programmatic dependent (resident since the update kernel in front of it
-    // issued its last loads): wait for that kernel to complete before reading its tile Grams
+    // issued its last loads): wait for that kernel to complete before reading its tile Grams.  It then runs as a few CTAs that walk
+    // the nvb virtual blocks of 256 threads (gridDim.x == nvb otherwise).
     if (chained) pdl_wait();
     if (st->converged) return;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int sub = t & 3;
-    const int i = t >> 2;
-    float acc = 0.f;
-    if (i < nelem) {
-        int g = sub;
-        for (; g + 28 < nparts; g += 32) {
-            float v[8];
+    for (int vb = blockIdx.x; vb < nvb; vb += gridDim.x) {
+        const int t = vb * blockDim.x + threadIdx.x;
+        const int sub = t & 3;
+        const int i = t >> 2;
+        float acc = 0.f;
+        if (i < nelem) {
+            int g = sub;
+            for (; g + 28 < nparts; g += 32) {
+                float v[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = __ldcg(part + (size_t)(g + 4 * u) * nelem + i);
-            acc += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+                for (int u = 0; u < 8; ++u) v[u] = __ldcg(part + (size_t)(g + 4 * u) * nelem + i);
+                acc += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+            }
+            for (; g < nparts; g += 4) acc += __ldcg(part + (size_t)g * nelem + i);
         }
-        for (; g < nparts; g += 4) acc += __ldcg(part + (size_t)g * nelem + i);
-    }
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    if (i < nelem && sub == 0) {
-        if (gram_masked(st, i)) acc = 0.f;   // batched replicates: block-diagonal Gram
-        P[i] = acc;
-        if (do_split) {
-            bf16 hi = __float2bfloat16_rn(acc);
-            Phi[i] = hi;
-            Plo[i] = __float2bfloat16_rn(acc - __bfloat162float(hi));
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (i < nelem && sub == 0) {
+            if (gram_masked(st, i)) acc = 0.f;   // batched replicates: block-diagonal Gram
+            P[i] = acc;
+            if (do_split) {
+                bf16 hi = __float2bfloat16_rn(acc);
+                Phi[i] = hi;
+                Plo[i] = __float2bfloat16_rn(acc - __bfloat162float(hi));
+            }
         }
     }
 }
