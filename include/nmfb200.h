@@ -109,6 +109,13 @@ int nmfb200_set_stream(nmfb200_handle* h, void* stream);
  *   "tc_pdl"       = "0" | "1"               -- 1 (default): the tensor-core update kernels are launched as programmatic
  *                                               dependents of the small reduce kernel in front of them (their X streaming
  *                                               overlaps it); 0: plain stream order.  Results are identical.
+ *   "tc_chain"     = "0" | "1" | "<n>"        -- MultUpdate(:mse) on one GPU, k <= 128: 1 (default) = the kernels of the loop form one chain
+ *                                               of programmatic dependents and an update launch is released by a counter of finished
+ *                                               tiles of the launch before it instead of a kernel boundary (-6 % per iteration at
+ *                                               config 2); the small reduce kernels then run as one CTA per SM (n > 1: n CTAs).
+ *                                               0 = kernel-boundary hand-over.  Results are identical.
+ *   "tc_prefetch_next" = "<n>"               -- experiment, default 0: L2 prefetch of the first n k-blocks of the next launch's X
+ *                                               panel from the epilogue (measured: no gain, profiles/r2b_prefetch_next.md).
  *   "tc_div_fused" = "0" | "1"               -- MultUpdate(:div) on the tensor-core engine: 1 (default) keeps the quotient
  *                                               tile X./(WH+delta) on chip between two tensor-core products; 0 writes it
  *                                               as a bf16 panel through HBM (older form, kept for comparison).

@@ -280,6 +280,7 @@ int nmfb200_create(nmfb200_handle** out, int device, int flags) {
     nmfb200_handle* h = new (std::nothrow) nmfb200_handle();
     if (!h) return NMFB200_ENOMEM;
     h->device = device;
+    h->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return NMFB200_ECUDA; }
     h->stream = h->own_stream;
     *out = h;

@@ -124,8 +124,10 @@ struct nmfb200_handle {
     int emulate_shards = 0;  // > 1: run the row-sharded tensor-core algorithm with this many LOGICAL ranks on this one GPU
     int tc_xmul_opt = 1;   // ProjectedALS / CoordinateDescent / ALSPGrad (Float32): X-sized products on the tensor cores (split operands)
     int tc_flush = -1;     // k-blocks per TMEM accumulation chunk of the update kernel (0 = one long chain; -1 = default: 8)
-    int tc_chain = 0;      // MultUpdate(:mse), single GPU, k <= 128: 1 = the reduce kernels are programmatic dependents too (resident while the
-                           // update kernel in front of them finishes its epilogues) and publish a flag the next update kernel polls
+    int tc_chain = 1;      // MultUpdate(:mse), single GPU, k <= 128: 1 (default) = the iteration is one chain of programmatic dependents and the
+                           // hand-over between update launches is a per-tile completion counter, not a kernel boundary (tc_update.cuh);
+                           // the reduce kernels run as one CTA per SM walking their virtual blocks; > 1 = that many CTAs; 0 = off
+    int sm_count = 148;
     int tc_prefetch_next = 0;  // update kernel (single GPU, bf16 mode): k-blocks of the NEXT launch's X panel each CTA prefetches into L2
                                // while it sits in its epilogue (0 = off)
     int tc_precision = 0;  // 0 = bf16 operands; 1 = bf16x3 (hi/lo split of X and of the streamed factor: fp32-class products)

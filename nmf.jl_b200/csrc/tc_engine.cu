@@ -69,7 +69,7 @@ struct TcSolver {
     float* cross_part = nullptr;     // verbose W-step: per-tile sums of Num .* F_new for the NEXT launch_update (trace identity)
     int gtl_slot = 0;                // diagnostics (tc_debug bit 7): which half of the per-CTA timeline buffer the NEXT launch_update fills
     bool chain = false;              // option tc_chain: update and reduce kernels of the loop form one chain of programmatic dependents
-    int chain_blocks = 40;           //   CTAs of a chained reduce kernel (they walk its virtual blocks; all resident early, none in the way)
+    int chain_blocks = 148;          //   CTAs of a chained reduce kernel (they walk its virtual blocks; all resident early, none in the way)
     unsigned int chain_tiles = 0;    //   tiles of all chained update launches so far in this solve (what the next one waits for)
     const bf16* pf_X = nullptr;      // option tc_prefetch_next: the X panel of the launch AFTER the next launch_update ...
     int pf_tiles = 0, pf_tile_rows = 0, pf_nkb = 0;   // ... and its geometry (reset by the caller)
@@ -287,7 +287,7 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
 
     TcSolver<KP> s{h, st, state};
     s.chain = h->tc_chain != 0 && !a.verbose;
-    if (h->tc_chain > 1) s.chain_blocks = h->tc_chain;   // tc_chain = 1: default CTA count of the chained reduce kernels; > 1: that many
+    s.chain_blocks = h->tc_chain > 1 ? h->tc_chain : h->sm_count;   // one CTA per SM unless told otherwise
     if (h->tc_precision == 1) { s.refresh_bTlo(W); s.refresh_bTlo(H); }
     s.launch_gram(W, true);                   // P_W = W'W for the first H-step
     if (!a.update_H) s.launch_gram(H, true);  // H never changes: P_H once
