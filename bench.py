@@ -378,7 +378,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "parity_check": parity["status"] if parity else None, "parity": parity,
             "gpu_launches": int(res.kernel_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": traffic, "traffic_source": "profiles/r2_update_kernel_ncu_full.md (ncu --set full, same workload)",
+                         "traffic": traffic, "traffic_source": "profiles/r2c_update_kernel_ncu_full.md (ncu --set full, same workload)",
                          "kernel": "mu_update_kernel<128,0>", "kernel_ms": kern_ms, "launches_timed": launches,
                          "loop_ms_per_step_with_kernel_events": res_k.solve_ms / max(res_k.niters, 1),
                          "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
