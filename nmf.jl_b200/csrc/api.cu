@@ -333,6 +333,8 @@ int nmfb200_set_option(nmfb200_handle* h, const char* key, const char* value) {
             else throw Error{NMFB200_EINVAL, "tc_xchg must be p2p|nccl"};
         } else if (k == "tc_xmul") {
             h->tc_xmul_opt = atoi(value);
+        } else if (k == "tc_skew") {
+            h->tc_skew = atoi(value);
         } else if (k == "tc_chain") {
             h->tc_chain = atoi(value);
         } else if (k == "tc_prefetch_next") {

@@ -127,6 +127,7 @@ struct nmfb200_handle {
     int tc_chain = 1;      // MultUpdate(:mse), single GPU, k <= 128: 1 (default) = the iteration is one chain of programmatic dependents and the
                            // hand-over between update launches is a per-tile completion counter, not a kernel boundary (tc_update.cuh);
                            // the reduce kernels run as one CTA per SM walking their virtual blocks; > 1 = that many CTAs; 0 = off
+    int tc_skew = 0;       // on top of tc_chain: two groups of tiles half a period apart (one streams while the other is in its epilogues)
     int sm_count = 148;
     int tc_prefetch_next = 0;  // update kernel (single GPU, bf16 mode): k-blocks of the NEXT launch's X panel each CTA prefetches into L2
                                // while it sits in its epilogue (0 = off)

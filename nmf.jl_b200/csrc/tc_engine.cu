@@ -69,6 +69,8 @@ struct TcSolver {
     float* cross_part = nullptr;     // verbose W-step: per-tile sums of Num .* F_new for the NEXT launch_update (trace identity)
     int gtl_slot = 0;                // diagnostics (tc_debug bit 7): which half of the per-CTA timeline buffer the NEXT launch_update fills
     bool chain = false;              // option tc_chain: update and reduce kernels of the loop form one chain of programmatic dependents
+    bool skew = false;               // option tc_skew (needs chain): two groups of tiles half a period apart
+    unsigned int skew_a = 0, skew_b = 0, skew_mid = 0;   //   cumulative tiles of group A / B and A CTAs of all skewed launches so far
     int chain_blocks = 148;          //   CTAs of a chained reduce kernel (they walk its virtual blocks; all resident early, none in the way)
     unsigned int chain_tiles = 0;    //   tiles of all chained update launches so far in this solve (what the next one waits for)
     const bf16* pf_X = nullptr;      // option tc_prefetch_next: the X panel of the launch AFTER the next launch_update ...
@@ -141,7 +143,21 @@ struct TcSolver {
         }
         const bool timed_ = h->time_kernels == 1 && mode != 2 && mode != 6;
         const bool chained = chain && pdl && mode == 0 && fused_gram && sl == nullptr && !timed_;
-        if (chained) {
+        const bool skewed = chained && skew && F.tile_rows == 128 && O.tile_rows == 128 && F.tiles >= 2 && O.tiles >= 2 &&
+                            F.tiles <= h->sm_count && O.tiles <= h->sm_count;
+        if (skewed) {
+            const int split = F.tiles / 2;
+            prm.skew_cnt = state->skew;
+            prm.tile_split = split;
+            prm.kb_split = 2 * (O.tiles / 2);   // a 128-row tile of the other factor = two 64-wide k-blocks
+            prm.need_a = skew_a;
+            prm.need_b = skew_b;
+            prm.need_mid = skew_mid + (unsigned int)split;
+            prm.early_trigger = 2;
+            skew_a += (unsigned int)split;
+            skew_b += (unsigned int)(F.tiles - split);
+            skew_mid += (unsigned int)split;
+        } else if (chained) {
             prm.chain_flag = &state->chain;
             prm.chain_cnt = &state->chain;
             prm.chain_need = chain_tiles;
@@ -288,6 +304,7 @@ void tc_solve_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, 
     TcSolver<KP> s{h, st, state};
     s.chain = h->tc_chain != 0 && !a.verbose;
     s.chain_blocks = h->tc_chain > 1 ? h->tc_chain : h->sm_count;   // one CTA per SM unless told otherwise
+    s.skew = s.chain && h->tc_skew != 0 && a.update_H;
     if (h->tc_precision == 1) { s.refresh_bTlo(W); s.refresh_bTlo(H); }
     s.launch_gram(W, true);                   // P_W = W'W for the first H-step
     if (!a.update_H) s.launch_gram(H, true);  // H never changes: P_H once

@@ -24,7 +24,9 @@ struct TcState {
     // batched replicates (all zero otherwise): the Gram reduce keeps only the diagonal blk x blk blocks of the KP x KP Gram (kp = KP),
     // and the stop decision is taken per replicate in *bs; `converged` is raised once every replicate is done
     int blk, kp, nrep;
-    unsigned int chain;    // option tc_chain: sequence number of the last reduce kernel whose predecessor (an update launch) is COMPLETE
+    unsigned int chain;    // option tc_chain: tiles completed by all chained update launches of this solve
+    unsigned int skew[3];  // option tc_skew: the same per group (A, B) of tiles, and A CTAs past the middle of their k-loop
+    unsigned int pad3_;
     BatchState* bs;
 };
 
@@ -71,7 +73,16 @@ struct UpdateParams {
     const unsigned int* chain_flag;
     unsigned int* chain_cnt;
     unsigned int chain_need;
-    int early_trigger;
+    int early_trigger;  // 1: launch_dependents once the last load is issued; 2: at the top of the kernel (tc_skew)
+    // option tc_skew (on top of tc_chain): the tiles of a launch form two groups, A = [0, tile_split) and B, that run HALF A PERIOD APART, so
+    // that one group streams while the other sits in its epilogues (the one phase in which HBM idled).  A launch reads the other factor's
+    // group-A tiles in k-blocks [0, kb_split) and its group-B tiles behind them, so a CTA needs cnt A >= need_a to start and cnt B >= need_b
+    // only at the middle of its k-loop -- exactly when the late group of the launch before it is done.  The offset is enforced, not hoped
+    // for: a B CTA starts only when every A CTA of its own launch has passed its middle (skew_cnt[2] >= need_mid).  Every CTA triggers
+    // launch_dependents at its top, so the CTAs of the next launch enter one by one as SMs become free.
+    unsigned int* skew_cnt;   // [0] tiles of group A complete, [1] of group B, [2] A CTAs past their middle (all cumulative over launches)
+    unsigned int need_a, need_b, need_mid;
+    int tile_split, kb_split;
     int flush_chunk;    // > 0 (KP <= 128): the numerator MMAs accumulate at most this many k-blocks in TMEM; the epilogue warps add
                         // each finished chunk to fp32 register sums (round to nearest) while the next chunk accumulates.  The
                         // tensor core's accumulator TRUNCATES (measured: ~0.5 ulp lost per MMA, a relative bias of ~3e-8 per
@@ -259,6 +270,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (MODE == 0 && prm.early_trigger == 2 && threadIdx.x == 0) pdl_launch_dependents();   // tc_skew: successors enter as SMs become free
     if (*stop_slot != 0u) {  // uniform early exit
         if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
         return;
@@ -304,9 +316,49 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                 } while (true);
                 asm volatile("fence.proxy.async;" ::: "memory");   // the predecessor's bulk stores -> the TMA loads below
             }
-            GSTAMP(1);
+            const bool skewed = MODE == 0 && prm.skew_cnt != nullptr;
+            // bounded poll of a cumulative counter; also leaves when stop_condition was met (launches that see it publish nothing)
+            auto poll = [&](const unsigned int* p, unsigned int need) {
+                const long long t0 = clock64();
+                unsigned int seen;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p) : "memory");
+                    if ((int)(seen - need) >= 0) break;
+                    if (__ldcg(&prm.state->converged) != 0) break;
+                    if (clock64() - t0 > 20000000000LL) { printf("nmfb200: skew counter wait timed out (need %u, seen %u)\n", need, seen); __trap(); }
+                } while (true);
+                asm volatile("fence.proxy.async;" ::: "memory");
+            };
+            if (skewed) {
+                const bool grp_b = tile >= prm.tile_split;
+                if (grp_b) poll(prm.skew_cnt + 2, prm.need_mid);   // stay half a period behind group A
+                poll(prm.skew_cnt + 0, prm.need_a);
+                GSTAMP(1);
+                const int kb1 = min(prm.kb_split, nkb);
+                for (int kb = 0; kb < kb1; ++kb) {
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    mbar_arrive_expect_tx(&full_bar[s], num_tx);
+                    tma_load_2d(dst, &prm.tmA, &full_bar[s], 0, arow);
+                    tma_load_2d(dst + C::A_BYTES, &prm.tmB, &full_bar[s], 64 * kb, 0);
+                    arow += tile_rows;
+                    dst += C::STAGE_BYTES;
+                    if (++s == C::STAGES) { s = 0; ph ^= 1u; dst = smem; }
+                }
+                if (!grp_b) atomicAdd(prm.skew_cnt + 2, 1u);        // group A: past the middle
+                poll(prm.skew_cnt + 1, prm.need_b);
+                for (int kb = kb1; kb < nkb; ++kb) {
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    mbar_arrive_expect_tx(&full_bar[s], num_tx);
+                    tma_load_2d(dst, &prm.tmA, &full_bar[s], 0, arow);
+                    tma_load_2d(dst + C::A_BYTES, &prm.tmB, &full_bar[s], 64 * kb, 0);
+                    arow += tile_rows;
+                    dst += C::STAGE_BYTES;
+                    if (++s == C::STAGES) { s = 0; ph ^= 1u; dst = smem; }
+                }
+            }
+            if (!skewed) GSTAMP(1);
             const int arow0 = arow;
-            for (int pass = 0; pass < npass; ++pass) {   // one pass unless precision mode bf16x3
+            for (int pass = 0; pass < (skewed ? 0 : npass); ++pass) {   // one pass unless precision mode bf16x3
                 const CUtensorMap* mA = pass == 2 ? &prm.tmAlo : &prm.tmA;
                 const CUtensorMap* mB = pass == 1 ? &prm.tmBlo : &prm.tmB;
                 arow = arow0;
@@ -343,7 +395,7 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                 }
             }
             GSTAMP(2);
-            if (MODE == 0 && prm.early_trigger) pdl_launch_dependents();   // every load is issued: the reduce kernel behind us may take its seats
+            if (MODE == 0 && prm.early_trigger == 1) pdl_launch_dependents();   // every load is issued: the reduce kernel behind us may take its seats
             if (MODE == 0 && prm.pf_blocks > 0 && (int)blockIdx.x < prm.pf_tiles) {
                 // every load of this launch is in flight: warm L2 with the head of the next launch's panel (no smem destination,
                 // no completion tracking; a converged solve wastes them harmlessly)
@@ -803,6 +855,11 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                         asm volatile("fence.proxy.async;" ::: "memory");
                         __threadfence();
                         atomicAdd(prm.chain_cnt, 1u);
+                    }
+                    if (MODE == 0 && prm.skew_cnt != nullptr) {    // option tc_skew: the same, per group
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                        __threadfence();
+                        atomicAdd(prm.skew_cnt + (tile >= prm.tile_split ? 1 : 0), 1u);
                     }
                     if ((MODE == 2 || FUSED) && prm.G > 0 && !(MODE == 2 && prm.defer_signal)) {
                         // the peers' copies were written through the async proxy: order them, count this tile, and the last own

@@ -354,11 +354,12 @@ def test_tc_chain_option_changes_no_result(NMF, p, n, k, planted, tol, maxiter):
     converged and objvalue must be bit-identical, for every polling interval of the host."""
     X, W0, H0 = _problem(NMF, p, n, k, seed=p + k, planted=planted)
     out = []
-    for chain, check_every in ((0, 8), (1, 8), (1, 1), (40, 5)):
+    for chain, check_every, skew in ((0, 8, 0), (1, 8, 0), (1, 1, 0), (40, 5, 0), (1, 8, 1), (1, 3, 1)):
         for _ in range(2 if chain else 1):
             W, H = W0.copy(order="F"), H0.copy(order="F")
             with NMF.Session(engine="tc") as s:
                 s.set_option("tc_chain", chain)
+                s.set_option("tc_skew", skew)   # two groups of tiles half a period apart (needs tc_chain; <= one wave of CTAs)
                 s.set_option("check_every", check_every)
                 s.set_X(X)
                 r = s.solve(NMF.MultUpdate(np.float32, obj="mse", maxiter=maxiter, tol=tol), W, H)
