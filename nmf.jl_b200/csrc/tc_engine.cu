@@ -154,6 +154,7 @@ struct TcSolver {
             prm.need_b = skew_b;
             prm.need_mid = skew_mid + (unsigned int)split;
             prm.early_trigger = 2;
+            prm.diag_nob = (h->tc_debug & 256) ? 1 : 0;
             skew_a += (unsigned int)split;
             skew_b += (unsigned int)(F.tiles - split);
             skew_mid += (unsigned int)split;

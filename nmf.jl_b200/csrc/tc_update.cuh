@@ -83,6 +83,7 @@ struct UpdateParams {
     unsigned int* skew_cnt;   // [0] tiles of group A complete, [1] of group B, [2] A CTAs past their middle (all cumulative over launches)
     unsigned int need_a, need_b, need_mid;
     int tile_split, kb_split;
+    int diag_nob;       // diagnostics (tc_debug bit 8, skewed launches only): skip the B operand loads behind the first k-block
     int flush_chunk;    // > 0 (KP <= 128): the numerator MMAs accumulate at most this many k-blocks in TMEM; the epilogue warps add
                         // each finished chunk to fp32 register sums (round to nearest) while the next chunk accumulates.  The
                         // tensor core's accumulator TRUNCATES (measured: ~0.5 ulp lost per MMA, a relative bias of ~3e-8 per
@@ -335,11 +336,13 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                 poll(prm.skew_cnt + 0, prm.need_a);
                 GSTAMP(1);
                 const int kb1 = min(prm.kb_split, nkb);
+                const bool nob = prm.diag_nob != 0;   // diagnostics (tc_debug bit 8): B operand loaded for the first STAGES k-blocks only (WRONG results)
                 for (int kb = 0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[s], ph ^ 1u);
-                    mbar_arrive_expect_tx(&full_bar[s], num_tx);
+                    const bool ldb = !nob || kb < C::STAGES;   // every stage's B half holds finite data
+                    mbar_arrive_expect_tx(&full_bar[s], ldb ? num_tx : a_bytes);
                     tma_load_2d(dst, &prm.tmA, &full_bar[s], 0, arow);
-                    tma_load_2d(dst + C::A_BYTES, &prm.tmB, &full_bar[s], 64 * kb, 0);
+                    if (ldb) tma_load_2d(dst + C::A_BYTES, &prm.tmB, &full_bar[s], 64 * kb, 0);
                     arow += tile_rows;
                     dst += C::STAGE_BYTES;
                     if (++s == C::STAGES) { s = 0; ph ^= 1u; dst = smem; }
@@ -348,9 +351,9 @@ __global__ void __launch_bounds__(UpdCfg<KP>::THREADS, 1) mu_update_kernel(const
                 poll(prm.skew_cnt + 1, prm.need_b);
                 for (int kb = kb1; kb < nkb; ++kb) {
                     mbar_wait(&empty_bar[s], ph ^ 1u);
-                    mbar_arrive_expect_tx(&full_bar[s], num_tx);
+                    mbar_arrive_expect_tx(&full_bar[s], nob ? a_bytes : num_tx);
                     tma_load_2d(dst, &prm.tmA, &full_bar[s], 0, arow);
-                    tma_load_2d(dst + C::A_BYTES, &prm.tmB, &full_bar[s], 64 * kb, 0);
+                    if (!nob) tma_load_2d(dst + C::A_BYTES, &prm.tmB, &full_bar[s], 64 * kb, 0);
                     arow += tile_rows;
                     dst += C::STAGE_BYTES;
                     if (++s == C::STAGES) { s = 0; ph ^= 1u; dst = smem; }
