@@ -634,6 +634,28 @@ void tc_solve_batched_kp(nmfb200_handle* h, const SolveArgs& a, int nrep, float*
 
 #include "tc_div.cuh"
 
+// Row-sharded MultUpdate(:div) (multupd.jl:171-181): the k-split partial numerators W_g'Q_g of one rank summed in split order
+// -> one [R][KP] buffer whose size does not depend on the rank's row count (it is all-reduced over the ranks next)
+__global__ void sum_splits_kernel(const float4* __restrict__ part, int nsplits, int64_t stride4, int64_t n4, float4* __restrict__ out,
+                                  const TcState* st) {
+    if (st->converged) return;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 a = __ldcg(part + i);
+        for (int sp = 1; sp < nsplits; ++sp) {
+            const float4 v = __ldcg(part + (size_t)sp * stride4 + i);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        out[i] = a;
+    }
+}
+// stop_condition decision on sums that were all-reduced over the ranks (common.jl:105-106)
+__global__ void __launch_bounds__(256) conv_decide_kernel(const double* __restrict__ acc, int KP, int k, float tol, TcState* st) {
+    __shared__ float devs[256];
+    __shared__ int fail;
+    if (st->converged) return;
+    conv_decide(acc, KP, k, tol, st, devs, &fail);
+}
+
 template <int KP>
 void tc_solve_div_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t ldw, float* Hc, int64_t ldh, nmfb200_result* out) {
     TcSolver<KP>::set_attrs(h->device);
@@ -648,6 +670,7 @@ void tc_solve_div_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t l
     const float delta = std::sqrt(std::numeric_limits<float>::epsilon());
     const float lw = std::max((float)a.lambda_w, delta), lh = std::max((float)a.lambda_h, delta);  // multupd.jl:37-40
     const float tol = (float)a.tol;
+    const bool multi = h->comm != nullptr;   // rows of X / W sharded over ranks, H replicated: two NCCL all-reduces per H-step
     cudaEvent_t e0, e1, e2;
     NMF_CUDA(cudaEventCreate(&e0));
     NMF_CUDA(cudaEventCreate(&e1));
@@ -708,12 +731,15 @@ void tc_solve_div_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t l
         }
         return best;
     };
-    auto half_step = [&](Factor& Rf, Factor& Cf, const bf16* Xs, int nkb, int Kdim, float lambda) {
+    // reduce_ranks (row-sharded H-step): Cf = this rank's rows of W, so the column sums sW and the numerators W'Q are partial -- both are
+    // all-reduced over the ranks (NCCL on the solver's stream) before the ratio, which every rank then applies to its replica of H
+    auto half_step = [&](Factor& Rf, Factor& Cf, const bf16* Xs, int nkb, int Kdim, float lambda, bool reduce_ranks) {
         const uint64_t prow = (uint64_t)Rf.tiles * nkb * 128;
         const bool pdl = fused && h->tc_pdl != 0;
         colsum_tiles_kernel<<<Cf.tiles, 256, 0, st>>>(Cf.m, Cf.R, KP, cs_part, state);
         launch_k(colsum_reduce_kernel, dim3(KP / 32), dim3(256), 0, st, pdl, (const float*)cs_part, Cf.tiles, KP, Cf.colsum, (const TcState*)state);
         h->launches += 2;
+        if (reduce_ranks) h->allreduce_sum(Cf.colsum, (size_t)KP);
         if (fused) {
             DivFusedParams fp;
             fp.tmX = make_tmap_bf16(Xs, 64, prow, 64, 128);
@@ -730,6 +756,18 @@ void tc_solve_div_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t l
             fp.delta = delta;
             launch_k(div_fused_kernel<KP>, dim3(Rf.tiles, ksplit), dim3(DivFusedCfg<KP>::THREADS), (size_t)DivFusedCfg<KP>::SMEM_BYTES, st, pdl, fp);
             h->launches += 1;
+            if (reduce_ranks) {
+                // the number of k-splits follows the rank's own row count: sum them here, all-reduce a buffer every rank sizes alike
+                float* red = h->buf_t<float>("tc.div_num_red", (size_t)Rf.R * KP);
+                const int64_t n4 = (int64_t)Rf.R * KP / 4;
+                sum_splits_kernel<<<ew_grid(n4), 256, 0, st>>>((const float4*)fp.num_part, ksplit, n4, n4, (float4*)red, state);
+                h->launches += 1;
+                h->allreduce_sum(red, (size_t)Rf.R * KP);
+                s.num_splits = 1;
+                s.num_split_stride = 0;
+                s.launch_update(5, Rf, Cf, Xs, Kdim, lambda, delta, red);
+                return;
+            }
             s.num_splits = ksplit;
             s.num_split_stride = (int64_t)Rf.R * KP;
             s.launch_update(5, Rf, Cf, Xs, Kdim, lambda, delta, fp.num_part);
@@ -763,9 +801,16 @@ void tc_solve_div_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t l
     while (enq < a.maxiter) {
         int64_t batch = std::min<int64_t>(h->check_every, a.maxiter - enq);
         for (int64_t i = 0; i < batch; ++i) {
-            if (a.update_H) half_step(H, W, Xr, nkbH, (int)p, lh);   // multupd.jl:171-181
-            half_step(W, H, Xc, nkbW, (int)n, lw);                    // :183-192
-            conv_reduce_kernel<<<4 * (KP / 32), 256, 0, st>>>(W.conv, W.tiles, H.conv, H.tiles, KP, (int)k, a.update_H, acc, tol, state, 1, nullptr);
+            if (a.update_H) half_step(H, W, Xr, nkbH, (int)p, lh, multi);   // multupd.jl:171-181
+            half_step(W, H, Xc, nkbW, (int)n, lw, false);                    // :183-192 (local: H and its column sums are replicated)
+            if (multi) {   // the W-side sums of stop_condition run over this rank's rows only
+                conv_reduce_kernel<<<4 * (KP / 32), 256, 0, st>>>(W.conv, W.tiles, H.conv, H.tiles, KP, (int)k, a.update_H, acc, tol, state, 0, nullptr);
+                h->allreduce_sum(acc, (size_t)2 * KP);
+                conv_decide_kernel<<<1, 256, 0, st>>>(acc, KP, (int)k, tol, state);
+                h->launches += 1;
+            } else {
+                conv_reduce_kernel<<<4 * (KP / 32), 256, 0, st>>>(W.conv, W.tiles, H.conv, H.tiles, KP, (int)k, a.update_H, acc, tol, state, 1, nullptr);
+            }
             h->launches += 1;
         }
         enq += batch;
@@ -783,8 +828,17 @@ void tc_solve_div_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t l
     unpack_factor_kernel<<<ew_grid(p * k), 256, 0, st>>>(W.m, (int)p, (int)k, KP, Wd, 1, ldwd);
     unpack_factor_kernel<<<ew_grid(n * k), 256, 0, st>>>(H.m, (int)n, (int)k, KP, Hd, ldhd, 1);
     h->launches += 2;
-    double objv = 0;  // gkldiv (multupd.jl:148)
-    if (!tc_objective<KP>(h, 1, W, H, 0.0, 0.0, &objv)) objv = simt_objective_f32(h, 1, Wd, ldwd, Hd, ldhd, k, 0.0, 0.0);
+    double objv = 0;  // gkldiv (multupd.jl:148); row-sharded: the data term is a sum over the ranks' rows
+    if (h->all_ranks(tc_objective_covers((const float*)h->dX, h->p, h->n, h->ldx))) {
+        double* res = tc_objective_enqueue<KP>(h, "tc", 1, (const float*)h->dX, h->p, h->n, h->ldx, W, H, 0.0, 0.0);
+        h->allreduce_sum(res, 2);
+        double hres[3] = {0, 0, 0};
+        NMF_CUDA(cudaMemcpyAsync(hres, res, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        NMF_CUDA(cudaStreamSynchronize(st));
+        objv = tc_objective_value(1, hres, 0.0, 0.0);
+    } else {
+        objv = simt_objective_f32(h, 1, Wd, ldwd, Hd, ldhd, k, 0.0, 0.0);
+    }
     if (!a.on_device) {
         NMF_CUDA(cudaMemcpy2DAsync(Wc, ldw * sizeof(float), Wd, p * sizeof(float), p * sizeof(float), k, cudaMemcpyDeviceToHost, st));
         NMF_CUDA(cudaMemcpy2DAsync(Hc, ldh * sizeof(float), Hd, k * sizeof(float), k * sizeof(float), n, cudaMemcpyDeviceToHost, st));
@@ -965,7 +1019,8 @@ bool tc_supported(const nmfb200_handle* h, const SolveArgs& a) {
     // the reference's own tiny test problems -- laurberg6x3, 5x8 -- never see bf16 rounding).  engine = tc overrides.
     if (a.alg == 0 && h->engine_opt != 2 && h->p * h->n < ((int64_t)1 << 20)) return false;
     if (a.alg == 1) {                     // MultUpdate(:div): quotient kernel + update kernel; k <= 128, single GPU
-        if (h->comm != nullptr || h->emulate_shards > 1 || a.k > 128 || h->p < 128 || h->n < 128) return false;
+        if (h->emulate_shards > 1 || a.k > 128 || h->p < 128 || h->n < 128) return false;
+        if (h->comm != nullptr && h->tc_div_fused == 0) return false;   // row-sharded: the fused form only (its numerators are all-reduced)
         if (h->engine_opt != 2 && h->p * h->n < ((int64_t)1 << 20)) return false;
     }
     const bool sharded = h->comm != nullptr || h->emulate_shards > 1;
