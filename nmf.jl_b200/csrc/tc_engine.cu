@@ -928,7 +928,7 @@ void tc_solve_gcd_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t l
     float* bmax = h->buf_t<float>("tc.gcd_bmax", (size_t)maxtiles + 1);
     unsigned long long* d_updates = (unsigned long long*)h->buf("tc.gcd_updates", 16);
     NMF_CUDA(cudaMemsetAsync(state, 0, sizeof(TcState), st));
-    NMF_CUDA(cudaMemsetAsync(d_updates, 0, sizeof(unsigned long long), st));
+    NMF_CUDA(cudaMemsetAsync(d_updates, 0, 2 * sizeof(unsigned long long), st));
     NMF_CUDA(cudaMemsetAsync(W.bT, 0, (size_t)W.rowsT * W.ldT * sizeof(bf16), st));
     NMF_CUDA(cudaMemsetAsync(H.bT, 0, (size_t)H.rowsT * H.ldT * sizeof(bf16), st));
 
@@ -950,16 +950,43 @@ void tc_solve_gcd_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t l
     s.launch_gram(H, true);  // P = HH' for the first W-step (greedycd.jl:117)
     NMF_CUDA(cudaEventRecord(e1, st));
 
-    auto half_step = [&](Factor& F, Factor& O, const bf16* Xs, const bf16* Xs_lo, int Kdim, float lambda, int tiles128) {
+    // Row-sharded (rows of X and W over the ranks, H replicated):
+    //  * W-step: everything is local except p_init, a maximum over ALL rows of W (greedycd.jl:132-137): 1-float all-reduce (max).
+    //  * H-step: the gradient G = H (W'W) - X'W is a sum over the ranks of  H (W_g'W_g) - X_g'W_g  -- exactly what the update kernel
+    //    produces from this rank's rows and this rank's OWN Gram (whose bf16 split it already holds) -- so G is all-reduced once, lambda is
+    //    added on rank 0 only, p_init is recomputed from the complete G (the fused per-CTA maximum saw a partial one), and the coordinate
+    //    loop runs replicated on every rank with the all-reduced fp32 Gram.
+    const bool multi = h->comm != nullptr;
+    float* Pw_glob = multi ? h->buf_t<float>("tc.gcd_Pw_glob", (size_t)KP * KP) : nullptr;
+    const int nb_h = (int)ceil_div(n, GCD_WARPS);
+    float* bmax_h = multi ? h->buf_t<float>("tc.gcd_bmax_h", (size_t)nb_h + 1) : nullptr;
+    auto half_step = [&](Factor& F, Factor& O, const bf16* Xs, const bf16* Xs_lo, int Kdim, float lambda, int tiles128, bool is_h) {
         NMF_CUDA(cudaMemcpyAsync(prev, F.m, (size_t)F.R * KP * sizeof(float), cudaMemcpyDeviceToDevice, st));
         s.Xs_lo = Xs_lo;
-        s.launch_update(3, F, O, Xs, Kdim, lambda, 0.f, G, bmax);                                  // G = F P - X O (+lambda), per-CTA max D
-        max_partials_kernel<float><<<1, 256, 0, st>>>(bmax, F.tiles, bmax + maxtiles);            // p_init (:132-137)
-        gcd_rows_tc_kernel<KP><<<(unsigned)ceil_div(F.R, 8), 256, 0, st>>>(F.m, G, O.P, F.R, (int)k, bmax + maxtiles, d_updates);  // :139-165
+        const bool reduce_g = multi && is_h;
+        s.launch_update(3, F, O, Xs, Kdim, (reduce_g && h->rank != 0) ? 0.f : lambda, 0.f, G, bmax);   // G = F P - X O (+lambda), per-CTA max D
+        const float* P_rows = O.P;
+        const float* p_init = bmax + maxtiles;
+        if (reduce_g) {
+            h->allreduce_sum(G, (size_t)F.R * KP);
+            gcd_rowmax_kernel<float><<<nb_h, GCD_WARPS * 32, 0, st>>>(F.m, KP, 1, G, Pw_glob, F.R, KP, bmax_h);
+            max_partials_kernel<float><<<1, 256, 0, st>>>(bmax_h, nb_h, bmax_h + nb_h);
+            h->launches += 1;
+            P_rows = Pw_glob;
+            p_init = bmax_h + nb_h;
+        } else {
+            max_partials_kernel<float><<<1, 256, 0, st>>>(bmax, F.tiles, bmax + maxtiles);        // p_init (:132-137)
+            if (multi) h->allreduce_max(bmax + maxtiles, 1);                                      // ... over the rows of every rank
+        }
+        gcd_rows_tc_kernel<KP><<<(unsigned)ceil_div(F.R, 8), 256, 0, st>>>(F.m, G, P_rows, F.R, (int)k, p_init, d_updates + (is_h ? 1 : 0));  // :139-165
         gcd_repack_kernel<<<tiles128, 256, 0, st>>>(F.m, prev, F.R, KP, F.hi, F.lo, F.bT, F.ldT, F.conv);
         h->launches += 3;
         if (h->tc_precision == 1) s.refresh_bTlo(F);
         s.launch_gram(F, true);                                                                   // Gram of the updated factor
+        if (multi && !is_h) {   // W'W over all ranks for the H-step's coordinate loop; F.Phi / F.Plo keep this rank's own Gram
+            NMF_CUDA(cudaMemcpyAsync(Pw_glob, F.P, (size_t)KP * KP * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            h->allreduce_sum(Pw_glob, (size_t)KP * KP);
+        }
     };
 
     bool converged = false;
@@ -967,9 +994,16 @@ void tc_solve_gcd_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t l
     float devmax = 0.f;
     TcState hs;
     while (iters < a.maxiter && !converged) {  // one host check per iteration: the row kernel has no early-exit flag
-        half_step(W, H, Xc, Xc_lo, (int)n, lw, tilesW);                                            // W first (greedycd.jl:169-171)
-        if (a.update_H) half_step(H, W, Xr, Xr_lo, (int)p, lh, tilesH);                            // then H (:173-177)
-        conv_reduce_kernel<<<4 * (KP / 32), 256, 0, st>>>(W.conv, tilesW, H.conv, tilesH, KP, (int)k, a.update_H, acc, tol, state, 1, nullptr);
+        half_step(W, H, Xc, Xc_lo, (int)n, lw, tilesW, false);                                     // W first (greedycd.jl:169-171)
+        if (a.update_H) half_step(H, W, Xr, Xr_lo, (int)p, lh, tilesH, true);                      // then H (:173-177)
+        if (multi) {   // the W-side sums of stop_condition run over this rank's rows only
+            conv_reduce_kernel<<<4 * (KP / 32), 256, 0, st>>>(W.conv, tilesW, H.conv, tilesH, KP, (int)k, a.update_H, acc, tol, state, 0, nullptr);
+            h->allreduce_sum(acc, (size_t)2 * KP);
+            conv_decide_kernel<<<1, 256, 0, st>>>(acc, KP, (int)k, tol, state);
+            h->launches += 1;
+        } else {
+            conv_reduce_kernel<<<4 * (KP / 32), 256, 0, st>>>(W.conv, tilesW, H.conv, tilesH, KP, (int)k, a.update_H, acc, tol, state, 1, nullptr);
+        }
         h->launches += 1;
         NMF_CUDA(cudaGetLastError());
         NMF_CUDA(cudaMemcpyAsync(&hs, state, sizeof(TcState), cudaMemcpyDeviceToHost, st));
@@ -982,11 +1016,19 @@ void tc_solve_gcd_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t l
     unpack_factor_kernel<<<ew_grid(p * k), 256, 0, st>>>(W.m, (int)p, (int)k, KP, Wd, 1, ldwd);
     unpack_factor_kernel<<<ew_grid(n * k), 256, 0, st>>>(H.m, (int)n, (int)k, KP, Hd, ldhd, 1);
     h->launches += 2;
-    double objv = 0;  // greedycd.jl:82-92
-    if (!tc_objective<KP>(h, 2, W, H, a.lambda_w, a.lambda_h, &objv))
+    double objv = 0;  // greedycd.jl:82-92; row-sharded: the data term and |W|_1 are sums over the ranks' rows, |H|_1 is replicated
+    if (h->all_ranks(tc_objective_covers((const float*)h->dX, h->p, h->n, h->ldx))) {
+        double* res = tc_objective_enqueue<KP>(h, "tc", 2, (const float*)h->dX, h->p, h->n, h->ldx, W, H, a.lambda_w, a.lambda_h);
+        h->allreduce_sum(res, 2);
+        double hres[3] = {0, 0, 0};
+        NMF_CUDA(cudaMemcpyAsync(hres, res, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        NMF_CUDA(cudaStreamSynchronize(st));
+        objv = tc_objective_value(2, hres, a.lambda_w, a.lambda_h);
+    } else {
         objv = simt_objective_f32(h, 2, Wd, ldwd, Hd, ldhd, k, a.lambda_w, a.lambda_h);
-    unsigned long long upd = 0;
-    NMF_CUDA(cudaMemcpyAsync(&upd, d_updates, sizeof(upd), cudaMemcpyDeviceToHost, st));
+    }
+    unsigned long long upd2[2] = {0, 0};   // coordinate steps on W rows (this rank's) and on H rows (replicated)
+    NMF_CUDA(cudaMemcpyAsync(upd2, d_updates, sizeof(upd2), cudaMemcpyDeviceToHost, st));
     if (!a.on_device) {
         NMF_CUDA(cudaMemcpy2DAsync(Wc, ldw * sizeof(float), Wd, p * sizeof(float), p * sizeof(float), k, cudaMemcpyDeviceToHost, st));
         NMF_CUDA(cudaMemcpy2DAsync(Hc, ldh * sizeof(float), Hd, k * sizeof(float), k * sizeof(float), n, cudaMemcpyDeviceToHost, st));
@@ -1005,7 +1047,15 @@ void tc_solve_gcd_kp(nmfb200_handle* h, const SolveArgs& a, float* Wc, int64_t l
     out->last_dev = devmax;
     out->solve_ms = ms_loop;
     out->upload_ms = ms_up;
-    out->coordinate_updates = (int64_t)upd;
+    double w_upd = (double)upd2[0];
+    if (multi) {   // steps on W summed over the ranks; the steps on the replicated H count once
+        double* d = h->buf_t<double>("tc.gcd_upd_sum", 1);
+        NMF_CUDA(cudaMemcpyAsync(d, &w_upd, sizeof(double), cudaMemcpyHostToDevice, st));
+        h->allreduce_sum(d, 1);
+        NMF_CUDA(cudaMemcpyAsync(&w_upd, d, sizeof(double), cudaMemcpyDeviceToHost, st));
+        NMF_CUDA(cudaStreamSynchronize(st));
+    }
+    out->coordinate_updates = (int64_t)(w_upd + 0.5) + (int64_t)upd2[1];
     out->kernel_launches = h->launches;
     out->hot_kernel_ms = h->drain_event_pairs(&out->hot_kernel_launches);
 }
@@ -1027,8 +1077,8 @@ bool tc_supported(const nmfb200_handle* h, const SolveArgs& a) {
     if (sharded && h->tc_precision == 1 && h->engine_opt != 2) return false;   // parity mode on several ranks: the exact engine
     if (a.alg == 0 && h->comm != nullptr && !h->tc_xchg) return false;   // option tc_xchg=nccl: multi-GPU solves stay on the exact engine
     if (a.alg == 0 && sharded && (h->comm ? h->nranks : h->emulate_shards) > XCHG_MAX_RANKS) return false;
-    if (a.alg == 2) {                     // GreedyCD: bf16 gradients; single GPU; auto-selected for large problems only
-        if (sharded) return false;
+    if (a.alg == 2) {                     // GreedyCD: bf16 gradients; auto-selected for large problems only; several ranks: NCCL all-reduces
+        if (h->emulate_shards > 1) return false;
         if (h->engine_opt != 2 && h->p * h->n < ((int64_t)1 << 24)) return false;
     }
     if (a.verbose && (a.alg != 0 || h->n < 128 || h->p < 64 || (h->ldx % 4) != 0)) return false;  // per-iteration objective: MU-MSE only

@@ -31,7 +31,9 @@ def main():
              ("multmse", "tc", 2048, 1024, 200, 6, np.float32),    # KP = 256
              ("multdiv", "tc", 1024, 1280, 64, 8, np.float32),     # tensor-core :div, numerators and column sums all-reduced (NCCL)
              ("multdiv", "tc", 1001, 1152, 20, 6, np.float32),     # uneven shards: the ranks' k-splits differ, the all-reduced buffer does not
-             ("multdiv", "tc", 768, 1024, 32, 300, np.float32)]    # tolerance-bound: the W-side stop sums are all-reduced before the decision
+             ("multdiv", "tc", 768, 1024, 32, 300, np.float32),    # tolerance-bound: the W-side stop sums are all-reduced before the decision
+             ("greedycd", "tc", 1024, 896, 64, 4, np.float32),     # tensor-core GreedyCD: gradient of H and W'W all-reduced, p_init by max
+             ("greedycd", "tc", 1001, 1030, 200, 3, np.float32)]   # KP = 256, uneven shards
     for (algname, engine, p, n, k, iters, T) in cases:
         rng = np.random.default_rng(42)
         X = np.asfortranarray(rng.random((p, n)), dtype=T)
@@ -55,7 +57,8 @@ def main():
         ew, eh = relerr(Wl, Wo[lo:hi]), relerr(Hl, Ho)
         eo = abs(float(r.objvalue) - float(ro.objvalue)) / float(ro.objvalue)
         wtol = 5e-3 if engine == "tc" else (1e-8 if algname != "greedycd" else 1e-5)
-        good = (eo <= 1e-4 and (algname == "greedycd" or (ew <= wtol and eh <= wtol)) and r.info["engine"] == engine)
+        otol = 5e-3 if (algname == "greedycd" and engine == "tc") else 1e-4    # bf16 gradients: tests/test_gpu_tc.py states the same bar
+        good = (eo <= otol and (algname == "greedycd" or (ew <= wtol and eh <= wtol)) and r.info["engine"] == engine)
         if iters < 100:
             good = good and r.niters == ro.niters
         else:
