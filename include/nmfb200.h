@@ -263,8 +263,11 @@ int nmfb200_nndsvd_f64(nmfb200_handle* h, double* W, int64_t ldw, double* H, int
  * (torch.distributed / MPI / sockets).  After comm_init every solve on the handle treats its X, W
  * as the rank's row shard; H, niters, converged and objvalue come back identical on all ranks.
  * MultUpdate(:mse) Float32 exchanges the k x n numerators, the k x k Grams and the convergence partial
- * sums once per iteration through NVLink peer memory (CUDA IPC, no NCCL call in the loop); the other
- * algorithms all-reduce the same quantities over NCCL on the exact engine. */
+ * sums once per iteration through NVLink peer memory (CUDA IPC, no NCCL call in the loop).  MultUpdate(:div)
+ * and GreedyCD in Float32 stay on the tensor-core engine as well and all-reduce over NCCL on the solver's
+ * stream: :div the column sums of W and the numerators W'Q (multupd.jl:175-176), GreedyCD the gradient of H,
+ * W'W and -- a maximum -- p_init (greedycd.jl:132-137), both the W-side sums of stop_condition.  Everything
+ * else (Float64, small problems, the other algorithms) all-reduces the same quantities on the exact engine. */
 #define NMFB200_UNIQUE_ID_BYTES 128
 int nmfb200_comm_unique_id(void* out_id_128);
 /* Host-only helper (no GPU needed): which rows of H' (columns of H) rank `rank` of `ranks` OWNS in the row-sharded tensor-core

@@ -33,7 +33,7 @@ def main():
              ("multdiv", "tc", 1001, 1152, 20, 6, np.float32),     # uneven shards: the ranks' k-splits differ, the all-reduced buffer does not
              ("multdiv", "tc", 768, 1024, 32, 300, np.float32),    # tolerance-bound: the W-side stop sums are all-reduced before the decision
              ("greedycd", "tc", 1024, 896, 64, 4, np.float32),     # tensor-core GreedyCD: gradient of H and W'W all-reduced, p_init by max
-             ("greedycd", "tc", 1001, 1030, 200, 3, np.float32)]   # KP = 256, uneven shards
+             ("greedycd", "tc", 2047, 1536, 200, 3, np.float32)]   # KP = 256, uneven shards (1024 / 1023 rows)
     for (algname, engine, p, n, k, iters, T) in cases:
         rng = np.random.default_rng(42)
         X = np.asfortranarray(rng.random((p, n)), dtype=T)
