@@ -209,3 +209,123 @@ def test_ownership_protocol_gloo(world):
     for pr in procs:
         pr.join(timeout=60)
     assert sorted(res) == [(r, "ok") for r in range(world)], res
+
+
+# ---- round 2: the row-sharded tensor-core MultUpdate(:div) and GreedyCD (tc_engine.cu), restated with gloo + NumPy -----------------
+def _greedy_rows_numpy(F, G, P, p_init, T):
+    """greedycd.jl:139-165 for the rows given, with p_init supplied from outside (the sharded W-step gets it from an all-reduce)."""
+    rows, k = F.shape
+    eps = np.finfo(T).eps
+    steps = 0
+    for i in range(rows):
+        g, f, fnew = G[i].copy(), F[i].copy(), np.zeros(k, dtype=T)
+
+        def sd(w, gg):
+            s = np.maximum(0, w - gg / (eps + np.diag(P))) - w
+            return s, -gg * s - 0.5 * np.diag(P) * s * s
+        s, d = sd(f, g)
+        q = int(np.argmax(d))
+        for _ in range(k * k):
+            if not d[q] >= 0.001 * p_init:
+                break
+            sq = s[q]
+            fnew[q] += sq
+            g += sq * P[q, :]
+            s, d = sd(f, g)        # the reference recomputes S against the row as it was at the start of the half-step (:155)
+            q = int(np.argmax(d))
+            steps += 1
+        F[i] = np.maximum(0, f + fnew)
+    return steps
+
+
+def _row_max_d(F, G, P, T):
+    eps = np.finfo(T).eps
+    s = np.maximum(0, F - G / (eps + np.diag(P))) - F
+    d = -G * s - 0.5 * np.diag(P) * s * s
+    return max(-1.0, float(d.max(axis=1).max())) if F.shape[0] else -1.0
+
+
+def _div_gcd_worker(rank, world, port, q):
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        sys.path.insert(0, p)
+    import nmf_jl_b200 as NMF
+    import nmf_oracle as O
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def allsum(x):
+        t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64))
+        dist.all_reduce(t)
+        return t.numpy()
+
+    try:
+        T = np.float64
+        rng = np.random.default_rng(5)
+        p, n, k = 41, 33, 3
+        X = np.asfortranarray(rng.random((p, n)))
+        W0, H0 = O.randinit(p, n, k, T, rng, normalize=True)
+        lo, hi = NMF.dist.row_shard(p, rank, world)
+        Xg = X[lo:hi]
+        delta = np.sqrt(np.finfo(T).eps)
+
+        # (1) MultUpdate(:div), multupd.jl:171-192: all-reduce [colsum(W_g) | W_g'Q_g], ratio on every rank's replica of H, W-step local
+        Wg, H = np.asfortranarray(W0[lo:hi]), H0.copy(order="F")
+        lam = delta                                        # the constructor's floor (multupd.jl:37-40)
+        for _ in range(6):
+            Q = Xg / (Wg @ H + delta)
+            sW = allsum(Wg.sum(axis=0))                     # column sums over ALL rows of W
+            WtQ = allsum(Wg.T @ Q)                          # numerators, summed over the ranks
+            H *= WtQ / (sW[:, None] + lam)
+            Q = Xg / (Wg @ H + delta)
+            Wg *= (Q @ H.T) / (H.sum(axis=1)[None, :] + lam)
+        Wr, Hr = W0.copy(order="F"), H0.copy(order="F")
+        ref = O.solve(O.MultUpdate(T, obj="div", maxiter=6, tol=1e-30), X, Wr, Hr)
+        assert ref.niters == 6
+        np.testing.assert_allclose(H, Hr, rtol=1e-10)
+        np.testing.assert_allclose(Wg, Wr[lo:hi], rtol=1e-10)
+        obj = float(allsum(np.array([np.sum(np.where(Xg > 0, Xg * np.log(np.where(Xg > 0, Xg, 1) / (Wg @ H)) - Xg + Wg @ H, Wg @ H))]))[0])
+        assert abs(obj - float(ref.objvalue)) <= 1e-9 * float(ref.objvalue)    # the objective's data term is a sum over the ranks' rows
+
+        # (2) GreedyCD, greedycd.jl:94-178.  W-step local except p_init (max over all ranks).  H-step: every rank forms
+        #     H (W_g'W_g) - X_g'W_g from ITS rows and ITS OWN Gram; the sum over ranks is the gradient (lambda added on rank 0 only);
+        #     p_init from the complete gradient; the coordinate loop runs replicated with the all-reduced W'W.
+        lam_w, lam_h = 1e-3, 2e-3
+        Wg, Ht = np.asfortranarray(W0[lo:hi]), np.array(H0.T, order="C", copy=True)   # (ascontiguousarray would alias H0)
+        for _ in range(3):
+            Ph = Ht.T @ Ht                                                     # replicated
+            Gw = Wg @ Ph - Xg @ Ht + lam_w
+            pw = torch.tensor([_row_max_d(Wg, Gw, Ph, T)], dtype=torch.float64)
+            dist.all_reduce(pw, op=dist.ReduceOp.MAX)                          # 1-float all-reduce (max)
+            _greedy_rows_numpy(Wg, Gw, Ph, float(pw.item()), T)
+            Pw_own = Wg.T @ Wg
+            Gh = allsum(Ht @ Pw_own - Xg.T @ Wg + (lam_h if rank == 0 else 0.0))
+            Pw = allsum(Pw_own)
+            _greedy_rows_numpy(Ht, Gh, Pw, _row_max_d(Ht, Gh, Pw, T), T)       # replicated: identical on every rank
+        Wr, Hr = W0.copy(order="F"), H0.copy(order="F")
+        ref = O.solve(O.GreedyCD(T, maxiter=3, tol=1e-30, lambda_w=lam_w, lambda_h=lam_h), X, Wr, Hr)
+        np.testing.assert_allclose(Ht.T, Hr, rtol=1e-8, atol=1e-12)
+        np.testing.assert_allclose(Wg, Wr[lo:hi], rtol=1e-8, atol=1e-12)
+        same = [torch.empty_like(torch.from_numpy(Ht)) for _ in range(world)]
+        dist.all_gather(same, torch.from_numpy(Ht))
+        assert all((s_ == same[0]).all() for s_ in same)                        # the replicated H is bit-identical on every rank
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, f"FAIL {type(e).__name__}: {e} {traceback.format_exc()[-600:]}"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_div_and_greedycd_protocol_gloo(world):
+    """What tc_solve_div_kp / tc_solve_gcd_kp exchange between ranks (NCCL there, gloo here): the same iterates as the unsharded oracle."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() + 7 * world) % 90
+    procs = [ctx.Process(target=_div_gcd_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for pr in procs:
+        pr.join(timeout=60)
+    assert sorted(res) == [(r, "ok") for r in range(world)], res

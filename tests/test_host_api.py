@@ -263,3 +263,67 @@ def test_julia_status_codes_match_header():
     m = re.search(r"const ([A-Z, ]+) = 0:(\d+)", jl)
     names = [x.strip() for x in m.group(1).split(",")]
     assert [c[0].replace("NMFB200_", "") for c in sorted(codes, key=lambda c: int(c[1]))] == names and int(m.group(2)) == len(names) - 1
+
+
+# ---- solve_replicates (interf.jl:85-101): grouping into stacked solves, draw order, fallback -- host logic, no GPU -----------------
+class _FakeReplicateSession:
+    """Duck-typed Session: records the initial factors it is handed; the 'objective' of a solve is the sum of its initial W."""
+
+    def __init__(self, p, n, batched_ok=True):
+        self.shape, self.batched_ok, self.calls, self.seen = (p, n), batched_ok, [], []
+
+    def _result(self, NMF, W, H, extra=None):
+        self.seen.append(W.copy())
+        return NMF.Result(W, H, 3, False, float(W.sum()), extra or {})
+
+    def solve(self, alg, W, H):
+        import nmf_jl_b200 as NMF
+        self.calls.append(1)
+        return self._result(NMF, W, H)
+
+    def solve_batched(self, alg, Ws, Hs):
+        import nmf_jl_b200 as NMF
+        if not self.batched_ok:
+            raise NotImplementedError("not covered")
+        self.calls.append(len(Ws))
+        return [self._result(NMF, W, H, {"batched": len(Ws)}) for W, H in zip(Ws, Hs)]
+
+
+def test_solve_replicates_groups_draw_order_and_fallback(NMF):
+    p, n = 40, 30
+    alg = NMF.MultUpdate(np.float32, obj="mse", maxiter=5)
+
+    def run(k, replicates, batched, batched_ok=True, algo=alg):
+        rng = np.random.default_rng(99)
+        W, H = NMF.randinit(p, n, k, algo.T, normalize=True, rng=rng)
+        s = _FakeReplicateSession(p, n, batched_ok)
+        r = NMF.solve_replicates(algo, s, W, H, replicates=replicates, initH=True, rng=rng, batched=batched)
+        return s, r
+
+    one, r1 = run(100, 7, batched=False)
+    grp, r2 = run(100, 7, batched=True)
+    assert one.calls == [1] * 7 and grp.calls == [2, 2, 2, 1]               # groups of 256 // 100 replicates, the rest one by one
+    assert all((a == b).all() for a, b in zip(one.seen, grp.seen))           # the restarts are drawn in the reference's order
+    assert (r1.W == r2.W).all() and r1.objvalue == r2.objvalue               # the same replicate wins (first smallest objvalue)
+    assert float(r1.objvalue) == min(float(w.sum(dtype=np.float32)) for w in one.seen)
+    small, _ = run(8, 40, batched=True)
+    assert small.calls == [32, 8]                                            # at most 32 replicates per stacked solve
+    fb, r3 = run(100, 5, batched=True, batched_ok=False)                     # library says ENOTSUP: the same factors, one by one
+    assert fb.calls == [1] * 5 and (r3.W == run(100, 5, batched=False)[1].W).all()
+    for other in (NMF.MultUpdate(np.float32, obj="div", maxiter=5), NMF.MultUpdate(np.float64, maxiter=5), NMF.GreedyCD(np.float32, maxiter=5)):
+        s, _ = run(8, 4, batched=True, algo=other)                           # only Float32 MultUpdate(:mse) is stacked
+        assert s.calls == [1] * 4
+
+
+def test_nnmf_sparse_validation_before_gpu(NMF):
+    sp = pytest.importorskip("scipy.sparse")
+    X = sp.random(12, 9, density=0.4, format="csr", dtype=np.float64, random_state=np.random.default_rng(0))
+    assert NMF.api._is_sparse(X) and not NMF.api._is_sparse(X.toarray())
+    bad = X.copy()
+    bad.data[0] = -1.0
+    with pytest.raises(NMF.ArgumentError, match="non-negative"):             # interf.jl:15 on the stored entries
+        NMF.nnmf(bad, 3)
+    with pytest.raises(NMF.ArgumentError, match="should not exceed"):        # interf.jl:18
+        NMF.nnmf(X, 10)
+    with pytest.raises(NMF.ArgumentError, match="eltype"):
+        NMF.nnmf(X.astype(np.int32), 3)
