@@ -114,6 +114,9 @@ int nmfb200_set_stream(nmfb200_handle* h, void* stream);
  *                                               tiles of the launch before it instead of a kernel boundary (-6 % per iteration at
  *                                               config 2); the small reduce kernels then run as one CTA per SM (n > 1: n CTAs).
  *                                               0 = kernel-boundary hand-over.  Results are identical.
+ *   "tc_skew"      = "0" | "1"               -- experiment on top of tc_chain, default 0: two groups of tiles half a period apart (one
+ *                                               streams while the other is in its epilogues).  Identical results; measured: no gain,
+ *                                               one SM streams ~52 GB/s whatever the others do (profiles/r2c_chain_handover.md).
  *   "tc_prefetch_next" = "<n>"               -- experiment, default 0: L2 prefetch of the first n k-blocks of the next launch's X
  *                                               panel from the epilogue (measured: no gain, profiles/r2b_prefetch_next.md).
  *   "tc_div_fused" = "0" | "1"               -- MultUpdate(:div) on the tensor-core engine: 1 (default) keeps the quotient
