@@ -292,7 +292,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     parity = None
     if not args.no_e2e:
         e2e_iters = iters
-        Wh, Hh = W0.copy(order="F"), H0.copy(order="F")
+        # the factors travel from / to PINNED host memory like X (a pageable W, H costs two staged copies of 8 MB each way)
+        twh = torch.empty((k, rows), dtype=torch.float32, pin_memory=True)
+        thh = torch.empty((n, k), dtype=torch.float32, pin_memory=True)
+        Wh, Hh = twh.numpy().T, thh.numpy().T          # column-major rows x k and k x n views of the pinned buffers
+        assert Wh.flags.f_contiguous and Hh.flags.f_contiguous and Wh.shape == W0.shape and Hh.shape == H0.shape
         sess2 = NMF.Session(device=local_rank, engine="tc")
         if world > 1:
             uid = [NMF.Session.comm_unique_id() if rank == 0 else None]
